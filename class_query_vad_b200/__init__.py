@@ -1,0 +1,18 @@
+"""class_query_vad_b200 -- B200-native (sm_100a) class-query decoder hot path of dlrudco/class-query-vad.
+
+Host side = thin Python/PyTorch mirror of the reference's operator interfaces (same class names, forward signatures,
+parameter names); all arithmetic runs in hand-written CUDA behind the C ABI of include/cqvad.h (libcqvad.so).
+"""
+from . import _lib
+from .engine import DecoderEngine, pack_decoder_weights
+from .functions.ms_deform_attn_func import MSDeformAttnFunction, ms_deform_attn_indices
+from .modules.ms_deform_attn import MSDeformAttn3D
+from .modules.attention import MultiheadAttention
+from .modules.position_encoding import PositionEmbeddingSine_3D, build_position_encoding, gen_sineembed_for_position
+from .modules.decoder import (MLP, ConvBlock, TransformerDecoderLayer, TransformerClassDecoderLayer, TransformerDecoder,
+                              build_decoder)
+
+__all__ = ["DecoderEngine", "pack_decoder_weights", "MSDeformAttnFunction", "ms_deform_attn_indices", "MSDeformAttn3D",
+           "MultiheadAttention", "PositionEmbeddingSine_3D", "build_position_encoding", "gen_sineembed_for_position",
+           "MLP", "ConvBlock", "TransformerDecoderLayer", "TransformerClassDecoderLayer", "TransformerDecoder",
+           "build_decoder"]

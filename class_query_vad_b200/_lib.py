@@ -1,0 +1,93 @@
+"""ctypes binding of libcqvad.so (include/cqvad.h).  There is NO fallback: if the library is missing the import of any
+op fails loudly -- build it with `python -c "import __graft_entry__ as g; g.build()"` (or `make -C class_query_vad_b200/csrc`)."""
+import ctypes
+import os
+from ctypes import c_int, c_long, c_size_t, c_void_p, c_float, c_char_p, POINTER, Structure
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcqvad.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+DEC_SKIP_CLS_HS = 1
+
+
+class DecoderDesc(Structure):
+    _fields_ = [("dtype", c_int), ("BT", c_int), ("nq", c_int), ("h", c_int), ("w", c_int), ("K", c_int), ("F", c_int),
+                ("layers", c_int), ("out_f32", c_int), ("flags", c_int)]
+
+
+class CqvadError(RuntimeError):
+    pass
+
+
+# every symbol include/cqvad.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "cqvad_version": (c_int, []),
+    "cqvad_last_error": (c_char_p, []),
+    "cqvad_msda3d_forward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
+    "cqvad_msda3d_backward": (c_int, [c_int] + [c_void_p] * 9 + [c_int] * 7 + [c_void_p]),
+    "cqvad_msda3d_indices": (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_void_p]),
+    "cqvad_layernorm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_long, c_int, c_void_p]),
+    "cqvad_linear": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_void_p]),
+    "cqvad_convblock_workspace_bytes": (c_size_t, [c_int, c_long, c_int, c_int]),
+    "cqvad_convblock_forward": (c_int, [c_int] + [c_void_p] * 10 + [c_long, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "cqvad_mha_core": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
+    "cqvad_posenc3d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "cqvad_sine_embed": (c_int, [c_void_p, c_void_p, c_long, c_void_p]),
+    "cqvad_decoder_num_weights": (c_int, [c_int]),
+    "cqvad_decoder_weight_name": (c_char_p, [c_int, c_int]),
+    "cqvad_decoder_weight_kind": (c_int, [c_int, c_int]),
+    "cqvad_decoder_workspace_bytes": (c_size_t, [POINTER(DecoderDesc)]),
+    "cqvad_decoder_forward": (c_int, [POINTER(DecoderDesc), POINTER(c_void_p)] + [c_void_p] * 11 + [c_void_p, c_size_t, c_void_p]),
+    "cqvad_last_launch_count": (c_long, []),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: the CUDA extension has not been built "
+                              "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU/PyTorch fallback.")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        l.cqvad_debug_force_simt.restype = None
+        l.cqvad_debug_force_simt.argtypes = [c_int]
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise CqvadError(f"libcqvad error {rc}: {lib().cqvad_last_error().decode()}")
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dtype_id(torch_dtype):
+    import torch
+    if torch_dtype == torch.float32:
+        return F32
+    if torch_dtype == torch.bfloat16:
+        return BF16
+    raise CqvadError(f"unsupported dtype {torch_dtype}: libcqvad computes in float32 or bfloat16")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("Not implemented on the CPU")  # same message as ops/src/cpu/ms_deform_attn_cpu.cpp:26

@@ -1,0 +1,492 @@
+// Decoder driver: TransformerDecoder.forward (models/detr/dab_transformer.py:722-852) + DETR heads
+// (models/model.py:191-221) as one natively-enqueued kernel sequence, plus the C-ABI wrappers of the building blocks.
+//
+// Not a translation of the reference graph (about 130 aten ops per layer on (nq,BT,...)-major tensors with permute /
+// expand / cat copies): activations live as row-major [rows,256] matrices in instance-major order
+// (instance i = n*BT + b; pixels (i,s); class tokens (i,k)), the ConvBlock chain runs on a y-padded NHWC layout
+// [N, h+1, w, 256] whose zero separator rows give the 3x3 conv its vertical halo for free, per-head
+// [content | position] concatenations are never materialised, and bias / activation / residual / LayerNorm are
+// GEMM epilogues.
+#include <string.h>
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "kernels_mem.cuh"
+#include "attention.cuh"
+
+namespace cqvad {
+
+// ---- error / launch-count state (thread-local) -------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static thread_local long g_launches = 0;
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void count_launch(int n) { g_launches += n; }
+void reset_launch_count() { g_launches = 0; }
+
+// ---- weight table --------------------------------------------------------------------------------------------
+// kind: 0 = matrix stored in the activation dtype, 1 = fp32
+struct Slot { const char* name; int kind; };
+#define LIN(n) {n ".weight", 0}, {n ".bias", 1}
+#define LNP(n) {n ".weight", 1}, {n ".bias", 1}
+static const Slot kLocSlots[] = {
+    LIN("sa_qcontent_proj"), LIN("sa_qpos_proj"), LIN("sa_kcontent_proj"), LIN("sa_kpos_proj"), LIN("sa_v_proj"),
+    LIN("self_attn.out_proj"), LNP("norm1"), {"lvl_w_embed.weight", 1}, {"lvl_w_embed.bias", 1},
+    LIN("ca_qcontent_proj"), LIN("ca_qpos_proj"), LIN("ca_kcontent_proj"), LIN("ca_kpos_proj"), LIN("ca_v_proj"),
+    LIN("ca_qpos_sine_proj"), LIN("cross_attn.out_proj"), LIN("linear1"), LIN("linear2"), LNP("norm2"), LNP("norm3"),
+    LNP("norm_")};
+enum LocIdx { SA_QC = 0, SA_QP = 2, SA_KC = 4, SA_KP = 6, SA_V = 8, SA_O = 10, NORM1 = 12, LVLW = 14, CA_QC = 16,
+              CA_QP = 18, CA_KC = 20, CA_KP = 22, CA_V = 24, CA_QS = 26, CA_O = 28, LIN1 = 30, LIN2 = 32, NORM2 = 34,
+              NORM3 = 36, NORMU = 38, LOC_COUNT = 40 };
+static const Slot kClsSlots[] = {
+    LIN("cls_linear1"), LIN("cls_linear2"), LNP("cls_norm"), LNP("conv_norm"), LIN("conv_blocks.0.conv1"),
+    LNP("conv_blocks.0.norm"), LIN("conv_blocks.0.conv2"), LIN("conv_blocks.0.conv3"), LIN("self_attn.out_proj"),
+    LNP("norm1"), LIN("k_proj"), LIN("v_proj"), LIN("cls_qpos_sine_proj"), LIN("cross_attn.out_proj"),
+    LIN("cls_linear1_"), LIN("cls_linear2_"), LNP("cls_norm_")};
+enum ClsIdx { C_L1 = 0, C_L2 = 2, C_NORM = 4, C_CONVNORM = 6, C_CONV1 = 8, C_CBNORM = 10, C_CONV2 = 12, C_CONV3 = 14,
+              C_SA_O = 16, C_NORM1 = 18, C_KPROJ = 20, C_VPROJ = 22, C_QPS = 24, C_CA_O = 26, C_L1_ = 28, C_L2_ = 30,
+              C_NORM_ = 32, CLS_COUNT = 34 };
+static const Slot kGlobSlots[] = {
+    LNP("norm"), LNP("cls_norm2"), LIN("query_scale.layers.0"), LIN("query_scale.layers.1"),
+    LIN("ref_point_head.layers.0"), LIN("ref_point_head.layers.1"), LIN("ref_anchor_head.layers.0"),
+    {"ref_anchor_head.layers.1.weight", 1}, {"ref_anchor_head.layers.1.bias", 1}, {"class_queries.weight", 0},
+    LIN("bbox_embed.layers.0"), LIN("bbox_embed.layers.1"), {"bbox_embed.layers.2.weight", 1},
+    {"bbox_embed.layers.2.bias", 1}, {"heads.class_embed_b.weight", 1}, {"heads.class_embed_b.bias", 1}};
+enum GlobIdx { G_NORM = 0, G_CLSNORM2 = 2, G_QS0 = 4, G_QS1 = 6, G_RPH0 = 8, G_RPH1 = 10, G_RAH0 = 12, G_RAH1 = 14,
+               G_CQ = 16, G_BB0 = 17, G_BB1 = 19, G_BB2 = 21, G_CEB = 23, GLOB_COUNT = 25 };
+static_assert(sizeof(kLocSlots) / sizeof(Slot) == LOC_COUNT, "loc slots");
+static_assert(sizeof(kClsSlots) / sizeof(Slot) == CLS_COUNT, "cls slots");
+static_assert(sizeof(kGlobSlots) / sizeof(Slot) == GLOB_COUNT, "glob slots");
+
+static thread_local std::string g_name;
+static bool weight_slot(int idx, int layers, std::string* name, int* kind) {
+  if (idx < 0) return false;
+  if (idx < layers * LOC_COUNT) {
+    const Slot& s = kLocSlots[idx % LOC_COUNT];
+    if (name) *name = "layers." + std::to_string(idx / LOC_COUNT) + "." + s.name;
+    if (kind) *kind = s.kind;
+    return true;
+  }
+  idx -= layers * LOC_COUNT;
+  if (idx < layers * CLS_COUNT) {
+    const Slot& s = kClsSlots[idx % CLS_COUNT];
+    if (name) *name = "cls_layers." + std::to_string(idx / CLS_COUNT) + "." + s.name;
+    if (kind) *kind = s.kind;
+    return true;
+  }
+  idx -= layers * CLS_COUNT;
+  if (idx < GLOB_COUNT) {
+    if (name) *name = kGlobSlots[idx].name;
+    if (kind) *kind = kGlobSlots[idx].kind;
+    return true;
+  }
+  return false;
+}
+
+// ---- workspace arena ---------------------------------------------------------------------------------------------
+struct Arena {
+  char* base; size_t cap; size_t off = 0; bool overflow = false;
+  Arena(void* b, size_t c) : base((char*)b), cap(c) {}
+  void* take(size_t bytes) {
+    off = (off + 1023) & ~(size_t)1023;
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    if (base && off > cap) overflow = true;
+    return p;
+  }
+};
+
+template <typename T>
+struct Decoder {
+  const cqvad_decoder_desc& d;
+  const void* const* w;
+  cudaStream_t st;
+  int BT, nq, h, wd, S, Sp, K, F, Lr;
+  long N, NS, Rp, NK;
+
+  // buffers
+  T *memc, *pos0c, *e512, *qpos, *tmpN, *pscale, *qse, *saq, *sak, *sav, *sao, *out, *actor, *acls, *qm, *kv, *kp, *qc,
+      *qs, *cao, *XA, *XB, *Xn, *Hc, *Qc[2], *cq1, *cq2, *saoc, *kx, *vx, *cqp, *caoc, *cls0, *Hf, *hsn, *bb1, *bb2;
+  float *r_cur, *r_next, *lvlw;
+
+  Decoder(const cqvad_decoder_desc& dd, const void* const* ww, cudaStream_t s) : d(dd), w(ww), st(s) {
+    BT = d.BT; nq = d.nq; h = d.h; wd = d.w; S = h * wd; Sp = (h + 1) * wd; K = d.K; F = d.F; Lr = d.layers;
+    N = (long)nq * BT; NS = N * S; Rp = N * Sp; NK = N * K;
+  }
+  size_t plan(Arena& a) {
+    auto t = [&](long n) { return (T*)a.take((size_t)n * sizeof(T)); };
+    auto f = [&](long n) { return (float*)a.take((size_t)n * sizeof(float)); };
+    const long Fm = F > kC ? F : kC;
+    memc = t(4L * S * BT * kC); pos0c = t((long)S * BT * kC);
+    e512 = t(N * 512); qpos = t(N * kC); tmpN = t(N * Fm); pscale = t(N * kC); qse = t(N * kC);
+    saq = t(N * kC); sak = t(N * kC); sav = t(N * kC); sao = t(N * kC); out = t(N * kC); actor = t(N * kC);
+    acls = t(N * kC); qm = t(NS * kC); kv = t(NS * 2 * kC); kp = t((long)S * BT * kC); qc = t(N * kC); qs = t(N * kC);
+    cao = t(N * kC); XA = t(Rp * kC); XB = t(Rp * kC); Xn = t(Rp * kC); Hc = t(Rp * 4 * kC);
+    Qc[0] = t(NK * kC); Qc[1] = t(NK * kC); cq1 = t((long)K * kC); cq2 = t((long)K * kC); saoc = t(NK * kC);
+    kx = t(Rp * kC); vx = t(NS * kC); cqp = t(N * kC); caoc = t(NK * kC); cls0 = t(NK * kC); Hf = t(NK * F);
+    hsn = t(N * kC); bb1 = t(N * kC); bb2 = t(N * kC);
+    r_cur = f(N * 4); r_next = f(N * 4); lvlw = f(N * 4);
+    return a.off;
+  }
+
+  const T* Wm(int i) const { return (const T*)w[i]; }
+  const float* Wf(int i) const { return (const float*)w[i]; }
+  int loc(int l, int s) const { return l * LOC_COUNT + s; }
+  int cls(int l, int s) const { return Lr * LOC_COUNT + l * CLS_COUNT + s; }
+  int glob(int s) const { return Lr * (LOC_COUNT + CLS_COUNT) + s; }
+
+  // C[M,N] = act(A . W^T + b) (+res) (-> LN)
+  int lin(const T* A, long M, int Kd, int widx, T* C, int Nn, int act = CQVAD_ACT_NONE, const T* res = nullptr,
+          int ln_idx = -1, float eps = 1e-5f, long ldc = -1, long lda = -1) {
+    Epilogue e;
+    e.bias = Wf(widx + 1); e.act = act; e.res = res; e.ldr = ldc < 0 ? Nn : ldc;
+    if (ln_idx >= 0) { e.ln_g = Wf(ln_idx); e.ln_b = Wf(ln_idx + 1); e.ln_eps = eps; }
+    return gemm<T>(A, lda < 0 ? Kd : lda, Wm(widx), C, ldc < 0 ? Nn : ldc, M, Nn, Kd, e, nullptr, st);
+  }
+  // Y = LN?( res + W2.act(W1.X + b1) + b2 ), hidden in `hid` ([M,Fh]) unless the fused tensor-core kernel takes it
+  int mlp(const T* X, long M, int Fh, int w1, int w2, int act, const T* res, int ln_idx, float eps, T* Y, T* hid,
+          int zero_period = 0, int zero_valid = 0);
+
+  int run(const float* tgt, const float* memory, const float* pos, const uint8_t* mask, const float* ref_u, void* hs,
+          void* cls_hs, float* refs, float* pred_logits, float* pred_boxes, float* pred_logits_b);
+};
+
+template <>
+int Decoder<float>::mlp(const float* X, long M, int Fh, int w1, int w2, int act, const float* res, int ln_idx, float eps,
+                        float* Y, float* hid, int zero_period, int zero_valid) {
+  CQ_TRY(lin(X, M, kC, w1, hid, Fh, act));
+  Epilogue e;
+  e.bias = Wf(w2 + 1); e.res = res; e.ldr = kC; e.zero_period = zero_period; e.zero_valid = zero_valid;
+  if (ln_idx >= 0) { e.ln_g = Wf(ln_idx); e.ln_b = Wf(ln_idx + 1); e.ln_eps = eps; }
+  return gemm<float>(hid, Fh, Wm(w2), Y, kC, M, kC, Fh, e, nullptr, st);
+}
+template <>
+int Decoder<bf16>::mlp(const bf16* X, long M, int Fh, int w1, int w2, int act, const bf16* res, int ln_idx, float eps,
+                       bf16* Y, bf16* hid, int zero_period, int zero_valid) {
+  if (!force_simt()) {
+    int r = mlp_tc(X, Wm(w1), Wf(w1 + 1), Wm(w2), Wf(w2 + 1), act, res, ln_idx >= 0 ? Wf(ln_idx) : nullptr,
+                   ln_idx >= 0 ? Wf(ln_idx + 1) : nullptr, eps, Y, M, kC, Fh, zero_period, zero_valid, st);
+    if (r <= 0) return r;
+  }
+  CQ_TRY(lin(X, M, kC, w1, hid, Fh, act));
+  Epilogue e;
+  e.bias = Wf(w2 + 1); e.res = res; e.ldr = kC; e.zero_period = zero_period; e.zero_valid = zero_valid;
+  if (ln_idx >= 0) { e.ln_g = Wf(ln_idx); e.ln_b = Wf(ln_idx + 1); e.ln_eps = eps; }
+  return gemm<bf16>(hid, Fh, Wm(w2), Y, kC, M, kC, Fh, e, nullptr, st);
+}
+
+template <typename T>
+int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, const uint8_t* mask, const float* ref_u,
+                    void* hs, void* cls_hs, float* refs, float* pred_logits, float* pred_boxes, float* pred_logits_b) {
+  const bool of32 = d.out_f32 != 0;
+  const size_t osz = of32 ? sizeof(float) : sizeof(T);
+  // inputs -> compute dtype.  Only pos[0] is ever used (dab_transformer.py:958, :810).
+  CQ_TRY(convert_f32<T>(memory, memc, 4L * S * BT * kC, st));
+  CQ_TRY(convert_f32<T>(pos, pos0c, (long)S * BT * kC, st));
+  CQ_TRY(convert_f32<T>(tgt, out, N * kC, st));
+  CQ_CUDA(cudaMemsetAsync(XA, 0, (size_t)Rp * kC * sizeof(T), st));  // zero separator rows (never written afterwards)
+  CQ_CUDA(cudaMemsetAsync(XB, 0, (size_t)Rp * kC * sizeof(T), st));
+  CQ_TRY(sigmoid4(ref_u, r_cur, refs, N, nq, BT, st));               // :735; refs[0]
+
+  for (int l = 0; l < Lr; ++l) {
+    const bool first = (l == 0);
+    // ---- prologue :742-763 ----
+    CQ_TRY(sine_embed<T>(r_cur, e512, N, st));
+    CQ_TRY(lin(e512, N, 512, glob(G_RPH0), tmpN, kC, CQVAD_ACT_RELU));
+    CQ_TRY(lin(tmpN, N, kC, glob(G_RPH1), qpos, kC));
+    if (!first) {
+      CQ_TRY(lin(out, N, kC, glob(G_QS0), tmpN, kC, CQVAD_ACT_RELU));
+      CQ_TRY(lin(tmpN, N, kC, glob(G_QS1), pscale, kC));
+    }
+    CQ_TRY(lin(out, N, kC, glob(G_RAH0), tmpN, kC, CQVAD_ACT_RELU));
+    CQ_TRY(qse_modulate<T>(r_cur, first ? nullptr : pscale, tmpN, Wf(glob(G_RAH1)), Wf(glob(G_RAH1) + 1), qse, N, st));
+
+    // ---- localisation layer: self-attention over the nq actors of a frame :921-938 ----
+    CQ_TRY(lin(out, N, kC, loc(l, SA_QC), saq, kC));
+    CQ_TRY(lin(qpos, N, kC, loc(l, SA_QP), saq, kC, CQVAD_ACT_NONE, saq));
+    CQ_TRY(lin(out, N, kC, loc(l, SA_KC), sak, kC));
+    CQ_TRY(lin(qpos, N, kC, loc(l, SA_KP), sak, kC, CQVAD_ACT_NONE, sak));
+    CQ_TRY(lin(out, N, kC, loc(l, SA_V), sav, kC));
+    {
+      StdStrides ss{};
+      ss.q_ls = ss.k_ls = ss.v_ls = ss.o_ls = (long)BT * kC;
+      ss.q_bs = ss.k_bs = ss.v_bs = ss.o_bs = kC;
+      CQ_TRY(mha_std<T>(saq, nullptr, sak, nullptr, sav, nullptr, sao, nq, nq, BT, kH, 32, 32, ss, st));
+    }
+    CQ_TRY(lin(sao, N, kC, loc(l, SA_O), out, kC, CQVAD_ACT_NONE, out, loc(l, NORM1)));
+    // ---- level-weighted query-specific memory :943-946 ----
+    CQ_TRY(linear_smalln<T>(out, Wf(loc(l, LVLW)), Wf(loc(l, LVLW) + 1), lvlw, N, 4, true, st));
+    CQ_TRY(lvlmix_ln<T>(memc, lvlw, Wf(loc(l, NORMU)), Wf(loc(l, NORMU) + 1), qm, N, S, BT, st));
+    // ---- cross-attention with per-actor keys :951-988 ----
+    CQ_TRY(lin(qm, NS, kC, loc(l, CA_KC), kv, kC, CQVAD_ACT_NONE, nullptr, -1, 1e-5f, 2 * kC));
+    CQ_TRY(lin(qm, NS, kC, loc(l, CA_V), kv + kC, kC, CQVAD_ACT_NONE, nullptr, -1, 1e-5f, 2 * kC));
+    CQ_TRY(lin(pos0c, (long)S * BT, kC, loc(l, CA_KP), kp, kC));
+    CQ_TRY(lin(out, N, kC, loc(l, CA_QC), qc, kC));
+    if (first) {
+      CQ_CHECK_ARG(w[loc(l, CA_QP)] != nullptr, "layers.0.ca_qpos_proj is required");
+      CQ_TRY(lin(qpos, N, kC, loc(l, CA_QP), qc, kC, CQVAD_ACT_NONE, qc));
+    }
+    CQ_TRY(lin(qse, N, kC, loc(l, CA_QS), qs, kC));
+    CQ_TRY(dec_qsk_attn<T>(qc, qs, kv, kv + kC, 2 * kC, kp, mask, cao, N, S, BT, first, st));
+    CQ_TRY(lin(cao, N, kC, loc(l, CA_O), actor, kC, CQVAD_ACT_NONE, out, loc(l, NORM2)));   // tgt_temp :992-993
+    CQ_TRY(mlp(actor, N, F, loc(l, LIN1), loc(l, LIN2), CQVAD_ACT_RELU, actor, loc(l, NORM3), 1e-5f, out, tmpN));
+
+    // ---- class-query layer :1040-1079 ----
+    CQ_TRY(mlp(actor, N, F, cls(l, C_L1), cls(l, C_L2), CQVAD_ACT_RELU, actor, cls(l, C_NORM), 1e-5f, acls, tmpN));
+    CQ_TRY(add_ln_pad<T>(acls, qm, Wf(cls(l, C_CONVNORM)), Wf(cls(l, C_CONVNORM) + 1), XA, N, S, Sp, st));
+    T* xin = XA; T* xout = XB;
+    for (int blk = 0; blk < 3; ++blk) {   // the same ConvBlock three times (:1017-1018, :1055-1056)
+      Epilogue e;
+      e.bias = Wf(cls(l, C_CONV1) + 1);
+      e.ln_g = Wf(cls(l, C_CBNORM)); e.ln_b = Wf(cls(l, C_CBNORM) + 1); e.ln_eps = 1e-6f;
+      ConvGeom cg; cg.h = h; cg.w = wd;
+      CQ_TRY(gemm<T>(xin, kC, Wm(cls(l, C_CONV1)), Xn, kC, Rp, kC, 9 * kC, e, &cg, st));
+      CQ_TRY(mlp(Xn, Rp, 4 * kC, cls(l, C_CONV2), cls(l, C_CONV3), CQVAD_ACT_GELU, xin, -1, 0.f, xout, Hc, Sp, S));
+      T* t = xin; xin = xout; xout = t;
+    }
+    const T* X3 = xin;
+    // class-query self-attention :1059-1065
+    T* Qin = Qc[l & 1];
+    const T* Qprev = Qc[(l + 1) & 1];
+    if (first) {   // identical for every actor instance: computed once on K rows, then broadcast
+      StdStrides ss{};
+      ss.q_ls = ss.k_ls = ss.v_ls = ss.o_ls = kC;
+      CQ_TRY(mha_std<T>(Wm(glob(G_CQ)), nullptr, Wm(glob(G_CQ)), nullptr, Wm(glob(G_CQ)), nullptr, cq1, K, K, 1, kH, 32, 32, ss, st));
+      CQ_TRY(lin(cq1, K, kC, cls(l, C_SA_O), cq2, kC, CQVAD_ACT_NONE, Wm(glob(G_CQ)), cls(l, C_NORM1)));
+      CQ_TRY(broadcast_rows<T>(cq2, Qin, NK, K, st));
+    } else {
+      StdStrides ss{};
+      ss.q_ls = ss.k_ls = ss.v_ls = ss.o_ls = kC;
+      ss.q_bs = ss.k_bs = ss.v_bs = ss.o_bs = (long)K * kC;
+      CQ_TRY(mha_std<T>(Qprev, nullptr, Qprev, nullptr, Qprev, nullptr, saoc, K, K, (int)N, kH, 32, 32, ss, st));
+      CQ_TRY(lin(saoc, NK, kC, cls(l, C_SA_O), Qin, kC, CQVAD_ACT_NONE, Qprev, cls(l, C_NORM1)));
+    }
+    // class cross-attention :1067-1071.  512-wide q/k split contiguously into 8 heads of 64 (attention.py:336,339):
+    // heads 0-3 = (class query . k_proj(conv feature)), heads 4-7 = (actor sine pos . spatial pos).
+    CQ_TRY(lin(X3, Rp, kC, cls(l, C_KPROJ), kx, kC));
+    CQ_TRY(lin(qm, NS, kC, cls(l, C_VPROJ), vx, kC));
+    CQ_TRY(lin(qse, N, kC, cls(l, C_QPS), cqp, kC));
+    {
+      StdStrides ss{};
+      ss.q_ls = kC; ss.q_bs = (long)K * kC;             // Qin rows (i,k)
+      ss.q2_ls = 0; ss.q2_bs = kC;                      // cqp row i, same for every class
+      ss.k_ls = kC; ss.k_bs = (long)Sp * kC;            // kx on the padded layout
+      ss.k2_ls = (long)BT * kC; ss.k2_bs = kC; ss.k2_bmod = BT;   // pos0[s, b], b = i % BT
+      ss.v_ls = kC; ss.v_bs = (long)S * kC;
+      ss.o_ls = kC; ss.o_bs = (long)K * kC;
+      CQ_TRY(mha_std<T>(Qin, cqp, kx, pos0c, vx, nullptr, caoc, K, S, (int)N, kH, 64, 32, ss, st));
+    }
+    CQ_TRY(lin(caoc, NK, kC, cls(l, C_CA_O), cls0, kC));
+    T* cls_out = Qc[l & 1];   // Qin is dead after the attention; reuse its buffer for the layer output / next query
+    CQ_TRY(mlp(cls0, NK, F, cls(l, C_L1_), cls(l, C_L2_), CQVAD_ACT_RELU, cls0, cls(l, C_NORM_), 1e-5f, cls_out, Hf));
+
+    // ---- outputs of this layer :826-827 and heads (models/model.py:192-221) ----
+    CQ_TRY(layernorm_rows<T>(out, nullptr, Wf(glob(G_NORM)), Wf(glob(G_NORM) + 1), 1e-5f, hsn, false, N, st));
+    CQ_TRY(layernorm_permute<T>(out, Wf(glob(G_NORM)), Wf(glob(G_NORM) + 1), 1e-5f, (char*)hs + (size_t)l * N * kC * osz,
+                                of32, N, nq, BT, 1, nullptr, st));
+    {
+      void* dst = cls_hs ? (void*)((char*)cls_hs + (size_t)l * NK * kC * osz) : nullptr;
+      float* lg = pred_logits ? pred_logits + (size_t)l * NK : nullptr;
+      if (dst || lg)
+        CQ_TRY(layernorm_permute<T>(cls_out, Wf(glob(G_CLSNORM2)), Wf(glob(G_CLSNORM2) + 1), 1e-5f, dst, of32, NK, nq, BT,
+                                    K, lg, st));
+    }
+    if (pred_logits_b)
+      CQ_TRY(logits_b<T>(hsn, Wf(glob(G_CEB)), Wf(glob(G_CEB) + 1), pred_logits_b + (size_t)l * N * 3, N, nq, BT, st));
+    if (pred_boxes) {
+      CQ_TRY(lin(hsn, N, kC, glob(G_BB0), bb1, kC, CQVAD_ACT_RELU));
+      CQ_TRY(lin(bb1, N, kC, glob(G_BB1), bb2, kC, CQVAD_ACT_RELU));
+      CQ_TRY(box_refine<T>(bb2, Wf(glob(G_BB2)), Wf(glob(G_BB2) + 1), r_cur, nullptr, pred_boxes + (size_t)l * N * 4, N, nq,
+                           BT, false, st));
+    }
+    // ---- iterative box refinement :813-823 ----
+    CQ_TRY(lin(out, N, kC, glob(G_BB0), bb1, kC, CQVAD_ACT_RELU));
+    CQ_TRY(lin(bb1, N, kC, glob(G_BB1), bb2, kC, CQVAD_ACT_RELU));
+    CQ_TRY(box_refine<T>(bb2, Wf(glob(G_BB2)), Wf(glob(G_BB2) + 1), r_cur, r_next,
+                         (l != Lr - 1) ? refs + (size_t)(l + 1) * N * 4 : nullptr, N, nq, BT, false, st));
+    float* t = r_cur; r_cur = r_next; r_next = t;
+  }
+  return 0;
+}
+
+template <typename T>
+static int run_decoder(const cqvad_decoder_desc* d, const void* const* weights, const float* tgt, const float* memory,
+                       const float* pos, const uint8_t* mask, const float* ref_u, void* hs, void* cls_hs, float* refs,
+                       float* pl, float* pb, float* plb, void* ws, size_t ws_bytes, cudaStream_t st) {
+  Decoder<T> dec(*d, weights, st);
+  const size_t skew = (1024 - (((uintptr_t)ws) & 1023)) & 1023;   // tiles / TMA bases want 1024-byte alignment
+  if (ws_bytes < skew) return set_error(CQVAD_E_WORKSPACE, "decoder workspace too small");
+  Arena a((char*)ws + skew, ws_bytes - skew);
+  dec.plan(a);
+  if (a.overflow)
+    return set_error(CQVAD_E_WORKSPACE, "decoder workspace too small (%zu needed, %zu given)", a.off + 1024, ws_bytes);
+  return dec.run(tgt, memory, pos, mask, ref_u, hs, cls_hs, refs, pl, pb, plb);
+}
+
+static int check_desc(const cqvad_decoder_desc* d) {
+  CQ_CHECK_ARG(d != nullptr, "decoder: null descriptor");
+  CQ_CHECK_ARG(d->dtype == CQVAD_F32 || d->dtype == CQVAD_BF16, "decoder: unknown dtype %d", d->dtype);
+  CQ_CHECK_ARG(d->BT >= 1 && d->nq >= 1 && d->h >= 1 && d->w >= 1 && d->K >= 1 && d->layers >= 1, "decoder: bad extents");
+  CQ_CHECK_SHAPE(d->F >= 8 && d->F % 8 == 0, "decoder: dim_feedforward must be a multiple of 8");
+  CQ_CHECK_SHAPE(d->w <= 128, "decoder: feature-map width %d > 128 not supported", d->w);
+  return 0;
+}
+
+}  // namespace cqvad
+
+using namespace cqvad;
+
+extern "C" int cqvad_version(void) { return CQVAD_VERSION; }
+extern "C" const char* cqvad_last_error(void) { return g_err; }
+extern "C" long cqvad_last_launch_count(void) { return g_launches; }
+extern "C" void cqvad_debug_force_simt(int v) { set_force_simt(v != 0); }
+
+extern "C" int cqvad_decoder_num_weights(int layers) { return layers * (LOC_COUNT + CLS_COUNT) + GLOB_COUNT; }
+extern "C" const char* cqvad_decoder_weight_name(int idx, int layers) {
+  if (!weight_slot(idx, layers, &g_name, nullptr)) return nullptr;
+  return g_name.c_str();
+}
+extern "C" int cqvad_decoder_weight_kind(int idx, int layers) {
+  int k = -1;
+  weight_slot(idx, layers, nullptr, &k);
+  return k;
+}
+
+extern "C" size_t cqvad_decoder_workspace_bytes(const cqvad_decoder_desc* d) {
+  if (check_desc(d) != 0) return 0;
+  Arena a(nullptr, 0);
+  if (d->dtype == CQVAD_F32) { Decoder<float> dec(*d, nullptr, nullptr); dec.plan(a); }
+  else { Decoder<bf16> dec(*d, nullptr, nullptr); dec.plan(a); }
+  return a.off + 1024;
+}
+
+extern "C" int cqvad_decoder_forward(const cqvad_decoder_desc* d, const void* const* weights, const float* tgt,
+                                     const float* memory, const float* pos, const uint8_t* mask,
+                                     const float* refpoints_unsigmoid, void* hs, void* cls_hs, float* refs,
+                                     float* pred_logits, float* pred_boxes, float* pred_logits_b, void* workspace,
+                                     size_t ws_bytes, void* stream) {
+  CQ_TRY(check_desc(d));
+  CQ_CHECK_ARG(weights && tgt && memory && pos && refpoints_unsigmoid && hs && refs && workspace, "decoder: null pointer");
+  CQ_CHECK_ARG(cls_hs || (d->flags & CQVAD_DEC_SKIP_CLS_HS), "decoder: cls_hs is NULL without CQVAD_DEC_SKIP_CLS_HS");
+  const int nw = cqvad_decoder_num_weights(d->layers);
+  for (int i = 0; i < nw; ++i) {
+    if (weights[i] == nullptr) {
+      std::string nm; weight_slot(i, d->layers, &nm, nullptr);
+      const bool optional = nm.find("ca_qpos_proj") != std::string::npos && nm.rfind("layers.0.", 0) != 0;
+      CQ_CHECK_ARG(optional, "decoder: weight '%s' is NULL", nm.c_str());
+    }
+  }
+  reset_launch_count();
+  if (d->dtype == CQVAD_F32)
+    return run_decoder<float>(d, weights, tgt, memory, pos, mask, refpoints_unsigmoid, hs, cls_hs, refs, pred_logits,
+                              pred_boxes, pred_logits_b, workspace, ws_bytes, as_stream(stream));
+  return run_decoder<bf16>(d, weights, tgt, memory, pos, mask, refpoints_unsigmoid, hs, cls_hs, refs, pred_logits,
+                           pred_boxes, pred_logits_b, workspace, ws_bytes, as_stream(stream));
+}
+
+// ---- building blocks ---------------------------------------------------------------------------------------------
+extern "C" int cqvad_layernorm(int dtype, const void* x, const void* res, const float* gamma, const float* beta, float eps,
+                               void* out, int out_f32, long rows, int C, void* stream) {
+  CQ_CHECK_ARG(x && gamma && beta && out && rows >= 0, "layernorm: bad argument");
+  CQ_CHECK_SHAPE(C == kC, "layernorm: C must be 256 (got %d)", C);
+  if (dtype == CQVAD_F32) return layernorm_rows<float>((const float*)x, (const float*)res, gamma, beta, eps, out, out_f32 != 0, rows, as_stream(stream));
+  if (dtype == CQVAD_BF16) return layernorm_rows<bf16>((const bf16*)x, (const bf16*)res, gamma, beta, eps, out, out_f32 != 0, rows, as_stream(stream));
+  return set_error(CQVAD_E_INVALID_ARG, "layernorm: unknown dtype %d", dtype);
+}
+
+extern "C" int cqvad_linear(int dtype, const void* A, const void* W, const float* bias, const void* res, void* C, long M,
+                            int N, int K, int act, void* stream) {
+  CQ_CHECK_ARG(A && W && C && M >= 0 && N >= 1 && K >= 1, "linear: bad argument");
+  CQ_CHECK_ARG(act >= CQVAD_ACT_NONE && act <= CQVAD_ACT_GELU, "linear: unknown activation %d", act);
+  Epilogue e;
+  e.bias = bias; e.act = act; e.res = res; e.ldr = N;
+  if (dtype == CQVAD_F32) return gemm<float>((const float*)A, K, (const float*)W, (float*)C, N, M, N, K, e, nullptr, as_stream(stream));
+  if (dtype == CQVAD_BF16) return gemm<bf16>((const bf16*)A, K, (const bf16*)W, (bf16*)C, N, M, N, K, e, nullptr, as_stream(stream));
+  return set_error(CQVAD_E_INVALID_ARG, "linear: unknown dtype %d", dtype);
+}
+
+extern "C" size_t cqvad_convblock_workspace_bytes(int dtype, long n_img, int h, int w) {
+  const size_t es = dtype == CQVAD_F32 ? 4 : 2;
+  const size_t rp = (size_t)n_img * (h + 1) * w;
+  return (rp * kC * 3 + rp * 4 * kC) * es + 8 * 1024;
+}
+
+template <typename T>
+static int convblock_t(const T* x, T* y, const T* w1, const float* b1, const float* g, const float* b, const T* w2,
+                       const float* b2, const T* w3, const float* b3, long n_img, int h, int w, void* ws, size_t ws_bytes,
+                       cudaStream_t st) {
+  const int S = h * w, Sp = (h + 1) * w;
+  const long Rp = n_img * Sp;
+  Arena a(ws, ws_bytes);
+  T* xp = (T*)a.take((size_t)Rp * kC * sizeof(T));
+  T* xn = (T*)a.take((size_t)Rp * kC * sizeof(T));
+  T* yp = (T*)a.take((size_t)Rp * kC * sizeof(T));
+  T* hid = (T*)a.take((size_t)Rp * 4 * kC * sizeof(T));
+  if (a.overflow) return set_error(CQVAD_E_WORKSPACE, "convblock: workspace too small (%zu needed)", a.off);
+  CQ_CUDA(cudaMemsetAsync(xp, 0, (size_t)Rp * kC * sizeof(T), st));
+  CQ_TRY(pad_copy<T>(x, xp, n_img, S, Sp, true, st));
+  Epilogue e;
+  e.bias = b1; e.ln_g = g; e.ln_b = b; e.ln_eps = 1e-6f;
+  ConvGeom cg; cg.h = h; cg.w = w;
+  CQ_TRY(gemm<T>(xp, kC, w1, xn, kC, Rp, kC, 9 * kC, e, &cg, st));
+  bool done = false;
+  if (DT<T>::id == CQVAD_BF16 && !force_simt()) {
+    int r = mlp_tc((const bf16*)xn, (const bf16*)w2, b2, (const bf16*)w3, b3, CQVAD_ACT_GELU, (const bf16*)xp, nullptr,
+                   nullptr, 0.f, (bf16*)yp, Rp, kC, 4 * kC, Sp, S, st);
+    if (r < 0) return r;
+    done = (r == 0);
+  }
+  if (!done) {
+    Epilogue e1; e1.bias = b2; e1.act = CQVAD_ACT_GELU;
+    CQ_TRY(gemm<T>(xn, kC, w2, hid, 4 * kC, Rp, 4 * kC, kC, e1, nullptr, st));
+    Epilogue e2; e2.bias = b3; e2.res = xp; e2.ldr = kC; e2.zero_period = Sp; e2.zero_valid = S;
+    CQ_TRY(gemm<T>(hid, 4 * kC, w3, yp, kC, Rp, kC, 4 * kC, e2, nullptr, st));
+  }
+  return pad_copy<T>(yp, y, n_img, S, Sp, false, st);
+}
+
+extern "C" int cqvad_convblock_forward(int dtype, const void* x, void* y, const void* w1, const float* b1,
+                                       const float* ln_g, const float* ln_b, const void* w2, const float* b2,
+                                       const void* w3, const float* b3, long n_img, int h, int w, void* workspace,
+                                       size_t ws_bytes, void* stream) {
+  CQ_CHECK_ARG(x && y && w1 && b1 && ln_g && ln_b && w2 && b2 && w3 && b3 && workspace, "convblock: null pointer");
+  CQ_CHECK_SHAPE(n_img >= 0 && h >= 1 && w >= 1 && w <= 128, "convblock: bad extents");
+  if (dtype == CQVAD_F32)
+    return convblock_t<float>((const float*)x, (float*)y, (const float*)w1, b1, ln_g, ln_b, (const float*)w2, b2, (const float*)w3, b3, n_img, h, w, workspace, ws_bytes, as_stream(stream));
+  if (dtype == CQVAD_BF16)
+    return convblock_t<bf16>((const bf16*)x, (bf16*)y, (const bf16*)w1, b1, ln_g, ln_b, (const bf16*)w2, b2, (const bf16*)w3, b3, n_img, h, w, workspace, ws_bytes, as_stream(stream));
+  return set_error(CQVAD_E_INVALID_ARG, "convblock: unknown dtype %d", dtype);
+}
+
+extern "C" int cqvad_mha_core(int dtype, int mode, const void* q, const void* k, const void* v,
+                              const uint8_t* key_padding_mask, void* o, int L, int S, int Nb, int H, int E, int Ev,
+                              void* stream) {
+  CQ_CHECK_ARG(q && k && v && o, "mha_core: null pointer");
+  CQ_CHECK_ARG(mode == 0 || mode == 1, "mha_core: mode must be 0 or 1");
+  const long q_ls = (long)Nb * E, q_bs = E, o_ls = (long)Nb * Ev, o_bs = Ev;
+  long k_ls, k_bs, k_qs, v_ls, v_bs, v_qs;
+  k_ls = (long)Nb * E; k_bs = E; k_qs = (long)S * Nb * E;
+  v_ls = (long)Nb * Ev; v_bs = Ev; v_qs = (long)S * Nb * Ev;
+  if (dtype == CQVAD_F32)
+    return mha_core<float>(mode, (const float*)q, (const float*)k, (const float*)v, key_padding_mask, (float*)o, L, S, Nb, H, E, Ev, q_ls, q_bs, k_ls, k_bs, k_qs, v_ls, v_bs, v_qs, o_ls, o_bs, as_stream(stream));
+  if (dtype == CQVAD_BF16)
+    return mha_core<bf16>(mode, (const bf16*)q, (const bf16*)k, (const bf16*)v, key_padding_mask, (bf16*)o, L, S, Nb, H, E, Ev, q_ls, q_bs, k_ls, k_bs, k_qs, v_ls, v_bs, v_qs, o_ls, o_bs, as_stream(stream));
+  return set_error(CQVAD_E_INVALID_ARG, "mha_core: unknown dtype %d", dtype);
+}
+
+extern "C" int cqvad_posenc3d(const uint8_t* mask, float* pos, int B, int T, int H, int W, int num_pos_feats, void* stream) {
+  CQ_CHECK_ARG(mask && pos && B >= 0 && T >= 1 && H >= 1 && W >= 1, "posenc3d: bad argument");
+  CQ_CHECK_SHAPE(num_pos_feats % 8 == 0, "posenc3d: num_pos_feats must be a multiple of 8");
+  if (B == 0) return 0;
+  return posenc3d(mask, pos, B, T, H, W, num_pos_feats, as_stream(stream));
+}
+
+extern "C" int cqvad_sine_embed(const float* ref, float* out, long rows, void* stream) {
+  CQ_CHECK_ARG(ref && out && rows >= 0, "sine_embed: bad argument");
+  return sine_embed<float>(ref, out, rows, as_stream(stream));
+}

@@ -1,0 +1,278 @@
+// 3-D multi-scale deformable attention sampling for sm_100a (HBM/L2-bound gather).
+// Replaces ms_deformable_im2col_gpu_kernel / ms_deformable_col2im_* of the reference
+// (ops/src/cuda/ms_deform_im2col_cuda_t.cuh:374-439, 441-549).
+//
+// Design (not a port): the reference runs one thread per output scalar, so every channel of a head redoes the same
+// floor/weight/offset arithmetic for all L*P points and issues 8 scalar loads per point.  Here one WARP owns one
+// (batch, query, head): lane p first computes the integer corner offsets, validity bits and trilinear weights of
+// sampling point p (L*P points spread over the lanes, coalesced 12-byte/4-byte loads of loc/attn), then the warp
+// walks the points, broadcasting them by shuffle, and each lane gathers its channel(s): a corner read is one
+// coalesced D*sizeof(T) segment.  Index arithmetic follows the kernel contract bit-exactly:
+//   x_im = fl32(fl32(loc * dim) - 0.5)   (__fmul_rn then __fsub_rn: no FMA contraction; cuh:424-426)
+//   low = (int)floorf(x_im); point used iff -1 < x_im < dim on all axes (cuh:428); corner validity cuh:63-109.
+#include "common.cuh"
+
+namespace cqvad {
+
+namespace {
+
+struct PointGeom {
+  int base;       // element offset of corner (t_low,h_low,w_low) relative to the level start, in rows of M*D
+  int ht, hh;     // strides in rows
+  unsigned mask;  // 8 corner-valid bits
+  float lt, lh, lw;
+};
+
+__device__ __forceinline__ void point_geometry(float loc_x, float loc_y, float loc_t, int T, int H, int W, int& tl,
+                                               int& hl, int& wl, unsigned& mask, float& lt, float& lh, float& lw) {
+  const float t_im = __fsub_rn(__fmul_rn(loc_t, (float)T), 0.5f);
+  const float h_im = __fsub_rn(__fmul_rn(loc_y, (float)H), 0.5f);
+  const float w_im = __fsub_rn(__fmul_rn(loc_x, (float)W), 0.5f);
+  tl = (int)floorf(t_im); hl = (int)floorf(h_im); wl = (int)floorf(w_im);
+  lt = t_im - (float)tl; lh = h_im - (float)hl; lw = w_im - (float)wl;
+  const bool inside = t_im > -1.f && h_im > -1.f && w_im > -1.f && t_im < (float)T && h_im < (float)H && w_im < (float)W;
+  mask = 0;
+  if (inside) {
+    const bool t0 = tl >= 0, t1 = tl + 1 <= T - 1, h0 = hl >= 0, h1 = hl + 1 <= H - 1, w0 = wl >= 0, w1 = wl + 1 <= W - 1;
+    mask = (unsigned)(t0 && h0 && w0) | ((unsigned)(t0 && h0 && w1) << 1) | ((unsigned)(t0 && h1 && w0) << 2) |
+           ((unsigned)(t0 && h1 && w1) << 3) | ((unsigned)(t1 && h0 && w0) << 4) | ((unsigned)(t1 && h0 && w1) << 5) |
+           ((unsigned)(t1 && h1 && w0) << 6) | ((unsigned)(t1 && h1 && w1) << 7);
+  }
+}
+
+__global__ void msda_indices_kernel(const int64_t* __restrict__ shapes, const float* __restrict__ loc,
+                                    int32_t* __restrict__ tlo, int32_t* __restrict__ hlo, int32_t* __restrict__ wlo,
+                                    uint8_t* __restrict__ cmask, long total, int L, int P) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int l = (int)((idx / P) % L);
+  const int T = (int)shapes[l * 3], H = (int)shapes[l * 3 + 1], W = (int)shapes[l * 3 + 2];
+  int tl, hl, wl; unsigned m; float a, b, c;
+  point_geometry(loc[idx * 3], loc[idx * 3 + 1], loc[idx * 3 + 2], T, H, W, tl, hl, wl, m, a, b, c);
+  tlo[idx] = tl; hlo[idx] = hl; wlo[idx] = wl; cmask[idx] = (uint8_t)m;
+}
+
+constexpr int kWarps = 8;
+
+// Forward.  Warp per (b,q,m); D <= 32*CPL channels per head, lane owns channels lane + 32*j.
+template <typename T, int CPL>
+__global__ void __launch_bounds__(kWarps * 32) msda_fwd_kernel(const T* __restrict__ value,
+                                                               const int64_t* __restrict__ shapes,
+                                                               const int64_t* __restrict__ lsi,
+                                                               const float* __restrict__ loc,
+                                                               const float* __restrict__ attn, T* __restrict__ out,
+                                                               long n_warps_total, int Len, int M, int D, int L, int Lq,
+                                                               int P) {
+  const long wid = (long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= n_warps_total) return;
+  const int m = (int)(wid % M);
+  const long bq = wid / M;
+  const int b = (int)(bq / Lq);
+  const int LP = L * P;
+  const long row_stride = (long)M * D;
+  const T* vbase = value + (long)b * Len * row_stride + (long)m * D;
+  const float* locp = loc + wid * LP * 3;
+  const float* attp = attn + wid * LP;
+  float acc[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) acc[j] = 0.f;
+
+  for (int p0 = 0; p0 < LP; p0 += 32) {
+    // phase 1: lane -> point p0+lane
+    const int pt = p0 + lane;
+    int g_base = 0, g_hs = 0, g_ts = 0; unsigned g_mask = 0; float g_lt = 0, g_lh = 0, g_lw = 0, g_a = 0;
+    if (pt < LP) {
+      const int l = pt / P;
+      const int Tt = (int)shapes[l * 3], H = (int)shapes[l * 3 + 1], W = (int)shapes[l * 3 + 2];
+      int tl, hl, wl;
+      point_geometry(locp[pt * 3], locp[pt * 3 + 1], locp[pt * 3 + 2], Tt, H, W, tl, hl, wl, g_mask, g_lt, g_lh, g_lw);
+      g_hs = W; g_ts = H * W;
+      g_base = (int)lsi[l] + (tl * H + hl) * W + wl;
+      g_a = attp[pt];
+    }
+    // phase 2: walk the points
+    const int np = min(32, LP - p0);
+    for (int j = 0; j < np; ++j) {
+      const unsigned mk = __shfl_sync(0xffffffffu, g_mask, j);
+      if (mk == 0) continue;  // warp-uniform
+      const int base = __shfl_sync(0xffffffffu, g_base, j);
+      const int hs = __shfl_sync(0xffffffffu, g_hs, j), ts = __shfl_sync(0xffffffffu, g_ts, j);
+      const float lt = __shfl_sync(0xffffffffu, g_lt, j), lh = __shfl_sync(0xffffffffu, g_lh, j);
+      const float lw = __shfl_sync(0xffffffffu, g_lw, j), a = __shfl_sync(0xffffffffu, g_a, j);
+      const float ht = 1.f - lt, hh = 1.f - lh, hw = 1.f - lw;
+      const float wgt[8] = {ht * hh * hw, ht * hh * lw, ht * lh * hw, ht * lh * lw,
+                            lt * hh * hw, lt * hh * lw, lt * lh * hw, lt * lh * lw};
+      const int off[8] = {0, 1, hs, hs + 1, ts, ts + 1, ts + hs, ts + hs + 1};
+#pragma unroll
+      for (int cj = 0; cj < CPL; ++cj) {
+        const int c = lane + 32 * cj;
+        if (c < D) {
+          float val = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (mk & (1u << k)) val = fmaf(wgt[k], to_f(vbase[(long)(base + off[k]) * row_stride + c]), val);
+          acc[cj] = fmaf(val, a, acc[cj]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int cj = 0; cj < CPL; ++cj) {
+    const int c = lane + 32 * cj;
+    if (c < D) out[wid * D + c] = from_f<T>(acc[cj]);
+  }
+}
+
+// Backward (mathematical gradient of the forward).  Same warp mapping; grad_value via red.global.add.f32 (one
+// coalesced 128-byte reduction per corner), grad_loc / grad_attn reduced over the head's channels by shuffle and
+// written once by the owning warp (no atomics).
+template <typename T, int CPL>
+__global__ void __launch_bounds__(kWarps * 32) msda_bwd_kernel(const T* __restrict__ value,
+                                                               const int64_t* __restrict__ shapes,
+                                                               const int64_t* __restrict__ lsi,
+                                                               const float* __restrict__ loc,
+                                                               const float* __restrict__ attn,
+                                                               const T* __restrict__ grad_out,
+                                                               float* __restrict__ grad_value,
+                                                               float* __restrict__ grad_loc,
+                                                               float* __restrict__ grad_attn, long n_warps_total,
+                                                               int Len, int M, int D, int L, int Lq, int P) {
+  const long wid = (long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= n_warps_total) return;
+  const int m = (int)(wid % M);
+  const long bq = wid / M;
+  const int b = (int)(bq / Lq);
+  const int LP = L * P;
+  const long row_stride = (long)M * D;
+  const long voff = (long)b * Len * row_stride + (long)m * D;
+  const T* vbase = value + voff;
+  float* gvbase = grad_value + voff;
+  const float* locp = loc + wid * LP * 3;
+  const float* attp = attn + wid * LP;
+  float go[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int c = lane + 32 * j;
+    go[j] = c < D ? to_f(grad_out[wid * D + c]) : 0.f;
+  }
+  for (int pt = 0; pt < LP; ++pt) {
+    const int l = pt / P;
+    const int T_ = (int)shapes[l * 3], H = (int)shapes[l * 3 + 1], W = (int)shapes[l * 3 + 2];
+    int tl, hl, wl; unsigned mk; float lt, lh, lw;
+    point_geometry(locp[pt * 3], locp[pt * 3 + 1], locp[pt * 3 + 2], T_, H, W, tl, hl, wl, mk, lt, lh, lw);
+    float g_w = 0.f, g_h = 0.f, g_t = 0.f, g_a = 0.f;
+    if (mk != 0) {
+      const float a = attp[pt];
+      const int base = (int)lsi[l] + (tl * H + hl) * W + wl;
+      const int hs = W, ts = H * W;
+      const float ht = 1.f - lt, hh = 1.f - lh, hw = 1.f - lw;
+      const float ft[2] = {ht, lt}, fh[2] = {hh, lh}, fw[2] = {hw, lw};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (!(mk & (1u << k))) continue;
+        const int kt = k >> 2, kh = (k >> 1) & 1, kw = k & 1;
+        const long row = (long)(base + kt * ts + kh * hs + kw) * row_stride;
+        const float wgt = ft[kt] * fh[kh] * fw[kw];
+        float dot = 0.f;
+#pragma unroll
+        for (int cj = 0; cj < CPL; ++cj) {
+          const int c = lane + 32 * cj;
+          if (c < D) {
+            dot = fmaf(to_f(vbase[row + c]), go[cj], dot);
+            atomicAdd(gvbase + row + c, a * wgt * go[cj]);
+          }
+        }
+        g_a = fmaf(wgt, dot, g_a);
+        g_w = fmaf((kw ? 1.f : -1.f) * ft[kt] * fh[kh], dot, g_w);
+        g_h = fmaf((kh ? 1.f : -1.f) * ft[kt] * fw[kw], dot, g_h);
+        g_t = fmaf((kt ? 1.f : -1.f) * fh[kh] * fw[kw], dot, g_t);
+      }
+      g_w *= a * (float)W; g_h *= a * (float)H; g_t *= a * (float)T_;
+    }
+    g_a = warp_sum(g_a); g_w = warp_sum(g_w); g_h = warp_sum(g_h); g_t = warp_sum(g_t);
+    if (lane == 0) {
+      grad_attn[wid * LP + pt] = g_a;
+      float* gl = grad_loc + (wid * LP + pt) * 3;
+      gl[0] = g_w; gl[1] = g_h; gl[2] = g_t;
+    }
+  }
+}
+
+template <typename T>
+int msda_fwd_t(const void* value, const int64_t* shapes, const int64_t* lsi, const float* loc, const float* attn, void* out,
+               int N, int Len, int M, int D, int L, int Lq, int P, cudaStream_t st) {
+  const long nw = (long)N * Lq * M;
+  if (nw == 0) return 0;
+  const unsigned grid = (unsigned)cdiv(nw, kWarps);
+  if (D <= 32)
+    msda_fwd_kernel<T, 1><<<grid, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, loc, attn, (T*)out, nw, Len, M, D, L, Lq, P);
+  else if (D <= 64)
+    msda_fwd_kernel<T, 2><<<grid, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, loc, attn, (T*)out, nw, Len, M, D, L, Lq, P);
+  else
+    msda_fwd_kernel<T, 4><<<grid, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, loc, attn, (T*)out, nw, Len, M, D, L, Lq, P);
+  CQ_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int msda_bwd_t(const void* value, const int64_t* shapes, const int64_t* lsi, const float* loc, const float* attn,
+               const void* go, float* gv, float* gl, float* ga, int N, int Len, int M, int D, int L, int Lq, int P,
+               cudaStream_t st) {
+  const long nw = (long)N * Lq * M;
+  if (nw == 0) return 0;
+  const unsigned grid = (unsigned)cdiv(nw, kWarps);
+  if (D <= 32)
+    msda_bwd_kernel<T, 1><<<grid, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, loc, attn, (const T*)go, gv, gl, ga, nw, Len, M, D, L, Lq, P);
+  else if (D <= 64)
+    msda_bwd_kernel<T, 2><<<grid, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, loc, attn, (const T*)go, gv, gl, ga, nw, Len, M, D, L, Lq, P);
+  else
+    msda_bwd_kernel<T, 4><<<grid, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, loc, attn, (const T*)go, gv, gl, ga, nw, Len, M, D, L, Lq, P);
+  CQ_LAUNCH_CHECK();
+  return 0;
+}
+
+int check_dims(int N, int Len, int M, int D, int L, int Lq, int P) {
+  CQ_CHECK_ARG(N >= 0 && Len >= 0 && M >= 1 && D >= 1 && L >= 1 && Lq >= 0 && P >= 1, "msda3d: bad dimensions");
+  CQ_CHECK_SHAPE(D <= 128, "msda3d: head dim D=%d > 128 not supported", D);
+  CQ_CHECK_SHAPE((long)Len * M * D < (1L << 31), "msda3d: Len*M*D must fit int32 (as in the reference, cuh:49-60)");
+  return 0;
+}
+
+}  // namespace
+}  // namespace cqvad
+
+using namespace cqvad;
+
+extern "C" int cqvad_msda3d_forward(int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                                    const float* loc, const float* attn, void* out, int N, int Len, int M, int D, int L,
+                                    int Lq, int P, void* stream) {
+  CQ_TRY(check_dims(N, Len, M, D, L, Lq, P));
+  CQ_CHECK_ARG(value && shapes && level_start && loc && attn && out, "msda3d_forward: null pointer");
+  if (dtype == CQVAD_F32) return msda_fwd_t<float>(value, shapes, level_start, loc, attn, out, N, Len, M, D, L, Lq, P, as_stream(stream));
+  if (dtype == CQVAD_BF16) return msda_fwd_t<bf16>(value, shapes, level_start, loc, attn, out, N, Len, M, D, L, Lq, P, as_stream(stream));
+  return set_error(CQVAD_E_INVALID_ARG, "msda3d_forward: unknown dtype %d", dtype);
+}
+
+extern "C" int cqvad_msda3d_backward(int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                                     const float* loc, const float* attn, const void* grad_out, float* grad_value,
+                                     float* grad_loc, float* grad_attn, int N, int Len, int M, int D, int L, int Lq, int P,
+                                     void* stream) {
+  CQ_TRY(check_dims(N, Len, M, D, L, Lq, P));
+  CQ_CHECK_ARG(value && shapes && level_start && loc && attn && grad_out && grad_value && grad_loc && grad_attn,
+               "msda3d_backward: null pointer");
+  if (dtype == CQVAD_F32) return msda_bwd_t<float>(value, shapes, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, N, Len, M, D, L, Lq, P, as_stream(stream));
+  if (dtype == CQVAD_BF16) return msda_bwd_t<bf16>(value, shapes, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, N, Len, M, D, L, Lq, P, as_stream(stream));
+  return set_error(CQVAD_E_INVALID_ARG, "msda3d_backward: unknown dtype %d", dtype);
+}
+
+extern "C" int cqvad_msda3d_indices(const int64_t* shapes, const float* loc, int32_t* t_low, int32_t* h_low,
+                                    int32_t* w_low, uint8_t* corner_mask, int N, int Lq, int M, int L, int P, void* stream) {
+  CQ_CHECK_ARG(shapes && loc && t_low && h_low && w_low && corner_mask, "msda3d_indices: null pointer");
+  const long total = (long)N * Lq * M * L * P;
+  if (total == 0) return 0;
+  msda_indices_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(shapes, loc, t_low, h_low, w_low, corner_mask, total, L, P);
+  CQ_LAUNCH_CHECK();
+  return 0;
+}

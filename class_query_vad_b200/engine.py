@@ -1,0 +1,112 @@
+"""Host driver of the native decoder: packs a reference-named state_dict into the weight table of
+cqvad_decoder_forward (include/cqvad.h) and owns the device workspace.  torch is used for device memory and streams
+only; every arithmetic step is a kernel of libcqvad.so."""
+import ctypes
+from ctypes import c_void_p, byref
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _as_tensor(v):
+    if isinstance(v, torch.Tensor):
+        return v.detach()
+    return torch.from_numpy(np.ascontiguousarray(v))
+
+
+def pack_decoder_weights(state, layers, dtype, device):
+    """state: mapping of reference TransformerDecoder state_dict names (+ optional
+    'heads.class_embed_b.*') to tensors / ndarrays.  Returns (keepalive list, ctypes pointer array).
+
+    Matrices are stored in `dtype`; biases, LayerNorm parameters and the four small-N linears stay fp32; the 3x3 conv
+    weight [O,I,3,3] is re-laid out as [O][ky*3+kx][I] (K-major for the implicit GEMM); 1x1 conv weights are [O,I]."""
+    lib = _lib.lib()
+    n = lib.cqvad_decoder_num_weights(layers)
+    keep, arr = [], (c_void_p * n)()
+    for i in range(n):
+        name = lib.cqvad_decoder_weight_name(i, layers).decode()
+        kind = lib.cqvad_decoder_weight_kind(i, layers)
+        if name not in state:
+            if "ca_qpos_proj" in name and not name.startswith("layers.0."):
+                arr[i] = None   # ca_qpos_proj is None for layers >= 1 (dab_transformer.py:711-713)
+                keep.append(None)
+                continue
+            if name.startswith("heads.class_embed_b"):
+                t = torch.zeros((3, 256) if name.endswith("weight") else (3,))
+            else:
+                raise KeyError(f"decoder weight '{name}' missing from the state dict")
+        else:
+            t = _as_tensor(state[name])
+        t = t.to(device=device, dtype=torch.float32)
+        if name.endswith("conv1.weight"):
+            t = t.permute(0, 2, 3, 1).reshape(t.shape[0], -1)           # [O,I,3,3] -> [O, (ky,kx,I)]
+        elif t.dim() == 4:
+            t = t.reshape(t.shape[0], t.shape[1])                        # 1x1 conv
+        t = t.contiguous().to(torch.float32 if kind == 1 else dtype).contiguous()
+        keep.append(t)
+        arr[i] = t.data_ptr()
+    return keep, arr
+
+
+class DecoderEngine:
+    """TransformerDecoder.forward (+ DETR heads) on one GPU.
+
+    >>> eng = DecoderEngine(state_dict, nq=15, K=80, layers=6, F=2048, dtype=torch.bfloat16, device="cuda")
+    >>> out = eng.forward(tgt, memory, mask, pos, refpoints_unsigmoid, (h, w))
+    """
+
+    def __init__(self, state, nq, K, layers, F=2048, dtype=torch.bfloat16, device="cuda", out_f32=True):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("Not implemented on the CPU")
+        self.dtype, self.nq, self.K, self.layers, self.F, self.out_f32 = dtype, nq, K, layers, F, out_f32
+        self._keep, self._wtab = pack_decoder_weights(state, layers, dtype, self.device)
+        self._ws = None
+        self.last_launches = 0
+
+    def _workspace(self, desc):
+        need = _lib.lib().cqvad_decoder_workspace_bytes(byref(desc))
+        if need == 0:
+            _lib.check(-1)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def forward(self, tgt, memory, mask, pos, refpoints_unsigmoid, orig_res, heads=True, skip_cls_hs=False):
+        """tgt [nq,BT,256], memory/pos [4,S,BT,256], mask [BT,S] bool or None, refpoints_unsigmoid [nq,BT,4]
+        (layouts of dab_transformer.py:391-396).  Returns dict(hs, cls_hs, refs[, pred_logits, pred_boxes, pred_logits_b])."""
+        lib = _lib.lib()
+        h, w = orig_res
+        nq, BT = tgt.shape[0], tgt.shape[1]
+        S = h * w
+        if nq != self.nq or tuple(memory.shape) != (4, S, BT, 256) or tuple(refpoints_unsigmoid.shape) != (nq, BT, 4):
+            raise ValueError(f"decoder input shapes do not match: tgt {tuple(tgt.shape)}, memory {tuple(memory.shape)}, "
+                             f"refpoints {tuple(refpoints_unsigmoid.shape)}, orig_res {orig_res}")
+        _lib.require_cuda(tgt, memory, pos, refpoints_unsigmoid)
+        f32 = lambda t: t.to(device=self.device, dtype=torch.float32).contiguous()
+        tgt, memory, pos0, ref = f32(tgt), f32(memory), f32(pos[0]), f32(refpoints_unsigmoid)
+        m8 = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        desc = _lib.DecoderDesc(_lib.dtype_id(self.dtype), BT, nq, h, w, self.K, self.F, self.layers,
+                                1 if self.out_f32 else 0, _lib.DEC_SKIP_CLS_HS if skip_cls_hs else 0)
+        ws = self._workspace(desc)
+        odt = torch.float32 if self.out_f32 else self.dtype
+        Lr, K = self.layers, self.K
+        hs = torch.empty((Lr, BT, nq, 256), dtype=odt, device=self.device)
+        cls_hs = None if skip_cls_hs else torch.empty((Lr, BT, nq, K, 256), dtype=odt, device=self.device)
+        refs = torch.empty((Lr, BT, nq, 4), dtype=torch.float32, device=self.device)
+        pl = pb = plb = None
+        if heads:
+            pl = torch.empty((Lr, BT, nq, K), dtype=torch.float32, device=self.device)
+            pb = torch.empty((Lr, BT, nq, 4), dtype=torch.float32, device=self.device)
+            plb = torch.empty((Lr, BT, nq, 3), dtype=torch.float32, device=self.device)
+        p = _lib.ptr
+        rc = lib.cqvad_decoder_forward(byref(desc), self._wtab, p(tgt), p(memory), p(pos0), p(m8), p(ref), p(hs), p(cls_hs),
+                                       p(refs), p(pl), p(pb), p(plb), p(ws), ws.numel(), _lib.stream_ptr())
+        _lib.check(rc)
+        self.last_launches = lib.cqvad_last_launch_count()
+        out = dict(hs=hs, cls_hs=cls_hs, refs=refs)
+        if heads:
+            out.update(pred_logits=pl, pred_boxes=pb, pred_logits_b=plb)
+        return out

@@ -1,0 +1,82 @@
+"""Drop-in for the reference `ops.modules.MSDeformAttn3D` (ops/modules/ms_deform_attn.py:117-203): same constructor,
+forward signature, parameter names and initialisation; the four linears run through cqvad_linear and the sampling
+through MSDeformAttnFunction (libcqvad.so)."""
+import math
+import warnings
+
+import torch
+from torch import nn
+from torch.nn.init import xavier_uniform_, constant_
+
+from ..functions.ms_deform_attn_func import MSDeformAttnFunction
+from .ops import linear, softmax_lastdim
+
+
+def _is_power_of_2(n):
+    if (not isinstance(n, int)) or (n < 0):
+        raise ValueError("invalid input for _is_power_of_2: {} (type: {})".format(n, type(n)))
+    return (n & (n - 1) == 0) and n != 0
+
+
+class MSDeformAttn3D(nn.Module):
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
+        super().__init__()
+        if d_model % n_heads != 0:
+            raise ValueError('d_model must be divisible by n_heads, but got {} and {}'.format(d_model, n_heads))
+        if not _is_power_of_2(d_model // n_heads):
+            warnings.warn("You'd better set d_model in MSDeformAttn3D to make the dimension of each attention head a power of 2")
+        self.im2col_step = 64
+        self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
+        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 3)
+        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        # ops/modules/ms_deform_attn.py:149-165
+        constant_(self.sampling_offsets.weight.data, 0.)
+        thetas = torch.arange(self.n_heads // 2, dtype=torch.float32) * (2.0 * math.pi / (self.n_heads // 2))
+        t_extent = torch.cat([torch.ones(self.n_heads // 2), torch.zeros(self.n_heads // 2)], 0)
+        grid_init = torch.stack([thetas.cos().repeat(2), thetas.sin().repeat(2), t_extent], -1)
+        grid_init = (grid_init / grid_init.abs().max(-1, keepdim=True)[0]).view(self.n_heads, 1, 1, 3) \
+            .repeat(1, self.n_levels, self.n_points, 1)
+        for i in range(self.n_points):
+            grid_init[:, :, i, :] *= i + 1
+        with torch.no_grad():
+            self.sampling_offsets.bias = nn.Parameter(grid_init.view(-1))
+        constant_(self.attention_weights.weight.data, 0.)
+        constant_(self.attention_weights.bias.data, 0.)
+        xavier_uniform_(self.value_proj.weight.data)
+        constant_(self.value_proj.bias.data, 0.)
+        xavier_uniform_(self.output_proj.weight.data)
+        constant_(self.output_proj.bias.data, 0.)
+
+    def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
+                input_padding_mask=None):
+        N, Len_q, _ = query.shape
+        N, Len_in, _ = input_flatten.shape
+        assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1] * input_spatial_shapes[:, 2]).sum() == Len_in
+        value = linear(input_flatten, self.value_proj.weight, self.value_proj.bias)
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None], float(0))
+        value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
+        offs = linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias) \
+            .view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 3)
+        attw = linear(query, self.attention_weights.weight, self.attention_weights.bias) \
+            .view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
+        attw = softmax_lastdim(attw).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
+        if reference_points.shape[-1] == 3:
+            # normaliser stacked as (T_l, W_l, H_l) against (x,y,t) offsets: reference quirk kept (ms_deform_attn.py:192)
+            offset_normalizer = torch.stack([input_spatial_shapes[..., 0], input_spatial_shapes[..., 2],
+                                             input_spatial_shapes[..., 1]], -1)
+            sampling_locations = reference_points[:, :, None, :, None, :] \
+                + offs / offset_normalizer[None, None, None, :, None, :]
+        elif reference_points.shape[-1] == 6:
+            sampling_locations = reference_points[:, :, None, :, None, :3] \
+                + offs / self.n_points * reference_points[:, :, None, :, None, 3:] * 0.5
+        else:
+            raise ValueError('Last dim of reference_points must be 3, but get {} instead.'.format(reference_points.shape[-1]))
+        output = MSDeformAttnFunction.apply(value.contiguous(), input_spatial_shapes, input_level_start_index,
+                                            sampling_locations.contiguous(), attw.contiguous(), self.im2col_step)
+        return linear(output, self.output_proj.weight, self.output_proj.bias)

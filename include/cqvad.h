@@ -1,0 +1,136 @@
+/*
+ * cqvad.h -- C ABI of libcqvad.so: the B200 (sm_100a) implementation of the class-query decoder hot path of
+ * dlrudco/class-query-vad.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions (all entry points):
+ *   - return 0 on success, a negative CQVAD_E_* code otherwise; cqvad_last_error() gives the thread-local message.
+ *     Nothing throws.  (The reference raises C++ exceptions through pybind: ops/src/ms_deform_attn.h:20-61; its
+ *     kernel-launch errors are only printf'ed, ops/src/cuda/ms_deform_im2col_cuda_t.cuh:1123-1127 -- here they
+ *     are returned.)
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; tensors are contiguous, row-major.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no host synchronisation, no device allocation:
+ *     the caller owns outputs and passes an explicit workspace where one is needed.
+ *   - `dtype` selects the storage/compute type of activations and matrix weights: CQVAD_F32 (CUDA-core FFMA path,
+ *     the "rel 1e-3, TF32 off" parity mode) or CQVAD_BF16 (tcgen05 tensor-core path, fp32 accumulation).
+ *     Biases, LayerNorm affine parameters, reference points and the four "small-N" linears are always fp32.
+ */
+#ifndef CQVAD_H_
+#define CQVAD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CQVAD_VERSION 1
+
+enum { CQVAD_F32 = 0, CQVAD_BF16 = 1 };
+enum { CQVAD_OK = 0, CQVAD_E_INVALID_ARG = -1, CQVAD_E_UNSUPPORTED_SHAPE = -2, CQVAD_E_CUDA = -3, CQVAD_E_WORKSPACE = -4 };
+enum { CQVAD_ACT_NONE = 0, CQVAD_ACT_RELU = 1, CQVAD_ACT_GELU = 2 };
+
+int cqvad_version(void);
+const char* cqvad_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * ops/ path: 3-D multi-scale deformable attention.
+ * Replaces the pybind functions `ms_deform_attn_forward` / `ms_deform_attn_backward` of the reference module
+ * `MultiScaleDeformableAttention` (ops/src/vision.cpp:13-16, ops/src/ms_deform_attn.h:20-61,
+ * ops/src/cuda/ms_deform_attn_cuda_t.cu:20-80 and :83-153), i.e. what
+ * `MSDeformAttnFunction.forward/backward` bind (ops/functions/ms_deform_attn_func.py:26,42).
+ *   value   [N, Len, M, D]  (dtype)          shapes      [L,3] int64 (T,H,W)     level_start [L] int64
+ *   loc     [N, Lq, M, L, P, 3] fp32 (x,y,t) in [0,1]     attn   [N, Lq, M, L, P] fp32
+ *   out     [N, Lq, M*D]    (dtype)
+ * No im2col_step: the whole batch is one launch (the reference chunks the batch, ms_deform_attn_cuda_t.cu:61-75).
+ * backward: grad_value [N,Len,M,D] fp32 must be ZERO-FILLED by the caller (accumulated with red.global.add);
+ * grad_loc / grad_attn fp32 are fully overwritten.  The gradient is the mathematical gradient of the forward
+ * (the reference backward kernel is not: SURVEY.md section 8a, DESIGN.md "Deliberate divergences").
+ */
+int cqvad_msda3d_forward(int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                         const float* loc, const float* attn, void* out,
+                         int N, int Len, int M, int D, int L, int Lq, int P, void* stream);
+int cqvad_msda3d_backward(int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                          const float* loc, const float* attn, const void* grad_out,
+                          float* grad_value, float* grad_loc, float* grad_attn,
+                          int N, int Len, int M, int D, int L, int Lq, int P, void* stream);
+/* Integer part of the sampling (the bit-exact contract, cuh:38-60,424-428): per (n,q,m,l,p) the int32 low corner
+ * and an 8-bit corner-validity mask (bit k = corner v(k+1) of cuh:63-109 is read; 0 = point skipped). */
+int cqvad_msda3d_indices(const int64_t* shapes, const float* loc, int32_t* t_low, int32_t* h_low, int32_t* w_low,
+                         uint8_t* corner_mask, int N, int Lq, int M, int L, int P, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Building blocks (used by the drop-in nn.Modules; each is also a step of cqvad_decoder_forward).
+ */
+/* y = LayerNorm(x (+ res)) over the last dim C (C == 256).  Replaces F.layer_norm call sites
+ * models/detr/dab_transformer.py:92,826-827,938,946,992,996,1045,1054,1065,1076.  `out_f32` != 0 writes fp32. */
+int cqvad_layernorm(int dtype, const void* x, const void* res, const float* gamma, const float* beta, float eps,
+                    void* out, int out_f32, long rows, int C, void* stream);
+/* C[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ res).  nn.Linear / 1x1 conv (dab_transformer.py:47, 1067-1070).
+ * BF16: tcgen05 kernel when K % 64 == 0 and N % 8 == 0, CUDA-core kernel otherwise. */
+int cqvad_linear(int dtype, const void* A, const void* W, const float* bias, const void* res, void* C,
+                 long M, int N, int K, int act, void* stream);
+/* y = x + W3.gelu(W2.LN(conv3x3(x)+b1)+b2)+b3 : ConvBlock.forward (dab_transformer.py:88-98) on NHWC input
+ * x [Nimg, h, w, 256] (dtype) -> y same shape.  w1 is [256 out][9 taps (ky*3+kx)][256 in] (dtype).
+ * workspace: cqvad_convblock_workspace_bytes(). */
+size_t cqvad_convblock_workspace_bytes(int dtype, long n_img, int h, int w);
+int cqvad_convblock_forward(int dtype, const void* x, void* y, const void* w1, const float* b1,
+                            const float* ln_g, const float* ln_b, const void* w2, const float* b2,
+                            const void* w3, const float* b3, long n_img, int h, int w,
+                            void* workspace, size_t ws_bytes, void* stream);
+/* Projection-free multi-head attention core of models/detr/attention.py:190-422 up to (not including) out_proj:
+ *   mode 0 (standard, :336-341,377,409): q [L,Nb,E], k [S,Nb,E], v [S,Nb,Ev] -> o [L,Nb,Ev]
+ *   mode 1 (query_specific_key, :343-346,379,411): q [L,Nb,E], k [L,S,Nb,E], v [L,S,Nb,Ev] -> o [L,Nb,Ev]
+ * q is scaled by (E/H)^-0.5 (:291-293); key_padding_mask [Nb,S] uint8 (non-zero = ignore, :390-396) or NULL;
+ * softmax after explicit max subtraction (:400-401); dropout is identity (eval). */
+int cqvad_mha_core(int dtype, int mode, const void* q, const void* k, const void* v, const uint8_t* key_padding_mask,
+                   void* o, int L, int S, int Nb, int H, int E, int Ev, void* stream);
+/* PositionEmbeddingSine_3D.forward (models/position_encoding.py:32-73, normalize=True): mask [B,T,H,W] uint8
+ * -> pos [B, num_pos_feats, T, H, W] fp32. */
+int cqvad_posenc3d(const uint8_t* mask, float* pos, int B, int T, int H, int W, int num_pos_feats, void* stream);
+/* gen_sineembed_for_position (dab_transformer.py:50-76): ref [rows,4] fp32 (x,y,w,h) -> [rows,512] fp32. */
+int cqvad_sine_embed(const float* ref, float* out, long rows, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * The decoder: TransformerDecoder.forward (dab_transformer.py:722-852) + DETR heads (models/model.py:191-221),
+ * eval semantics (dropout = identity).  One call enqueues the whole forward.
+ */
+typedef struct cqvad_decoder_desc {
+  int dtype;        /* CQVAD_F32 | CQVAD_BF16                                                        */
+  int BT;           /* B*T' frame-batch (dab_transformer.py:391-393)                                   */
+  int nq;           /* actor queries (MODEL.QUERY_NUM)                                                 */
+  int h, w;         /* orig_res, S = h*w keys                                                          */
+  int K;            /* class queries (DATA.NUM_CLASSES)                                                */
+  int F;            /* dim_feedforward                                                                 */
+  int layers;       /* DEC_LAYERS                                                                      */
+  int out_f32;      /* 1: hs/cls_hs written as fp32 (reference dtype); 0: written in `dtype`           */
+  int flags;        /* CQVAD_DEC_* below                                                               */
+} cqvad_decoder_desc;
+enum { CQVAD_DEC_SKIP_CLS_HS = 1 /* do not materialise cls_hs (only pred_logits) */ };
+
+/* Weight table: an array of device pointers ordered as cqvad_decoder_weight_name(i, layers) enumerates them
+ * (reference state_dict names, SURVEY.md App. C, + "heads.class_embed_b.*").  kind 0 = matrix stored in `dtype`
+ * ([out,in] row-major; conv1 as [out][ky*3+kx][in]); kind 1 = fp32 (biases, LayerNorm, small-N linears,
+ * class_queries).  NULL is allowed only for layers.{i>0}.ca_qpos_proj.* (dab_transformer.py:711-713). */
+int cqvad_decoder_num_weights(int layers);
+const char* cqvad_decoder_weight_name(int idx, int layers);
+int cqvad_decoder_weight_kind(int idx, int layers);
+
+size_t cqvad_decoder_workspace_bytes(const cqvad_decoder_desc* d);
+/* tgt [nq,BT,256] fp32, memory/pos [4,S,BT,256] fp32, mask [BT,S] uint8, refpoints_unsigmoid [nq,BT,4] fp32.
+ * Outputs: hs [layers,BT,nq,256], cls_hs [layers,BT,nq,K,256] (fp32 or dtype per out_f32; cls_hs may be NULL with
+ * CQVAD_DEC_SKIP_CLS_HS), refs [layers,BT,nq,4] fp32; heads (any may be NULL): pred_logits [layers,BT,nq,K],
+ * pred_boxes [layers,BT,nq,4], pred_logits_b [layers,BT,nq,3] fp32. */
+int cqvad_decoder_forward(const cqvad_decoder_desc* d, const void* const* weights,
+                          const float* tgt, const float* memory, const float* pos, const uint8_t* mask,
+                          const float* refpoints_unsigmoid,
+                          void* hs, void* cls_hs, float* refs,
+                          float* pred_logits, float* pred_boxes, float* pred_logits_b,
+                          void* workspace, size_t ws_bytes, void* stream);
+/* Number of kernels the last cqvad_decoder_forward on this thread launched (bench.py's gpu_launches). */
+long cqvad_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CQVAD_H_ */

@@ -1,0 +1,115 @@
+"""GPU parity tests proper: the CUDA decoder (through the C ABI) against (a) the committed golden fixtures produced by
+the reference itself and (b) the CPU oracle on the same seeded inputs.  Tolerances are BASELINE.json's:
+rel 1e-3 in fp32 (no TF32 anywhere: the fp32 path is FFMA), 2e-2 in bf16."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, case_from_meta, rel_err, TOL_FP32, TOL_BF16
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["dec_tiny", "dec_tiny_masked", "dec_small_masked", "dec_ucf_like", "dec_jhmdb_like", "dec_ava_csn_b1_l2",
+         "dec_ava_vitb_b1"]
+
+
+def run_engine(cfg, W, inp, dtype, **kw):
+    from class_query_vad_b200 import DecoderEngine
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(a).to(dev)
+    eng = DecoderEngine(W, nq=cfg["nq"], K=cfg["K"], layers=cfg["layers"], F=cfg["F"], dtype=dtype, device=dev)
+    out = eng.forward(t(inp["tgt"]), t(inp["memory"]), t(inp["mask"]), t(inp["pos"]), t(inp["refpoints_unsigmoid"]),
+                      inp["orig_res"], **kw)
+    torch.cuda.synchronize()
+    return {k: (None if v is None else v.float().cpu().numpy()) for k, v in out.items()}, eng
+
+
+def check_against_golden(out, g, tol):
+    errs = {}
+    for k in ("hs", "refs", "pred_logits", "pred_boxes", "pred_logits_b"):
+        errs[k] = rel_err(out[k], g[k])
+    if "cls_hs" in g:
+        errs["cls_hs"] = rel_err(out["cls_hs"], g["cls_hs"])
+    else:
+        errs["cls_hs_sub"] = rel_err(out["cls_hs"][:, :, ::4, ::7, ::5], g["cls_hs_sub"])
+    bad = {k: v for k, v in errs.items() if not (v < tol)}
+    assert not bad, f"rel errors above {tol}: {bad} (all: {errs})"
+    return errs
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_decoder_fp32_matches_reference_golden(name):
+    g = load_golden(name)
+    cfg, B, W, inp = case_from_meta(g["meta"])
+    out, _ = run_engine(cfg, W, inp, torch.float32)
+    check_against_golden(out, g, TOL_FP32)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_decoder_bf16_matches_reference_golden(name):
+    g = load_golden(name)
+    cfg, B, W, inp = case_from_meta(g["meta"])
+    out, eng = run_engine(cfg, W, inp, torch.bfloat16)
+    check_against_golden(out, g, TOL_BF16)
+    assert eng.last_launches > 0
+
+
+def test_decoder_bf16_simt_and_tensor_core_paths_agree():
+    """The tcgen05 GEMM/conv kernels against the CUDA-core kernels on identical bf16 inputs (debug switch)."""
+    from class_query_vad_b200 import _lib
+    g = load_golden("dec_small_masked")
+    cfg, B, W, inp = case_from_meta(g["meta"])
+    out_tc, _ = run_engine(cfg, W, inp, torch.bfloat16)
+    _lib.lib().cqvad_debug_force_simt(1)
+    try:
+        out_simt, _ = run_engine(cfg, W, inp, torch.bfloat16)
+    finally:
+        _lib.lib().cqvad_debug_force_simt(0)
+    for k in ("hs", "cls_hs", "refs"):
+        assert rel_err(out_tc[k], out_simt[k]) < 1e-2, k
+
+
+def test_decoder_vs_oracle_batch_independence():
+    """Size-independent property at a larger batch: clips are independent, so decoding a batch equals decoding its
+    halves (the multi-GPU sharding contract), and matches the CPU oracle on a sampled clip."""
+    from oracle import synth, decoder_np
+    cfg = dict(synth.CONFIGS["ava_vitb"]); cfg["layers"] = 2
+    W = synth.make_decoder_weights(cfg["K"], cfg["layers"], cfg["F"], seed=7)
+    inp = synth.make_decoder_inputs(cfg, 6, seed=7)
+    full, _ = run_engine(cfg, W, inp, torch.bfloat16)
+    half = {k: (v[:, :, :3] if k in ("tgt", "refpoints_unsigmoid") else v) for k, v in inp.items()}
+    half["memory"] = np.ascontiguousarray(inp["memory"][:, :, :3]); half["pos"] = np.ascontiguousarray(inp["pos"][:, :, :3])
+    half["mask"] = inp["mask"][:3]
+    half["tgt"] = np.ascontiguousarray(inp["tgt"][:, :3]); half["refpoints_unsigmoid"] = np.ascontiguousarray(inp["refpoints_unsigmoid"][:, :3])
+    part, _ = run_engine(cfg, W, half, torch.bfloat16)
+    for k in ("hs", "cls_hs", "refs", "pred_logits"):
+        np.testing.assert_array_equal(full[k][:, :3], part[k])   # bit-identical: no cross-clip arithmetic
+    one = {k: v for k, v in half.items()}
+    for k in ("tgt", "refpoints_unsigmoid"):
+        one[k] = np.ascontiguousarray(inp[k][:, 4:5])
+    for k in ("memory", "pos"):
+        one[k] = np.ascontiguousarray(inp[k][:, :, 4:5])
+    one["mask"] = inp["mask"][4:5]
+    hs, cls_hs, refs = decoder_np.decoder_forward(W, one["tgt"], one["memory"], one["mask"], one["pos"],
+                                                  one["refpoints_unsigmoid"], one["orig_res"], cfg["layers"])
+    assert rel_err(full["hs"][:, 4:5], hs) < TOL_BF16
+    assert rel_err(full["cls_hs"][:, 4:5], cls_hs) < TOL_BF16
+    assert rel_err(full["refs"][:, 4:5], refs) < TOL_BF16
+
+
+def test_decoder_module_drop_in_fp32():
+    """nn.Module boundary: build_decoder() + load_state_dict of reference-named weights + reference forward signature."""
+    from class_query_vad_b200 import build_decoder
+    g = load_golden("dec_tiny_masked")
+    cfg, B, W, inp = case_from_meta(g["meta"])
+    dec = build_decoder(cfg["nq"], cfg["K"], cfg["layers"], cfg["F"])
+    sd = {k: torch.from_numpy(v) for k, v in W.items() if not k.startswith("heads.")}
+    dec.load_state_dict(sd, strict=True)
+    dec = dec.cuda().eval()
+    dec.compute_dtype = torch.float32
+    t = lambda a: torch.from_numpy(a).cuda()
+    hs, cls_hs, refs = dec(t(inp["tgt"]), t(inp["memory"]), memory_key_padding_mask=t(inp["mask"]), pos=t(inp["pos"]),
+                           refpoints_unsigmoid=t(inp["refpoints_unsigmoid"]), orig_res=inp["orig_res"])
+    assert rel_err(hs.cpu().numpy(), g["hs"]) < TOL_FP32
+    assert rel_err(cls_hs.cpu().numpy(), g["cls_hs"]) < TOL_FP32
+    assert rel_err(refs.cpu().numpy(), g["refs"]) < TOL_FP32
