@@ -30,6 +30,8 @@ SYMBOLS = {
     "cqvad_msda3d_indices": (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_void_p]),
     "cqvad_layernorm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_long, c_int, c_void_p]),
     "cqvad_linear": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_void_p]),
+    "cqvad_mlp": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float,
+                          c_void_p, c_void_p, c_long, c_int, c_void_p]),
     "cqvad_convblock_workspace_bytes": (c_size_t, [c_int, c_long, c_int, c_int]),
     "cqvad_convblock_forward": (c_int, [c_int] + [c_void_p] * 10 + [c_long, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "cqvad_mha_core": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),

@@ -410,6 +410,35 @@ extern "C" int cqvad_linear(int dtype, const void* A, const void* W, const float
   return set_error(CQVAD_E_INVALID_ARG, "linear: unknown dtype %d", dtype);
 }
 
+template <typename T>
+static int mlp_t(const T* X, const T* W1, const float* b1, const T* W2, const float* b2, int act, const T* res,
+                 const float* g, const float* b, float eps, T* Y, T* hid, long M, int F, cudaStream_t st) {
+  if (DT<T>::id == CQVAD_BF16 && !force_simt()) {
+    int r = mlp_tc((const bf16*)X, (const bf16*)W1, b1, (const bf16*)W2, b2, act, (const bf16*)res, g, b, eps, (bf16*)Y, M,
+                   kC, F, 0, 0, st);
+    if (r <= 0) return r;
+  }
+  CQ_CHECK_ARG(hid != nullptr, "mlp: hidden scratch buffer required on this path");
+  Epilogue e1; e1.bias = b1; e1.act = act;
+  CQ_TRY(gemm<T>(X, kC, W1, hid, F, M, F, kC, e1, nullptr, st));
+  Epilogue e2; e2.bias = b2; e2.res = res; e2.ldr = kC; e2.ln_g = g; e2.ln_b = b; e2.ln_eps = eps;
+  return gemm<T>(hid, F, W2, Y, kC, M, kC, F, e2, nullptr, st);
+}
+
+extern "C" int cqvad_mlp(int dtype, const void* X, const void* W1, const float* b1, const void* W2, const float* b2, int act,
+                         const void* res, const float* ln_g, const float* ln_b, float ln_eps, void* Y, void* hidden, long M,
+                         int F, void* stream) {
+  CQ_CHECK_ARG(X && W1 && b1 && W2 && b2 && Y && M >= 0 && F >= 8, "mlp: bad argument");
+  CQ_CHECK_ARG(act == CQVAD_ACT_RELU || act == CQVAD_ACT_GELU, "mlp: activation must be ReLU or GELU");
+  CQ_CHECK_ARG((ln_g == nullptr) == (ln_b == nullptr), "mlp: ln_g and ln_b must both be given or both be NULL");
+  if (M == 0) return 0;
+  if (dtype == CQVAD_F32)
+    return mlp_t<float>((const float*)X, (const float*)W1, b1, (const float*)W2, b2, act, (const float*)res, ln_g, ln_b, ln_eps, (float*)Y, (float*)hidden, M, F, as_stream(stream));
+  if (dtype == CQVAD_BF16)
+    return mlp_t<bf16>((const bf16*)X, (const bf16*)W1, b1, (const bf16*)W2, b2, act, (const bf16*)res, ln_g, ln_b, ln_eps, (bf16*)Y, (bf16*)hidden, M, F, as_stream(stream));
+  return set_error(CQVAD_E_INVALID_ARG, "mlp: unknown dtype %d", dtype);
+}
+
 extern "C" size_t cqvad_convblock_workspace_bytes(int dtype, long n_img, int h, int w) {
   const size_t es = dtype == CQVAD_F32 ? 4 : 2;
   const size_t rp = (size_t)n_img * (h + 1) * w;

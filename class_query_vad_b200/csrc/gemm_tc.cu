@@ -312,9 +312,4 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
   return 0;
 }
 
-int mlp_tc(const bf16*, const bf16*, const float*, const bf16*, const float*, int, const bf16*, const float*, const float*,
-           float, bf16*, long, int, int, int, int, cudaStream_t) {
-  return 1;  // fused MLP kernel: see mlp_tc.cu (not enabled in this build)
-}
-
 }  // namespace cqvad

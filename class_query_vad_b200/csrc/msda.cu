@@ -16,13 +16,6 @@ namespace cqvad {
 
 namespace {
 
-struct PointGeom {
-  int base;       // element offset of corner (t_low,h_low,w_low) relative to the level start, in rows of M*D
-  int ht, hh;     // strides in rows
-  unsigned mask;  // 8 corner-valid bits
-  float lt, lh, lw;
-};
-
 __device__ __forceinline__ void point_geometry(float loc_x, float loc_y, float loc_t, int T, int H, int W, int& tl,
                                                int& hl, int& wl, unsigned& mask, float& lt, float& lh, float& lw) {
   const float t_im = __fsub_rn(__fmul_rn(loc_t, (float)T), 0.5f);
@@ -249,6 +242,7 @@ extern "C" int cqvad_msda3d_forward(int dtype, const void* value, const int64_t*
                                     const float* loc, const float* attn, void* out, int N, int Len, int M, int D, int L,
                                     int Lq, int P, void* stream) {
   CQ_TRY(check_dims(N, Len, M, D, L, Lq, P));
+  if ((long)N * Lq == 0) return 0;   // empty query set: nothing to write (pointers of empty tensors may be NULL)
   CQ_CHECK_ARG(value && shapes && level_start && loc && attn && out, "msda3d_forward: null pointer");
   if (dtype == CQVAD_F32) return msda_fwd_t<float>(value, shapes, level_start, loc, attn, out, N, Len, M, D, L, Lq, P, as_stream(stream));
   if (dtype == CQVAD_BF16) return msda_fwd_t<bf16>(value, shapes, level_start, loc, attn, out, N, Len, M, D, L, Lq, P, as_stream(stream));
@@ -260,6 +254,7 @@ extern "C" int cqvad_msda3d_backward(int dtype, const void* value, const int64_t
                                      float* grad_loc, float* grad_attn, int N, int Len, int M, int D, int L, int Lq, int P,
                                      void* stream) {
   CQ_TRY(check_dims(N, Len, M, D, L, Lq, P));
+  if ((long)N * Lq == 0) return 0;
   CQ_CHECK_ARG(value && shapes && level_start && loc && attn && grad_out && grad_value && grad_loc && grad_attn,
                "msda3d_backward: null pointer");
   if (dtype == CQVAD_F32) return msda_bwd_t<float>(value, shapes, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, N, Len, M, D, L, Lq, P, as_stream(stream));

@@ -35,9 +35,29 @@ def layer_norm(x, weight, bias, eps=1e-5, res=None):
     r = None if res is None else res.reshape(-1, C).to(dt).contiguous()
     out = torch.empty_like(x2)
     p = _lib.ptr
-    _lib.check(_lib.lib().cqvad_layernorm(_lib.dtype_id(dt), p(x2), p(r), p(_w(weight, torch.float32)),
-                                          p(_w(bias, torch.float32)), float(eps), p(out), 0, x2.shape[0], C,
-                                          _lib.stream_ptr()))
+    g, b = _w(weight, torch.float32), _w(bias, torch.float32)   # keep the converted copies alive across the launch
+    _lib.check(_lib.lib().cqvad_layernorm(_lib.dtype_id(dt), p(x2), p(r), p(g), p(b), float(eps), p(out), 0,
+                                          x2.shape[0], C, _lib.stream_ptr()))
+    return out.view(x.shape)
+
+
+def ffn(x, w1, b1, w2, b2, act=_lib.ACT_RELU, res=None, ln_weight=None, ln_bias=None, eps=1e-5):
+    """LN?( res + w2 . act(w1 . x + b1) + b2 ) through cqvad_mlp (fused tcgen05 kernel in bf16 when F % 128 == 0)."""
+    _lib.require_cuda(x)
+    dt = x.dtype
+    C = x.shape[-1]
+    x2 = x.reshape(-1, C).contiguous()
+    W1, W2 = _w(w1, dt), _w(w2, dt)
+    B1, B2 = _w(b1, torch.float32), _w(b2, torch.float32)
+    F = W1.shape[0]
+    r = None if res is None else res.reshape(-1, C).to(dt).contiguous()
+    g = None if ln_weight is None else _w(ln_weight, torch.float32)
+    b = None if ln_bias is None else _w(ln_bias, torch.float32)
+    out = torch.empty_like(x2)
+    hid = torch.empty((x2.shape[0], F), dtype=dt, device=x.device)
+    p = _lib.ptr
+    _lib.check(_lib.lib().cqvad_mlp(_lib.dtype_id(dt), p(x2), p(W1), p(B1), p(W2), p(B2), act, p(r), p(g), p(b), float(eps),
+                                    p(out), p(hid), x2.shape[0], F, _lib.stream_ptr()))
     return out.view(x.shape)
 
 
@@ -77,7 +97,9 @@ def conv_block(x_nhwc, conv1_w, conv1_b, ln_w, ln_b, conv2_w, conv2_b, conv3_w, 
     f32 = lambda t: _w(t, torch.float32)
     p = _lib.ptr
     import ctypes
-    _lib.check(lib.cqvad_convblock_forward(_lib.dtype_id(dt), p(x), p(y), p(w1), p(f32(conv1_b)), p(f32(ln_w)), p(f32(ln_b)),
-                                           p(_w(conv2_w, dt)), p(f32(conv2_b)), p(_w(conv3_w, dt)), p(f32(conv3_b)),
-                                           n, h, w, ctypes.c_void_p(ws.data_ptr() + off), nbytes, _lib.stream_ptr()))
+    # converted copies are bound to names so they outlive the (asynchronous) launch
+    b1, g, b, w2, b2, w3, b3 = f32(conv1_b), f32(ln_w), f32(ln_b), _w(conv2_w, dt), f32(conv2_b), _w(conv3_w, dt), f32(conv3_b)
+    _lib.check(lib.cqvad_convblock_forward(_lib.dtype_id(dt), p(x), p(y), p(w1), p(b1), p(g), p(b), p(w2), p(b2), p(w3),
+                                           p(b3), n, h, w, ctypes.c_void_p(ws.data_ptr() + off), nbytes,
+                                           _lib.stream_ptr()))
     return y

@@ -70,6 +70,12 @@ int cqvad_layernorm(int dtype, const void* x, const void* res, const float* gamm
  * BF16: tcgen05 kernel when K % 64 == 0 and N % 8 == 0, CUDA-core kernel otherwise. */
 int cqvad_linear(int dtype, const void* A, const void* W, const float* bias, const void* res, void* C,
                  long M, int N, int K, int act, void* stream);
+/* Y[M,256] = LN?( res + W2 . act(W1 . X + b1) + b2 ): the FFN blocks of the decoder (dab_transformer.py:994-996,
+ * 1043-1045, 1074-1076).  X [M,256], W1 [F,256], W2 [256,F] (dtype); ln_g/ln_b may be NULL (no LayerNorm); res may be
+ * NULL.  hidden [M,F] (dtype) is scratch used only when the fused tensor-core kernel does not apply (fp32, or F % 128). */
+int cqvad_mlp(int dtype, const void* X, const void* W1, const float* b1, const void* W2, const float* b2, int act,
+              const void* res, const float* ln_g, const float* ln_b, float ln_eps, void* Y, void* hidden, long M, int F,
+              void* stream);
 /* y = x + W3.gelu(W2.LN(conv3x3(x)+b1)+b2)+b3 : ConvBlock.forward (dab_transformer.py:88-98) on NHWC input
  * x [Nimg, h, w, 256] (dtype) -> y same shape.  w1 is [256 out][9 taps (ky*3+kx)][256 in] (dtype).
  * workspace: cqvad_convblock_workspace_bytes(). */
