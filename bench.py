@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- decoder clips/s of the class-query decoder hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+A step = one pass of TransformerDecoder.forward + DETR heads (cqvad_decoder_forward) over one batch of synthetic clips
+(AVA22_ViT-B shapes: nq 15, S 14x14, K 80, 6 layers, F 2048), bf16 tensor-core path.
+  value : whole-job clips/s with inputs already resident in HBM (CUDA events, max over ranks)
+  e2e   : same metric through the public API (DecoderEngine.forward) with pinned-HOST inputs: H2D copy of the step's
+          inputs and D2H read of the detections inside the timed region
+  roofline     : the dominant kernel (tcgen05 implicit-GEMM 3x3 conv + LN), timed live with CUDA events on the launch
+                 stream (library profiler scopes), algorithmic FLOPs / duration vs the measured bf16 peak
+  cpu_baseline : the numpy oracle port of the reference decoder on the host cores, bounded sample (rank 0, N=1 only)
+`--impl reference` times the CPU oracle port of the reference path (the reference is Python and cannot travel to the GPU
+box; /root/reference is never read here).
+Multi-GPU: one process per GPU (torchrun), clips sharded across ranks (weak scaling: --batch clips per GPU), one NCCL
+all-gather of the per-clip detections per step.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CFG = "ava_vitb"
+FWD_GFLOP_PER_CLIP = 148.18            # BASELINE.md section 3 (reference flop count, AVA22_ViT-B decoder forward)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_oracle_clips_per_s(max_seconds=25.0, min_reps=1):
+    """The oracle port (numpy restatement of the reference decoder) on one AVA22_ViT-B clip, host cores."""
+    from oracle import synth, decoder_np
+    cfg = synth.CONFIGS[CFG]
+    W = synth.make_decoder_weights(cfg["K"], cfg["layers"], cfg["F"], seed=0)
+    inp = synth.make_decoder_inputs(CFG, 1, seed=0)
+    times = []
+    t_all = time.time()
+    while len(times) < min_reps or (time.time() - t_all < max_seconds and len(times) < 5):
+        t0 = time.time()
+        hs, cls_hs, refs = decoder_np.decoder_forward(W, inp["tgt"], inp["memory"], inp["mask"], inp["pos"],
+                                                      inp["refpoints_unsigmoid"], inp["orig_res"], cfg["layers"])
+        decoder_np.detr_heads(W, hs, cls_hs, refs)
+        times.append(time.time() - t0)
+    return 1.0 / float(np.median(times)), len(times)
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path = the oracle port, all host threads (numpy BLAS), bounded sample."""
+    if rank != 0:
+        return
+    from oracle import synth, decoder_np
+    cfg = synth.CONFIGS[CFG]
+    W = synth.make_decoder_weights(cfg["K"], cfg["layers"], cfg["F"], seed=0)
+    inp = synth.make_decoder_inputs(CFG, 1, seed=0)
+
+    def step():
+        hs, cls_hs, refs = decoder_np.decoder_forward(W, inp["tgt"], inp["memory"], inp["mask"], inp["pos"],
+                                                      inp["refpoints_unsigmoid"], inp["orig_res"], cfg["layers"])
+        decoder_np.detr_heads(W, hs, cls_hs, refs)
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    steps = min(args.steps, 5)          # bounded: each step is one clip (~seconds of CPU work)
+    t0 = time.time()
+    for _ in range(steps):
+        step()
+    dt = time.time() - t0
+    v = steps / dt
+    cores = os.cpu_count()
+    sample = f"{steps} steps x 1 clip (AVA22_ViT-B decoder forward + heads, fp32 numpy oracle port), median-free wall clock"
+    print(json.dumps({
+        "impl": "reference", "metric": "decoder clips/s", "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "AVA22_ViT-B class-query decoder forward + heads, 6 layers, nq 15, S 196, K 80; 1 clip per step on host CPU"},
+        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from class_query_vad_b200 import DecoderEngine, _lib
+    from oracle import synth
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = synth.CONFIGS[CFG]
+    B = args.batch
+    nq, K, Lr, F = cfg["nq"], cfg["K"], cfg["layers"], cfg["F"]
+    W = synth.make_decoder_weights(K, Lr, F, seed=0)
+    eng = DecoderEngine(W, nq=nq, K=K, layers=Lr, F=F, dtype=torch.bfloat16, device=dev, out_f32=False)
+    lib = _lib.lib()
+
+    # synthetic inputs: NSETS different batches cycled so that no step finds its inputs in L2 (126 MB); the
+    # intermediates of one step (~0.8 GB) exceed L2 by themselves.
+    NSETS = 4
+    host_sets, dev_sets = [], []
+    for s in range(NSETS):
+        inp = synth.make_decoder_inputs(CFG, B, seed=100 * rank + s)
+        hp = {k: torch.from_numpy(np.ascontiguousarray(inp[k])).pin_memory() for k in ("tgt", "memory", "pos", "mask", "refpoints_unsigmoid")}
+        host_sets.append(hp)
+        dev_sets.append({k: v.to(dev) for k, v in hp.items()})
+    orig_res = (cfg["h"], cfg["w"])
+    det_local = torch.empty((B, nq, K + 4 + 3), dtype=torch.float32, device=dev)
+    det_all = torch.empty((world * B, nq, K + 4 + 3), dtype=torch.float32, device=dev) if world > 1 else det_local
+    det_host = torch.empty((B, nq, K + 4 + 3), dtype=torch.float32).pin_memory()
+
+    def step(inp):
+        out = eng.forward(inp["tgt"], inp["memory"], inp["mask"], inp["pos"], inp["refpoints_unsigmoid"], orig_res,
+                          heads=True, skip_cls_hs=False)
+        # detections of the last layer: [B, nq, K | 4 | 3] (the row format of utils/video_action_recognition.py:234)
+        torch.cat([out["pred_logits"][-1], out["pred_boxes"][-1], out["pred_logits_b"][-1]], dim=-1, out=det_local)
+        if world > 1:
+            dist.all_gather_into_tensor(det_all, det_local)
+        return out
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- warm-up ----
+    for i in range(args.warmup):
+        step(dev_sets[i % NSETS])
+    sync_all()
+
+    # ---- timed: device-resident inputs ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.cqvad_profile_enable(1)
+    ms = timed(lambda i: step(dev_sets[i % NSETS]), args.steps)
+    prof = {}
+    for c in range(lib.cqvad_profile_num_classes()):
+        tot, sc, ln = ctypes.c_double(), ctypes.c_long(), ctypes.c_long()
+        lib.cqvad_profile_read(c, ctypes.byref(tot), ctypes.byref(sc), ctypes.byref(ln))
+        prof[lib.cqvad_profile_class_name(c).decode()] = dict(ms_per_step=tot.value / args.steps, scopes=sc.value // max(args.steps, 1),
+                                                             launches=ln.value // max(args.steps, 1))
+    lib.cqvad_profile_enable(0)
+    launches_per_step = eng.last_launches + 1 + (1 if world > 1 else 0)     # + torch.cat (+ NCCL all-gather)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed: end to end through the public API with pinned host inputs ----
+    h2d = sum(host_sets[0][k].numel() * host_sets[0][k].element_size() for k in host_sets[0])
+    d2h = det_host.numel() * 4
+
+    def e2e_step(i):
+        hp = host_sets[i % NSETS]
+        inp = {k: v.to(dev, non_blocking=True) for k, v in hp.items()}
+        step(inp)
+        det_host.copy_(det_local, non_blocking=True)
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    clips = world * B * args.steps
+    value = clips / (ms / 1e3)
+    peaks = load_peaks()
+    # ---- roofline of the dominant kernel: implicit-GEMM conv3x3 (+bias+LN epilogue), 3 launches per layer ----
+    S = cfg["h"] * cfg["w"]
+    Nrows = B * nq * S                                   # algorithmic output pixels per launch
+    conv = prof["conv3x3_ln (tcgen05 implicit GEMM)"]
+    conv_launch_ms = conv["ms_per_step"] / max(conv["scopes"], 1)
+    conv_flops = 2.0 * Nrows * 256 * 2304               # 2*N*S*C^2*9 per ConvBlock conv
+    achieved = conv_flops / (conv_launch_ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("conv3x3_ln_bytes_per_launch")
+    roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (conv mode)", "achieved": achieved, "peak": peaks["tf_sust"],
+            "unit": "TFLOP/s", "frac": achieved / peaks["tf_sust"], "traffic": traffic, "peak_source": peaks["src"] + " sustained bf16",
+            "launch_ms": conv_launch_ms, "flops_per_launch": conv_flops}
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        v, reps = cpu_oracle_clips_per_s()
+        cpu = {"value": v, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{reps} x 1 clip, same workload shape (AVA22_ViT-B decoder forward + heads), fp32 numpy oracle port"}
+    line = {
+        "metric": "decoder clips/s", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"AVA22_ViT-B class-query decoder FORWARD + heads (6 layers, nq 15, S 196, K 80, F 2048), "
+                               f"{B} clips/GPU; backward not implemented yet (BASELINE configs[1] names fwd+bwd)",
+                   "batch_per_gpu": B, "parallelism": f"clip-sharded x{world}", "l2": "4 input sets cycled (128 MB) + ~0.8 GB of intermediates per step >> 126 MB L2",
+                   "decoder_tflops": value * FWD_GFLOP_PER_CLIP / 1e3 / world},
+        "clocks": clocks,
+        "e2e": {"value": clips / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in prof.items()},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

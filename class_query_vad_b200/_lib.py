@@ -43,6 +43,11 @@ SYMBOLS = {
     "cqvad_decoder_workspace_bytes": (c_size_t, [POINTER(DecoderDesc)]),
     "cqvad_decoder_forward": (c_int, [POINTER(DecoderDesc), POINTER(c_void_p)] + [c_void_p] * 11 + [c_void_p, c_size_t, c_void_p]),
     "cqvad_last_launch_count": (c_long, []),
+    "cqvad_profile_enable": (None, [c_int]),
+    "cqvad_profile_num_classes": (c_int, []),
+    "cqvad_profile_class_name": (c_char_p, [c_int]),
+    "cqvad_profile_read": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(c_long), POINTER(c_long)]),
+    "cqvad_debug_force_simt": (None, [c_int]),
 }
 
 _lib = None
@@ -59,8 +64,6 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        l.cqvad_debug_force_simt.restype = None
-        l.cqvad_debug_force_simt.argtypes = [c_int]
         _lib = l
     return _lib
 

@@ -137,7 +137,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) dec_qsk_kernel(const T* __restrict__ qc, const T* __restrict__ qs,
                                                       const T* __restrict__ kc, const T* __restrict__ v, long ldkv,
                                                       const T* __restrict__ kp, const uint8_t* __restrict__ mask,
-                                                      T* __restrict__ o, int S, int BT, int first) {
+                                                      T* __restrict__ o, int S, int Sq, int BT, int first) {
   extern __shared__ float smem[];
   const long i = blockIdx.x;
   const int bb = (int)(i % BT);
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) dec_qsk_kernel(const T* __restrict__ qc, 
   const float qcv = to_f(qc[i * kC + c]) * 0.125f;
   const float qsv = to_f(qs[i * kC + c]) * 0.125f;
   const float qk = first ? qcv + qsv : qsv;  // coefficient of kp: first layer adds kp to the content key too (:964-967)
-  const T* kcb = kc + i * S * ldkv + c;
+  const T* kcb = kc + i * Sq * ldkv + c;
   const T* kpb = kp + (long)bb * kC + c;
   float mx = -INFINITY;
   int s = 0;
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) dec_qsk_kernel(const T* __restrict__ qc, 
   }
   sum = warp_sum(sum);
   __syncwarp();
-  const T* vb = v + i * S * ldkv + c;
+  const T* vb = v + i * Sq * ldkv + c;
   float acc = 0.f;
 #pragma unroll 4
   for (int m = 0; m < S; ++m) acc = fmaf(my_sc[m], to_f(vb[(long)m * ldkv]), acc);
@@ -244,15 +244,15 @@ template int mha_core<bf16>(int, const bf16*, const bf16*, const bf16*, const ui
 
 template <typename T>
 int dec_qsk_attn(const T* qc, const T* qs, const T* kc, const T* v, long ldkv, const T* kp, const uint8_t* mask, T* o,
-                 long N, int S, int BT, bool first, cudaStream_t stm) {
+                 long N, int S, int Sq, int BT, bool first, cudaStream_t stm) {
   if (N == 0) return 0;
   const size_t smem = (size_t)kH * S * sizeof(float);
   CQ_TRY(set_smem(dec_qsk_kernel<T>, smem));
-  dec_qsk_kernel<T><<<(unsigned)N, 256, smem, stm>>>(qc, qs, kc, v, ldkv, kp, mask, o, S, BT, first ? 1 : 0);
+  dec_qsk_kernel<T><<<(unsigned)N, 256, smem, stm>>>(qc, qs, kc, v, ldkv, kp, mask, o, S, Sq, BT, first ? 1 : 0);
   CQ_LAUNCH_CHECK();
   return 0;
 }
-template int dec_qsk_attn<float>(const float*, const float*, const float*, const float*, long, const float*, const uint8_t*, float*, long, int, int, bool, cudaStream_t);
-template int dec_qsk_attn<bf16>(const bf16*, const bf16*, const bf16*, const bf16*, long, const bf16*, const uint8_t*, bf16*, long, int, int, bool, cudaStream_t);
+template int dec_qsk_attn<float>(const float*, const float*, const float*, const float*, long, const float*, const uint8_t*, float*, long, int, int, int, bool, cudaStream_t);
+template int dec_qsk_attn<bf16>(const bf16*, const bf16*, const bf16*, const bf16*, long, const bf16*, const uint8_t*, bf16*, long, int, int, int, bool, cudaStream_t);
 
 }  // namespace cqvad

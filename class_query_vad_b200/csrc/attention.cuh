@@ -13,5 +13,5 @@ int mha_std(const T* q, const T* q2, const T* k, const T* k2, const T* v, const 
             int H, int hd, int vd, const StdStrides& st, cudaStream_t stm);
 template <typename T>
 int dec_qsk_attn(const T* qc, const T* qs, const T* kc, const T* v, long ldkv, const T* kp, const uint8_t* mask, T* o,
-                 long N, int S, int BT, bool first, cudaStream_t stm);
+                 long N, int S, int Sq, int BT, bool first, cudaStream_t stm);
 }  // namespace cqvad

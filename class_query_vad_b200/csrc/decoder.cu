@@ -13,8 +13,12 @@
 #include "common.cuh"
 #include "kernels_mem.cuh"
 #include "attention.cuh"
+#include "prof.cuh"
 
 namespace cqvad {
+
+int cls_xattn_tc(const bf16* Qin, const bf16* cqp, const bf16* kx, const bf16* pos0, const bf16* vt, long ldvt,
+                 const float* bv, bf16* out, long N, int K, int S, int Sq, int Sp_rows, int BT, cudaStream_t st);
 
 // ---- error / launch-count state (thread-local) -------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -28,6 +32,7 @@ int set_error(int code, const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 void reset_launch_count() { g_launches = 0; }
+long launch_count_now() { return g_launches; }
 
 // ---- weight table --------------------------------------------------------------------------------------------
 // kind: 0 = matrix stored in the activation dtype, 1 = fp32
@@ -106,17 +111,19 @@ struct Decoder {
   const cqvad_decoder_desc& d;
   const void* const* w;
   cudaStream_t st;
-  int BT, nq, h, wd, S, Sp, K, F, Lr;
-  long N, NS, Rp, NK;
+  int BT, nq, h, wd, S, Sp, Sq, K, F, Lr;   // Sq: per-instance row pitch of q_memory (S rounded up to 8)
+  long N, NS, NSq, Rp, NK;
 
   // buffers
   T *memc, *pos0c, *e512, *qpos, *tmpN, *pscale, *qse, *saq, *sak, *sav, *sao, *out, *actor, *acls, *qm, *kv, *kp, *qc,
-      *qs, *cao, *XA, *XB, *Xn, *Hc, *Qc[2], *cq1, *cq2, *saoc, *kx, *vx, *cqp, *caoc, *cls0, *Hf, *hsn, *bb1, *bb2;
+      *qs, *cao, *XA, *XB, *Xn, *Hc, *Qc[2], *cq1, *cq2, *saoc, *kx, *vx, *vt, *cqp, *caoc, *cls0, *Hf, *hsn, *bb1, *bb2;
+  long ldvt;
   float *r_cur, *r_next, *lvlw;
 
   Decoder(const cqvad_decoder_desc& dd, const void* const* ww, cudaStream_t s) : d(dd), w(ww), st(s) {
     BT = d.BT; nq = d.nq; h = d.h; wd = d.w; S = h * wd; Sp = (h + 1) * wd; K = d.K; F = d.F; Lr = d.layers;
-    N = (long)nq * BT; NS = N * S; Rp = N * Sp; NK = N * K;
+    Sq = (S + 7) & ~7;
+    N = (long)nq * BT; NS = N * S; NSq = N * Sq; Rp = N * Sp; NK = N * K;
   }
   size_t plan(Arena& a) {
     auto t = [&](long n) { return (T*)a.take((size_t)n * sizeof(T)); };
@@ -125,10 +132,10 @@ struct Decoder {
     memc = t(4L * S * BT * kC); pos0c = t((long)S * BT * kC);
     e512 = t(N * 512); qpos = t(N * kC); tmpN = t(N * Fm); pscale = t(N * kC); qse = t(N * kC);
     saq = t(N * kC); sak = t(N * kC); sav = t(N * kC); sao = t(N * kC); out = t(N * kC); actor = t(N * kC);
-    acls = t(N * kC); qm = t(NS * kC); kv = t(NS * 2 * kC); kp = t((long)S * BT * kC); qc = t(N * kC); qs = t(N * kC);
+    acls = t(N * kC); qm = t(NSq * kC); kv = t(NSq * 2 * kC); kp = t((long)S * BT * kC); qc = t(N * kC); qs = t(N * kC);
     cao = t(N * kC); XA = t(Rp * kC); XB = t(Rp * kC); Xn = t(Rp * kC); Hc = t(Rp * 4 * kC);
     Qc[0] = t(NK * kC); Qc[1] = t(NK * kC); cq1 = t((long)K * kC); cq2 = t((long)K * kC); saoc = t(NK * kC);
-    kx = t(Rp * kC); vx = t(NS * kC); cqp = t(N * kC); caoc = t(NK * kC); cls0 = t(NK * kC); Hf = t(NK * F);
+    kx = t(Rp * kC); vx = t(NSq * kC); ldvt = NSq + 64; vt = t(kC * ldvt); cqp = t(N * kC); caoc = t(NK * kC); cls0 = t(NK * kC); Hf = t(NK * F);
     hsn = t(N * kC); bb1 = t(N * kC); bb2 = t(N * kC);
     r_cur = f(N * 4); r_next = f(N * 4); lvlw = f(N * 4);
     return a.off;
@@ -151,6 +158,10 @@ struct Decoder {
   // Y = LN?( res + W2.act(W1.X + b1) + b2 ), hidden in `hid` ([M,Fh]) unless the fused tensor-core kernel takes it
   int mlp(const T* X, long M, int Fh, int w1, int w2, int act, const T* res, int ln_idx, float eps, T* Y, T* hid,
           int zero_period = 0, int zero_valid = 0);
+
+  // class cross-attention (dab_transformer.py:1067-1071): fills caoc [N*K,256] from Qin, X3 (padded), qm, qse
+  int xattn(int l, const T* Qin, const T* X3);
+  int xattn_generic(int l, const T* Qin, const T* X3);
 
   int run(const float* tgt, const float* memory, const float* pos, const uint8_t* mask, const float* ref_u, void* hs,
           void* cls_hs, float* refs, float* pred_logits, float* pred_boxes, float* pred_logits_b);
@@ -180,22 +191,64 @@ int Decoder<bf16>::mlp(const bf16* X, long M, int Fh, int w1, int w2, int act, c
   return gemm<bf16>(hid, Fh, Wm(w2), Y, kC, M, kC, Fh, e, nullptr, st);
 }
 
+// class cross-attention :1067-1071.  512-wide q/k split contiguously into 8 heads of 64 (attention.py:336,339):
+// heads 0-3 = (class query . k_proj(conv feature)), heads 4-7 = (actor sine pos . spatial pos).
+template <typename T>
+int Decoder<T>::xattn_generic(int l, const T* Qin, const T* X3) {
+  { ProfScope ps(P_BIG_PROJ, st);
+    CQ_TRY(lin(X3, Rp, kC, cls(l, C_KPROJ), kx, kC));
+    CQ_TRY(lin(qm, NSq, kC, cls(l, C_VPROJ), vx, kC));
+    CQ_TRY(lin(qse, N, kC, cls(l, C_QPS), cqp, kC)); }
+  ProfScope ps(P_CLS_XATTN, st);
+  StdStrides ss{};
+  ss.q_ls = kC; ss.q_bs = (long)K * kC;             // Qin rows (i,k)
+  ss.q2_ls = 0; ss.q2_bs = kC;                      // cqp row i, same for every class
+  ss.k_ls = kC; ss.k_bs = (long)Sp * kC;            // kx on the padded layout
+  ss.k2_ls = (long)BT * kC; ss.k2_bs = kC; ss.k2_bmod = BT;   // pos0[s, b], b = i % BT
+  ss.v_ls = kC; ss.v_bs = (long)Sq * kC;
+  ss.o_ls = kC; ss.o_bs = (long)K * kC;
+  return mha_std<T>(Qin, cqp, kx, pos0c, vx, nullptr, caoc, K, S, (int)N, kH, 64, 32, ss, st);
+}
+template <>
+int Decoder<float>::xattn(int l, const float* Qin, const float* X3) { return xattn_generic(l, Qin, X3); }
+template <>
+int Decoder<bf16>::xattn(int l, const bf16* Qin, const bf16* X3) {
+  if (force_simt() || K > 128 || ((S + 15) & ~15) > 256) return xattn_generic(l, Qin, X3);
+  { ProfScope ps(P_BIG_PROJ, st);
+    CQ_TRY(lin(X3, Rp, kC, cls(l, C_KPROJ), kx, kC));
+    // V^T[256, N*S] = W_v . q_memory^T : the v_proj 1x1 conv with swapped operands (bias added after the softmax-weighted
+    // sum, exact because the weights sum to one)
+    Epilogue e;
+    CQ_TRY(gemm<bf16>(Wm(cls(l, C_VPROJ)), kC, qm, vt, ldvt, kC, (int)NSq, kC, e, nullptr, st));
+    CQ_TRY(lin(qse, N, kC, cls(l, C_QPS), cqp, kC)); }
+  ProfScope ps(P_CLS_XATTN, st);
+  int r = cls_xattn_tc(Qin, cqp, kx, pos0c, vt, ldvt, Wf(cls(l, C_VPROJ) + 1), caoc, N, K, S, Sq, Sp, BT, st);
+  if (r == 1) return set_error(CQVAD_E_UNSUPPORTED_SHAPE, "class cross-attention: shape rejected by the tensor-core kernel");
+  return r;
+}
+
 template <typename T>
 int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, const uint8_t* mask, const float* ref_u,
                     void* hs, void* cls_hs, float* refs, float* pred_logits, float* pred_boxes, float* pred_logits_b) {
   const bool of32 = d.out_f32 != 0;
   const size_t osz = of32 ? sizeof(float) : sizeof(T);
   // inputs -> compute dtype.  Only pos[0] is ever used (dab_transformer.py:958, :810).
+  ProfScope* ps = new ProfScope(P_INPUT, st);
   CQ_TRY(convert_f32<T>(memory, memc, 4L * S * BT * kC, st));
   CQ_TRY(convert_f32<T>(pos, pos0c, (long)S * BT * kC, st));
   CQ_TRY(convert_f32<T>(tgt, out, N * kC, st));
   CQ_CUDA(cudaMemsetAsync(XA, 0, (size_t)Rp * kC * sizeof(T), st));  // zero separator rows (never written afterwards)
   CQ_CUDA(cudaMemsetAsync(XB, 0, (size_t)Rp * kC * sizeof(T), st));
+  if (Sq != S) CQ_CUDA(cudaMemsetAsync(qm, 0, (size_t)NSq * kC * sizeof(T), st));   // pad rows stay zero (finite)
   CQ_TRY(sigmoid4(ref_u, r_cur, refs, N, nq, BT, st));               // :735; refs[0]
+  delete ps;
+#define PROF(c) { delete ps; ps = new ProfScope(c, st); }
+  ps = nullptr;
 
   for (int l = 0; l < Lr; ++l) {
     const bool first = (l == 0);
     // ---- prologue :742-763 ----
+    PROF(P_SMALL);
     CQ_TRY(sine_embed<T>(r_cur, e512, N, st));
     CQ_TRY(lin(e512, N, 512, glob(G_RPH0), tmpN, kC, CQVAD_ACT_RELU));
     CQ_TRY(lin(tmpN, N, kC, glob(G_RPH1), qpos, kC));
@@ -221,35 +274,44 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
     CQ_TRY(lin(sao, N, kC, loc(l, SA_O), out, kC, CQVAD_ACT_NONE, out, loc(l, NORM1)));
     // ---- level-weighted query-specific memory :943-946 ----
     CQ_TRY(linear_smalln<T>(out, Wf(loc(l, LVLW)), Wf(loc(l, LVLW) + 1), lvlw, N, 4, true, st));
-    CQ_TRY(lvlmix_ln<T>(memc, lvlw, Wf(loc(l, NORMU)), Wf(loc(l, NORMU) + 1), qm, N, S, BT, st));
+    PROF(P_LVLMIX);
+    CQ_TRY(lvlmix_ln<T>(memc, lvlw, Wf(loc(l, NORMU)), Wf(loc(l, NORMU) + 1), qm, N, S, Sq, BT, st));
     // ---- cross-attention with per-actor keys :951-988 ----
-    CQ_TRY(lin(qm, NS, kC, loc(l, CA_KC), kv, kC, CQVAD_ACT_NONE, nullptr, -1, 1e-5f, 2 * kC));
-    CQ_TRY(lin(qm, NS, kC, loc(l, CA_V), kv + kC, kC, CQVAD_ACT_NONE, nullptr, -1, 1e-5f, 2 * kC));
+    PROF(P_BIG_PROJ);
+    CQ_TRY(lin(qm, NSq, kC, loc(l, CA_KC), kv, kC, CQVAD_ACT_NONE, nullptr, -1, 1e-5f, 2 * kC));
+    CQ_TRY(lin(qm, NSq, kC, loc(l, CA_V), kv + kC, kC, CQVAD_ACT_NONE, nullptr, -1, 1e-5f, 2 * kC));
     CQ_TRY(lin(pos0c, (long)S * BT, kC, loc(l, CA_KP), kp, kC));
+    PROF(P_SMALL);
     CQ_TRY(lin(out, N, kC, loc(l, CA_QC), qc, kC));
     if (first) {
       CQ_CHECK_ARG(w[loc(l, CA_QP)] != nullptr, "layers.0.ca_qpos_proj is required");
       CQ_TRY(lin(qpos, N, kC, loc(l, CA_QP), qc, kC, CQVAD_ACT_NONE, qc));
     }
     CQ_TRY(lin(qse, N, kC, loc(l, CA_QS), qs, kC));
-    CQ_TRY(dec_qsk_attn<T>(qc, qs, kv, kv + kC, 2 * kC, kp, mask, cao, N, S, BT, first, st));
+    PROF(P_LOC_QSK);
+    CQ_TRY(dec_qsk_attn<T>(qc, qs, kv, kv + kC, 2 * kC, kp, mask, cao, N, S, Sq, BT, first, st));
+    PROF(P_SMALL);
     CQ_TRY(lin(cao, N, kC, loc(l, CA_O), actor, kC, CQVAD_ACT_NONE, out, loc(l, NORM2)));   // tgt_temp :992-993
     CQ_TRY(mlp(actor, N, F, loc(l, LIN1), loc(l, LIN2), CQVAD_ACT_RELU, actor, loc(l, NORM3), 1e-5f, out, tmpN));
 
     // ---- class-query layer :1040-1079 ----
     CQ_TRY(mlp(actor, N, F, cls(l, C_L1), cls(l, C_L2), CQVAD_ACT_RELU, actor, cls(l, C_NORM), 1e-5f, acls, tmpN));
-    CQ_TRY(add_ln_pad<T>(acls, qm, Wf(cls(l, C_CONVNORM)), Wf(cls(l, C_CONVNORM) + 1), XA, N, S, Sp, st));
+    PROF(P_ADDLN);
+    CQ_TRY(add_ln_pad<T>(acls, qm, Wf(cls(l, C_CONVNORM)), Wf(cls(l, C_CONVNORM) + 1), XA, N, S, Sq, Sp, st));
     T* xin = XA; T* xout = XB;
     for (int blk = 0; blk < 3; ++blk) {   // the same ConvBlock three times (:1017-1018, :1055-1056)
       Epilogue e;
       e.bias = Wf(cls(l, C_CONV1) + 1);
       e.ln_g = Wf(cls(l, C_CBNORM)); e.ln_b = Wf(cls(l, C_CBNORM) + 1); e.ln_eps = 1e-6f;
       ConvGeom cg; cg.h = h; cg.w = wd;
+      PROF(P_CONV);
       CQ_TRY(gemm<T>(xin, kC, Wm(cls(l, C_CONV1)), Xn, kC, Rp, kC, 9 * kC, e, &cg, st));
+      PROF(P_CONV_MLP);
       CQ_TRY(mlp(Xn, Rp, 4 * kC, cls(l, C_CONV2), cls(l, C_CONV3), CQVAD_ACT_GELU, xin, -1, 0.f, xout, Hc, Sp, S));
       T* t = xin; xin = xout; xout = t;
     }
     const T* X3 = xin;
+    PROF(P_CLS_SATTN);
     // class-query self-attention :1059-1065
     T* Qin = Qc[l & 1];
     const T* Qprev = Qc[(l + 1) & 1];
@@ -266,26 +328,16 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
       CQ_TRY(mha_std<T>(Qprev, nullptr, Qprev, nullptr, Qprev, nullptr, saoc, K, K, (int)N, kH, 32, 32, ss, st));
       CQ_TRY(lin(saoc, NK, kC, cls(l, C_SA_O), Qin, kC, CQVAD_ACT_NONE, Qprev, cls(l, C_NORM1)));
     }
-    // class cross-attention :1067-1071.  512-wide q/k split contiguously into 8 heads of 64 (attention.py:336,339):
-    // heads 0-3 = (class query . k_proj(conv feature)), heads 4-7 = (actor sine pos . spatial pos).
-    CQ_TRY(lin(X3, Rp, kC, cls(l, C_KPROJ), kx, kC));
-    CQ_TRY(lin(qm, NS, kC, cls(l, C_VPROJ), vx, kC));
-    CQ_TRY(lin(qse, N, kC, cls(l, C_QPS), cqp, kC));
-    {
-      StdStrides ss{};
-      ss.q_ls = kC; ss.q_bs = (long)K * kC;             // Qin rows (i,k)
-      ss.q2_ls = 0; ss.q2_bs = kC;                      // cqp row i, same for every class
-      ss.k_ls = kC; ss.k_bs = (long)Sp * kC;            // kx on the padded layout
-      ss.k2_ls = (long)BT * kC; ss.k2_bs = kC; ss.k2_bmod = BT;   // pos0[s, b], b = i % BT
-      ss.v_ls = kC; ss.v_bs = (long)S * kC;
-      ss.o_ls = kC; ss.o_bs = (long)K * kC;
-      CQ_TRY(mha_std<T>(Qin, cqp, kx, pos0c, vx, nullptr, caoc, K, S, (int)N, kH, 64, 32, ss, st));
-    }
+    delete ps; ps = nullptr;
+    CQ_TRY(xattn(l, Qin, X3));
+    PROF(P_CLS_OPROJ);
     CQ_TRY(lin(caoc, NK, kC, cls(l, C_CA_O), cls0, kC));
+    PROF(P_CLS_FFN);
     T* cls_out = Qc[l & 1];   // Qin is dead after the attention; reuse its buffer for the layer output / next query
     CQ_TRY(mlp(cls0, NK, F, cls(l, C_L1_), cls(l, C_L2_), CQVAD_ACT_RELU, cls0, cls(l, C_NORM_), 1e-5f, cls_out, Hf));
 
     // ---- outputs of this layer :826-827 and heads (models/model.py:192-221) ----
+    PROF(P_OUT_LN);
     CQ_TRY(layernorm_rows<T>(out, nullptr, Wf(glob(G_NORM)), Wf(glob(G_NORM) + 1), 1e-5f, hsn, false, N, st));
     CQ_TRY(layernorm_permute<T>(out, Wf(glob(G_NORM)), Wf(glob(G_NORM) + 1), 1e-5f, (char*)hs + (size_t)l * N * kC * osz,
                                 of32, N, nq, BT, 1, nullptr, st));
@@ -305,12 +357,15 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
                            BT, false, st));
     }
     // ---- iterative box refinement :813-823 ----
+    PROF(P_SMALL);
     CQ_TRY(lin(out, N, kC, glob(G_BB0), bb1, kC, CQVAD_ACT_RELU));
     CQ_TRY(lin(bb1, N, kC, glob(G_BB1), bb2, kC, CQVAD_ACT_RELU));
     CQ_TRY(box_refine<T>(bb2, Wf(glob(G_BB2)), Wf(glob(G_BB2) + 1), r_cur, r_next,
                          (l != Lr - 1) ? refs + (size_t)(l + 1) * N * 4 : nullptr, N, nq, BT, false, st));
     float* t = r_cur; r_cur = r_next; r_next = t;
   }
+  delete ps;
+#undef PROF
   return 0;
 }
 

@@ -265,7 +265,9 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t*
 int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, int N, int K, const Epilogue& epi,
             const ConvGeom* conv, cudaStream_t st) {
   // shapes the kernel takes; anything else goes to the CUDA-core kernel (return 1)
-  if (K % BLOCK_K != 0 || N % 8 != 0 || lda % 8 != 0 || ldc % 8 != 0 || M < 1) return 1;
+  if (K % BLOCK_K != 0 || lda % 8 != 0 || ldc % 8 != 0 || M < 1) return 1;
+  // N % 8 != 0 is taken only for a bare GEMM whose row pitch covers the rounded-up width (8-wide vector stores)
+  if (N % 8 != 0 && (ldc < ((N + 7) & ~7) || epi.bias || epi.res || epi.ln_g)) return 1;
   if ((((uintptr_t)A) & 15) || (((uintptr_t)W) & 15) || (((uintptr_t)C) & 15)) return 1;
   if (epi.res && ((((uintptr_t)epi.res) & 15) || epi.ldr % 8 != 0)) return 1;
   if (epi.ln_g && N != BLOCK_N) return 1;

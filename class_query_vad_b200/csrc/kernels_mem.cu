@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kThreads) layernorm_permute_kernel(const T* __
 template <typename T>
 __global__ void __launch_bounds__(kThreads) lvlmix_ln_kernel(const T* __restrict__ mem, const float* __restrict__ lvlw,
                                                              const float* __restrict__ g, const float* __restrict__ b,
-                                                             T* __restrict__ qm, long rows, int S, int BT) {
+                                                             T* __restrict__ qm, long rows, int S, int Sq, int BT) {
   const long row = (long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -80,21 +80,21 @@ __global__ void __launch_bounds__(kThreads) lvlmix_ln_kernel(const T* __restrict
     for (int j = 0; j < 8; ++j) v[j] = fmaf(w[l], m[j], v[j]);
   }
   warp_layernorm256(v, g, b, 1e-5f, lane);
-  store8(qm + row * kC + lane * 8, v);
+  store8(qm + (i * Sq + s) * kC + lane * 8, v);   // per-instance row pitch Sq >= S (multiple of 8: TMA alignment)
 }
 
 // ---- cls_feature0 = conv_norm(actor[i] + q_memory[i,s])  -> y-padded NHWC (dab_transformer.py:1049-1054) --------
 template <typename T>
 __global__ void __launch_bounds__(kThreads) add_ln_pad_kernel(const T* __restrict__ actor, const T* __restrict__ qm,
                                                               const float* __restrict__ g, const float* __restrict__ b,
-                                                              T* __restrict__ xpad, long rows, int S, int Sp) {
+                                                              T* __restrict__ xpad, long rows, int S, int Sq, int Sp) {
   const long row = (long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const long i = row / S;
   const int s = (int)(row % S);
   float v[8], a[8];
-  load8(qm + row * kC + lane * 8, v);
+  load8(qm + (i * Sq + s) * kC + lane * 8, v);
   load8(actor + i * kC + lane * 8, a);
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] += a[j];
@@ -372,24 +372,24 @@ template int layernorm_permute<float>(const float*, const float*, const float*, 
 template int layernorm_permute<bf16>(const bf16*, const float*, const float*, float, void*, bool, long, int, int, int, float*, cudaStream_t);
 
 template <typename T>
-int lvlmix_ln(const T* mem, const float* lvlw, const float* g, const float* b, T* qm, long N, int S, int BT, cudaStream_t st) {
+int lvlmix_ln(const T* mem, const float* lvlw, const float* g, const float* b, T* qm, long N, int S, int Sq, int BT, cudaStream_t st) {
   const long rows = N * S;
-  lvlmix_ln_kernel<T><<<row_grid(rows), kThreads, 0, st>>>(mem, lvlw, g, b, qm, rows, S, BT);
+  lvlmix_ln_kernel<T><<<row_grid(rows), kThreads, 0, st>>>(mem, lvlw, g, b, qm, rows, S, Sq, BT);
   CQ_LAUNCH_CHECK();
   return 0;
 }
-template int lvlmix_ln<float>(const float*, const float*, const float*, const float*, float*, long, int, int, cudaStream_t);
-template int lvlmix_ln<bf16>(const bf16*, const float*, const float*, const float*, bf16*, long, int, int, cudaStream_t);
+template int lvlmix_ln<float>(const float*, const float*, const float*, const float*, float*, long, int, int, int, cudaStream_t);
+template int lvlmix_ln<bf16>(const bf16*, const float*, const float*, const float*, bf16*, long, int, int, int, cudaStream_t);
 
 template <typename T>
-int add_ln_pad(const T* actor, const T* qm, const float* g, const float* b, T* xpad, long N, int S, int Sp, cudaStream_t st) {
+int add_ln_pad(const T* actor, const T* qm, const float* g, const float* b, T* xpad, long N, int S, int Sq, int Sp, cudaStream_t st) {
   const long rows = N * S;
-  add_ln_pad_kernel<T><<<row_grid(rows), kThreads, 0, st>>>(actor, qm, g, b, xpad, rows, S, Sp);
+  add_ln_pad_kernel<T><<<row_grid(rows), kThreads, 0, st>>>(actor, qm, g, b, xpad, rows, S, Sq, Sp);
   CQ_LAUNCH_CHECK();
   return 0;
 }
-template int add_ln_pad<float>(const float*, const float*, const float*, const float*, float*, long, int, int, cudaStream_t);
-template int add_ln_pad<bf16>(const bf16*, const bf16*, const float*, const float*, bf16*, long, int, int, cudaStream_t);
+template int add_ln_pad<float>(const float*, const float*, const float*, const float*, float*, long, int, int, int, cudaStream_t);
+template int add_ln_pad<bf16>(const bf16*, const bf16*, const float*, const float*, bf16*, long, int, int, int, cudaStream_t);
 
 template <typename T>
 int pad_copy(const T* src, T* dst, long n_img, int S, int Sp, bool to_padded, cudaStream_t st) {

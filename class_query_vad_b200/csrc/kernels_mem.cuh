@@ -5,9 +5,9 @@ namespace cqvad {
 template <typename T> int layernorm_permute(const T* x, const float* g, const float* b, float eps, void* out, bool out_f32,
                                             long rows, int nq, int BT, int K, float* row_mean_out, cudaStream_t st);
 template <typename T> int lvlmix_ln(const T* mem, const float* lvlw, const float* g, const float* b, T* qm, long N, int S,
-                                    int BT, cudaStream_t st);
+                                    int Sq, int BT, cudaStream_t st);
 template <typename T> int add_ln_pad(const T* actor, const T* qm, const float* g, const float* b, T* xpad, long N, int S,
-                                     int Sp, cudaStream_t st);
+                                     int Sq, int Sp, cudaStream_t st);
 template <typename T> int pad_copy(const T* src, T* dst, long n_img, int S, int Sp, bool to_padded, cudaStream_t st);
 template <typename T> int convert_f32(const float* in, T* out, long n, cudaStream_t st);
 template <typename O> int sine_embed(const float* ref, O* out, long rows, cudaStream_t st);

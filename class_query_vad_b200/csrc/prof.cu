@@ -1,0 +1,59 @@
+#include <vector>
+#include "common.cuh"
+#include "prof.cuh"
+
+namespace cqvad {
+namespace {
+struct Pair { cudaEvent_t a, b; };
+struct ClassState { std::vector<Pair> pool; size_t used = 0; long launches_at_begin = 0; long launches = 0; };
+ClassState g_cls[P_COUNT];
+bool g_on = false;
+const char* kNames[P_COUNT] = {"conv3x3_ln (tcgen05 implicit GEMM)", "convblock_mlp (tcgen05 fused MLP)",
+                               "class_ffn (tcgen05 fused MLP + LN)", "kv/k/v projections (tcgen05 GEMM)",
+                               "class cross-attention", "class self-attention", "class out_proj GEMMs",
+                               "loc query-specific-key attention", "level mix + LN", "actor add + conv_norm",
+                               "output LN / heads", "small-row ops (prologue, loc SA, FFNs, box head)", "input conversion"};
+}  // namespace
+long launch_count_now();
+bool prof_enabled() { return g_on; }
+void prof_begin(int cls, cudaStream_t st) {
+  ClassState& c = g_cls[cls];
+  if (c.used == c.pool.size()) {
+    Pair p;
+    cudaEventCreate(&p.a);
+    cudaEventCreate(&p.b);
+    c.pool.push_back(p);
+  }
+  c.launches_at_begin = launch_count_now();
+  cudaEventRecord(c.pool[c.used].a, st);
+}
+void prof_end(int cls, cudaStream_t st) {
+  ClassState& c = g_cls[cls];
+  cudaEventRecord(c.pool[c.used].b, st);
+  c.launches += launch_count_now() - c.launches_at_begin;
+  c.used++;
+}
+}  // namespace cqvad
+
+using namespace cqvad;
+extern "C" void cqvad_profile_enable(int on) {
+  g_on = on != 0;
+  for (int i = 0; i < P_COUNT; ++i) { g_cls[i].used = 0; g_cls[i].launches = 0; }
+}
+extern "C" int cqvad_profile_num_classes(void) { return P_COUNT; }
+extern "C" const char* cqvad_profile_class_name(int cls) { return (cls >= 0 && cls < P_COUNT) ? kNames[cls] : nullptr; }
+// total elapsed ms, number of timed scopes and kernel launches inside them since cqvad_profile_enable(1); synchronises.
+extern "C" int cqvad_profile_read(int cls, double* total_ms, long* scopes, long* launches) {
+  if (cls < 0 || cls >= P_COUNT) return CQVAD_E_INVALID_ARG;
+  ClassState& c = g_cls[cls];
+  double tot = 0;
+  for (size_t i = 0; i < c.used; ++i) {
+    cudaEventSynchronize(c.pool[i].b);
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c.pool[i].a, c.pool[i].b) == cudaSuccess) tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (scopes) *scopes = (long)c.used;
+  if (launches) *launches = c.launches;
+  return 0;
+}

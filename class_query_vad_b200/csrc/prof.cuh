@@ -1,0 +1,16 @@
+// Optional per-kernel-class timing with CUDA events recorded on the launch stream (bench.py's roofline object and the
+// per-step breakdown in profiles/).  Disabled by default: zero cost beyond one branch per scope.
+#pragma once
+#include <cuda_runtime.h>
+namespace cqvad {
+enum ProfClass { P_CONV = 0, P_CONV_MLP, P_CLS_FFN, P_BIG_PROJ, P_CLS_XATTN, P_CLS_SATTN, P_CLS_OPROJ, P_LOC_QSK, P_LVLMIX,
+                 P_ADDLN, P_OUT_LN, P_SMALL, P_INPUT, P_COUNT };
+bool prof_enabled();
+void prof_begin(int cls, cudaStream_t st);
+void prof_end(int cls, cudaStream_t st);
+struct ProfScope {
+  int cls; cudaStream_t st; bool on;
+  ProfScope(int c, cudaStream_t s) : cls(c), st(s), on(prof_enabled()) { if (on) prof_begin(cls, st); }
+  ~ProfScope() { if (on) prof_end(cls, st); }
+};
+}  // namespace cqvad

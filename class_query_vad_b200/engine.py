@@ -87,7 +87,10 @@ class DecoderEngine:
         _lib.require_cuda(tgt, memory, pos, refpoints_unsigmoid)
         f32 = lambda t: t.to(device=self.device, dtype=torch.float32).contiguous()
         tgt, memory, pos0, ref = f32(tgt), f32(memory), f32(pos[0]), f32(refpoints_unsigmoid)
-        m8 = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        m8 = None
+        if mask is not None:
+            m8 = mask.to(self.device).contiguous()
+            m8 = m8.view(torch.uint8) if m8.dtype == torch.bool else m8.to(torch.uint8)   # zero-copy for bool masks
         desc = _lib.DecoderDesc(_lib.dtype_id(self.dtype), BT, nq, h, w, self.K, self.F, self.layers,
                                 1 if self.out_f32 else 0, _lib.DEC_SKIP_CLS_HS if skip_cls_hs else 0)
         ws = self._workspace(desc)

@@ -136,6 +136,19 @@ int cqvad_decoder_forward(const cqvad_decoder_desc* d, const void* const* weight
 /* Number of kernels the last cqvad_decoder_forward on this thread launched (bench.py's gpu_launches). */
 long cqvad_last_launch_count(void);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py).  cqvad_profile_enable(1) makes cqvad_decoder_forward bracket each kernel class with
+ * CUDA events on the launch stream; cqvad_profile_read() synchronises and returns the accumulated milliseconds, the
+ * number of timed scopes and of kernel launches inside them since the enable call.  Replaces the reference's host
+ * wall-clock meters (utils/video_action_recognition.py:31-32,64-65,176-186). */
+void cqvad_profile_enable(int on);
+int cqvad_profile_num_classes(void);
+const char* cqvad_profile_class_name(int cls);
+int cqvad_profile_read(int cls, double* total_ms_host, long* scopes_host, long* launches_host);
+/* Debug switch: route bf16 GEMMs through the CUDA-core kernel instead of tcgen05 (used by the parity tests to
+ * cross-check the two implementations; not a fallback -- both are CUDA kernels of this library). */
+void cqvad_debug_force_simt(int on);
+
 #ifdef __cplusplus
 }
 #endif
