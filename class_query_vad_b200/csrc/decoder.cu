@@ -179,7 +179,9 @@ int Decoder<float>::mlp(const float* X, long M, int Fh, int w1, int w2, int act,
 template <>
 int Decoder<bf16>::mlp(const bf16* X, long M, int Fh, int w1, int w2, int act, const bf16* res, int ln_idx, float eps,
                        bf16* Y, bf16* hid, int zero_period, int zero_valid) {
-  if (!force_simt()) {
+  // the fused kernel walks the hidden dimension serially per 128-row tile: with few row tiles (small-row FFNs, M = nq*BT)
+  // two plain GEMMs spread the F dimension over more SMs
+  if (!force_simt() && M > 2048) {
     int r = mlp_tc(X, Wm(w1), Wf(w1 + 1), Wm(w2), Wf(w2 + 1), act, res, ln_idx >= 0 ? Wf(ln_idx) : nullptr,
                    ln_idx >= 0 ? Wf(ln_idx + 1) : nullptr, eps, Y, M, kC, Fh, zero_period, zero_valid, st);
     if (r <= 0) return r;

@@ -207,18 +207,25 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           for (int g8 = 0; g8 < 4; ++g8) {
             float bs[8];
             load8(b1 + g8 * 8, bs);
-            float v[8];
+            uint32_t pk[4];
+            if (p.act == CQVAD_ACT_GELU) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float x = __uint_as_float(r[g8 * 8 + e]) + bs[e];
-              v[e] = p.act == CQVAD_ACT_GELU ? gelu_erf(x) : fmaxf(x, 0.f);
+              for (int e = 0; e < 4; ++e) {
+                const uint64_t x2 = f2add(f2pack(__uint_as_float(r[g8 * 8 + 2 * e]), __uint_as_float(r[g8 * 8 + 2 * e + 1])),
+                                          f2pack(bs[2 * e], bs[2 * e + 1]));
+                pk[e] = f2_to_bf16x2(gelu2(x2));
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                pk[e] = pack_bf16(fmaxf(__uint_as_float(r[g8 * 8 + 2 * e]) + bs[2 * e], 0.f),
+                                  fmaxf(__uint_as_float(r[g8 * 8 + 2 * e + 1]) + bs[2 * e + 1], 0.f));
             }
             // hidden column cc = c + g8*8 -> k-block cc/64, 16-byte chunk (cc%64)/8, swizzled with (row & 7)
             const int cc = c + g8 * 8;
             const uint32_t chunk = (uint32_t)((cc & 63) >> 3) ^ (uint32_t)(row_in_tile & 7);
             const uint32_t addr = hs_row + (uint32_t)(cc >> 6) * 16384u + chunk * 16u;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16(v[0], v[1])),
-                         "r"(pack_bf16(v[2], v[3])), "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7]))
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
                          : "memory");
           }
         }

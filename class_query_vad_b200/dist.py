@@ -1,0 +1,51 @@
+"""Multi-GPU plumbing of the decoder path: one process per GPU, clips sharded across ranks, no data-path collective
+inside the decoder (clips are independent: SURVEY.md section 8e); one all-gather of the per-clip detections replaces the
+reference's per-rank text files + barrier (utils/video_action_recognition.py:231-255).
+
+NCCL over NVLink on GPUs; the same code runs on the `gloo` backend for the CPU tests (tests/test_dist_cpu.py).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_clips, world, rank):
+    """Contiguous, balanced shard [lo, hi) of n_clips for `rank` (first n_clips % world ranks get one extra clip)."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world {world}")
+    base, rem = divmod(n_clips, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_detections(pred_logits, pred_boxes, pred_logits_b):
+    """[B, nq, K | 4 | 3] rows: class scores, box, person logits -- the row format the reference writes per detection
+    (utils/video_action_recognition.py:234)."""
+    return torch.cat([pred_logits, pred_boxes, pred_logits_b], dim=-1).contiguous()
+
+
+def gather_detections(det_local, n_clips_total=None, group=None):
+    """All-gather per-rank detections [B_local, nq, D] into [sum B_local, nq, D] in rank order.  Ragged shards (as
+    produced by shard_range) are padded to the largest shard for the collective and trimmed afterwards."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return det_local
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if n_clips_total is None:
+        sizes = torch.tensor([det_local.shape[0]], dtype=torch.int64, device=det_local.device)
+        all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+        dist.all_gather(all_sizes, sizes, group=group)
+        counts = [int(s.item()) for s in all_sizes]
+    else:
+        counts = [shard_range(n_clips_total, world, r)[1] - shard_range(n_clips_total, world, r)[0] for r in range(world)]
+    if counts[rank] != det_local.shape[0]:
+        raise ValueError(f"rank {rank}: local shard has {det_local.shape[0]} clips, expected {counts[rank]}")
+    bmax = max(counts)
+    padded = det_local
+    if det_local.shape[0] != bmax:
+        padded = det_local.new_zeros((bmax,) + tuple(det_local.shape[1:]))
+        padded[: det_local.shape[0]] = det_local
+    out = det_local.new_empty((world * bmax,) + tuple(det_local.shape[1:]))
+    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+    if all(c == bmax for c in counts):
+        return out
+    return torch.cat([out[r * bmax: r * bmax + counts[r]] for r in range(world)], dim=0)

@@ -1,0 +1,66 @@
+"""world_size-2 gloo tests (CPU) of the N>1 host path: balanced clip sharding and the detection all-gather."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from class_query_vad_b200.dist import shard_range, gather_detections, pack_detections
+
+
+def test_shard_range_covers_everything():
+    for n in (0, 1, 7, 32, 33, 255):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_clips, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(1234)
+        full = torch.randn(n_clips, 3, 11, generator=g)            # the "single-GPU" result, identical on all ranks
+        lo, hi = shard_range(n_clips, world, rank)
+        logits, boxes, lb = full[lo:hi, :, :4], full[lo:hi, :, 4:8], full[lo:hi, :, 8:]
+        det = pack_detections(logits, boxes, lb)
+        out_a = gather_detections(det, n_clips_total=n_clips)
+        out_b = gather_detections(det)                              # sizes exchanged by a first all-gather
+        ok = bool(torch.equal(out_a, full) and torch.equal(out_b, full))
+        if rank == 0:
+            q.put(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_clips", [8, 7])      # even and ragged shards
+def test_gather_detections_world2_gloo(n_clips):
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_clips, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get() is True
+
+
+def test_gather_is_identity_without_process_group():
+    x = torch.randn(3, 2, 5)
+    assert gather_detections(x) is x
