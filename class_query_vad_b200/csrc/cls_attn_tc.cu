@@ -26,22 +26,26 @@ int tc_num_sms();
 namespace {
 
 constexpr int QT_BYTES = 128 * 128;        // Q tile [128 x 64] bf16
-constexpr int KT_BYTES = 256 * 128;        // K tile [<=256 x 64]
-constexpr int VT_BYTES = 4 * 32 * 128;     // V^T: 4 k-blocks of [32 x 64]
-constexpr int PT_BYTES = 4 * 128 * 128;    // P: 4 k-blocks of [128 x 64]
-constexpr int SMEM_DATA = QT_BYTES + KT_BYTES + VT_BYTES + PT_BYTES;   // 128 KB
-constexpr int SMEM_BYTES = SMEM_DATA + 1024 + 128;
 constexpr int NUM_THREADS = 160;
 
+// Generic projection-free attention tile on tcgen05 (one CTA per (head, instance)):
+//   class cross-attention heads 0-3 : hd 64, keys = k_proj rows of the padded map, V^T = W_v . q_memory^T
+//   class self-attention  heads 0-7 : hd 32 (two heads share one 64-column swizzle atom: the head's 32 columns are
+//                                      selected by issuing only its two UMMA k-steps), keys = queries = class tokens,
+//                                      V^T = transposed class tokens written by the class-FFN epilogue
+// Shared memory: [Q | K] then V^T; the P tile ALIASES [Q | K] (dead once S = QK^T has completed), which is what lets
+// two (cross) / four (self) CTAs share an SM.
 struct XaParams {
-  bf16* out;              // [N*K, 256]; this kernel writes columns [h*32, h*32+32), h in 0..3
-  const float* bv;        // v_proj bias [256]
-  int K, S, Sp16;         // classes, keys, keys padded to a multiple of 16
-  int Sp_rows;            // rows per instance of the padded key layout ((h+1)*w)
-  int Sq;                 // per-instance column pitch of V^T (multiple of 8: TMA needs a 16-byte aligned inner start)
-  int o_col;              // TMEM column of the O accumulator
-  int tmem_cols;
-  int stage;              // debug bisect: stop after stage n (0 = run everything)
+  bf16* out;              // [N*K, 256]; head h writes columns [h*32, h*32+32)
+  const float* bv;        // bias added to the output (v_proj bias) or nullptr
+  int K, S, Sp16;         // valid query rows per instance, valid keys, keys padded to a multiple of 16
+  int q_rows;             // query-row pitch per instance (= K)
+  int k_rows;             // key-row pitch per instance ((h+1)*w for the padded map, K for self-attention)
+  int v_pitch;            // per-instance column pitch of V^T (multiple of 8: TMA needs a 16-byte aligned inner start)
+  int hd;                 // 64 or 32
+  float scale_log2;       // hd^-0.5 * log2(e)
+  int o_col, tmem_cols;
+  uint32_t off_k, off_v, off_bar;   // byte offsets from the 1024-aligned base (Q and P at 0)
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -59,12 +63,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-cls_xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, const XaParams p) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const XaParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base, sK = sQ + QT_BYTES, sV = sK + KT_BYTES, sP = sV + VT_BYTES;
-  const uint32_t bars = base + SMEM_DATA;
+  const uint32_t sQ = base, sK = base + p.off_k, sV = base + p.off_v, sP = base;
+  const uint32_t bars = base + p.off_bar;
   const uint32_t bar_qk = bars, bar_v = bars + 8, bar_s = bars + 16, bar_p = bars + 24, bar_o = bars + 32, tmem_slot = bars + 40;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x;
@@ -86,30 +90,24 @@ cls_xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---- loads ---- (debug stages: 1 none, 2 Q, 3 Q+K, 4 Q+K+V, 5 +QK^T, 6 +softmax, 7/0 everything)
-      const int stg = p.stage == 0 ? 99 : p.stage;
-      if (stg >= 2) {
-        mbar_arrive_expect_tx(bar_qk, (uint32_t)(QT_BYTES + (stg >= 3 ? p.Sp16 * 128 : 0)));
-        tma_load_2d(sQ, &tmQ, bar_qk, h * 64, (int)(i * p.K));
-        if (stg >= 3) tma_load_2d(sK, &tmK, bar_qk, h * 64, (int)(i * p.Sp_rows));
-      }
-      if (stg >= 4) {
-        mbar_arrive_expect_tx(bar_v, (uint32_t)(nkb * 32 * 128));
-        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sV + kb * 4096, &tmV, bar_v, (int)(i * p.Sq) + kb * 64, h * 32);
-      }
-      if (stg >= 2) mbar_wait(bar_qk, 0);
-      if (stg >= 4) mbar_wait(bar_v, 0);
-      if (stg >= 5) {
+      const int col0 = ((h * p.hd) >> 6) << 6;          // 64-column block holding this head's q/k columns
+      const int k0 = ((h * p.hd) & 63) >> 4;            // first UMMA k-step of the head inside the block
+      const int nk = p.hd >> 4;                         // k-steps per head (4 for hd 64, 2 for hd 32)
+      mbar_arrive_expect_tx(bar_qk, (uint32_t)(QT_BYTES + p.Sp16 * 128));
+      tma_load_2d(sQ, &tmQ, bar_qk, col0, (int)(i * p.q_rows));
+      tma_load_2d(sK, &tmK, bar_qk, col0, (int)(i * p.k_rows));
+      mbar_arrive_expect_tx(bar_v, (uint32_t)(nkb * 32 * 128));
+      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sV + kb * 4096, &tmV, bar_v, (int)(i * p.v_pitch) + kb * 64, h * 32);
+      // ---- S = Q K^T ----
+      mbar_wait(bar_qk, 0);
       tc_fence_after();
       {
         const uint32_t idesc = make_idesc_bf16(128, p.Sp16);
         const uint64_t a_desc = make_smem_desc_sw128(sQ), b_desc = make_smem_desc_sw128(sK);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(t_s, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, k ? 1u : 0u);
+        for (int k = 0; k < nk; ++k)
+          umma_bf16(t_s, a_desc + (uint64_t)(2 * (k0 + k)), b_desc + (uint64_t)(2 * (k0 + k)), idesc, k ? 1u : 0u);
         umma_commit(bar_s);
       }
-      }
-      if (stg >= 7) {
       // ---- O = P V ----
       mbar_wait(bar_p, 0);
       mbar_wait(bar_v, 0);
@@ -125,18 +123,15 @@ cls_xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         umma_commit(bar_o);
       }
-      }
     }
-  } else if (p.stage == 0 || p.stage >= 5) {
-    const int stg = p.stage == 0 ? 99 : p.stage;
-    // ---- softmax / epilogue warps 1..4: TMEM lane quarter q = warp % 4, one thread per class row ----
+  } else {
+    // ---- softmax / epilogue warps 1..4: TMEM lane quarter q = warp % 4, one thread per query row ----
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    mbar_wait(bar_s, 0);
+    mbar_wait(bar_s, 0);       // S complete => the tensor core has finished reading Q and K: P may overwrite them
     tc_fence_after();
     const int S = p.S, Sp16 = p.Sp16;
-    if (stg >= 6) {
     // pass 1: row max of the raw scores over the valid keys
     float mx = -INFINITY;
     for (int c = 0; c < Sp16; c += 32) {
@@ -154,8 +149,8 @@ cls_xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int e = 0; e < 16; ++e) if (c + e < S) mx = fmaxf(mx, __uint_as_float(r[e]));
       }
     }
-    // pass 2: p = exp((s - max) / sqrt(64)); unnormalised bf16 P into the swizzled A tile; fp32 row sum
-    const float sc = 0.125f * 1.4426950408889634f;   // exp(x/8) = exp2(x * log2(e) / 8)
+    // pass 2: p = exp((s - max) * hd^-0.5); unnormalised bf16 P into the swizzled A tile; fp32 row sum
+    const float sc = p.scale_log2;
     const float mxs = mx * sc;
     float sum = 0.f;
     const uint32_t p_row = sP + (uint32_t)row * 128u;
@@ -187,7 +182,6 @@ cls_xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_p);
-    if (stg >= 7) {
     // epilogue
     mbar_wait(bar_o, 0);
     tc_fence_after();
@@ -197,17 +191,14 @@ cls_xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (row < p.K) {
       const float inv = 1.0f / sum;
       bf16* orow = p.out + (i * p.K + row) * kC + h * 32;
-      const float* bv = p.bv + h * 32;
 #pragma unroll
       for (int g8 = 0; g8 < 4; ++g8) {
-        float bs[8], v[8];
-        load8(bv + g8 * 8, bs);
+        float bs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, v[8];
+        if (p.bv) load8(p.bv + h * 32 + g8 * 8, bs);
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = fmaf(__uint_as_float(r[g8 * 8 + e]), inv, bs[e]);
         store8(orow + g8 * 8, v);
       }
-    }
-    }
     }
   }
   tc_fence_before();
@@ -277,49 +268,73 @@ __global__ void __launch_bounds__(128) cls_xattn_pos_kernel(const bf16* __restri
   for (int k = 0; k < K; ++k) out[(i * K + k) * kC + c0 + lane] = ob;
 }
 
-bool g_attr = false;
+int g_attr_bytes = 0;
 
-}  // namespace
-
-// Returns 1 when the shape is outside what the tensor-core kernel takes (caller uses the CUDA-core kernel).
-int cls_xattn_tc(const bf16* Qin, const bf16* cqp, const bf16* kx, const bf16* pos0, const bf16* vt, long ldvt,
-                 const float* bv, bf16* out, long N, int K, int S, int Sq, int Sp_rows, int BT, cudaStream_t st) {
+// Launch attn_tc_kernel.  q: [N*q_rows, 256] rows; kmat: [N*k_rows(+), 256]; vt: [256, ldvt] with per-instance pitch.
+int launch_attn_tc(const bf16* q, long q_total_rows, const bf16* kmat, long k_total_rows, const bf16* vt, long ldvt,
+                   long v_total_cols, const float* bv, bf16* out, long N, int heads, int hd, int K, int S, int q_rows,
+                   int k_rows, int v_pitch, cudaStream_t st) {
   const int Sp16 = (S + 15) & ~15;
-  if (K > 128 || K < 1 || Sp16 > 256 || ldvt % 8 != 0 || Sq % 8 != 0) return 1;
+  if (K > 128 || K < 1 || Sp16 > 256 || ldvt % 8 != 0 || v_pitch % 8 != 0 || (hd != 64 && hd != 32)) return 1;
   if (tc_num_sms() <= 0) return set_error(CQVAD_E_CUDA, "tcgen05 path: initialisation failed");
-  if (!g_attr) {
-    CQ_CUDA(cudaFuncSetAttribute(cls_xattn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    g_attr = true;
+  const int nkb = (Sp16 + 63) >> 6;
+  XaParams p{};
+  const uint32_t k_bytes = ((uint32_t)Sp16 * 128u + 1023u) & ~1023u;
+  const uint32_t p_bytes = (uint32_t)nkb * 16384u;
+  const uint32_t region_a = (QT_BYTES + k_bytes) > p_bytes ? (QT_BYTES + k_bytes) : p_bytes;
+  p.off_k = QT_BYTES; p.off_v = region_a; p.off_bar = region_a + (uint32_t)nkb * 4096u;
+  const int smem_bytes = (int)p.off_bar + 64 + 1024;
+  if (smem_bytes > g_attr_bytes) {
+    CQ_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    g_attr_bytes = smem_bytes;
   }
   CUtensorMap tmQ, tmK, tmV;
   {
-    const cuuint64_t dims[2] = {(cuuint64_t)kC, (cuuint64_t)(N * K)};
+    const cuuint64_t dims[2] = {(cuuint64_t)kC, (cuuint64_t)q_total_rows};
     const cuuint64_t strides[1] = {(cuuint64_t)kC * 2};
     const cuuint32_t box[2] = {64, 128};
-    CQ_TRY(make_tmap_bf16(&tmQ, Qin, 2, dims, strides, box));
+    CQ_TRY(make_tmap_bf16(&tmQ, q, 2, dims, strides, box));
   }
   {
-    const cuuint64_t dims[2] = {(cuuint64_t)kC, (cuuint64_t)(N * Sp_rows)};
+    const cuuint64_t dims[2] = {(cuuint64_t)kC, (cuuint64_t)k_total_rows};
     const cuuint64_t strides[1] = {(cuuint64_t)kC * 2};
     const cuuint32_t box[2] = {64, (cuuint32_t)Sp16};
-    CQ_TRY(make_tmap_bf16(&tmK, kx, 2, dims, strides, box));
+    CQ_TRY(make_tmap_bf16(&tmK, kmat, 2, dims, strides, box));
   }
   {
-    const cuuint64_t dims[2] = {(cuuint64_t)(N * Sq), (cuuint64_t)kC};
+    const cuuint64_t dims[2] = {(cuuint64_t)v_total_cols, (cuuint64_t)kC};
     const cuuint64_t strides[1] = {(cuuint64_t)ldvt * 2};
     const cuuint32_t box[2] = {64, 32};
     CQ_TRY(make_tmap_bf16(&tmV, vt, 2, dims, strides, box));
   }
-  XaParams p{};
-  p.out = out; p.bv = bv; p.K = K; p.S = S; p.Sp16 = Sp16; p.Sp_rows = Sp_rows; p.Sq = Sq;
-  if (Sp16 <= 224) { p.o_col = 224; p.tmem_cols = 256; } else { p.o_col = 256; p.tmem_cols = 512; }
-  { const char* e = getenv("CQVAD_XATTN_STAGE"); p.stage = e ? atoi(e) : 0; }
-  dim3 grid(4, (unsigned)N);
-  cls_xattn_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+  p.out = out; p.bv = bv; p.K = K; p.S = S; p.Sp16 = Sp16; p.q_rows = q_rows; p.k_rows = k_rows; p.v_pitch = v_pitch;
+  p.hd = hd; p.scale_log2 = 1.4426950408889634f / sqrtf((float)hd);
+  int cols = 32;
+  while (cols < Sp16 + 32) cols <<= 1;
+  p.tmem_cols = cols; p.o_col = cols - 32;
+  dim3 grid((unsigned)heads, (unsigned)N);
+  attn_tc_kernel<<<grid, NUM_THREADS, smem_bytes, st>>>(tmQ, tmK, tmV, p);
   CQ_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+// Class cross-attention (dab_transformer.py:1067-1071).  Returns 1 when the shape is outside what the tensor-core kernel
+// takes (caller uses the CUDA-core kernel).
+int cls_xattn_tc(const bf16* Qin, const bf16* cqp, const bf16* kx, const bf16* pos0, const bf16* vt, long ldvt,
+                 const float* bv, bf16* out, long N, int K, int S, int Sq, int Sp_rows, int BT, cudaStream_t st) {
+  int r = launch_attn_tc(Qin, N * K, kx, N * Sp_rows, vt, ldvt, N * Sq, bv, out, N, 4, 64, K, S, K, Sp_rows, Sq, st);
+  if (r != 0) return r;
   cls_xattn_pos_kernel<<<(unsigned)N, 128, 4 * S * sizeof(float), st>>>(cqp, pos0, vt, ldvt, bv, out, K, S, Sq, BT);
   CQ_LAUNCH_CHECK();
   return 0;
+}
+
+// Class-query self-attention (dab_transformer.py:1063): q = k = v = class tokens x [N*K,256], 8 heads of 32;
+// xt = x^T [256, ldxt] with per-instance column pitch K8 (written by the class-FFN epilogue).  Output [N*K,256].
+int cls_sattn_tc(const bf16* x, const bf16* xt, long ldxt, bf16* out, long N, int K, int K8, cudaStream_t st) {
+  return launch_attn_tc(x, N * K, x, N * K, xt, ldxt, N * K8, nullptr, out, N, 8, 32, K, K, K, K, K8, st);
 }
 
 }  // namespace cqvad

@@ -124,6 +124,10 @@ struct Epilogue {
   float ln_eps = 1e-5f;
   // rows of C that must be written as zeros (y-padded NHWC separator rows): row % period >= valid  (period 0 = off)
   int zero_period = 0, zero_valid = 0;
+  // fp32 side channels of the class-token stream (bf16 path): residual read in fp32 instead of `res`, and an fp32 copy
+  // of C (same leading dimension), so that the values feeding cls_norm_/cls_norm2 skip two un-averaged bf16 roundings
+  const float* res32 = nullptr;
+  float* c32 = nullptr;
 };
 struct ConvGeom {  // implicit-GEMM 3x3 conv on the y-padded NHWC layout [n_img, h+1, w, 256]
   int h = 0, w = 0;
@@ -142,7 +146,8 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
 // fused MLP  Y = LN?( res? + act(X.W1^T + b1).W2^T + b2 )  (tcgen05; returns 1 if unsupported)
 int mlp_tc(const bf16* X, const bf16* W1, const float* b1, const bf16* W2, const float* b2, int act, const bf16* res,
            const float* ln_g, const float* ln_b, float ln_eps, bf16* Y, long M, int C, int F, int zero_period,
-           int zero_valid, cudaStream_t st);
+           int zero_valid, cudaStream_t st, bf16* YT = nullptr, long ldyt = 0, int yt_rows = 0, int yt_pitch = 0,
+           const float* res32 = nullptr, float* Y32 = nullptr);
 
 template <typename T>
 int layernorm_rows(const T* x, const T* res, const float* g, const float* b, float eps, void* out, bool out_f32,

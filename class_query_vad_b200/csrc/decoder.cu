@@ -19,6 +19,7 @@ namespace cqvad {
 
 int cls_xattn_tc(const bf16* Qin, const bf16* cqp, const bf16* kx, const bf16* pos0, const bf16* vt, long ldvt,
                  const float* bv, bf16* out, long N, int K, int S, int Sq, int Sp_rows, int BT, cudaStream_t st);
+int cls_sattn_tc(const bf16* x, const bf16* xt, long ldxt, bf16* out, long N, int K, int K8, cudaStream_t st);
 
 // ---- error / launch-count state (thread-local) -------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -116,9 +117,9 @@ struct Decoder {
 
   // buffers
   T *memc, *pos0c, *e512, *qpos, *tmpN, *pscale, *qse, *saq, *sak, *sav, *sao, *out, *actor, *acls, *qm, *kv, *kp, *qc,
-      *qs, *cao, *XA, *XB, *Xn, *Hc, *Qc[2], *cq1, *cq2, *saoc, *kx, *vx, *vt, *cqp, *caoc, *cls0, *Hf, *hsn, *bb1, *bb2;
-  long ldvt;
-  float *r_cur, *r_next, *lvlw;
+      *qs, *cao, *XA, *XB, *Xn, *Hc, *Qc[2], *cq1, *cq2, *saoc, *kx, *vx, *vt, *qt, *cqp, *caoc, *cls0, *Hf, *hsn, *bb1, *bb2;
+  long ldvt, ldqt; int K8;
+  float *r_cur, *r_next, *lvlw, *cls0_32, *clsout_32;   // *_32: fp32 side copies of the class-token stream (bf16 path)
 
   Decoder(const cqvad_decoder_desc& dd, const void* const* ww, cudaStream_t s) : d(dd), w(ww), st(s) {
     BT = d.BT; nq = d.nq; h = d.h; wd = d.w; S = h * wd; Sp = (h + 1) * wd; K = d.K; F = d.F; Lr = d.layers;
@@ -135,9 +136,14 @@ struct Decoder {
     acls = t(N * kC); qm = t(NSq * kC); kv = t(NSq * 2 * kC); kp = t((long)S * BT * kC); qc = t(N * kC); qs = t(N * kC);
     cao = t(N * kC); XA = t(Rp * kC); XB = t(Rp * kC); Xn = t(Rp * kC); Hc = t(Rp * 4 * kC);
     Qc[0] = t(NK * kC); Qc[1] = t(NK * kC); cq1 = t((long)K * kC); cq2 = t((long)K * kC); saoc = t(NK * kC);
-    kx = t(Rp * kC); vx = t(NSq * kC); ldvt = NSq + 64; vt = t(kC * ldvt); cqp = t(N * kC); caoc = t(NK * kC); cls0 = t(NK * kC); Hf = t(NK * F);
+    kx = t(Rp * kC); vx = t(NSq * kC); ldvt = NSq + 64; vt = t(kC * ldvt);
+    K8 = (K + 7) & ~7; ldqt = N * K8 + 64; qt = t(kC * ldqt); cqp = t(N * kC); caoc = t(NK * kC); cls0 = t(NK * kC); Hf = t(NK * F);
     hsn = t(N * kC); bb1 = t(N * kC); bb2 = t(N * kC);
     r_cur = f(N * 4); r_next = f(N * 4); lvlw = f(N * 4);
+    cls0_32 = clsout_32 = nullptr;
+    // fp32 side copies of the class-token stream: measured on B200 to leave the bf16 error unchanged (it is dominated by
+    // GEMM operand rounding, tools/diag_bf16.py) while costing 0.33 ms/step -> off unless CQVAD_DEC_FP32_CLS_STREAM
+    if (DT<T>::id == CQVAD_BF16 && (d.flags & 2)) { cls0_32 = f(NK * kC); clsout_32 = f(NK * kC); }
     return a.off;
   }
 
@@ -157,7 +163,10 @@ struct Decoder {
   }
   // Y = LN?( res + W2.act(W1.X + b1) + b2 ), hidden in `hid` ([M,Fh]) unless the fused tensor-core kernel takes it
   int mlp(const T* X, long M, int Fh, int w1, int w2, int act, const T* res, int ln_idx, float eps, T* Y, T* hid,
-          int zero_period = 0, int zero_valid = 0);
+          int zero_period = 0, int zero_valid = 0, bool emit_qt = false, const float* res32 = nullptr, float* y32 = nullptr);
+  bool y32_valid = false;
+  bool qt_valid = false;   // qt holds the transposed class tokens of the previous layer
+  int sattn(int l, const T* Qprev, T* Qin);
 
   // class cross-attention (dab_transformer.py:1067-1071): fills caoc [N*K,256] from Qin, X3 (padded), qm, qse
   int xattn(int l, const T* Qin, const T* X3);
@@ -169,7 +178,7 @@ struct Decoder {
 
 template <>
 int Decoder<float>::mlp(const float* X, long M, int Fh, int w1, int w2, int act, const float* res, int ln_idx, float eps,
-                        float* Y, float* hid, int zero_period, int zero_valid) {
+                        float* Y, float* hid, int zero_period, int zero_valid, bool, const float*, float*) {
   CQ_TRY(lin(X, M, kC, w1, hid, Fh, act));
   Epilogue e;
   e.bias = Wf(w2 + 1); e.res = res; e.ldr = kC; e.zero_period = zero_period; e.zero_valid = zero_valid;
@@ -178,19 +187,44 @@ int Decoder<float>::mlp(const float* X, long M, int Fh, int w1, int w2, int act,
 }
 template <>
 int Decoder<bf16>::mlp(const bf16* X, long M, int Fh, int w1, int w2, int act, const bf16* res, int ln_idx, float eps,
-                       bf16* Y, bf16* hid, int zero_period, int zero_valid) {
+                       bf16* Y, bf16* hid, int zero_period, int zero_valid, bool emit_qt, const float* res32, float* y32) {
+  if (emit_qt) qt_valid = false;
+  if (y32) y32_valid = false;
   // the fused kernel walks the hidden dimension serially per 128-row tile: with few row tiles (small-row FFNs, M = nq*BT)
   // two plain GEMMs spread the F dimension over more SMs
   if (!force_simt() && M > 2048) {
     int r = mlp_tc(X, Wm(w1), Wf(w1 + 1), Wm(w2), Wf(w2 + 1), act, res, ln_idx >= 0 ? Wf(ln_idx) : nullptr,
-                   ln_idx >= 0 ? Wf(ln_idx + 1) : nullptr, eps, Y, M, kC, Fh, zero_period, zero_valid, st);
+                   ln_idx >= 0 ? Wf(ln_idx + 1) : nullptr, eps, Y, M, kC, Fh, zero_period, zero_valid, st,
+                   emit_qt ? qt : nullptr, ldqt, K, K8, res32, y32);
+    if (r == 0 && emit_qt) qt_valid = true;
+    if (r == 0 && y32) y32_valid = true;
     if (r <= 0) return r;
   }
   CQ_TRY(lin(X, M, kC, w1, hid, Fh, act));
   Epilogue e;
-  e.bias = Wf(w2 + 1); e.res = res; e.ldr = kC; e.zero_period = zero_period; e.zero_valid = zero_valid;
+  e.bias = Wf(w2 + 1); e.res = res; e.ldr = kC; e.zero_period = zero_period; e.zero_valid = zero_valid; e.res32 = res32;
   if (ln_idx >= 0) { e.ln_g = Wf(ln_idx); e.ln_b = Wf(ln_idx + 1); e.ln_eps = eps; }
-  return gemm<bf16>(hid, Fh, Wm(w2), Y, kC, M, kC, Fh, e, nullptr, st);
+  return gemm<bf16>(hid, Fh, Wm(w2), Y, kC, M, kC, Fh, e, nullptr, st);   // y32 not produced here: y32_valid stays false
+}
+
+// class-query self-attention :1063-1065 for layers >= 1 (q = k = v = previous layer's class tokens)
+template <typename T>
+static int sattn_generic(Decoder<T>& d, int l, const T* Qprev, T* Qin) {
+  StdStrides ss{};
+  ss.q_ls = ss.k_ls = ss.v_ls = ss.o_ls = kC;
+  ss.q_bs = ss.k_bs = ss.v_bs = ss.o_bs = (long)d.K * kC;
+  CQ_TRY(mha_std<T>(Qprev, nullptr, Qprev, nullptr, Qprev, nullptr, d.saoc, d.K, d.K, (int)d.N, kH, 32, 32, ss, d.st));
+  return d.lin(d.saoc, d.NK, kC, d.cls(l, C_SA_O), Qin, kC, CQVAD_ACT_NONE, Qprev, d.cls(l, C_NORM1));
+}
+template <>
+int Decoder<float>::sattn(int l, const float* Qprev, float* Qin) { return sattn_generic<float>(*this, l, Qprev, Qin); }
+template <>
+int Decoder<bf16>::sattn(int l, const bf16* Qprev, bf16* Qin) {
+  if (force_simt() || !qt_valid || K > 128) return sattn_generic<bf16>(*this, l, Qprev, Qin);
+  int r = cls_sattn_tc(Qprev, qt, ldqt, saoc, N, K, K8, st);
+  if (r == 1) return sattn_generic<bf16>(*this, l, Qprev, Qin);
+  if (r != 0) return r;
+  return lin(saoc, NK, kC, cls(l, C_SA_O), Qin, kC, CQVAD_ACT_NONE, Qprev, cls(l, C_NORM1));
 }
 
 // class cross-attention :1067-1071.  512-wide q/k split contiguously into 8 heads of 64 (attention.py:336,339):
@@ -241,6 +275,8 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
   CQ_TRY(convert_f32<T>(tgt, out, N * kC, st));
   CQ_CUDA(cudaMemsetAsync(XA, 0, (size_t)Rp * kC * sizeof(T), st));  // zero separator rows (never written afterwards)
   CQ_CUDA(cudaMemsetAsync(XB, 0, (size_t)Rp * kC * sizeof(T), st));
+  CQ_CUDA(cudaMemsetAsync(qt, 0, (size_t)kC * ldqt * sizeof(T), st));   // pad columns of the transposed class tokens stay finite
+  qt_valid = false;
   if (Sq != S) CQ_CUDA(cudaMemsetAsync(qm, 0, (size_t)NSq * kC * sizeof(T), st));   // pad rows stay zero (finite)
   CQ_TRY(sigmoid4(ref_u, r_cur, refs, N, nq, BT, st));               // :735; refs[0]
   delete ps;
@@ -324,19 +360,20 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
       CQ_TRY(lin(cq1, K, kC, cls(l, C_SA_O), cq2, kC, CQVAD_ACT_NONE, Wm(glob(G_CQ)), cls(l, C_NORM1)));
       CQ_TRY(broadcast_rows<T>(cq2, Qin, NK, K, st));
     } else {
-      StdStrides ss{};
-      ss.q_ls = ss.k_ls = ss.v_ls = ss.o_ls = kC;
-      ss.q_bs = ss.k_bs = ss.v_bs = ss.o_bs = (long)K * kC;
-      CQ_TRY(mha_std<T>(Qprev, nullptr, Qprev, nullptr, Qprev, nullptr, saoc, K, K, (int)N, kH, 32, 32, ss, st));
-      CQ_TRY(lin(saoc, NK, kC, cls(l, C_SA_O), Qin, kC, CQVAD_ACT_NONE, Qprev, cls(l, C_NORM1)));
+      CQ_TRY(sattn(l, Qprev, Qin));
     }
     delete ps; ps = nullptr;
     CQ_TRY(xattn(l, Qin, X3));
     PROF(P_CLS_OPROJ);
-    CQ_TRY(lin(caoc, NK, kC, cls(l, C_CA_O), cls0, kC));
+    {
+      Epilogue e;
+      e.bias = Wf(cls(l, C_CA_O) + 1); e.c32 = cls0_32;
+      CQ_TRY(gemm<T>(caoc, kC, Wm(cls(l, C_CA_O)), cls0, kC, NK, kC, kC, e, nullptr, st));
+    }
     PROF(P_CLS_FFN);
     T* cls_out = Qc[l & 1];   // Qin is dead after the attention; reuse its buffer for the layer output / next query
-    CQ_TRY(mlp(cls0, NK, F, cls(l, C_L1_), cls(l, C_L2_), CQVAD_ACT_RELU, cls0, cls(l, C_NORM_), 1e-5f, cls_out, Hf));
+    CQ_TRY(mlp(cls0, NK, F, cls(l, C_L1_), cls(l, C_L2_), CQVAD_ACT_RELU, cls0, cls(l, C_NORM_), 1e-5f, cls_out, Hf, 0, 0,
+               /*emit_qt=*/l + 1 < Lr, cls0_32, clsout_32));
 
     // ---- outputs of this layer :826-827 and heads (models/model.py:192-221) ----
     PROF(P_OUT_LN);
@@ -346,7 +383,10 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
     {
       void* dst = cls_hs ? (void*)((char*)cls_hs + (size_t)l * NK * kC * osz) : nullptr;
       float* lg = pred_logits ? pred_logits + (size_t)l * NK : nullptr;
-      if (dst || lg)
+      if ((dst || lg) && clsout_32 && y32_valid)   // bf16 path: cls_norm2 reads the fp32 copy of the class tokens
+        CQ_TRY(layernorm_permute_f32in(clsout_32, Wf(glob(G_CLSNORM2)), Wf(glob(G_CLSNORM2) + 1), 1e-5f, dst, of32, NK, nq,
+                                       BT, K, lg, st));
+      else if (dst || lg)
         CQ_TRY(layernorm_permute<T>(cls_out, Wf(glob(G_CLSNORM2)), Wf(glob(G_CLSNORM2) + 1), 1e-5f, dst, of32, NK, nq, BT,
                                     K, lg, st));
     }

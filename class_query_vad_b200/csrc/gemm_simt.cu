@@ -2,6 +2,7 @@
 // fallback for shapes the tcgen05 kernel does not take (K % 64 != 0, tiny N).  Also does the 3x3 conv as an
 // implicit GEMM over the y-padded NHWC layout (models/detr/dab_transformer.py:81,90).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace cqvad {
 
@@ -107,9 +108,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
       if (epi.bias) v += epi.bias[c];
       if (epi.act == CQVAD_ACT_RELU) v = fmaxf(v, 0.f);
       else if (epi.act == CQVAD_ACT_GELU) v = gelu_erf(v);
-      if (res) v += to_f(res[r * epi.ldr + c]);
+      if (epi.res32) v += epi.res32[r * epi.ldr + c];
+      else if (res) v += to_f(res[r * epi.ldr + c]);
       if (zero_row) v = 0.f;
       C[r * ldc + c] = from_f<T>(v);
+      if (epi.c32) epi.c32[r * ldc + c] = v;
     }
   }
 }
@@ -125,6 +128,7 @@ int gemm_simt(const T* A, long lda, const T* W, T* C, long ldc, long M, int N, i
   CQ_CHECK_SHAPE(grid.y <= 65535u * 32u, "gemm_simt: M too large");
   Epilogue e = epi;
   e.ln_g = nullptr;  // LayerNorm (if any) is applied by a second kernel below
+  if (epi.ln_g) e.c32 = nullptr;   // the fp32 copy must hold the normalised values: only the tensor-core epilogue fuses that
   if (conv) {
     CQ_CHECK_SHAPE(K == 9 * kC, "conv: K must be 9*256");
     gemm_simt_kernel<T, true><<<grid, 256, 0, st>>>(A, lda, W, C, ldc, M, N, K, e, conv->w);
@@ -157,7 +161,8 @@ int gemm<float>(const float* A, long lda, const float* W, float* C, long ldc, lo
 template <>
 int gemm<bf16>(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, int N, int K, const Epilogue& epi,
                const ConvGeom* conv, cudaStream_t st) {
-  if (!g_force_simt) {
+  static const long small_m = [] { const char* e = getenv("CQVAD_SMALL_M"); return e ? atol(e) : 0L; }();
+  if (!g_force_simt && !(M <= small_m && !conv)) {
     int r = gemm_tc(A, lda, W, C, ldc, M, N, K, epi, conv, st);
     if (r <= 0) return r;  // 0 ok, <0 error; 1 = shape not supported by the tensor-core kernel
   }

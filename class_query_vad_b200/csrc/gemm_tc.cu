@@ -26,13 +26,15 @@ constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, STAGES = 4, UMMA_K = 1
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
 constexpr int SMEM_TILES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
-constexpr int SMEM_BYTES = SMEM_TILES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int NUM_THREADS = 192;
+// aux: barriers 256 | bias [2][256] f32 (per TMEM buffer) | gamma [256] | beta [256] | LN partial sums [2][2][128][2] f32
+constexpr int AUX_BIAS = 256, AUX_GAM = AUX_BIAS + 2048, AUX_BET = AUX_GAM + 1024, AUX_STATS = AUX_BET + 1024, AUX_BYTES = AUX_STATS + 4096;
+constexpr int SMEM_BYTES = SMEM_TILES + 1024 /*align slack*/ + AUX_BYTES;
+constexpr int NUM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter: 128 columns each)
 constexpr int TMEM_COLS = 512;
 
 struct TcParams {
   bf16* C; long ldc; long M; int N; int K;
-  const float* bias; int act; const bf16* res; long ldr;
+  const float* bias; int act; const bf16* res; long ldr; const float* res32; float* c32;
   const float* ln_g; const float* ln_b; float ln_eps;
   int zero_period, zero_valid;
   // conv
@@ -40,6 +42,11 @@ struct TcParams {
   int m_tiles, n_tiles;
 };
 
+__device__ __forceinline__ void unpack8(const uint4& r, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -58,7 +65,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 8); }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -118,38 +125,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===== epilogue warps (2..5): TMEM lane quarter q = warp % 4 =====
-    const int q = warp & 3;
+    // ===== epilogue warps 2..9: TMEM lane quarter q = warp % 4, column half g = (warp-2)/4 =====
+    // Two warps per SM sub-partition (latency hiding) and every per-column vector (bias, gamma, beta) staged in shared
+    // memory: the ncu source page of the first version showed 42% of all stall samples on FADDs waiting for the
+    // global bias loads (long scoreboard) with a single exposed epilogue warp per sub-partition.
+    const int q = warp & 3, g = (warp - 2) >> 2;
+    const int et = (warp - 2) * 32 + lane;          // 0..255
     const int row_in_tile = q * 32 + lane;
+    float* aux = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)));
+    float* bias_s = aux + AUX_BIAS / 4; float* gam_s = aux + AUX_GAM / 4; float* bet_s = aux + AUX_BET / 4;
+    float* stats_s = aux + AUX_STATS / 4;
+    const bool do_ln = p.ln_g != nullptr;
+    if (do_ln) { gam_s[et] = p.ln_g[et]; bet_s[et] = p.ln_b[et]; }   // N == 256, one n-tile
     int acc = 0; uint32_t acc_phase = 0;
     const int tile_rows = p.conv ? p.cw * p.rt : BLOCK_M;
+    const int c0 = g * 128;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
-      mbar_wait(tfull_bar + 8 * acc, acc_phase);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      const int n0 = nt * BLOCK_N;
+      float* bcur = bias_s + acc * 256;
+      bcur[et] = (p.bias && n0 + et < p.N) ? p.bias[n0 + et] : 0.f;
       const long grow = (long)mt * tile_rows + row_in_tile;
       const bool row_ok = row_in_tile < tile_rows && grow < p.M;
+      // bf16 residual fetched one 32-column step ahead (4 x 16 bytes in flight per thread)
+      const bool res_bf16 = p.res != nullptr && p.res32 == nullptr && row_ok;
+      const bf16* rbase = p.res + (res_bf16 ? grow * p.ldr + n0 + c0 : 0);
+      auto ld_res = [&](int col) -> uint4 {   // col relative to c0, multiple of 8
+        return (res_bf16 && n0 + c0 + col < p.N) ? *reinterpret_cast<const uint4*>(rbase + col) : make_uint4(0u, 0u, 0u, 0u);
+      };
+      uint4 rnext[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rnext[u] = ld_res(u * 8);
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // bias (and gamma/beta) visible to the 8 epilogue warps
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
       const bool zero_row = p.zero_period > 0 && (int)(grow % p.zero_period) >= p.zero_valid;
-      const int n0 = nt * BLOCK_N;
-      bf16* crow = p.C + grow * p.ldc + n0;
-      const bf16* rrow = p.res ? p.res + grow * p.ldr + n0 : nullptr;
-      const bool do_ln = p.ln_g != nullptr;
+      bf16* crow = p.C + grow * p.ldc + n0 + c0;
+      const float* rrow32 = p.res32 ? p.res32 + grow * p.ldr + n0 + c0 : nullptr;
+      float* crow32 = p.c32 ? p.c32 + grow * p.ldc + n0 + c0 : nullptr;
       float mean = 0.f, rstd = 1.f;
       if (do_ln) {
-        // pass 1: v = acc + bias (+res); stash v in TMEM; row statistics
+        // pass 1: v = act(acc + bias) (+res); stash v in TMEM; partial row statistics over this warp's 128 columns
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
+        for (int c = 0; c < 128; c += 32) {
+          uint4 rcur[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) rcur[u] = rnext[u];
+          if (c + 32 < 128) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rnext[u] = ld_res(c + 32 + u * 8);
+          }
           uint32_t r[32];
           tmem_ld32(t_addr + c, r);
           tmem_ld_wait();
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
             float rs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (rrow && row_ok) load8(rrow + c + g8 * 8, rs);
-            float bs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (p.bias) load8(p.bias + n0 + c + g8 * 8, bs);
+            if (rrow32) { if (row_ok) load8(rrow32 + c + g8 * 8, rs); }
+            else unpack8(rcur[g8], rs);
+            float bs[8];
+            load8(bcur + c0 + c + g8 * 8, bs);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float v = __uint_as_float(r[g8 * 8 + j]) + bs[j];
@@ -163,32 +200,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_st32(t_addr + c, r);
         }
         tmem_st_wait();
-        mean = s1 * (1.0f / BLOCK_N);
-        const float var = fmaxf(s2 * (1.0f / BLOCK_N) - mean * mean, 0.f);
+        float* st = stats_s + acc * 512;
+        st[(g * 128 + row_in_tile) * 2] = s1;
+        st[(g * 128 + row_in_tile) * 2 + 1] = s2;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float o1 = st[((g ^ 1) * 128 + row_in_tile) * 2], o2 = st[((g ^ 1) * 128 + row_in_tile) * 2 + 1];
+        mean = (s1 + o1) * (1.0f / BLOCK_N);
+        const float var = fmaxf((s2 + o2) * (1.0f / BLOCK_N) - mean * mean, 0.f);
         rstd = rsqrtf(var + p.ln_eps);
       }
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        if (n0 + c >= p.N) break;  // warp-uniform
+      for (int c = 0; c < 128; c += 32) {
+        if (n0 + c0 + c >= p.N) break;  // warp-uniform
+        uint4 rcur[4];
+        if (!do_ln) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) rcur[u] = rnext[u];
+          if (c + 32 < 128) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rnext[u] = ld_res(c + 32 + u * 8);
+          }
+        }
         uint32_t r[32];
         tmem_ld32(t_addr + c, r);
         tmem_ld_wait();
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
           const int cb = c + g8 * 8;
-          if (n0 + cb >= p.N) break;
+          if (n0 + c0 + cb >= p.N) continue;
           float v[8];
           if (do_ln) {
-            float g[8], b[8];
-            load8(p.ln_g + n0 + cb, g);
-            load8(p.ln_b + n0 + cb, b);
+            float gm[8], bt[8];
+            load8(gam_s + c0 + cb, gm);
+            load8(bet_s + c0 + cb, bt);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (__uint_as_float(r[g8 * 8 + j]) - mean) * rstd * g[j] + b[j];
+            for (int j = 0; j < 8; ++j) v[j] = (__uint_as_float(r[g8 * 8 + j]) - mean) * rstd * gm[j] + bt[j];
           } else {
             float rs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (rrow && row_ok) load8(rrow + cb, rs);
-            float bs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (p.bias) load8(p.bias + n0 + cb, bs);
+            if (rrow32) { if (row_ok) load8(rrow32 + cb, rs); }
+            else unpack8(rcur[g8], rs);
+            float bs[8];
+            load8(bcur + c0 + cb, bs);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float x = __uint_as_float(r[g8 * 8 + j]) + bs[j];
@@ -201,7 +253,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = 0.f;
           }
-          if (row_ok) store8(crow + cb, v);
+          if (row_ok) {
+            store8(crow + cb, v);
+            if (crow32) store8(crow32 + cb, v);
+          }
         }
       }
       // release the accumulator buffer to the MMA warp
@@ -270,6 +325,7 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
   if (N % 8 != 0 && (ldc < ((N + 7) & ~7) || epi.bias || epi.res || epi.ln_g)) return 1;
   if ((((uintptr_t)A) & 15) || (((uintptr_t)W) & 15) || (((uintptr_t)C) & 15)) return 1;
   if (epi.res && ((((uintptr_t)epi.res) & 15) || epi.ldr % 8 != 0)) return 1;
+  if ((epi.res32 && ((((uintptr_t)epi.res32) & 15) || epi.ldr % 8 != 0)) || (epi.c32 && (((uintptr_t)epi.c32) & 15))) return 1;
   if (epi.ln_g && N != BLOCK_N) return 1;
   if (conv && (conv->w > 128 || lda != kC || K != 9 * kC)) return 1;
   std::call_once(g_once, init_once);
@@ -277,7 +333,7 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
 
   TcParams p{};
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
-  p.bias = epi.bias; p.act = epi.act; p.res = (const bf16*)epi.res; p.ldr = epi.ldr;
+  p.bias = epi.bias; p.act = epi.act; p.res = (const bf16*)epi.res; p.ldr = epi.ldr; p.res32 = epi.res32; p.c32 = epi.c32;
   p.ln_g = epi.ln_g; p.ln_b = epi.ln_b; p.ln_eps = epi.ln_eps;
   p.zero_period = epi.zero_period; p.zero_valid = epi.zero_valid;
   p.n_tiles = (N + BLOCK_N - 1) / BLOCK_N;

@@ -369,6 +369,17 @@ int layernorm_permute(const T* x, const float* g, const float* b, float eps, voi
   return 0;
 }
 template int layernorm_permute<float>(const float*, const float*, const float*, float, void*, bool, long, int, int, int, float*, cudaStream_t);
+// fp32 input (side channel of the bf16 path), output fp32 or bf16
+int layernorm_permute_f32in(const float* x, const float* g, const float* b, float eps, void* out, bool out_f32, long rows,
+                            int nq, int BT, int K, float* row_mean_out, cudaStream_t st) {
+  if (rows == 0) return 0;
+  if (out_f32)
+    layernorm_permute_kernel<float, float><<<row_grid(rows), kThreads, 0, st>>>(x, g, b, eps, (float*)out, rows, nq, BT, K, row_mean_out);
+  else
+    layernorm_permute_kernel<float, bf16><<<row_grid(rows), kThreads, 0, st>>>(x, g, b, eps, (bf16*)out, rows, nq, BT, K, row_mean_out);
+  CQ_LAUNCH_CHECK();
+  return 0;
+}
 template int layernorm_permute<bf16>(const bf16*, const float*, const float*, float, void*, bool, long, int, int, int, float*, cudaStream_t);
 
 template <typename T>

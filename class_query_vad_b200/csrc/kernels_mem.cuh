@@ -4,6 +4,8 @@
 namespace cqvad {
 template <typename T> int layernorm_permute(const T* x, const float* g, const float* b, float eps, void* out, bool out_f32,
                                             long rows, int nq, int BT, int K, float* row_mean_out, cudaStream_t st);
+int layernorm_permute_f32in(const float* x, const float* g, const float* b, float eps, void* out, bool out_f32, long rows,
+                            int nq, int BT, int K, float* row_mean_out, cudaStream_t st);
 template <typename T> int lvlmix_ln(const T* mem, const float* lvlw, const float* g, const float* b, T* qm, long N, int S,
                                     int Sq, int BT, cudaStream_t st);
 template <typename T> int add_ln_pad(const T* actor, const T* qm, const float* g, const float* b, T* xpad, long N, int S,

@@ -6,7 +6,8 @@
 //     GEMM1(j):  Hacc[j%2] (TMEM, 128 cols)  = X(smem) . W1_j^T            16 x UMMA 128x128x16
 //     epi(j)  :  Hs[j%2] (smem, 128-B swizzle) = bf16(act(Hacc + b1_j))     epilogue group j%2 (4 warps)
 //     GEMM2(j):  Yacc (TMEM, 256 cols)      += Hs[j%2] . W2_j^T             8 x UMMA 128x256x16
-// with GEMM2(j-1) issued after GEMM1(j) so the tensor pipe works while the epilogue of chunk j runs.
+// with GEMM2(j-2) issued after GEMM1(j) (four H buffers in flight) so the tensor pipe has independent work queued while
+// the epilogue of a chunk runs.
 // Warps: 0 = TMA producer (X tile + 3-slot x 32 KB weight ring), 1 = MMA issuer + TMEM allocator, 2-5 = epilogue
 // group 0, 6-9 = epilogue group 1.  Both groups share the final Y epilogue (128 columns each; LayerNorm statistics
 // are exchanged through shared memory).
@@ -22,25 +23,33 @@ int tc_num_sms();
 
 namespace {
 
-constexpr int BM = 128, CH = 128 /*hidden chunk*/, BK = 64, C = 256;
+constexpr int BM = 128, CH = 64 /*hidden chunk*/, BK = 64, C = 256;
+constexpr int NB = 4;                          // H buffers in flight (TMEM accumulators and smem tiles)
+constexpr int LA = 2;                          // GEMM2(j-LA) is issued after GEMM1(j)
 constexpr int X_BYTES = BM * C * 2;            // 64 KB: 4 k-blocks of [128 x 64]
-constexpr int HS_BYTES = BM * CH * 2;          // 32 KB: 2 k-blocks of [128 x 64]
-constexpr int SLOT_BYTES = 32 * 1024;          // W1: 2 k-blocks of [128 x 64]; W2: 1 k-block of [256 x 64]
+constexpr int HS_BYTES = BM * CH * 2;          // 16 KB: one k-block [128 x 64]
+constexpr int SLOT_BYTES = 32 * 1024;          // W1 chunk: 4 k-blocks of [64 x 64]; W2 chunk: one k-block of [256 x 64]
 constexpr int SLOTS = 3;
-constexpr int SMEM_DATA = X_BYTES + 2 * HS_BYTES + SLOTS * SLOT_BYTES;   // 229 376
-constexpr int SMEM_BYTES = SMEM_DATA + 1024 + 1280;
+constexpr int SMEM_DATA = X_BYTES + NB * HS_BYTES + SLOTS * SLOT_BYTES;   // 229 376
+constexpr int SMEM_AUX = 256 /*barriers*/ + 1024 /*b1 chunk, double buffered: [2 groups][2][64] f32*/;
+constexpr int SMEM_BYTES = SMEM_DATA + SMEM_AUX;   // <= 227 KB; the dynamic buffer is declared 1024-aligned (no slack)
 constexpr int NUM_THREADS = 320;
 
 struct MlpParams {
   bf16* Y; long M; int F;
   const float* b1; const float* b2; int act;
-  const bf16* res;
+  const bf16* res; const float* res32; float* Y32;
   const float* ln_g; const float* ln_b; float ln_eps;
   int zero_period, zero_valid;
   int m_tiles;
+  bf16* YT; long ldyt; int yt_rows, yt_pitch;   // optional transposed copy: YT[c][(row/yt_rows)*yt_pitch + row%yt_rows]
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ void unpack8(const uint4& r, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -49,28 +58,33 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
               const __grid_constant__ CUtensorMap tmW2, const MlpParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sX = base, sH = base + X_BYTES, sW = sH + 2 * HS_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);   // 1024-byte aligned (128-B swizzle atoms)
+  const uint32_t sX = base, sH = base + X_BYTES, sW = sH + NB * HS_BYTES;
   const uint32_t bars = base + SMEM_DATA;
   // barriers (8 bytes each)
-  const uint32_t w_full = bars, w_empty = bars + 8 * SLOTS;          // weight ring
-  const uint32_t x_full = bars + 16 * SLOTS, x_empty = x_full + 8;   // X tile
-  const uint32_t hacc_full = x_empty + 8, hacc_empty = hacc_full + 16;   // TMEM H accumulators [2]
-  const uint32_t hs_full = hacc_empty + 16, hs_empty = hs_full + 16;     // smem H buffers [2]
-  const uint32_t y_full = hs_empty + 16, y_empty = y_full + 8;
-  const uint32_t tmem_slot = y_empty + 8;
-  const uint32_t stats = tmem_slot + 8;                                   // float[2][128][2] LN partial sums (2 KB.. uses 1024 B)
+  const uint32_t w_full = bars, w_empty = bars + 8 * SLOTS;            // weight ring            [0,48)
+  const uint32_t x_full = bars + 48, x_empty = bars + 56;              // X tile                 [48,64)
+  const uint32_t hacc_full = bars + 64, hacc_empty = bars + 96;        // TMEM H accumulators [4] [64,128)
+  const uint32_t hs_full = bars + 128, hs_empty = bars + 160;          // smem H tiles [4]        [128,192)
+  const uint32_t y_full = bars + 192, y_empty = bars + 200;
+  const uint32_t tmem_slot = bars + 208;
+  const uint32_t b1s = bars + 256;                                     // float[2 groups][2][64]: b1 of the chunk in flight
+  // LN partial sums float[2][128][2] alias the first 2 KB of Hs[0]: all GEMM2 reads of Hs are complete once y_full fires
+  const uint32_t stats = sH;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = p.F / CH;
+  // (a per-CTA rotation of the chunk order was tried against L2 hot-spotting: no gain on B200, and it makes the fp32
+  //  summation order depend on the CTA index, breaking bit-exact batch independence -> chunks are walked in order)
+  constexpr int rot = 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
     for (int s = 0; s < SLOTS; ++s) { mbar_init(w_full + 8 * s, 1); mbar_init(w_empty + 8 * s, 1); }
     mbar_init(x_full, 1); mbar_init(x_empty, 1);
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(hacc_full + 8 * g, 1); mbar_init(hacc_empty + 8 * g, 4);
-      mbar_init(hs_full + 8 * g, 4); mbar_init(hs_empty + 8 * g, 1);
+    for (int b = 0; b < NB; ++b) {
+      mbar_init(hacc_full + 8 * b, 1); mbar_init(hacc_empty + 8 * b, 4);
+      mbar_init(hs_full + 8 * b, 4); mbar_init(hs_empty + 8 * b, 1);
     }
     mbar_init(y_full, 1); mbar_init(y_empty, 8);
     mbar_fence_init();
@@ -85,21 +99,20 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer =====
+      // ===== TMA producer: loads in exactly the order the MMA warp consumes them =====
       int slot = 0; uint32_t wphase = 0; uint32_t xphase = 0;
-      auto load_w1 = [&](int j, int half) {   // k-blocks 2*half, 2*half+1 of W1 chunk j: two boxes [64 x 128 rows]
+      auto load_w1 = [&](int j) {   // W1 rows [j*64, j*64+64): four k-block boxes [64 k x 64 rows] of 8 KB
         mbar_wait(w_empty + 8 * slot, wphase ^ 1);
         const uint32_t fb = w_full + 8 * slot;
         mbar_arrive_expect_tx(fb, SLOT_BYTES);
-        tma_load_2d(sW + slot * SLOT_BYTES, &tmW1, fb, (2 * half) * BK, j * CH);
-        tma_load_2d(sW + slot * SLOT_BYTES + 16384, &tmW1, fb, (2 * half + 1) * BK, j * CH);
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d(sW + slot * SLOT_BYTES + kb * 8192, &tmW1, fb, kb * BK, j * CH);
         if (++slot == SLOTS) { slot = 0; wphase ^= 1; }
       };
-      auto load_w2 = [&](int j, int kk) {     // W2[:, j*128 + kk*64 .. +64): one box [64 x 256 rows]
+      auto load_w2 = [&](int j) {   // W2[:, j*64 .. j*64+64): one box [64 k x 256 rows]
         mbar_wait(w_empty + 8 * slot, wphase ^ 1);
         const uint32_t fb = w_full + 8 * slot;
         mbar_arrive_expect_tx(fb, SLOT_BYTES);
-        tma_load_2d(sW + slot * SLOT_BYTES, &tmW2, fb, j * CH + kk * BK, 0);
+        tma_load_2d(sW + slot * SLOT_BYTES, &tmW2, fb, j * CH, 0);
         if (++slot == SLOTS) { slot = 0; wphase ^= 1; }
       };
       for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
@@ -108,42 +121,39 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         for (int kb = 0; kb < 4; ++kb) tma_load_2d(sX + kb * 16384, &tmX, x_full, kb * BK, tile * BM);
         xphase ^= 1;
         for (int j = 0; j < nch; ++j) {
-          load_w1(j, 0); load_w1(j, 1);
-          if (j >= 1) { load_w2(j - 1, 0); load_w2(j - 1, 1); }
+          load_w1((j + rot) % nch);
+          if (j >= LA) load_w2((j - LA + rot) % nch);
         }
-        load_w2(nch - 1, 0); load_w2(nch - 1, 1);
+        for (int c = nch - LA; c < nch; ++c) load_w2((c + rot) % nch);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc1 = make_idesc_bf16(BM, CH);    // 128 x 128
+      constexpr uint32_t idesc1 = make_idesc_bf16(BM, CH);    // 128 x 64
       constexpr uint32_t idesc2 = make_idesc_bf16(BM, C);     // 128 x 256
       int slot = 0; uint32_t wphase = 0, xphase = 0, yphase = 0;
-      uint32_t hacc_ph[2] = {0, 0}, hs_ph[2] = {0, 0};
+      uint32_t hacc_ph = 0, hs_ph = 0;    // one phase bit per buffer
       bool y_started = false;
       auto gemm2 = [&](int c) {
-        const int g = c & 1;
+        const int b = c & (NB - 1);
         if (!y_started) {   // first GEMM2 of the tile: the previous tile's Y epilogue must have drained TMEM
           mbar_wait(y_empty, yphase ^ 1);
           tc_fence_after();
         }
-        mbar_wait(hs_full + 8 * g, hs_ph[g]);
-        hs_ph[g] ^= 1;
+        mbar_wait(hs_full + 8 * b, (hs_ph >> b) & 1u);
+        hs_ph ^= 1u << b;
+        mbar_wait(w_full + 8 * slot, wphase);
         tc_fence_after();
-        for (int kk = 0; kk < 2; ++kk) {
-          mbar_wait(w_full + 8 * slot, wphase);
-          tc_fence_after();
-          const uint64_t a_desc = make_smem_desc_sw128(sH + g * HS_BYTES + kk * 16384);
-          const uint64_t b_desc = make_smem_desc_sw128(sW + slot * SLOT_BYTES);
+        const uint64_t a_desc = make_smem_desc_sw128(sH + b * HS_BYTES);
+        const uint64_t b_desc = make_smem_desc_sw128(sW + slot * SLOT_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(t_y, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc2, (y_started || kk || k) ? 1u : 0u);
-          umma_commit(w_empty + 8 * slot);
-          if (++slot == SLOTS) { slot = 0; wphase ^= 1; }
-        }
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(t_y, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc2, (y_started || k) ? 1u : 0u);
+        umma_commit(w_empty + 8 * slot);
+        if (++slot == SLOTS) { slot = 0; wphase ^= 1; }
         y_started = true;
-        umma_commit(hs_empty + 8 * g);
+        umma_commit(hs_empty + 8 * b);
       };
       for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
         mbar_wait(x_full, xphase);
@@ -151,58 +161,67 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         tc_fence_after();
         y_started = false;
         for (int j = 0; j < nch; ++j) {
-          const int g = j & 1;
-          mbar_wait(hacc_empty + 8 * g, hacc_ph[g] ^ 1);
-          hacc_ph[g] ^= 1;
+          const int b = j & (NB - 1);
+          mbar_wait(hacc_empty + 8 * b, ((hacc_ph >> b) & 1u) ^ 1u);   // epilogue of chunk j-4 has drained TMEM buffer b
+          hacc_ph ^= 1u << b;
+          mbar_wait(w_full + 8 * slot, wphase);
           tc_fence_after();
-          const uint32_t t_h = t_h0 + g * CH;
-          for (int half = 0; half < 2; ++half) {
-            mbar_wait(w_full + 8 * slot, wphase);
-            tc_fence_after();
+          const uint32_t t_h = t_h0 + b * CH;
 #pragma unroll
-            for (int t2 = 0; t2 < 2; ++t2) {
-              const int kb = 2 * half + t2;
-              const uint64_t a_desc = make_smem_desc_sw128(sX + kb * 16384);
-              const uint64_t b_desc = make_smem_desc_sw128(sW + slot * SLOT_BYTES + t2 * 16384);
+          for (int kb = 0; kb < 4; ++kb) {
+            const uint64_t a_desc = make_smem_desc_sw128(sX + kb * 16384);
+            const uint64_t b_desc = make_smem_desc_sw128(sW + slot * SLOT_BYTES + kb * 8192);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(t_h, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc1, (kb || k) ? 1u : 0u);
-            }
-            umma_commit(w_empty + 8 * slot);
-            if (++slot == SLOTS) { slot = 0; wphase ^= 1; }
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(t_h, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc1, (kb || k) ? 1u : 0u);
           }
-          umma_commit(hacc_full + 8 * g);
+          umma_commit(w_empty + 8 * slot);
+          if (++slot == SLOTS) { slot = 0; wphase ^= 1; }
+          umma_commit(hacc_full + 8 * b);
           if (j == nch - 1) umma_commit(x_empty);   // all GEMM1 of this tile issued: X may be overwritten when they finish
-          if (j >= 1) gemm2(j - 1);
+          if (j >= LA) gemm2(j - LA);
         }
-        gemm2(nch - 1);
+        for (int c = nch - LA; c < nch; ++c) gemm2(c);
         umma_commit(y_full);
         yphase ^= 1;
       }
     }
   } else {
-    // ===== epilogue groups: g = 0 (warps 2-5), g = 1 (warps 6-9) =====
+    // ===== epilogue groups: g = 0 (warps 2-5) takes even chunks, g = 1 (warps 6-9) odd chunks =====
     const int g = (warp - 2) >> 2;
     const int q = warp & 3;                       // TMEM lane quarter
     const int row_in_tile = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    uint32_t hacc_ph = 0, hs_ph = 0, yphase = 0;
-    float* stats_f = reinterpret_cast<float*>(smem_raw + (stats - smem_u32(smem_raw)));
+    uint32_t hacc_ph = 0, hs_ph = 0, yphase = 0;  // bit b = phase of buffer b (this group touches b = g and g+2)
+    float* stats_f = reinterpret_cast<float*>(smem_raw + (stats - base));
+    float* b1s_f = reinterpret_cast<float*>(smem_raw + (b1s - base)) + g * 128;   // this group's two 64-float buffers
+    const int tg = ((warp - 2) & 3) * 32 + lane;                                   // thread index inside the group
+    // b1 of the group's next chunk is prefetched into a register one chunk ahead, published through shared memory and
+    // read back as broadcast LDS.128 (a global load per 8 columns left the epilogue exposed to the full L2 latency:
+    // ncu source page of the first version, profiles/)
+    float nb = tg < CH ? p.b1[((g + rot) % nch) * CH + tg] : 0.f;
+    uint32_t bpar = 0;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
       for (int j = g; j < nch; j += 2) {
-        mbar_wait(hacc_full + 8 * g, hacc_ph);
-        hacc_ph ^= 1;
+        const int b = j & (NB - 1);
+        float* bcur = b1s_f + bpar * 64;
+        if (tg < CH) bcur[tg] = nb;
+        bpar ^= 1;
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+        if (tg < CH) nb = p.b1[((((j + 2 < nch) ? (j + 2) : g) + rot) % nch) * CH + tg];
+        mbar_wait(hacc_full + 8 * b, (hacc_ph >> b) & 1u);
+        hacc_ph ^= 1u << b;
         tc_fence_after();
-        mbar_wait(hs_empty + 8 * g, hs_ph ^ 1);   // GEMM2 of chunk j-2 has finished reading Hs[g]
-        hs_ph ^= 1;
-        const uint32_t t_h = t_h0 + g * CH + lane_off;
-        const uint32_t hs_row = sH + g * HS_BYTES + row_in_tile * 128;
-#pragma unroll 1
+        mbar_wait(hs_empty + 8 * b, ((hs_ph >> b) & 1u) ^ 1u);   // GEMM2 of chunk j-4 has finished reading Hs[b]
+        hs_ph ^= 1u << b;
+        const uint32_t t_h = t_h0 + b * CH + lane_off;
+        const uint32_t hs_row = sH + b * HS_BYTES + row_in_tile * 128;
+#pragma unroll
         for (int c = 0; c < CH; c += 32) {
           uint32_t r[32];
           tmem_ld32(t_h + c, r);
           tmem_ld_wait();
-          const float* b1 = p.b1 + j * CH + c;
+          const float* b1 = bcur + c;
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
             float bs[8];
@@ -221,10 +240,10 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                 pk[e] = pack_bf16(fmaxf(__uint_as_float(r[g8 * 8 + 2 * e]) + bs[2 * e], 0.f),
                                   fmaxf(__uint_as_float(r[g8 * 8 + 2 * e + 1]) + bs[2 * e + 1], 0.f));
             }
-            // hidden column cc = c + g8*8 -> k-block cc/64, 16-byte chunk (cc%64)/8, swizzled with (row & 7)
+            // hidden column cc = c + g8*8 of this 64-wide k-block: 16-byte chunk cc/8, swizzled with (row & 7)
             const int cc = c + g8 * 8;
-            const uint32_t chunk = (uint32_t)((cc & 63) >> 3) ^ (uint32_t)(row_in_tile & 7);
-            const uint32_t addr = hs_row + (uint32_t)(cc >> 6) * 16384u + chunk * 16u;
+            const uint32_t chunk = (uint32_t)(cc >> 3) ^ (uint32_t)(row_in_tile & 7);
+            const uint32_t addr = hs_row + chunk * 16u;
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
                          : "memory");
           }
@@ -232,14 +251,22 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         tc_fence_before();
         fence_proxy_async_smem();   // make the st.shared above visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) { mbar_arrive(hacc_empty + 8 * g); mbar_arrive(hs_full + 8 * g); }
+        if (lane == 0) { mbar_arrive(hacc_empty + 8 * b); mbar_arrive(hs_full + 8 * b); }
       }
       // ---- final epilogue of the tile: group g owns output columns [g*128, g*128+128) ----
+      const long grow = (long)tile * BM + row_in_tile;
+      const bool row_ok = grow < p.M;
+      // The bf16 residual is fetched one 32-column step ahead (4 x 16 bytes in flight per thread): one exposed L2 round
+      // trip per step instead of one per 8 columns (ncu: 18% of all stall samples sat on these loads while Y blocked the
+      // next tile).  Hoisting all 16 loads above the y_full wait was tried and lost to register spills.
+      const bool res_bf16 = p.res != nullptr && p.res32 == nullptr && row_ok;
+      const uint4* rp = reinterpret_cast<const uint4*>(p.res + (res_bf16 ? grow * C + g * 128 : 0));
+      uint4 rnext[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rnext[u] = res_bf16 ? rp[u] : make_uint4(0u, 0u, 0u, 0u);
       mbar_wait(y_full, yphase);
       yphase ^= 1;
       tc_fence_after();
-      const long grow = (long)tile * BM + row_in_tile;
-      const bool row_ok = grow < p.M;
       const bool zero_row = p.zero_period > 0 && (int)(grow % p.zero_period) >= p.zero_valid;
       const uint32_t t_yrow = t_y + lane_off + g * 128;
       const int col0 = g * 128;
@@ -249,6 +276,13 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
         for (int c = 0; c < 128; c += 32) {
+          uint4 rcur[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) rcur[u] = rnext[u];
+          if (c + 32 < 128) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rnext[u] = res_bf16 ? rp[((c + 32) >> 3) + u] : make_uint4(0u, 0u, 0u, 0u);
+          }
           uint32_t r[32];
           tmem_ld32(t_yrow + c, r);
           tmem_ld_wait();
@@ -256,7 +290,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           for (int g8 = 0; g8 < 4; ++g8) {
             float bs[8], rs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             load8(p.b2 + col0 + c + g8 * 8, bs);
-            if (p.res && row_ok) load8(p.res + grow * C + col0 + c + g8 * 8, rs);
+            if (p.res32) { if (row_ok) load8(p.res32 + grow * C + col0 + c + g8 * 8, rs); }
+            else unpack8(rcur[g8], rs);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const float v = __uint_as_float(r[g8 * 8 + e]) + bs[e] + rs[e];
@@ -277,6 +312,15 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       }
 #pragma unroll 1
       for (int c = 0; c < 128; c += 32) {
+        uint4 rcur[4];
+        if (!do_ln) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) rcur[u] = rnext[u];
+          if (c + 32 < 128) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rnext[u] = res_bf16 ? rp[((c + 32) >> 3) + u] : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
         uint32_t r[32];
         tmem_ld32(t_yrow + c, r);
         tmem_ld_wait();
@@ -293,7 +337,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           } else {
             float bs[8], rs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             load8(p.b2 + cb, bs);
-            if (p.res && row_ok) load8(p.res + grow * C + cb, rs);
+            if (p.res32) { if (row_ok) load8(p.res32 + grow * C + cb, rs); }
+            else unpack8(rcur[g8], rs);
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g8 * 8 + e]) + bs[e] + rs[e];
           }
@@ -301,7 +346,15 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = 0.f;
           }
-          if (row_ok) store8(p.Y + grow * C + cb, v);
+          if (row_ok) {
+            store8(p.Y + grow * C + cb, v);
+            if (p.Y32) store8(p.Y32 + grow * C + cb, v);
+            if (p.YT) {   // lanes = consecutive rows -> consecutive columns of YT: coalesced 2-byte stores
+              const long col = (grow / p.yt_rows) * p.yt_pitch + grow % p.yt_rows;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) p.YT[(long)(cb + e) * p.ldyt + col] = __float2bfloat16_rn(v[e]);
+            }
+          }
         }
       }
       tc_fence_before();
@@ -326,8 +379,8 @@ bool g_attr_set = false;
 
 int mlp_tc(const bf16* X, const bf16* W1, const float* b1, const bf16* W2, const float* b2, int act, const bf16* res,
            const float* ln_g, const float* ln_b, float ln_eps, bf16* Y, long M, int Cc, int F, int zero_period,
-           int zero_valid, cudaStream_t st) {
-  if (Cc != C || F % CH != 0 || F < 2 * CH || M < 1) return 1;
+           int zero_valid, cudaStream_t st, bf16* YT, long ldyt, int yt_rows, int yt_pitch, const float* res32, float* Y32) {
+  if (Cc != C || F % CH != 0 || F < 256 || M < 1) return 1;
   if (act != CQVAD_ACT_RELU && act != CQVAD_ACT_GELU) return 1;
   if ((((uintptr_t)X) & 15) || (((uintptr_t)Y) & 15) || (((uintptr_t)W1) & 15) || (((uintptr_t)W2) & 15) ||
       (res && (((uintptr_t)res) & 15)))
@@ -361,6 +414,8 @@ int mlp_tc(const bf16* X, const bf16* W1, const float* b1, const bf16* W2, const
   p.Y = Y; p.M = M; p.F = F; p.b1 = b1; p.b2 = b2; p.act = act; p.res = res;
   p.ln_g = ln_g; p.ln_b = ln_b; p.ln_eps = ln_eps; p.zero_period = zero_period; p.zero_valid = zero_valid;
   p.m_tiles = (int)((M + BM - 1) / BM);
+  p.res32 = res32; p.Y32 = Y32;
+  p.YT = YT; p.ldyt = ldyt; p.yt_rows = yt_rows > 0 ? yt_rows : 1; p.yt_pitch = yt_pitch;
   const int grid = p.m_tiles < sms ? p.m_tiles : sms;
   mlp_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmX, tmW1, tmW2, p);
   CQ_LAUNCH_CHECK();

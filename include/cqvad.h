@@ -112,7 +112,8 @@ typedef struct cqvad_decoder_desc {
   int out_f32;      /* 1: hs/cls_hs written as fp32 (reference dtype); 0: written in `dtype`           */
   int flags;        /* CQVAD_DEC_* below                                                               */
 } cqvad_decoder_desc;
-enum { CQVAD_DEC_SKIP_CLS_HS = 1 /* do not materialise cls_hs (only pred_logits) */ };
+enum { CQVAD_DEC_SKIP_CLS_HS = 1 /* do not materialise cls_hs (only pred_logits) */,
+       CQVAD_DEC_FP32_CLS_STREAM = 2 /* bf16 path: keep fp32 side copies of the class-token residual/output stream */ };
 
 /* Weight table: an array of device pointers ordered as cqvad_decoder_weight_name(i, layers) enumerates them
  * (reference state_dict names, SURVEY.md App. C, + "heads.class_embed_b.*").  kind 0 = matrix stored in `dtype`
