@@ -45,10 +45,13 @@ static const Slot kLocSlots[] = {
     LIN("self_attn.out_proj"), LNP("norm1"), {"lvl_w_embed.weight", 1}, {"lvl_w_embed.bias", 1},
     LIN("ca_qcontent_proj"), LIN("ca_qpos_proj"), LIN("ca_kcontent_proj"), LIN("ca_kpos_proj"), LIN("ca_v_proj"),
     LIN("ca_qpos_sine_proj"), LIN("cross_attn.out_proj"), LIN("linear1"), LIN("linear2"), LNP("norm2"), LNP("norm3"),
-    LNP("norm_")};
+    LNP("norm_"),
+    // synthesised at pack time (not a reference parameter): [ca_kcontent_proj ; ca_v_proj] stacked to [512,256] so that the
+    // two projections of q_memory are ONE GEMM (q_memory is read once)
+    LIN("__ca_kv")};
 enum LocIdx { SA_QC = 0, SA_QP = 2, SA_KC = 4, SA_KP = 6, SA_V = 8, SA_O = 10, NORM1 = 12, LVLW = 14, CA_QC = 16,
               CA_QP = 18, CA_KC = 20, CA_KP = 22, CA_V = 24, CA_QS = 26, CA_O = 28, LIN1 = 30, LIN2 = 32, NORM2 = 34,
-              NORM3 = 36, NORMU = 38, LOC_COUNT = 40 };
+              NORM3 = 36, NORMU = 38, CA_KV = 40, LOC_COUNT = 42 };
 static const Slot kClsSlots[] = {
     LIN("cls_linear1"), LIN("cls_linear2"), LNP("cls_norm"), LNP("conv_norm"), LIN("conv_blocks.0.conv1"),
     LNP("conv_blocks.0.norm"), LIN("conv_blocks.0.conv2"), LIN("conv_blocks.0.conv3"), LIN("self_attn.out_proj"),
@@ -316,8 +319,12 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
     CQ_TRY(lvlmix_ln<T>(memc, lvlw, Wf(loc(l, NORMU)), Wf(loc(l, NORMU) + 1), qm, N, S, Sq, BT, st));
     // ---- cross-attention with per-actor keys :951-988 ----
     PROF(P_BIG_PROJ);
-    CQ_TRY(lin(qm, NSq, kC, loc(l, CA_KC), kv, kC, CQVAD_ACT_NONE, nullptr, -1, 1e-5f, 2 * kC));
-    CQ_TRY(lin(qm, NSq, kC, loc(l, CA_V), kv + kC, kC, CQVAD_ACT_NONE, nullptr, -1, 1e-5f, 2 * kC));
+    if (w[loc(l, CA_KV)] != nullptr) {
+      CQ_TRY(lin(qm, NSq, kC, loc(l, CA_KV), kv, 2 * kC));          // [k | v] in one pass over q_memory
+    } else {
+      CQ_TRY(lin(qm, NSq, kC, loc(l, CA_KC), kv, kC, CQVAD_ACT_NONE, nullptr, -1, 1e-5f, 2 * kC));
+      CQ_TRY(lin(qm, NSq, kC, loc(l, CA_V), kv + kC, kC, CQVAD_ACT_NONE, nullptr, -1, 1e-5f, 2 * kC));
+    }
     CQ_TRY(lin(pos0c, (long)S * BT, kC, loc(l, CA_KP), kp, kC));
     PROF(P_SMALL);
     CQ_TRY(lin(out, N, kC, loc(l, CA_QC), qc, kC));
@@ -474,7 +481,8 @@ extern "C" int cqvad_decoder_forward(const cqvad_decoder_desc* d, const void* co
   for (int i = 0; i < nw; ++i) {
     if (weights[i] == nullptr) {
       std::string nm; weight_slot(i, d->layers, &nm, nullptr);
-      const bool optional = nm.find("ca_qpos_proj") != std::string::npos && nm.rfind("layers.0.", 0) != 0;
+      const bool optional = (nm.find("ca_qpos_proj") != std::string::npos && nm.rfind("layers.0.", 0) != 0) ||
+                            nm.find(".__") != std::string::npos;   // synthesised (fused) entries are optional
       CQ_CHECK_ARG(optional, "decoder: weight '%s' is NULL", nm.c_str());
     }
   }

@@ -25,7 +25,7 @@ namespace {
 
 constexpr int BM = 128, CH = 64 /*hidden chunk*/, BK = 64, C = 256;
 constexpr int NB = 4;                          // H buffers in flight (TMEM accumulators and smem tiles)
-constexpr int LA = 2;                          // GEMM2(j-LA) is issued after GEMM1(j)
+constexpr int LA = 3;                          // GEMM2(j-LA) is issued after GEMM1(j): three independent GEMM1s stay queued
 constexpr int X_BYTES = BM * C * 2;            // 64 KB: 4 k-blocks of [128 x 64]
 constexpr int HS_BYTES = BM * CH * 2;          // 16 KB: one k-block [128 x 64]
 constexpr int SLOT_BYTES = 32 * 1024;          // W1 chunk: 4 k-blocks of [64 x 64]; W2 chunk: one k-block of [256 x 64]

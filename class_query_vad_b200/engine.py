@@ -28,6 +28,14 @@ def pack_decoder_weights(state, layers, dtype, device):
     for i in range(n):
         name = lib.cqvad_decoder_weight_name(i, layers).decode()
         kind = lib.cqvad_decoder_weight_kind(i, layers)
+        if ".__ca_kv." in name:   # synthesised: [ca_kcontent_proj ; ca_v_proj] stacked along the output dimension
+            leaf = name.rsplit(".", 1)[1]
+            pre = name.split(".__ca_kv.")[0]
+            t = torch.cat([_as_tensor(state[f"{pre}.ca_kcontent_proj.{leaf}"]).float(), _as_tensor(state[f"{pre}.ca_v_proj.{leaf}"]).float()], 0)
+            t = t.to(device=device).contiguous().to(torch.float32 if kind == 1 else dtype).contiguous()
+            keep.append(t)
+            arr[i] = t.data_ptr()
+            continue
         if name not in state:
             if "ca_qpos_proj" in name and not name.startswith("layers.0."):
                 arr[i] = None   # ca_qpos_proj is None for layers >= 1 (dab_transformer.py:711-713)

@@ -118,7 +118,9 @@ enum { CQVAD_DEC_SKIP_CLS_HS = 1 /* do not materialise cls_hs (only pred_logits)
 /* Weight table: an array of device pointers ordered as cqvad_decoder_weight_name(i, layers) enumerates them
  * (reference state_dict names, SURVEY.md App. C, + "heads.class_embed_b.*").  kind 0 = matrix stored in `dtype`
  * ([out,in] row-major; conv1 as [out][ky*3+kx][in]); kind 1 = fp32 (biases, LayerNorm, small-N linears,
- * class_queries).  NULL is allowed only for layers.{i>0}.ca_qpos_proj.* (dab_transformer.py:711-713). */
+ * class_queries).  NULL is allowed only for layers.{i>0}.ca_qpos_proj.* (dab_transformer.py:711-713) and for the
+ * synthesised entries whose name contains ".__" (layers.{i}.__ca_kv.* = [ca_kcontent_proj ; ca_v_proj] stacked to
+ * [512,256] / [512]: when present the two projections of q_memory run as one GEMM). */
 int cqvad_decoder_num_weights(int layers);
 const char* cqvad_decoder_weight_name(int idx, int layers);
 int cqvad_decoder_weight_kind(int idx, int layers);
