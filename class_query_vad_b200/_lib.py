@@ -42,6 +42,10 @@ SYMBOLS = {
     "cqvad_decoder_weight_kind": (c_int, [c_int, c_int]),
     "cqvad_decoder_workspace_bytes": (c_size_t, [POINTER(DecoderDesc)]),
     "cqvad_decoder_forward": (c_int, [POINTER(DecoderDesc), POINTER(c_void_p)] + [c_void_p] * 11 + [c_void_p, c_size_t, c_void_p]),
+    "cqvad_decoder_train_workspace_bytes": (c_size_t, [POINTER(DecoderDesc)]),
+    "cqvad_decoder_train_forward": (c_int, [POINTER(DecoderDesc), POINTER(c_void_p)] + [c_void_p] * 8 + [c_void_p, c_size_t, c_void_p]),
+    "cqvad_decoder_backward": (c_int, [POINTER(DecoderDesc), POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p,
+                                       POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cqvad_last_launch_count": (c_long, []),
     "cqvad_profile_enable": (None, [c_int]),
     "cqvad_profile_num_classes": (c_int, []),

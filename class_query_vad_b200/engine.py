@@ -16,7 +16,7 @@ def _as_tensor(v):
     return torch.from_numpy(np.ascontiguousarray(v))
 
 
-def pack_decoder_weights(state, layers, dtype, device):
+def pack_decoder_weights(state, layers, dtype, device, meta=None):
     """state: mapping of reference TransformerDecoder state_dict names (+ optional
     'heads.class_embed_b.*') to tensors / ndarrays.  Returns (keepalive list, ctypes pointer array).
 
@@ -25,6 +25,8 @@ def pack_decoder_weights(state, layers, dtype, device):
     lib = _lib.lib()
     n = lib.cqvad_decoder_num_weights(layers)
     keep, arr = [], (c_void_p * n)()
+    if meta is not None:
+        meta.clear()
     for i in range(n):
         name = lib.cqvad_decoder_weight_name(i, layers).decode()
         kind = lib.cqvad_decoder_weight_kind(i, layers)
@@ -35,11 +37,15 @@ def pack_decoder_weights(state, layers, dtype, device):
             t = t.to(device=device).contiguous().to(torch.float32 if kind == 1 else dtype).contiguous()
             keep.append(t)
             arr[i] = t.data_ptr()
+            if meta is not None:
+                meta.append((name, tuple(t.shape), None))
             continue
         if name not in state:
             if "ca_qpos_proj" in name and not name.startswith("layers.0."):
                 arr[i] = None   # ca_qpos_proj is None for layers >= 1 (dab_transformer.py:711-713)
                 keep.append(None)
+                if meta is not None:
+                    meta.append((name, None, None))
                 continue
             if name.startswith("heads.class_embed_b"):
                 t = torch.zeros((3, 256) if name.endswith("weight") else (3,))
@@ -48,6 +54,7 @@ def pack_decoder_weights(state, layers, dtype, device):
         else:
             t = _as_tensor(state[name])
         t = t.to(device=device, dtype=torch.float32)
+        orig_shape = tuple(t.shape)
         if name.endswith("conv1.weight"):
             t = t.permute(0, 2, 3, 1).reshape(t.shape[0], -1)           # [O,I,3,3] -> [O, (ky,kx,I)]
         elif t.dim() == 4:
@@ -55,6 +62,8 @@ def pack_decoder_weights(state, layers, dtype, device):
         t = t.contiguous().to(torch.float32 if kind == 1 else dtype).contiguous()
         keep.append(t)
         arr[i] = t.data_ptr()
+        if meta is not None:
+            meta.append((name, tuple(t.shape), orig_shape))
     return keep, arr
 
 
@@ -70,8 +79,11 @@ class DecoderEngine:
         if self.device.type != "cuda":
             raise RuntimeError("Not implemented on the CPU")
         self.dtype, self.nq, self.K, self.layers, self.F, self.out_f32 = dtype, nq, K, layers, F, out_f32
-        self._keep, self._wtab = pack_decoder_weights(state, layers, dtype, self.device)
+        self._meta = []
+        self._keep, self._wtab = pack_decoder_weights(state, layers, dtype, self.device, self._meta)
         self._ws = None
+        self._tws = None
+        self._train_ctx = None
         self.last_launches = 0
 
     def _workspace(self, desc):
@@ -121,3 +133,100 @@ class DecoderEngine:
         if heads:
             out.update(pred_logits=pl, pred_boxes=pb, pred_logits_b=plb)
         return out
+
+    # ---- training step (BASELINE.json configs[1]: decoder fwd + bwd) ----------------------------------------------
+    def _grad_table(self):
+        """One flat fp32 buffer holding every weight gradient + the pointer table cqvad_decoder_backward takes."""
+        if getattr(self, "_gflat", None) is None:
+            sizes = [0 if shp is None else int(np.prod(shp)) for (_, shp, _) in self._meta]
+            offs = np.concatenate([[0], np.cumsum([(n + 63) // 64 * 64 for n in sizes])]).astype(np.int64)
+            self._gflat = torch.zeros(int(offs[-1]), dtype=torch.float32, device=self.device)
+            self._goffs, self._gsizes = offs, sizes
+            self._gtab = (c_void_p * len(sizes))()
+            for i, n in enumerate(sizes):
+                self._gtab[i] = None if self._meta[i][1] is None else self._gflat.data_ptr() + 4 * int(offs[i])
+        return self._gflat, self._gtab
+
+    def forward_train(self, tgt, memory, mask, pos, refpoints_unsigmoid, orig_res):
+        """TransformerDecoder.forward keeping what the backward needs.  Returns dict(hs, cls_hs, refs); follow with
+        `backward(grad_hs, grad_cls_hs, grad_refs)`."""
+        lib = _lib.lib()
+        h, w = orig_res
+        nq, BT = tgt.shape[0], tgt.shape[1]
+        S = h * w
+        if nq != self.nq or tuple(memory.shape) != (4, S, BT, 256) or tuple(refpoints_unsigmoid.shape) != (nq, BT, 4):
+            raise ValueError("decoder input shapes do not match")
+        _lib.require_cuda(tgt, memory, pos, refpoints_unsigmoid)
+        f32 = lambda t: t.to(device=self.device, dtype=torch.float32).contiguous()
+        tgt, memory, pos0, ref = f32(tgt), f32(memory), f32(pos[0]), f32(refpoints_unsigmoid)
+        m8 = None
+        if mask is not None:
+            m8 = mask.to(self.device).contiguous()
+            m8 = m8.view(torch.uint8) if m8.dtype == torch.bool else m8.to(torch.uint8)
+        desc = _lib.DecoderDesc(_lib.dtype_id(self.dtype), BT, nq, h, w, self.K, self.F, self.layers,
+                                1 if self.out_f32 else 0, 0)
+        need = lib.cqvad_decoder_train_workspace_bytes(byref(desc))
+        if need == 0:
+            _lib.check(-1)
+        if self._tws is None or self._tws.numel() < need:
+            self._tws = None
+            self._tws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        odt = torch.float32 if self.out_f32 else self.dtype
+        Lr, K = self.layers, self.K
+        hs = torch.empty((Lr, BT, nq, 256), dtype=odt, device=self.device)
+        cls_hs = torch.empty((Lr, BT, nq, K, 256), dtype=odt, device=self.device)
+        refs = torch.empty((Lr, BT, nq, 4), dtype=torch.float32, device=self.device)
+        p = _lib.ptr
+        rc = lib.cqvad_decoder_train_forward(byref(desc), self._wtab, p(tgt), p(memory), p(pos0), p(m8), p(ref), p(hs),
+                                             p(cls_hs), p(refs), p(self._tws), self._tws.numel(), _lib.stream_ptr())
+        _lib.check(rc)
+        self.last_launches = lib.cqvad_last_launch_count()
+        self._train_ctx = (desc, m8, (nq, BT, S))
+        return dict(hs=hs, cls_hs=cls_hs, refs=refs)
+
+    def backward(self, grad_hs=None, grad_cls_hs=None, grad_refs=None, zero=True, named=True):
+        """Backward of the last forward_train.  Returns dict(memory, tgt, refpoints_unsigmoid, params={reference name: grad})."""
+        if self._train_ctx is None:
+            raise RuntimeError("backward() without a preceding forward_train()")
+        lib = _lib.lib()
+        desc, m8, (nq, BT, S) = self._train_ctx
+        odt = torch.float32 if self.out_f32 else self.dtype
+        prep = lambda g, dt: None if g is None else g.to(device=self.device, dtype=dt).contiguous()
+        grad_hs, grad_cls_hs, grad_refs = prep(grad_hs, odt), prep(grad_cls_hs, odt), prep(grad_refs, torch.float32)
+        gflat, gtab = self._grad_table()
+        if zero or getattr(self, "_gin", None) is None or self._gin[0].shape[2] != BT:
+            if zero:
+                gflat.zero_()
+            self._gin = (torch.zeros((4, S, BT, 256), dtype=torch.float32, device=self.device),
+                         torch.zeros((nq, BT, 256), dtype=torch.float32, device=self.device),
+                         torch.zeros((nq, BT, 4), dtype=torch.float32, device=self.device))
+        gmem, gtgt, gref = self._gin
+        p = _lib.ptr
+        rc = lib.cqvad_decoder_backward(byref(desc), self._wtab, p(m8), p(grad_hs), p(grad_cls_hs), p(grad_refs), gtab, p(gmem),
+                                        p(gtgt), p(gref), p(self._tws), self._tws.numel(), _lib.stream_ptr())
+        _lib.check(rc)
+        self.last_launches_bwd = lib.cqvad_last_launch_count()
+        out = dict(memory=gmem, tgt=gtgt, refpoints_unsigmoid=gref)
+        if named:
+            out["params"] = self.named_grads()
+        return out
+
+    def named_grads(self):
+        """Weight gradients under the reference state_dict names and shapes."""
+        res = {}
+        for i, (name, shp, orig) in enumerate(self._meta):
+            if shp is None or name.startswith("heads."):
+                continue
+            g = self._gflat[int(self._goffs[i]):int(self._goffs[i]) + self._gsizes[i]].view(shp)
+            if ".__ca_kv." in name:
+                pre, leaf = name.split(".__ca_kv.")
+                half = shp[0] // 2
+                for nm, part in ((f"{pre}.ca_kcontent_proj.{leaf}", g[:half]), (f"{pre}.ca_v_proj.{leaf}", g[half:])):
+                    res[nm] = res[nm] + part if nm in res else part.clone()
+                continue
+            if name.endswith("conv1.weight"):
+                g = g.view(orig[0], 3, 3, orig[1]).permute(0, 3, 1, 2)
+            elif orig is not None and len(orig) == 4:
+                g = g.view(orig)
+            res[name] = res[name] + g if name in res else g.clone()
+        return res

@@ -140,6 +140,35 @@ int cqvad_decoder_forward(const cqvad_decoder_desc* d, const void* const* weight
 long cqvad_last_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Training step of the decoder (BASELINE.json configs[1] "full decoder fwd+bwd"): what torch autograd does to
+ * TransformerDecoder.forward in the reference training loop (train.py:126-182 -> loss.backward()).  Replaces, on the
+ * decoder, the autograd graph of dab_transformer.py:722-852 (there is no hand-written backward in the reference except
+ * the MSDA op, ops/functions/ms_deform_attn_func.py:36-45).
+ *   cqvad_decoder_train_forward : same inputs/outputs as cqvad_decoder_forward without the heads (hs, cls_hs, refs are
+ *       what TransformerDecoder.forward returns) and keeps every intermediate the backward needs in `workspace`
+ *       (cqvad_decoder_train_workspace_bytes; ~13 GB at 32 AVA clips in bf16).  Dropout is the identity.
+ *   cqvad_decoder_backward : given dL/d(hs), dL/d(cls_hs) (element type of the forward outputs: fp32 when out_f32, else
+ *       `dtype`) and dL/d(refs) (fp32); any may be NULL = zero.  MUST be called with the same descriptor, weights and
+ *       workspace as the preceding train_forward, before anything else touches the workspace.
+ *       Every gradient output is ACCUMULATED (+=) -- zero-fill for a plain backward, or keep across micro-batches:
+ *         grad_weights[i]  fp32, shape of weight i of the weight table (conv1 as [out][ky*3+kx][in]; the stacked
+ *                          __ca_kv entry receives d[ca_kcontent_proj ; ca_v_proj]); required for every non-NULL weight
+ *         grad_memory      [4,S,BT,256] fp32      grad_tgt [nq,BT,256] fp32 (may be NULL)
+ *         grad_refpoints_unsigmoid [nq,BT,4] fp32 (may be NULL)
+ *       Autograd semantics of the reference: reference points detached between layers (:823), actor feature detached on
+ *       entry to the class branch (:810); `pos` gets no gradient (it is not a decoder parameter; level_embed lives in
+ *       Transformer). */
+size_t cqvad_decoder_train_workspace_bytes(const cqvad_decoder_desc* d);
+int cqvad_decoder_train_forward(const cqvad_decoder_desc* d, const void* const* weights,
+                                const float* tgt, const float* memory, const float* pos, const uint8_t* mask,
+                                const float* refpoints_unsigmoid, void* hs, void* cls_hs, float* refs,
+                                void* workspace, size_t ws_bytes, void* stream);
+int cqvad_decoder_backward(const cqvad_decoder_desc* d, const void* const* weights, const uint8_t* mask,
+                           const void* grad_hs, const void* grad_cls_hs, const float* grad_refs,
+                           float* const* grad_weights, float* grad_memory, float* grad_tgt,
+                           float* grad_refpoints_unsigmoid, void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py).  cqvad_profile_enable(1) makes cqvad_decoder_forward bracket each kernel class with
  * CUDA events on the launch stream; cqvad_profile_read() synchronises and returns the accumulated milliseconds, the
  * number of timed scopes and of kernel launches inside them since the enable call.  Replaces the reference's host

@@ -1,0 +1,85 @@
+"""Generates tests/golden/grad_*.npz: gradients of the UNMODIFIED reference decoder (torch autograd, fp32, CPU, eval mode so
+that dropout is the identity) for the training-step parity of BASELINE.json configs[1] / SURVEY.md section 8(d) "Config 2":
+
+    loss = sum(w_h * hs) + sum(w_c * cls_hs) + sum(w_r * refs)          (fixed random w_*, oracle/synth.make_loss_weights)
+
+Run in the build container only (needs /root/reference):   python -m oracle.make_golden_grads [name ...]
+
+Fixture contents (kept small): full gradients of the inputs (memory, tgt, refpoints_unsigmoid) when they are small, else a
+seeded sample; for every parameter the full gradient when it has <= 4096 elements, else `synth.grad_sample_index` samples
+plus its L2 norm and its sum.  Parameters the reference never uses (grad None: decoder.cls_norm.*, cls_layers.*.q_proj.*,
+SURVEY.md section 8c "Gradient oracle") are recorded as zeros.
+"""
+import os
+import sys
+import numpy as np
+import torch
+
+from . import synth
+from .ref_import import import_reference
+from .make_golden import build_reference_decoder, GOLD
+
+# (fixture, config, B, layers override, seed, masked, tgt_zero)
+GRAD_CASES = [
+    ("grad_tiny", "tiny", 2, None, 0, False, True),
+    ("grad_tiny_masked", "tiny", 2, None, 1, True, False),
+    ("grad_small_masked", "small", 3, None, 2, True, True),
+    ("grad_jhmdb_like", dict(nq=5, tprime=2, h=16, w=16, K=21, layers=1, F=2048), 1, None, 5, False, True),
+    ("grad_ava_vitb_b1_l2", "ava_vitb", 1, 2, 0, False, True),      # BASELINE shape (nq 15, S 196, K 80, F 2048), 2 layers
+]
+
+
+def run_case(ref, name, cfg, B, layers, seed, masked, tgt_zero):
+    c = dict(synth.CONFIGS[cfg]) if isinstance(cfg, str) else dict(cfg)
+    if layers is not None:
+        c["layers"] = layers
+    W = synth.make_decoder_weights(c["K"], c["layers"], c["F"], seed=seed)
+    inp = synth.make_decoder_inputs(c, B, seed=seed, masked=masked, tgt_zero=tgt_zero)
+    lw = synth.make_loss_weights(c, B, seed=seed)
+    dec = build_reference_decoder(ref, c, W)
+    t = lambda a: torch.from_numpy(a.copy())
+    tgt = t(inp["tgt"]).requires_grad_(True)
+    memory = t(inp["memory"]).requires_grad_(True)
+    ref_u = t(inp["refpoints_unsigmoid"]).requires_grad_(True)
+    hs, cls_hs, refs = dec(tgt, memory, memory_key_padding_mask=t(inp["mask"]), pos=t(inp["pos"]),
+                           refpoints_unsigmoid=ref_u, orig_res=inp["orig_res"])
+    loss = (t(lw["w_hs"]) * hs).sum() + (t(lw["w_cls"]) * cls_hs).sum() + (t(lw["w_refs"]) * refs).sum()
+    loss.backward()
+    out = {"loss": np.array(loss.item(), dtype=np.float64)}
+    for nm, ten in (("memory", memory), ("tgt", tgt), ("refpoints_unsigmoid", ref_u)):
+        g = ten.grad.numpy()
+        if g.size <= 1 << 16:
+            out["gin." + nm] = g
+        else:
+            idx = synth.grad_sample_index(g.size, seed)
+            out["gin_s." + nm] = g.reshape(-1)[idx]
+            out["gin_n." + nm] = np.array([np.sqrt((g.astype(np.float64) ** 2).sum()), g.astype(np.float64).sum()])
+    params = dict(dec.named_parameters())
+    for nm in W:
+        if nm.startswith("heads.") or ".conv_blocks.1." in nm or ".conv_blocks.2." in nm:
+            continue
+        p = params[nm]
+        g = np.zeros(tuple(p.shape), dtype=np.float32) if p.grad is None else p.grad.numpy()
+        if g.size <= 4096:
+            out["g." + nm] = g
+        else:
+            idx = synth.grad_sample_index(g.size, seed)
+            out["gs." + nm] = g.reshape(-1)[idx]
+            out["gn." + nm] = np.array([np.sqrt((g.astype(np.float64) ** 2).sum()), g.astype(np.float64).sum()])
+    out["meta"] = np.array([B, c["nq"], c["tprime"], c["h"], c["w"], c["K"], c["layers"], c["F"], seed, int(masked),
+                            int(tgt_zero)], dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "loss", loss.item(), "entries", len(out))
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    sel = set(sys.argv[1:])
+    ref = import_reference()
+    for case in GRAD_CASES:
+        if not sel or any(s in case[0] for s in sel):
+            run_case(ref, *case)
+
+
+if __name__ == "__main__":
+    main()

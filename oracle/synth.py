@@ -168,3 +168,22 @@ def make_msda_inputs(N, shapes, M=8, D=32, Lq=None, P=8, seed=0, spread=0.35):
     a = np.exp(a - a.max(-1, keepdims=True)); a /= a.sum(-1, keepdims=True)
     attn = a.reshape(N, Lq, M, L, P).astype(np.float32)
     return dict(value=value, shapes=shapes, level_start=lsi, loc=loc, attn=attn)
+
+
+def make_loss_weights(cfg, B, seed=0):
+    """Fixed random weights of the synthetic training loss (Config 2):
+    loss = sum(w_hs*hs) + sum(w_cls*cls_hs) + sum(w_refs*refs), shapes of TransformerDecoder.forward's outputs
+    (dab_transformer.py:840-844): hs [Lr,BT,nq,C], cls_hs [Lr,BT,nq,K,C], refs [Lr,BT,nq,4]."""
+    c = CONFIGS[cfg] if isinstance(cfg, str) else cfg
+    BT = B * c["tprime"]
+    rs = np.random.RandomState(4000 + seed)
+    w_hs = rs.standard_normal((c["layers"], BT, c["nq"], D_MODEL)).astype(np.float32)
+    w_cls = (rs.standard_normal((c["layers"], BT, c["nq"], c["K"], D_MODEL)) / np.sqrt(c["K"])).astype(np.float32)
+    w_refs = rs.standard_normal((c["layers"], BT, c["nq"], 4)).astype(np.float32)
+    return dict(w_hs=w_hs, w_cls=w_cls, w_refs=w_refs)
+
+
+def grad_sample_index(size, seed=0, n=2048):
+    """Seeded flat indices at which large gradients are sampled in tests/golden/grad_*.npz."""
+    rs = np.random.RandomState(5000 + seed + size % 9973)
+    return np.sort(rs.randint(0, size, size=min(n, size)))
