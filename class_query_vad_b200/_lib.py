@@ -46,6 +46,9 @@ SYMBOLS = {
     "cqvad_decoder_train_forward": (c_int, [POINTER(DecoderDesc), POINTER(c_void_p)] + [c_void_p] * 8 + [c_void_p, c_size_t, c_void_p]),
     "cqvad_decoder_backward": (c_int, [POINTER(DecoderDesc), POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p,
                                        POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cqvad_wgrad_workspace_bytes": (c_size_t, []),
+    "cqvad_linear_wgrad": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_int, c_void_p,
+                                   c_size_t, c_void_p]),
     "cqvad_last_launch_count": (c_long, []),
     "cqvad_profile_enable": (None, [c_int]),
     "cqvad_profile_num_classes": (c_int, []),

@@ -24,6 +24,10 @@ int wgrad_simt(const T* dY, long lddy, const T* X, long ldx, float* dW, long ldw
 int wgrad_tc(const bf16* dY, long lddy, const bf16* X, long ldx, float* dW, long ldw, float* db, long M, int Nout, int Kin,
              const ConvGeom* conv, cudaStream_t st);
 
+// scratch for the split-K partial tiles of wgrad_tc (owned by the training workspace)
+void set_wgrad_scratch(float* p, size_t bytes);
+size_t wgrad_scratch_bytes();
+
 // dH *= act'(.)   ReLU: ref = post-activation H (mask H > 0);  GELU: ref = pre-activation (exact erf derivative)
 template <typename T> int act_bwd(T* dH, const T* ref, int act, long n, cudaStream_t st);
 template <typename T> int gelu_fwd(const T* pre, T* out, long n, cudaStream_t st);

@@ -12,7 +12,10 @@ const char* kNames[P_COUNT] = {"conv3x3_ln (tcgen05 implicit GEMM)", "convblock_
                                "class_ffn (tcgen05 fused MLP + LN)", "kv/k/v projections (tcgen05 GEMM)",
                                "class cross-attention", "class self-attention", "class out_proj GEMMs",
                                "loc query-specific-key attention", "level mix + LN", "actor add + conv_norm",
-                               "output LN / heads", "small-row ops (prologue, loc SA, FFNs, box head)", "input conversion"};
+                               "output LN / heads", "small-row ops (prologue, loc SA, FFNs, box head)", "input conversion",
+                               "train fwd: GEMM / conv", "train fwd: LN, attention, elementwise", "train bwd: dgrad GEMM / conv",
+                               "train bwd: wgrad", "train bwd: activation / residual", "train bwd: LayerNorm", "train bwd: attention",
+                               "train bwd: misc"};
 }  // namespace
 long launch_count_now();
 bool prof_enabled() { return g_on; }

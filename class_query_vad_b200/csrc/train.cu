@@ -130,24 +130,31 @@ struct Trainer {
     if (fwd()) {
       Epilogue e;
       e.bias = Wf(widx + 1); e.act = act; e.res = res ? res->p : nullptr; e.ldr = Nout; e.zero_period = zp; e.zero_valid = zv;
-      int r = gemm<T>(X->p, Kd, Wm(widx), Y->p, Nout, X->rows, Nout, Kd, e, nullptr, st);
+      int r;
+      { ProfScope ps(P_T_FWD_GEMM, st); r = gemm<T>(X->p, Kd, Wm(widx), Y->p, Nout, X->rows, Nout, Kd, e, nullptr, st); }
       if (r == 0) r = dbg("lin", widx);
       if (r != 0 && rc && *rc == 0) *rc = r;
     }
     if (rec()) {
       tape.push_back([=]() -> int {
         if (!Y->gi) return 0;
-        if (act == CQVAD_ACT_RELU) CQ_TRY(act_bwd<T>(Y->g, Y->p, CQVAD_ACT_RELU, Y->n(), st));
-        if (res && res->hg) CQ_TRY(axpby<T>(res->g, Y->g, beta(res), Y->n(), st));
+        {
+          ProfScope ps(P_T_ACT_BWD, st);
+          if (act == CQVAD_ACT_RELU) CQ_TRY(act_bwd<T>(Y->g, Y->p, CQVAD_ACT_RELU, Y->n(), st));
+          if (res && res->hg) CQ_TRY(axpby<T>(res->g, Y->g, beta(res), Y->n(), st));
+        }
         if (X->hg) {
+          ProfScope ps(P_T_DGRAD, st);
           CQ_TRY(build_wt(widx, Nout, Kd, false));
           Epilogue e;
           const float b = beta(X);
           if (b != 0.f) { e.res = X->g; e.ldr = Kd; }
           CQ_TRY(gemm<T>(Y->g, Nout, Wt, X->g, Kd, X->rows, Kd, Nout, e, nullptr, st));
         }
-        if (G(widx) || G(widx + 1))
+        if (G(widx) || G(widx + 1)) {
+          ProfScope ps(P_T_WGRAD, st);
           CQ_TRY(wgrad<T>(Y->g, Nout, X->p, Kd, G(widx), Kd, G(widx + 1), X->rows, Nout, Kd, nullptr, st));
+        }
         return 0;
       });
     }
@@ -157,7 +164,8 @@ struct Trainer {
   Ten<T>* ln(Ten<T>* X, Ten<T>* res, int lnidx, float eps, int* rc) {
     Ten<T>* Y = mk(X->rows, kC);
     if (fwd()) {
-      int r = layernorm_rows<T>(X->p, res ? res->p : nullptr, Wf(lnidx), Wf(lnidx + 1), eps, Y->p, false, X->rows, st);
+      int r;
+      { ProfScope ps(P_T_FWD_OTHER, st); r = layernorm_rows<T>(X->p, res ? res->p : nullptr, Wf(lnidx), Wf(lnidx + 1), eps, Y->p, false, X->rows, st); }
       if (r == 0) r = dbg("ln", lnidx);
       if (r != 0 && *rc == 0) *rc = r;
     }
@@ -167,6 +175,7 @@ struct Trainer {
         const float bx = X->hg ? beta(X) : 0.f;
         const bool rg = res && res->hg;
         const float br = rg ? beta(res) : 0.f;
+        ProfScope ps(P_T_LN_BWD, st);
         if (X->hg)
           return ln_bwd<T>(X->p, res ? res->p : nullptr, Wf(lnidx), eps, Y->g, false, 0, 0, 0, X->g, bx, rg ? res->g : nullptr,
                            br, G(lnidx), G(lnidx + 1), X->rows, st);
@@ -183,11 +192,12 @@ struct Trainer {
     A->rows = Hpre->rows; A->cols = Hpre->cols;
     A->p = take(A->n());
     A->g = Hpre->g; A->hg = Hpre->hg;
-    if (fwd()) { int r = gelu_fwd<T>(Hpre->p, A->p, A->n(), st); if (r != 0) *rc = r; }
+    if (fwd()) { ProfScope ps(P_T_FWD_OTHER, st); int r = gelu_fwd<T>(Hpre->p, A->p, A->n(), st); if (r != 0) *rc = r; }
     if (rec()) {
       tape.push_back([=]() -> int {
         if (!A->gi) return 0;
         Hpre->gi = true;
+        ProfScope ps(P_T_ACT_BWD, st);
         return act_bwd<T>(A->g, Hpre->p, CQVAD_ACT_GELU, A->n(), st);
       });
     }
@@ -201,7 +211,8 @@ struct Trainer {
     if (fwd()) {
       Epilogue e;
       e.bias = Wf(widx + 1);
-      int r = gemm<T>(X->p, kC, Wm(widx), Z->p, kC, X->rows, kC, 9 * kC, e, &cg, st);
+      int r;
+      { ProfScope ps(P_T_FWD_GEMM, st); r = gemm<T>(X->p, kC, Wm(widx), Z->p, kC, X->rows, kC, 9 * kC, e, &cg, st); }
       if (r == 0) r = dbg("conv", widx);
       if (r != 0 && *rc == 0) *rc = r;
     }
@@ -209,6 +220,7 @@ struct Trainer {
       tape.push_back([=]() -> int {
         if (!Z->gi) return 0;
         if (X->hg) {
+          ProfScope ps(P_T_DGRAD, st);
           CQ_TRY(build_wt(widx, 0, 0, true));
           Epilogue e;
           e.zero_period = Sp; e.zero_valid = S;
@@ -216,6 +228,7 @@ struct Trainer {
           if (b != 0.f) { e.res = X->g; e.ldr = kC; }
           CQ_TRY(gemm<T>(Z->g, kC, Wd, X->g, kC, X->rows, kC, 9 * kC, e, &cg, st));
         }
+        ProfScope ps(P_T_WGRAD, st);
         return wgrad<T>(Z->g, kC, X->p, kC, G(widx), 9 * kC, G(widx + 1), X->rows, kC, kC, &cg, st);
       });
     }
@@ -226,7 +239,8 @@ struct Trainer {
               StdStrides ss, int* rc) {
     Ten<T>* O = mk(orows, kC);
     if (fwd()) {
-      int r = mha_std<T>(q->p, q2 ? q2->p : nullptr, k->p, k2, v->p, nullptr, O->p, L, Skeys, Nb, kH, hd, vd, ss, st);
+      int r;
+      { ProfScope ps(P_T_FWD_OTHER, st); r = mha_std<T>(q->p, q2 ? q2->p : nullptr, k->p, k2, v->p, nullptr, O->p, L, Skeys, Nb, kH, hd, vd, ss, st); }
       if (r == 0) r = dbg("mha", L);
       if (r != 0 && *rc == 0) *rc = r;
     }
@@ -237,6 +251,7 @@ struct Trainer {
         // the same block, so later writers simply accumulate
         const float bv = beta(v), bk = beta(k), bq = beta(q);
         const float bq2 = q2 ? beta(q2) : 0.f;
+        ProfScope ps(P_T_ATTN_BWD, st);
         return mha_std_bwd<T>(q->p, q2 ? q2->p : nullptr, k->p, k2, v->p, nullptr, O->g, q->g, bq, q2 ? q2->g : nullptr, bq2, k->g,
                               bk, v->g, bv, L, Skeys, Nb, kH, hd, vd, ss, st);
       });
@@ -258,6 +273,7 @@ int Trainer<T>::run() {
   Ten<T>* out = mk(N, kC);
   Ten<T>* out_in = out;
   float* dmem32 = io.g_memory;                       // fp32 gradient of memory accumulates directly in the caller's buffer
+  float* wg_scratch = takef((long)(wgrad_scratch_bytes() / sizeof(float)));
   float* dkp32 = takef((long)S * BT * kC);           // fp32 staging of d(ca_kpos_proj(pos)) (summed over the nq actors)
   std::vector<float*> rl(Lr + 1), drl(Lr + 1);
   for (int l = 0; l <= Lr; ++l) { rl[l] = takef(N * 4); drl[l] = takef(N * 4); }
@@ -348,14 +364,17 @@ int Trainer<T>::run() {
     if (first) qc = lin(qpos, loc(l, CA_QP), kC, 0, qc, 0, 0, &rc);
     Ten<T>* qs = lin(qse, loc(l, CA_QS), kC, 0, nullptr, 0, 0, &rc);
     Ten<T>* cao = mk(N, kC);
-    if (fwd())
+    if (fwd()) {
+      ProfScope ps(P_T_FWD_OTHER, st);
       CQ_TRY(dec_qsk_attn<T>(qc->p, qs->p, kv->p, kv->p + kC, 2 * kC, kp->p, io.mask, cao->p, N, S, Sq, BT, first, st));
+    }
     if (rec()) {
       tape.push_back([=]() -> int {
         if (!cao->gi) return 0;
         if (Sq != S) CQ_CUDA(cudaMemsetAsync(kv->g, 0, (size_t)kv->n() * sizeof(T), st));
         CQ_CUDA(cudaMemsetAsync(dkp32, 0, (size_t)S * BT * kC * sizeof(float), st));
         const float bqc = beta(qc), bqs = beta(qs);
+        ProfScope ps(P_T_ATTN_BWD, st);
         CQ_TRY(dec_qsk_bwd<T>(qc->p, qs->p, kv->p, kv->p + kC, 2 * kC, kp->p, io.mask, cao->g, qc->g, bqc, qs->g, bqs, kv->g,
                               kv->g + kC, dkp32, N, S, Sq, BT, first, st));
         kv->gi = true;
@@ -433,6 +452,7 @@ int Trainer<T>::run() {
       // padding of vx): zero them right before the attention backward writes the valid rows
       Ten<T>* O = mk(NK, kC);
       if (fwd()) {
+        ProfScope ps(P_T_FWD_OTHER, st);
         int r = mha_std<T>(Qin->p, cqp->p, kx->p, pos0->p, vx->p, nullptr, O->p, K, S, (int)N, kH, 64, 32, s3, st);
         if (r != 0) rc = r;
       }
@@ -443,6 +463,7 @@ int Trainer<T>::run() {
           if (Sq != S) CQ_CUDA(cudaMemsetAsync(vx->g, 0, (size_t)vx->n() * sizeof(T), st));
           kx->gi = true; vx->gi = true;
           const float bq = beta(Qin), bq2 = beta(cqp);
+          ProfScope ps(P_T_ATTN_BWD, st);
           // kx/vx: beta 0 on valid rows is equivalent to accumulate-after-memset; use overwrite
           return mha_std_bwd<T>(Qin->p, cqp->p, kx->p, pos0->p, vx->p, nullptr, O->g, Qin->g, bq, cqp->g, bq2, kx->g, 0.f, vx->g,
                                 0.f, K, S, (int)N, kH, 64, 32, s3, st);
@@ -495,6 +516,7 @@ int Trainer<T>::run() {
   if (rec()) {
     // ---- backward: zero what is accumulated, then run the tape in reverse ----
     CQ_CUDA(cudaMemsetAsync(drl[0], 0, (size_t)N * 4 * sizeof(float), st));
+    set_wgrad_scratch(wg_scratch, wgrad_scratch_bytes());
     int ti = (int)tape.size();
     for (auto it = tape.rbegin(); it != tape.rend(); ++it) { CQ_TRY((*it)()); CQ_TRY(dbg("tape", --ti)); }
   }
@@ -570,4 +592,25 @@ extern "C" int cqvad_decoder_backward(const cqvad_decoder_desc* d, const void* c
   reset_launch_count();
   if (d->dtype == CQVAD_F32) return run_train<float>(d, weights, io, workspace, ws_bytes, as_stream(stream), REPLAY, nullptr);
   return run_train<bf16>(d, weights, io, workspace, ws_bytes, as_stream(stream), REPLAY, nullptr);
+}
+
+// Weight gradient of a Linear / 3x3 conv as a stand-alone op (used by the op-level tests and by nn.Module backward hooks).
+extern "C" size_t cqvad_wgrad_workspace_bytes(void) { return wgrad_scratch_bytes() + 1024; }
+extern "C" int cqvad_linear_wgrad(int dtype, const void* dY, const void* X, float* dW, float* db, long M, int N, int K,
+                                  int conv_h, int conv_w, void* workspace, size_t ws_bytes, void* stream) {
+  CQ_CHECK_ARG(dY && X && (dW || db) && M >= 0 && N >= 1 && K >= 1, "linear_wgrad: bad argument");
+  ConvGeom cg; cg.h = conv_h; cg.w = conv_w;
+  const ConvGeom* conv = conv_w > 0 ? &cg : nullptr;
+  const long ldw = conv ? 9L * K : K;
+  if (dtype == CQVAD_F32)
+    return wgrad<float>((const float*)dY, N, (const float*)X, K, dW, ldw, db, M, N, K, conv, as_stream(stream));
+  if (dtype != CQVAD_BF16) return set_error(CQVAD_E_INVALID_ARG, "linear_wgrad: unknown dtype %d", dtype);
+  if (workspace) {
+    const size_t skew = (1024 - (((uintptr_t)workspace) & 1023)) & 1023;
+    if (ws_bytes >= skew + wgrad_scratch_bytes()) set_wgrad_scratch((float*)((char*)workspace + skew), wgrad_scratch_bytes());
+    else set_wgrad_scratch(nullptr, 0);
+  } else {
+    set_wgrad_scratch(nullptr, 0);
+  }
+  return wgrad<bf16>((const bf16*)dY, N, (const bf16*)X, K, dW, ldw, db, M, N, K, conv, as_stream(stream));
 }

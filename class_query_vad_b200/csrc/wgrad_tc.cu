@@ -1,7 +1,312 @@
-// tcgen05 weight-gradient GEMM (placeholder until the MN-major kernel lands): reports "shape not supported" so that
-// wgrad<bf16> uses the CUDA-core kernel.
+// tcgen05 weight-gradient GEMM for sm_100a:  dW[n,k] += sum_m dY[m,n] * X[m,k]   (bf16 operands, fp32 accumulation in TMEM)
+//
+// The reduction runs over the ROW index of two row-major activations, i.e. both UMMA operands are "MN-major" (the
+// non-reduced index is the contiguous one).  No transposed copy is made: TMA boxes of [64 rows x 64 channels] land in
+// shared memory with the 128-byte swizzle exactly in the canonical MN-major SWIZZLE_128B layout
+// ((8 x 16 B, n atoms) x (8 rows, k groups)), described to the tensor core by an MN-major shared-memory descriptor
+// (LBO = byte distance between 64-channel atoms = one box, SBO = 8 rows x 128 B) and a_major = b_major = 1 in the
+// instruction descriptor.  One UMMA is 128(n) x 256(k) x 16(rows); a CTA owns a 256x256 tile of dW (two accumulators =
+// all 512 TMEM columns) over a contiguous range of rows, warp-specialised (TMA producer / MMA issuer / 4 epilogue warps)
+// with a 3-stage 64 KB ring.
+//
+// 3x3 conv (ConvBlock, models/detr/dab_transformer.py:81,90): one job per (filter tap, row range); the X operand is the
+// same shifted 3-D TMA box (64 ch x w x rt image rows) the forward implicit GEMM uses, so the horizontal halo is the TMA
+// out-of-bounds zero fill and the vertical halo the zero separator rows; stage rows beyond w*rt stay zero (zeroed once).
+//
+// Split-K partial tiles are written with plain coalesced stores to a scratch buffer and summed into dW by a second
+// kernel (fp32 RED throughput, ~1.3 cycles/lane/SM, would dominate: 64 K reductions per CTA).
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "bwd.cuh"
+#include <mutex>
+
 namespace cqvad {
-int wgrad_tc(const bf16*, long, const bf16*, long, float*, long, float*, long, int, int, const ConvGeom*, cudaStream_t) { return 1; }
+
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                   const cuuint32_t* box);
+int tc_num_sms();
+
+using namespace tc;
+
+namespace {
+
+constexpr int WROWS = 64, WSTAGES = 3;
+constexpr int BOX_BYTES = WROWS * 128;                 // one [64 rows x 64 ch] box
+constexpr int OPER_BYTES = 4 * BOX_BYTES;              // 256 channels of one operand per stage (32 KB)
+constexpr int STAGE_BYTES = 2 * OPER_BYTES;            // dY tile + X tile
+constexpr int WG_SMEM = WSTAGES * STAGE_BYTES + 1024 + 256;
+constexpr int WG_THREADS = 192;
+constexpr int TILE = 256;
+
+struct WgParams {
+  float* part;            // [jobs][256][256] fp32 partial tiles
+  long M; int Nout, Kin;
+  int n_tiles, k_tiles;
+  long rows_per_split;    // non-conv: rows (multiple of 64); conv: image rows of the padded layout (multiple of rt)
+  int conv, cw, rt; long ny;
+};
+
+// MN-major, SWIZZLE_128B: start>>4 | LBO>>4 (one box) | SBO>>4 (8 rows x 128 B) | version 1 | layout 2
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(BOX_BYTES >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + WSTAGES * STAGE_BYTES;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * WSTAGES, tfull_bar = bars + 16 * WSTAGES, tmem_slot = tfull_bar + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- job decode ----
+  const int job = blockIdx.x;
+  int nt = 0, kt = 0, tap = 0; long split;
+  if (p.conv) { tap = job % 9; split = job / 9; }
+  else { const int t = job % (p.n_tiles * p.k_tiles); split = job / (p.n_tiles * p.k_tiles); nt = t / p.k_tiles; kt = t % p.k_tiles; }
+  const long total = p.conv ? p.ny : p.M;
+  const long r0 = split * p.rows_per_split;
+  const long r1 = r0 + p.rows_per_split < total ? r0 + p.rows_per_split : total;
+  const int step = p.conv ? p.rt : WROWS;
+  const int iters = (int)((r1 - r0 + step - 1) / step);
+  const int valid_rows = p.conv ? p.cw * p.rt : WROWS;
+  const int ksteps = (valid_rows + 15) / 16;
+  const int n_slabs = (p.Nout - nt * TILE) > 128 ? 2 : 1;
+
+  if (p.conv && valid_rows < WROWS) {   // rows the TMA boxes never write must read as zeros
+    uint4* z = reinterpret_cast<uint4*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+    for (int i = threadIdx.x; i < WSTAGES * STAGE_BYTES / 16; i += WG_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < WSTAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t box_tx = (uint32_t)(p.conv ? p.cw * p.rt * 128 : BOX_BYTES);
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+        const uint32_t fb = full_bar + 8 * stage;
+        mbar_arrive_expect_tx(fb, 8 * box_tx);
+        const uint32_t sY = smem_base + stage * STAGE_BYTES, sX = sY + OPER_BYTES;
+        const long r = r0 + (long)it * step;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (p.conv) {
+            tma_load_3d(sY + j * BOX_BYTES, &tmY, fb, j * 64, 0, (int)r);
+            tma_load_3d(sX + j * BOX_BYTES, &tmX, fb, j * 64, tap % 3 - 1, (int)r + tap / 3 - 1);
+          } else {
+            tma_load_2d(sY + j * BOX_BYTES, &tmY, fb, nt * TILE + j * 64, (int)r);
+            tma_load_2d(sX + j * BOX_BYTES, &tmX, fb, kt * TILE + j * 64, (int)r);
+          }
+        }
+        if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 256) | (1u << 15) | (1u << 16);   // A and B MN-major
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(full_bar + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t sY = smem_base + stage * STAGE_BYTES, sX = sY + OPER_BYTES;
+        for (int j = 0; j < ksteps; ++j) {
+          const uint64_t b_desc = make_desc_mn_sw128(sX + j * 2048);
+          for (int s = 0; s < n_slabs; ++s) {
+            const uint64_t a_desc = make_desc_mn_sw128(sY + s * 2 * BOX_BYTES + j * 2048);
+            umma_bf16(tmem_base + (uint32_t)(s * 256), a_desc, b_desc, idesc, (it | j) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar + 8 * stage);
+        if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quarter q = warp % 4 =====
+    const int q = warp & 3;
+    float* out = p.part + (size_t)job * TILE * TILE;
+    if (iters > 0) {
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+    }
+    for (int s = 0; s < 2; ++s) {
+      float* orow = out + (size_t)(s * 128 + q * 32 + lane) * TILE;
+      for (int c = 0; c < TILE; c += 32) {
+        uint32_t r[32];
+        if (iters > 0 && s < n_slabs) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 256 + c), r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<uint4*>(orow + c + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dW[(n0+r)*ldw + tap*256 + k0 + c] += sum_split part[job][r][c]
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW, long ldw,
+                                                           int Nout, int Kin, int n_tiles, int k_tiles, int splits, int conv) {
+  const int tiles = conv ? 9 : n_tiles * k_tiles;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;      // over tiles * 256 * 64 float4
+  if (idx >= (long)tiles * TILE * (TILE / 4)) return;
+  const int c4 = (int)(idx % (TILE / 4)), r = (int)((idx / (TILE / 4)) % TILE), t = (int)(idx / ((long)TILE * (TILE / 4)));
+  const int nt = conv ? 0 : t / k_tiles, kt = conv ? 0 : t % k_tiles, tap = conv ? t : 0;
+  const int n = nt * TILE + r, k = kt * TILE + c4 * 4;
+  if (n >= Nout || k >= Kin) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    const long job = (long)s * tiles + t;
+    const float4 v = *reinterpret_cast<const float4*>(part + ((size_t)job * TILE + r) * TILE + c4 * 4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  float* d = dW + (long)n * ldw + (long)tap * 256 + k;
+  if (k + 3 < Kin) {
+    float4 o = *reinterpret_cast<float4*>(d);
+    o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+    *reinterpret_cast<float4*>(d) = o;
+  } else {
+    const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+    for (int i = 0; i < 4 && k + i < Kin; ++i) d[i] += a[i];
+  }
+}
+
+// db[n] += sum_m dY[m,n]: warp per row slice of 256 columns, 8 per lane; block partials through shared memory
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dY, long lddy, float* __restrict__ db, long M,
+                                                     int Nout) {
+  __shared__ float red[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.y * 256 + lane * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < Nout) {
+    for (long row = (long)blockIdx.x * 8 + warp; row < M; row += (long)gridDim.x * 8) {
+      float v[8];
+      load8(dY + row * lddy + c0, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  if (c < Nout) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    atomicAdd(db + c, s);
+  }
+}
+
+std::once_flag g_wg_once;
+int g_wg_err = 0;
+float* g_scratch = nullptr;
+size_t g_scratch_bytes = 0;
+
+}  // namespace
+
+void set_wgrad_scratch(float* p, size_t bytes) { g_scratch = p; g_scratch_bytes = bytes; }
+size_t wgrad_scratch_bytes() { return (size_t)160 * TILE * TILE * sizeof(float); }
+
+int wgrad_tc(const bf16* dY, long lddy, const bf16* X, long ldx, float* dW, long ldw, float* db, long M, int Nout, int Kin,
+             const ConvGeom* conv, cudaStream_t st) {
+  if (M < 1024 || lddy % 8 != 0 || ldx % 8 != 0 || Nout % 8 != 0 || Kin % 8 != 0 || ldw % 4 != 0) return 1;
+  if ((((uintptr_t)dY) & 15) || (((uintptr_t)X) & 15) || (dW && (((uintptr_t)dW) & 15))) return 1;
+  if (g_scratch == nullptr) return 1;
+  const int sms = tc_num_sms();
+  if (sms <= 0) return 1;
+  std::call_once(g_wg_once, [] {
+    if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM) != cudaSuccess) g_wg_err = 1;
+  });
+  if (g_wg_err) return set_error(CQVAD_E_CUDA, "wgrad_tc: cannot reserve %d bytes of shared memory", WG_SMEM);
+
+  WgParams p{};
+  p.part = g_scratch; p.M = M; p.Nout = Nout; p.Kin = Kin;
+  CUtensorMap tmY, tmX;
+  int tiles, splits;
+  if (conv) {
+    const int w = conv->w;
+    if (w > WROWS || lddy != kC || ldx != kC || Nout != kC || Kin != kC || M % w != 0) return 1;
+    const int rt = WROWS / w;
+    const long ny = M / w;
+    p.conv = 1; p.cw = w; p.rt = rt; p.ny = ny; p.n_tiles = p.k_tiles = 1;
+    tiles = 9;
+    splits = sms / 9 < 1 ? 1 : sms / 9;
+    long yps = cdiv(ny, splits);
+    yps = cdiv(yps, rt) * rt;
+    splits = (int)cdiv(ny, yps);
+    p.rows_per_split = yps;
+    const cuuint64_t dims[3] = {(cuuint64_t)kC, (cuuint64_t)w, (cuuint64_t)ny};
+    const cuuint64_t strides[2] = {(cuuint64_t)kC * 2, (cuuint64_t)w * kC * 2};
+    const cuuint32_t box[3] = {64, (cuuint32_t)w, (cuuint32_t)rt};
+    CQ_TRY(make_tmap_bf16(&tmY, dY, 3, dims, strides, box));
+    CQ_TRY(make_tmap_bf16(&tmX, X, 3, dims, strides, box));
+  } else {
+    p.conv = 0;
+    p.n_tiles = (Nout + TILE - 1) / TILE; p.k_tiles = (Kin + TILE - 1) / TILE;
+    tiles = p.n_tiles * p.k_tiles;
+    if (tiles > sms) return 1;
+    splits = sms / tiles;
+    long rps = cdiv(M, splits);
+    rps = cdiv(rps, WROWS) * WROWS;
+    splits = (int)cdiv(M, rps);
+    p.rows_per_split = rps;
+    {
+      const cuuint64_t dims[2] = {(cuuint64_t)Nout, (cuuint64_t)M};
+      const cuuint64_t strides[1] = {(cuuint64_t)lddy * 2};
+      const cuuint32_t box[2] = {64, WROWS};
+      CQ_TRY(make_tmap_bf16(&tmY, dY, 2, dims, strides, box));
+    }
+    {
+      const cuuint64_t dims[2] = {(cuuint64_t)Kin, (cuuint64_t)M};
+      const cuuint64_t strides[1] = {(cuuint64_t)ldx * 2};
+      const cuuint32_t box[2] = {64, WROWS};
+      CQ_TRY(make_tmap_bf16(&tmX, X, 2, dims, strides, box));
+    }
+  }
+  const int jobs = tiles * splits;
+  if ((size_t)jobs * TILE * TILE * sizeof(float) > g_scratch_bytes) return 1;
+  if (dW) {
+    wgrad_tc_kernel<<<jobs, WG_THREADS, WG_SMEM, st>>>(tmY, tmX, p);
+    CQ_LAUNCH_CHECK();
+    const long n4 = (long)tiles * TILE * (TILE / 4);
+    wgrad_reduce_kernel<<<(unsigned)cdiv(n4, 256), 256, 0, st>>>(g_scratch, dW, ldw, Nout, Kin, p.n_tiles, p.k_tiles, splits,
+                                                               p.conv);
+    CQ_LAUNCH_CHECK();
+  }
+  if (db) {
+    long gx = cdiv(M, 8 * 16);
+    if (gx > 4 * sms) gx = 4 * sms;
+    dim3 grid((unsigned)gx, (unsigned)cdiv(Nout, 256));
+    colsum_kernel<<<grid, 256, 0, st>>>(dY, lddy, db, M, Nout);
+    CQ_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 }  // namespace cqvad

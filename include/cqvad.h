@@ -168,6 +168,15 @@ int cqvad_decoder_backward(const cqvad_decoder_desc* d, const void* const* weigh
                            float* const* grad_weights, float* grad_memory, float* grad_tgt,
                            float* grad_refpoints_unsigmoid, void* workspace, size_t ws_bytes, void* stream);
 
+/* Weight gradient of nn.Linear / the 3x3 conv of ConvBlock (what autograd's AddmmBackward / ConvolutionBackward produce
+ * for dab_transformer.py:47,90): dW[n,k] += sum_m dY[m,n] X[m,k], db[n] += sum_m dY[m,n]   (fp32, ACCUMULATED; either
+ * may be NULL).  conv_w > 0: X and dY are y-padded NHWC maps [n_img,(conv_h+1),conv_w,256] flattened to M rows (separator
+ * rows zero) and dW is [N][ky*3+kx][K].  BF16 runs on tcgen05 (MN-major operands straight from the row-major activations)
+ * when M >= 1024 and `workspace` (cqvad_wgrad_workspace_bytes) is given, on CUDA cores otherwise. */
+size_t cqvad_wgrad_workspace_bytes(void);
+int cqvad_linear_wgrad(int dtype, const void* dY, const void* X, float* dW, float* db, long M, int N, int K,
+                       int conv_h, int conv_w, void* workspace, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py).  cqvad_profile_enable(1) makes cqvad_decoder_forward bracket each kernel class with
  * CUDA events on the launch stream; cqvad_profile_read() synchronises and returns the accumulated milliseconds, the

@@ -204,3 +204,61 @@ def test_module_level_layers_fp32():
     assert rel_err(qmem.cpu().numpy(), taps["l0.q_memory"]) < TOL_FP32
     cls_out, nxt = dec.cls_layers[0](actor, qmem, t(inp["pos"])[0], qse, dec.class_queries.weight, inp["orig_res"], cfg["nq"], True)
     assert rel_err(cls_out.cpu().numpy(), g["l0.cls_output"]) < TOL_FP32
+
+
+# ---- weight-gradient GEMM (tcgen05, MN-major operands) -----------------------------------------------------------------
+def _wgrad(dY, X, N, K, conv=None, use_ws=True):
+    from class_query_vad_b200 import _lib
+    lib = _lib.lib()
+    dev = dY.device
+    dW = torch.zeros((N, 9 * K) if conv else (N, K), dtype=torch.float32, device=dev)
+    db = torch.zeros(N, dtype=torch.float32, device=dev)
+    ws = torch.empty(lib.cqvad_wgrad_workspace_bytes(), dtype=torch.uint8, device=dev) if use_ws else None
+    h, w = conv if conv else (0, 0)
+    rc = lib.cqvad_linear_wgrad(_lib.dtype_id(dY.dtype), _lib.ptr(dY), _lib.ptr(X), _lib.ptr(dW), _lib.ptr(db), dY.shape[0], N, K, h, w,
+                                _lib.ptr(ws), 0 if ws is None else ws.numel(), _lib.stream_ptr())
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    return dW, db
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 256, 256), (5000, 1024, 256), (3011 * 8, 256, 1024), (2048, 128, 256), (2304, 512, 256),
+                                   (7777 * 8, 256, 2048)])
+def test_wgrad_tc_matches_fp32(M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    dY = torch.randn((M, N), device="cuda", generator=g).bfloat16()
+    X = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+    dW, db = _wgrad(dY, X, N, K)
+    ref = dY.double().t() @ X.double()
+    assert float((dW.double() - ref).abs().max() / ref.abs().max()) < 1e-4     # bf16-exact inputs, fp32 accumulation
+    assert float((db.double() - dY.double().sum(0)).abs().max() / dY.double().sum(0).abs().max()) < 1e-4
+    dW2, db2 = _wgrad(dY, X, N, K, use_ws=False)                                  # CUDA-core kernel, same contract
+    assert float((dW2.double() - ref).abs().max() / ref.abs().max()) < 1e-4
+    # accumulate semantics: a second call adds
+    from class_query_vad_b200 import _lib
+    lib = _lib.lib()
+    ws = torch.empty(lib.cqvad_wgrad_workspace_bytes(), dtype=torch.uint8, device="cuda")
+    rc = lib.cqvad_linear_wgrad(_lib.BF16, _lib.ptr(dY), _lib.ptr(X), _lib.ptr(dW), _lib.ptr(db), M, N, K, 0, 0, _lib.ptr(ws), ws.numel(),
+                                _lib.stream_ptr())
+    _lib.check(rc)
+    assert float((dW.double() - 2 * ref).abs().max() / ref.abs().max()) < 2e-4
+
+
+@pytest.mark.parametrize("n_img,h,w,dt", [(40, 14, 14, torch.bfloat16), (9, 16, 16, torch.bfloat16), (70, 3, 5, torch.bfloat16),
+                                          (6, 6, 7, torch.float32), (150, 7, 9, torch.bfloat16)])
+def test_conv_wgrad_matches_torch(n_img, h, w, dt):
+    """dW of the 3x3 conv on the y-padded NHWC layout against torch's conv2d weight gradient (fp64)."""
+    import torch.nn.functional as F
+    g = torch.Generator(device="cuda").manual_seed(n_img)
+    C = 256
+    x = torch.randn((n_img, h, w, C), device="cuda", generator=g).to(dt)
+    dy = torch.randn((n_img, h, w, C), device="cuda", generator=g).to(dt)
+    pad = lambda t: torch.cat([t, torch.zeros((n_img, 1, w, C), device="cuda", dtype=dt)], 1).reshape(-1, C).contiguous()
+    dW, db = _wgrad(pad(dy), pad(x), C, C, conv=(h, w))
+    xr = x.double().permute(0, 3, 1, 2).requires_grad_(False)
+    wt = torch.zeros((C, C, 3, 3), dtype=torch.float64, device="cuda", requires_grad=True)
+    out = F.conv2d(xr, wt, padding=1)
+    out.backward(dy.double().permute(0, 3, 1, 2))
+    ref = wt.grad.permute(0, 2, 3, 1).reshape(C, 9 * C)            # [O][ky*3+kx][I]
+    assert float((dW.double() - ref).abs().max() / ref.abs().max()) < 1e-4
+    assert float((db.double() - dy.double().sum((0, 1, 2))).abs().max()) / float(dy.double().sum((0, 1, 2)).abs().max()) < 1e-4
