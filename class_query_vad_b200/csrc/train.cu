@@ -23,7 +23,42 @@
 
 namespace cqvad {
 
+int cls_xattn_tc(const bf16* Qin, const bf16* cqp, const bf16* kx, const bf16* pos0, const bf16* vt, long ldvt,
+                 const float* bv, bf16* out, long N, int K, int S, int Sq, int Sp_rows, int BT, cudaStream_t st);
+int cls_sattn_tc(const bf16* x, const bf16* xt, long ldxt, bf16* out, long N, int K, int K8, cudaStream_t st);
+int cls_xattn_bwd_tc(const bf16* Qin, const bf16* cqp, const bf16* kx, const bf16* pos0, const bf16* vx, const bf16* dO, bf16* dQin,
+                     float beta_q, bf16* dcqp, float beta_q2, bf16* dkx, bf16* dvx, long N, int K, int S, int Sq, int Sp_rows, int BT,
+                     cudaStream_t st);
+int cls_sattn_bwd_tc(const bf16* x, const bf16* dO, bf16* dx, float beta, long N, int K, cudaStream_t st);
+int transpose_tokens(const bf16* x, bf16* xt, long ldxt, long N, int K, int K8, cudaStream_t st);
+
 namespace {
+
+// tensor-core attention paths exist for bf16 only; the float instantiation never calls them
+inline int tc_xattn_fwd(const bf16* Qin, const bf16* cqp, const bf16* kx, const bf16* pos0, const bf16* W, const bf16* qm, bf16* vt,
+                        long ldvt, const float* bv, bf16* out, long N, long NSq, int K, int S, int Sq, int Sp, int BT, cudaStream_t st) {
+  Epilogue e;   // V^T[256, N*Sq] = W_v . q_memory^T (bias added after the softmax-weighted sum: the weights sum to one)
+  CQ_TRY(gemm<bf16>(W, kC, qm, vt, ldvt, kC, (int)NSq, kC, e, nullptr, st));
+  return cls_xattn_tc(Qin, cqp, kx, pos0, vt, ldvt, bv, out, N, K, S, Sq, Sp, BT, st);
+}
+inline int tc_xattn_fwd(const float*, const float*, const float*, const float*, const float*, const float*, float*, long,
+                        const float*, float*, long, long, int, int, int, int, int, cudaStream_t) { return 1; }
+inline int tc_xattn_bwd(const bf16* Qin, const bf16* cqp, const bf16* kx, const bf16* pos0, const bf16* vx, const bf16* dO, bf16* dQin,
+                        float bq, bf16* dcqp, float bq2, bf16* dkx, bf16* dvx, long N, int K, int S, int Sq, int Sp, int BT,
+                        cudaStream_t st) {
+  return cls_xattn_bwd_tc(Qin, cqp, kx, pos0, vx, dO, dQin, bq, dcqp, bq2, dkx, dvx, N, K, S, Sq, Sp, BT, st);
+}
+inline int tc_xattn_bwd(const float*, const float*, const float*, const float*, const float*, const float*, float*, float, float*,
+                        float, float*, float*, long, int, int, int, int, int, cudaStream_t) { return 1; }
+inline int tc_sattn_fwd(const bf16* x, bf16* xt, long ldxt, bf16* out, long N, int K, int K8, cudaStream_t st) {
+  CQ_TRY(transpose_tokens(x, xt, ldxt, N, K, K8, st));
+  return cls_sattn_tc(x, xt, ldxt, out, N, K, K8, st);
+}
+inline int tc_sattn_fwd(const float*, float*, long, float*, long, int, int, cudaStream_t) { return 1; }
+inline int tc_sattn_bwd(const bf16* x, const bf16* dO, bf16* dx, float beta, long N, int K, cudaStream_t st) {
+  return cls_sattn_bwd_tc(x, dO, dx, beta, N, K, st);
+}
+inline int tc_sattn_bwd(const float*, const float*, float*, float, long, int, cudaStream_t) { return 1; }
 
 enum Mode { PLAN = 0, FWD = 1, REPLAY = 2 };
 
@@ -273,6 +308,12 @@ int Trainer<T>::run() {
   Ten<T>* out = mk(N, kC);
   Ten<T>* out_in = out;
   float* dmem32 = io.g_memory;                       // fp32 gradient of memory accumulates directly in the caller's buffer
+  const int K8 = (K + 7) & ~7;
+  const long ldvt = NSq + 64, ldxt = N * K8 + 64;
+  T* vt = take(kC * ldvt);          // V^T of the forward cross-attention kernel (transient, shared by the layers)
+  T* xt = take(kC * ldxt);          // transposed class tokens of the forward self-attention kernel
+  const bool use_tc = DT<T>::id == CQVAD_BF16 && !force_simt() && K <= 128 && ((S + 15) & ~15) <= 256;
+  if (fwd() && use_tc) CQ_CUDA(cudaMemsetAsync(xt, 0, (size_t)kC * ldxt * sizeof(T), st));
   float* wg_scratch = takef((long)(wgrad_scratch_bytes() / sizeof(float)));
   float* dkp32 = takef((long)S * BT * kC);           // fp32 staging of d(ca_kpos_proj(pos)) (summed over the nq actors)
   std::vector<float*> rl(Lr + 1), drl(Lr + 1);
@@ -432,7 +473,28 @@ int Trainer<T>::run() {
       }
     } else {
       s2.q_bs = s2.k_bs = s2.v_bs = s2.o_bs = (long)K * kC;
-      Ten<T>* saoc = mha(Qprev, nullptr, Qprev, nullptr, Qprev, NK, K, K, (int)N, 32, 32, s2, &rc);
+      Ten<T>* saoc;
+      if (use_tc) {
+        saoc = mk(NK, kC);
+        Ten<T>* Qp = Qprev;
+        if (fwd()) {
+          ProfScope ps(P_T_FWD_OTHER, st);
+          int r = tc_sattn_fwd(Qp->p, xt, ldxt, saoc->p, N, K, K8, st);
+          if (r == 1) r = set_error(CQVAD_E_UNSUPPORTED_SHAPE, "class self-attention: shape rejected by the tensor-core kernel");
+          if (r != 0) return r;
+        }
+        if (rec()) {
+          tape.push_back([=]() -> int {
+            if (!saoc->gi) return 0;
+            ProfScope ps(P_T_ATTN_BWD, st);
+            int r = tc_sattn_bwd(Qp->p, saoc->g, Qp->g, beta(Qp), N, K, st);
+            if (r == 1) r = set_error(CQVAD_E_UNSUPPORTED_SHAPE, "class self-attention backward: shape rejected");
+            return r;
+          });
+        }
+      } else {
+        saoc = mha(Qprev, nullptr, Qprev, nullptr, Qprev, NK, K, K, (int)N, 32, 32, s2, &rc);
+      }
       Qin = ln(lin(saoc, cls(l, C_SA_O), kC, 0, nullptr, 0, 0, &rc), Qprev, cls(l, C_NORM1), 1e-5f, &rc);
     }
     // class cross-attention :1067-1071
@@ -451,10 +513,14 @@ int Trainer<T>::run() {
       // gradient buffers of kx / vx must be zero on the rows the attention never touches (y-pad separator rows of kx, pitch
       // padding of vx): zero them right before the attention backward writes the valid rows
       Ten<T>* O = mk(NK, kC);
+      const int wv = cls(l, C_VPROJ);
       if (fwd()) {
         ProfScope ps(P_T_FWD_OTHER, st);
-        int r = mha_std<T>(Qin->p, cqp->p, kx->p, pos0->p, vx->p, nullptr, O->p, K, S, (int)N, kH, 64, 32, s3, st);
-        if (r != 0) rc = r;
+        int r = use_tc ? tc_xattn_fwd(Qin->p, cqp->p, kx->p, pos0->p, Wm(wv), qm->p, vt, ldvt, Wf(wv + 1), O->p, N, NSq, K, S, Sq, Sp,
+                                      BT, st)
+                       : mha_std<T>(Qin->p, cqp->p, kx->p, pos0->p, vx->p, nullptr, O->p, K, S, (int)N, kH, 64, 32, s3, st);
+        if (r == 1) r = set_error(CQVAD_E_UNSUPPORTED_SHAPE, "class cross-attention: shape rejected by the tensor-core kernel");
+        if (r != 0) return r;
       }
       if (rec()) {
         tape.push_back([=]() -> int {
@@ -465,6 +531,12 @@ int Trainer<T>::run() {
           const float bq = beta(Qin), bq2 = beta(cqp);
           ProfScope ps(P_T_ATTN_BWD, st);
           // kx/vx: beta 0 on valid rows is equivalent to accumulate-after-memset; use overwrite
+          if (use_tc) {
+            int r = tc_xattn_bwd(Qin->p, cqp->p, kx->p, pos0->p, vx->p, O->g, Qin->g, bq, cqp->g, bq2, kx->g, vx->g, N, K, S, Sq, Sp, BT,
+                                 st);
+            if (r == 1) r = set_error(CQVAD_E_UNSUPPORTED_SHAPE, "class cross-attention backward: shape rejected");
+            return r;
+          }
           return mha_std_bwd<T>(Qin->p, cqp->p, kx->p, pos0->p, vx->p, nullptr, O->g, Qin->g, bq, cqp->g, bq2, kx->g, 0.f, vx->g,
                                 0.f, K, S, (int)N, kH, 64, 32, s3, st);
         });

@@ -37,9 +37,9 @@ def run_train(cfg, B, W, inp, seed, dtype):
     return float(loss.item()), grads, eng
 
 
-def grad_errors(grads, g, seed, tgt_zero=True):
+def grad_errors(grads, g, seed, tgt_zero=True, want_l2=False):
     """{tensor name: rel error} for every gradient the fixture holds."""
-    errs = {}
+    errs, l2 = {}, {}
     P = {k: v.float().cpu().numpy() for k, v in grads["params"].items()}
     G = float(np.median([np.abs(g[k]).max() for k in g if k.startswith(("g.", "gs."))]))
 
@@ -51,6 +51,7 @@ def grad_errors(grads, g, seed, tgt_zero=True):
         if key_full in g:
             ref = g[key_full]
             errs[name] = float(np.abs(got.astype(np.float64) - ref).max() / max(np.abs(ref).max(), fl, 1e-12))
+            l2[name] = float(np.linalg.norm(got.astype(np.float64) - ref) / max(np.linalg.norm(ref), fl * np.sqrt(ref.size), 1e-12))
         else:
             idx = synth.grad_sample_index(got.size, seed)
             ref_s, (ref_norm, ref_sum) = g[key_s], g[key_n]
@@ -58,6 +59,8 @@ def grad_errors(grads, g, seed, tgt_zero=True):
             errs[name] = float(np.abs(got.reshape(-1)[idx] - ref_s).max() / scale)
             errs[name + "|norm"] = float(abs(np.sqrt((got.astype(np.float64) ** 2).sum()) - ref_norm) /
                                          max(ref_norm, fl * np.sqrt(got.size), 1e-12))
+            l2[name] = float(np.linalg.norm(got.reshape(-1)[idx].astype(np.float64) - ref_s) /
+                             max(np.linalg.norm(ref_s), fl * np.sqrt(ref_s.size), 1e-12))
 
     for nm in ("memory", "tgt", "refpoints_unsigmoid"):
         cmp("in." + nm, grads[nm].float().cpu().numpy(), "gin." + nm, "gin_s." + nm, "gin_n." + nm)
@@ -69,6 +72,8 @@ def grad_errors(grads, g, seed, tgt_zero=True):
             continue
         assert nm in P, f"no gradient returned for {nm}"
         cmp(nm, P[nm], "g." + nm, "gs." + nm, "gn." + nm)
+    if want_l2:
+        return errs, l2
     return errs
 
 

@@ -14,7 +14,8 @@ for name in names:
     seed = int(g["meta"][8])
     loss, grads, eng = run_train(cfg, B, W, inp, seed, dtype)
     print(name, "loss", loss, "ref", float(g["loss"]), "launches fwd", eng.last_launches, "bwd", eng.last_launches_bwd)
-    errs = grad_errors(grads, g, seed, tgt_zero=bool(int(g["meta"][10])))
+    errs, l2 = grad_errors(grads, g, seed, tgt_zero=bool(int(g["meta"][10])), want_l2=True)
+    print("   rel-L2: median", float(np.median(list(l2.values()))), "max", max(l2.items(), key=lambda kv: kv[1]), "p90", float(np.percentile(list(l2.values()), 90)))
     for k, v in sorted(errs.items(), key=lambda kv: -kv[1] if np.isfinite(kv[1]) else -1e30)[:int(os.environ.get("TOPN", "40"))]:
         print(f"   {v:10.3e}  {k}")
     print("   median", float(np.median(list(errs.values()))), "n", len(errs))

@@ -28,4 +28,17 @@ for it in range(4):
     torch.cuda.synchronize()
     print(f"iter {it}: fwd {e0.elapsed_time(e1):.2f} ms ({eng.last_launches} launches)  bwd {e1.elapsed_time(e2):.2f} ms ({eng.last_launches_bwd} launches)"
           f"  -> {B / (e0.elapsed_time(e2) * 1e-3):.1f} clips/s", flush=True)
+import ctypes
+from class_query_vad_b200 import _lib
+lib = _lib.lib()
+lib.cqvad_profile_enable(1)
+out = eng.forward_train(d["tgt"], d["memory"], d["mask"], d["pos"], d["refpoints_unsigmoid"], (cfg["h"], cfg["w"]))
+g = eng.backward(gh, gc, gr, named=False)
+torch.cuda.synchronize()
+for c in range(lib.cqvad_profile_num_classes()):
+    tot, sc, ln = ctypes.c_double(), ctypes.c_long(), ctypes.c_long()
+    lib.cqvad_profile_read(c, ctypes.byref(tot), ctypes.byref(sc), ctypes.byref(ln))
+    if sc.value:
+        print(f"   {tot.value:8.3f} ms  {sc.value:5d} scopes {ln.value:5d} launches  {lib.cqvad_profile_class_name(c).decode()}")
+lib.cqvad_profile_enable(0)
 print("workspace GB", eng._tws.numel() / 1e9)
