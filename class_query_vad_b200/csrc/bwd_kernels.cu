@@ -69,6 +69,27 @@ __device__ __forceinline__ void flush_gb(float (&ag)[8], float (&ab)[8], float* 
   }
 }
 
+// block-level reduction of NR x 256 per-lane partials (small-N linear weight gradients), one atomicAdd per element
+template <int NR>
+__device__ __forceinline__ void flush_rows(const float (&acc)[NR][8], float* __restrict__ dst, float* red /*[kWarps][NR*256]*/) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[(warp * NR + r) * 256 + lane * 8 + i] = acc[r][i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < NR * 256; c += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < kWarps; ++w) s += red[w * NR * 256 + c];
+    atomicAdd(dst + c, s);
+  }
+  __syncthreads();
+}
+inline unsigned small_grid(long rows) {
+  long b = cdiv(rows, kWarps * 4);
+  return (unsigned)(b < 1 ? 1 : (b > 64 ? 64 : b));
+}
+
 template <typename T>
 __device__ __forceinline__ void store_beta(T* p, const float (&v)[8], float beta) {
   if (beta != 0.f) {
@@ -181,27 +202,33 @@ __global__ void __launch_bounds__(kThreads) lvlw_bwd_kernel(const T* __restrict_
                                                             const float* __restrict__ p, const float* __restrict__ dp, T* dx,
                                                             float beta, float* __restrict__ dW, float* __restrict__ dB,
                                                             long rows) {
-  const long row = (long)blockIdx.x * kWarps + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float4 p4 = *reinterpret_cast<const float4*>(p + row * 4), d4 = *reinterpret_cast<const float4*>(dp + row * 4);
-  const float pv[4] = {p4.x, p4.y, p4.z, p4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
-  const float dot = pv[0] * dv[0] + pv[1] * dv[1] + pv[2] * dv[2] + pv[3] * dv[3];
-  float xv[8], o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  load8(x + row * kC + lane * 8, xv);
+  __shared__ float red[kWarps * 4 * 256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float aw[4][8], abias[4] = {0, 0, 0, 0};
 #pragma unroll
-  for (int l = 0; l < 4; ++l) {
-    const float dl = pv[l] * (dv[l] - dot);
-    float wv[8];
-    load8(w + l * kC + lane * 8, wv);
+  for (int l = 0; l < 4; ++l)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      o[j] = fmaf(dl, wv[j], o[j]);
-      atomicAdd(dW + l * kC + lane * 8 + j, dl * xv[j]);
+    for (int j = 0; j < 8; ++j) aw[l][j] = 0.f;
+  for (long row = (long)blockIdx.x * kWarps + warp; row < rows; row += (long)gridDim.x * kWarps) {
+    const float4 p4 = *reinterpret_cast<const float4*>(p + row * 4), d4 = *reinterpret_cast<const float4*>(dp + row * 4);
+    const float pv[4] = {p4.x, p4.y, p4.z, p4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+    const float dot = pv[0] * dv[0] + pv[1] * dv[1] + pv[2] * dv[2] + pv[3] * dv[3];
+    float xv[8], o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    load8(x + row * kC + lane * 8, xv);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float dl = pv[l] * (dv[l] - dot);
+      float wv[8];
+      load8(w + l * kC + lane * 8, wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { o[j] = fmaf(dl, wv[j], o[j]); aw[l][j] = fmaf(dl, xv[j], aw[l][j]); }
+      abias[l] += dl;
     }
-    if (lane == 0) atomicAdd(dB + l, dl);
+    store_beta(dx + row * kC + lane * 8, o, beta);
   }
-  store_beta(dx + row * kC + lane * 8, o, beta);
+  flush_rows<4>(aw, dW, red);
+  if (lane == 0)
+    for (int l = 0; l < 4; ++l) atomicAdd(dB + l, abias[l]);
 }
 
 // ---- conv_norm(actor[i] + qm[i,s]) backward: block per actor instance ---------------------------------------------
@@ -252,13 +279,17 @@ __global__ void __launch_bounds__(kThreads) qse_bwd_kernel(const float* __restri
                                                            T* dscale, float beta_s, T* dhidden, float beta_h,
                                                            float* __restrict__ dw1, float* __restrict__ db1,
                                                            float* __restrict__ dref, long rows) {
-  const long row = (long)blockIdx.x * kWarps + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  float hdn[8], wa[8], wb[8];
-  load8(hidden + row * kC + lane * 8, hdn);
+  __shared__ float red[kWarps * 2 * 256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float aw[2][8], ab0 = 0.f, ab1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { aw[0][j] = 0.f; aw[1][j] = 0.f; }
+  float wa[8], wb[8];
   load8(w1 + lane * 8, wa);
   load8(w1 + kC + lane * 8, wb);
+  for (long row = (long)blockIdx.x * kWarps + warp; row < rows; row += (long)gridDim.x * kWarps) {
+  float hdn[8];
+  load8(hidden + row * kC + lane * 8, hdn);
   float a0 = 0.f, a1 = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a0 = fmaf(hdn[j], wa[j], a0); a1 = fmaf(hdn[j], wb[j], a1); }
@@ -298,13 +329,12 @@ __global__ void __launch_bounds__(kThreads) qse_bwd_kernel(const float* __restri
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     dh[j] = dl0 * wa[j] + dl1 * wb[j];
-    atomicAdd(dw1 + lane * 8 + j, dl0 * hdn[j]);
-    atomicAdd(dw1 + kC + lane * 8 + j, dl1 * hdn[j]);
+    aw[0][j] = fmaf(dl0, hdn[j], aw[0][j]);
+    aw[1][j] = fmaf(dl1, hdn[j], aw[1][j]);
   }
   store_beta(dhidden + row * kC + lane * 8, dh, beta_h);
+  ab0 += dl0; ab1 += dl1;
   if (lane == 0) {
-    atomicAdd(db1, dl0);
-    atomicAdd(db1 + 1, dl1);
     if (dref) {
       dref[row * 4 + 0] += c_hi;                           // x
       dref[row * 4 + 1] += c_lo;                           // y
@@ -312,6 +342,9 @@ __global__ void __launch_bounds__(kThreads) qse_bwd_kernel(const float* __restri
       dref[row * 4 + 3] += -t_lo * a1 / (r.w * r.w);       // h
     }
   }
+  }
+  flush_rows<2>(aw, dw1, red);
+  if (lane == 0) { atomicAdd(db1, ab0); atomicAdd(db1 + 1, ab1); }
 }
 
 template <typename T>
@@ -362,34 +395,38 @@ __global__ void __launch_bounds__(kThreads) box_refine_bwd_kernel(const T* __res
                                                                   const float* __restrict__ dnew_perm, T* dhidden, float beta,
                                                                   float* __restrict__ dw2, float* __restrict__ db2,
                                                                   float* __restrict__ dref, long rows, int nq, int BT) {
-  const long row = (long)blockIdx.x * kWarps + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  float xv[8], dh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  load8(hidden + row * kC + lane * 8, xv);
-  const int n = (int)(row / BT), bb = (int)(row % BT);
-  const long prow = (long)bb * nq + n;
+  __shared__ float red[kWarps * 4 * 256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float aw[4][8], abias[4] = {0, 0, 0, 0};
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    float wv[8];
-    load8(w2 + c * kC + lane * 8, wv);
-    float a = 0.f;
+  for (int c = 0; c < 4; ++c)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a = fmaf(xv[j], wv[j], a);
-    const float rc = ref[row * 4 + c];
-    const float rn = sigmoidf_(warp_sum(a) + b2[c] + inv_sigmoid(rc));
-    const float dt = dnew_perm[prow * 4 + c] * rn * (1.f - rn);
+    for (int j = 0; j < 8; ++j) aw[c][j] = 0.f;
+  for (long row = (long)blockIdx.x * kWarps + warp; row < rows; row += (long)gridDim.x * kWarps) {
+    float xv[8], dh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    load8(hidden + row * kC + lane * 8, xv);
+    const int n = (int)(row / BT), bb = (int)(row % BT);
+    const long prow = (long)bb * nq + n;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      dh[j] = fmaf(dt, wv[j], dh[j]);
-      atomicAdd(dw2 + c * kC + lane * 8 + j, dt * xv[j]);
+    for (int c = 0; c < 4; ++c) {
+      float wv[8];
+      load8(w2 + c * kC + lane * 8, wv);
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a = fmaf(xv[j], wv[j], a);
+      const float rc = ref[row * 4 + c];
+      const float rn = sigmoidf_(warp_sum(a) + b2[c] + inv_sigmoid(rc));
+      const float dt = dnew_perm[prow * 4 + c] * rn * (1.f - rn);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { dh[j] = fmaf(dt, wv[j], dh[j]); aw[c][j] = fmaf(dt, xv[j], aw[c][j]); }
+      abias[c] += dt;
+      if (lane == 0 && dref) dref[row * 4 + c] += dt * inv_sigmoid_grad(rc);
     }
-    if (lane == 0) {
-      atomicAdd(db2 + c, dt);
-      if (dref) dref[row * 4 + c] += dt * inv_sigmoid_grad(rc);
-    }
+    store_beta(dhidden + row * kC + lane * 8, dh, beta);
   }
-  store_beta(dhidden + row * kC + lane * 8, dh, beta);
+  flush_rows<4>(aw, dw2, red);
+  if (lane == 0)
+    for (int c = 0; c < 4; ++c) atomicAdd(db2 + c, abias[c]);
 }
 
 __global__ void sigmoid4_bwd_kernel(const float* __restrict__ r, const float* __restrict__ dr, const float* __restrict__ dperm,
@@ -728,7 +765,7 @@ template <typename T>
 int lvlw_bwd(const T* x, const float* w, const float* p, const float* dp, T* dx, float beta, float* dW, float* dB, long rows,
              cudaStream_t st) {
   if (rows == 0) return 0;
-  lvlw_bwd_kernel<T><<<row_grid(rows), kThreads, 0, st>>>(x, w, p, dp, dx, beta, dW, dB, rows);
+  lvlw_bwd_kernel<T><<<small_grid(rows), kThreads, 0, st>>>(x, w, p, dp, dx, beta, dW, dB, rows);
   CQ_LAUNCH_CHECK();
   return 0;
 }
@@ -750,7 +787,7 @@ template <typename T>
 int qse_bwd(const float* ref, const T* scale, const T* hidden, const float* w1, const float* b1, const T* dqse, T* dscale,
             float beta_s, T* dhidden, float beta_h, float* dw1, float* db1, float* dref, long rows, cudaStream_t st) {
   if (rows == 0) return 0;
-  qse_bwd_kernel<T><<<row_grid(rows), kThreads, 0, st>>>(ref, scale, hidden, w1, b1, dqse, dscale, beta_s, dhidden, beta_h, dw1,
+  qse_bwd_kernel<T><<<small_grid(rows), kThreads, 0, st>>>(ref, scale, hidden, w1, b1, dqse, dscale, beta_s, dhidden, beta_h, dw1,
                                                          db1, dref, rows);
   CQ_LAUNCH_CHECK();
   return 0;
@@ -772,7 +809,7 @@ template <typename T>
 int box_refine_bwd(const T* hidden, const float* w2, const float* b2, const float* ref, const float* dnew_perm, T* dhidden,
                    float beta, float* dw2, float* db2, float* dref, long rows, int nq, int BT, cudaStream_t st) {
   if (rows == 0) return 0;
-  box_refine_bwd_kernel<T><<<row_grid(rows), kThreads, 0, st>>>(hidden, w2, b2, ref, dnew_perm, dhidden, beta, dw2, db2, dref,
+  box_refine_bwd_kernel<T><<<small_grid(rows), kThreads, 0, st>>>(hidden, w2, b2, ref, dnew_perm, dhidden, beta, dw2, db2, dref,
                                                                 rows, nq, BT);
   CQ_LAUNCH_CHECK();
   return 0;

@@ -128,6 +128,13 @@ struct Epilogue {
   // of C (same leading dimension), so that the values feeding cls_norm_/cls_norm2 skip two un-averaged bf16 roundings
   const float* res32 = nullptr;
   float* c32 = nullptr;
+  // training path: (a) second output c2 = act2(v) next to C = v (pre-activation kept for the backward, same ldc);
+  // (b) backward through an activation fused into the data-gradient GEMM: v *= act'(aux[row, col]) with aux of C's
+  //     shape / ldc -- mul_mode 1: ReLU mask (aux = post-activation, > 0), 2: exact erf-GELU derivative (aux = pre-activation)
+  void* c2 = nullptr;
+  int c2_act = CQVAD_ACT_NONE;
+  const void* mul_aux = nullptr;
+  int mul_mode = 0;
 };
 struct ConvGeom {  // implicit-GEMM 3x3 conv on the y-padded NHWC layout [n_img, h+1, w, 256]
   int h = 0, w = 0;

@@ -11,6 +11,9 @@ namespace {
 constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+}
 
 template <typename T>
 __device__ __forceinline__ void load4(const T* p, float (&v)[4]);
@@ -108,10 +111,15 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
       if (epi.bias) v += epi.bias[c];
       if (epi.act == CQVAD_ACT_RELU) v = fmaxf(v, 0.f);
       else if (epi.act == CQVAD_ACT_GELU) v = gelu_erf(v);
+      if (epi.mul_mode) {
+        const float a = to_f(reinterpret_cast<const T*>(epi.mul_aux)[r * ldc + c]);
+        v *= epi.mul_mode == 1 ? (a > 0.f ? 1.f : 0.f) : gelu_grad(a);
+      }
       if (epi.res32) v += epi.res32[r * epi.ldr + c];
       else if (res) v += to_f(res[r * epi.ldr + c]);
       if (zero_row) v = 0.f;
       C[r * ldc + c] = from_f<T>(v);
+      if (epi.c2) reinterpret_cast<T*>(epi.c2)[r * ldc + c] = from_f<T>(epi.c2_act == CQVAD_ACT_GELU ? gelu_erf(v) : (epi.c2_act == CQVAD_ACT_RELU ? fmaxf(v, 0.f) : v));
       if (epi.c32) epi.c32[r * ldc + c] = v;
     }
   }

@@ -37,6 +37,7 @@ struct TcParams {
   const float* bias; int act; const bf16* res; long ldr; const float* res32; float* c32;
   const float* ln_g; const float* ln_b; float ln_eps;
   int zero_period, zero_valid;
+  bf16* c2; int c2_act; const bf16* mul_aux; int mul_mode;
   // conv
   int conv; int cw; int rt;  // image width, image rows per tile
   int m_tiles, n_tiles;
@@ -48,7 +49,13 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&v)[8]) {
   for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
 
+// EXTRA = true: the training-path epilogue options (second activated output, activation-derivative mask); a separate
+// instantiation so that the inference epilogue carries none of their instructions.
+template <bool EXTRA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -164,6 +171,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       bf16* crow = p.C + grow * p.ldc + n0 + c0;
       const float* rrow32 = p.res32 ? p.res32 + grow * p.ldr + n0 + c0 : nullptr;
       float* crow32 = p.c32 ? p.c32 + grow * p.ldc + n0 + c0 : nullptr;
+      bf16* c2row = (EXTRA && p.c2) ? p.c2 + grow * p.ldc + n0 + c0 : nullptr;
+      const bf16* arow = (EXTRA && p.mul_mode) ? p.mul_aux + grow * p.ldc + n0 + c0 : nullptr;
       float mean = 0.f, rstd = 1.f;
       if (do_ln) {
         // pass 1: v = act(acc + bias) (+res); stash v in TMEM; partial row statistics over this warp's 128 columns
@@ -221,6 +230,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int u = 0; u < 4; ++u) rnext[u] = ld_res(c + 32 + u * 8);
           }
         }
+        uint4 anext[4];
+        if constexpr (EXTRA) {
+          if (p.mul_mode != 0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              anext[u] = (row_ok && n0 + c0 + c + u * 8 < p.N) ? *reinterpret_cast<const uint4*>(arow + c + u * 8) : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
         uint32_t r[32];
         tmem_ld32(t_addr + c, r);
         tmem_ld_wait();
@@ -246,8 +263,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float x = __uint_as_float(r[g8 * 8 + j]) + bs[j];
               if (p.act == CQVAD_ACT_RELU) x = fmaxf(x, 0.f);
               else if (p.act == CQVAD_ACT_GELU) x = gelu_erf(x);
-              v[j] = x + rs[j];
+              v[j] = x;
             }
+            if constexpr (EXTRA) {
+              if (p.mul_mode != 0) {
+                float ax[8];
+                unpack8(anext[g8], ax);
+                if (p.mul_mode == 1) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] = ax[j] > 0.f ? v[j] : 0.f;
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] *= gelu_grad_fast(ax[j]);
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += rs[j];
           }
           if (zero_row) {
 #pragma unroll
@@ -256,6 +288,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (row_ok) {
             store8(crow + cb, v);
             if (crow32) store8(crow32 + cb, v);
+            if constexpr (EXTRA) {
+              if (c2row) {
+                float v2[8];
+                if (p.c2_act == CQVAD_ACT_GELU) {
+#pragma unroll
+                  for (int j = 0; j < 8; j += 2) {
+                    float a, b;
+                    f2unpack(gelu2(f2pack(v[j], v[j + 1])), a, b);
+                    v2[j] = a; v2[j + 1] = b;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v2[j] = p.c2_act == CQVAD_ACT_RELU ? fmaxf(v[j], 0.f) : v[j];
+                }
+                store8(c2row + cb, v2);
+              }
+            }
           }
         }
       }
@@ -294,7 +343,8 @@ void init_once() {
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) g_init_err = 2;
 }
 
 }  // namespace
@@ -327,6 +377,8 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
   if (epi.res && ((((uintptr_t)epi.res) & 15) || epi.ldr % 8 != 0)) return 1;
   if ((epi.res32 && ((((uintptr_t)epi.res32) & 15) || epi.ldr % 8 != 0)) || (epi.c32 && (((uintptr_t)epi.c32) & 15))) return 1;
   if (epi.ln_g && N != BLOCK_N) return 1;
+  if ((epi.c2 || epi.mul_mode) && (epi.ln_g || N % 8 != 0)) return 1;
+  if ((epi.c2 && (((uintptr_t)epi.c2) & 15)) || (epi.mul_aux && (((uintptr_t)epi.mul_aux) & 15))) return 1;
   if (conv && (conv->w > 128 || lda != kC || K != 9 * kC)) return 1;
   std::call_once(g_once, init_once);
   if (g_init_err) return set_error(CQVAD_E_CUDA, "tcgen05 path: initialisation failed (%d)", g_init_err);
@@ -336,6 +388,7 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
   p.bias = epi.bias; p.act = epi.act; p.res = (const bf16*)epi.res; p.ldr = epi.ldr; p.res32 = epi.res32; p.c32 = epi.c32;
   p.ln_g = epi.ln_g; p.ln_b = epi.ln_b; p.ln_eps = epi.ln_eps;
   p.zero_period = epi.zero_period; p.zero_valid = epi.zero_valid;
+  p.c2 = (bf16*)epi.c2; p.c2_act = epi.c2_act; p.mul_aux = (const bf16*)epi.mul_aux; p.mul_mode = epi.mul_mode;
   p.n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
   CUtensorMap tmA, tmB;
   if (conv) {
@@ -365,7 +418,8 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
   }
   const long tiles = (long)p.m_tiles * p.n_tiles;
   const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
-  gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
+  if (p.c2 || p.mul_mode) gemm_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
+  else gemm_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
   CQ_LAUNCH_CHECK();
   return 0;
 }

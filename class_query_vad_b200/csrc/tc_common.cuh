@@ -167,6 +167,29 @@ __device__ __forceinline__ uint64_t gelu2(uint64_t x2) {
   const uint64_t hx = f2mul(x2, f2pack(0.5f, 0.5f));
   return f2fma(hx, e2, hx);
 }
+// scalar forms on the same erf polynomial: gelu(x) and d/dx gelu(x) = Phi(x) + x phi(x)  (phi through one MUFU.EX2)
+__device__ __forceinline__ float erf_poly(float z) {   // |z| clamped to 3
+  z = fminf(fmaxf(z, -3.0f), 3.0f);
+  const float u = z * z;
+  float q = 4.074209625e-08f;
+  q = fmaf(q, u, -1.944822197e-06f);
+  q = fmaf(q, u, 4.106051334e-05f);
+  q = fmaf(q, u, -5.110367538e-04f);
+  q = fmaf(q, u, 4.235426778e-03f);
+  q = fmaf(q, u, -2.510285923e-02f);
+  q = fmaf(q, u, 1.110793319e-01f);
+  q = fmaf(q, u, -3.753148729e-01f);
+  q = fmaf(q, u, 1.128268425e+00f);
+  return z * q;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float hx = 0.5f * x;
+  return fmaf(hx, erf_poly(x * 0.70710678118654752f), hx);
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  const float cdf = fmaf(0.5f, erf_poly(x * 0.70710678118654752f), 0.5f);
+  return fmaf(x * 0.3989422804014327f, exp2f(-0.7213475204444817f * x * x), cdf);
+}
 __device__ __forceinline__ uint32_t f2_to_bf16x2(uint64_t v) {
   float a, b;
   f2unpack(v, a, b);

@@ -70,6 +70,11 @@ struct Ten {
   int cols = 0;
   bool hg = false;  // a gradient flows into this tensor (g is valid outside PLAN mode)
   bool gi = false;  // gradient buffer holds a value (first writer overwrites, later writers accumulate)
+  // this tensor is act(.) of something: the gradient arriving here must be multiplied by act'(gref).  The single consumer's
+  // data-gradient GEMM does it in its epilogue (gmasked = true); otherwise the producer's backward runs an elementwise pass.
+  int gact = 0;             // 0 none, 1 ReLU (gref = this tensor), 2 GELU (gref = pre-activation)
+  const T* gref = nullptr;
+  bool gmasked = false;
   long n() const { return rows * cols; }
 };
 
@@ -157,14 +162,25 @@ struct Trainer {
 
   // ---- ops -------------------------------------------------------------------------------------------------------
   // Y = act(X.W^T + b) (+ res)   [rows, Nout];  zero_period/valid: rows written as zeros (y-padded layout)
+  Ten<T>* last_c2 = nullptr;   // second output of the last lin(..., c2_act)
   Ten<T>* lin(Ten<T>* X, int widx, int Nout, int act = CQVAD_ACT_NONE, Ten<T>* res = nullptr, int zp = 0, int zv = 0,
-              int* rc = nullptr) {
+              int* rc = nullptr, int c2_act = CQVAD_ACT_NONE) {
     Ten<T>* Y = mk(X->rows, Nout);
     const int Kd = X->cols;
+    if (act == CQVAD_ACT_RELU) { Y->gact = 1; Y->gref = Y->p; }
+    Ten<T>* A2 = nullptr;
+    if (c2_act != CQVAD_ACT_NONE) {   // A2 = act(Y) written by the same epilogue; shares Y's gradient buffer
+      tens.emplace_back();
+      A2 = &tens.back();
+      A2->rows = Y->rows; A2->cols = Y->cols; A2->p = take(Y->n()); A2->g = Y->g; A2->hg = true;
+      A2->gact = c2_act == CQVAD_ACT_GELU ? 2 : 1; A2->gref = Y->p;
+      last_c2 = A2;
+    }
     const T* Wt = X->hg ? WT(widx, (long)Nout * Kd) : nullptr;
     if (fwd()) {
       Epilogue e;
       e.bias = Wf(widx + 1); e.act = act; e.res = res ? res->p : nullptr; e.ldr = Nout; e.zero_period = zp; e.zero_valid = zv;
+      if (A2) { e.c2 = A2->p; e.c2_act = c2_act; }
       int r;
       { ProfScope ps(P_T_FWD_GEMM, st); r = gemm<T>(X->p, Kd, Wm(widx), Y->p, Nout, X->rows, Nout, Kd, e, nullptr, st); }
       if (r == 0) r = dbg("lin", widx);
@@ -172,10 +188,15 @@ struct Trainer {
     }
     if (rec()) {
       tape.push_back([=]() -> int {
+        if (A2) {   // the gradient arrived through the activated copy
+          if (!A2->gi) return 0;
+          Y->gi = true;
+          if (!A2->gmasked) { ProfScope ps(P_T_ACT_BWD, st); CQ_TRY(act_bwd<T>(Y->g, Y->p, c2_act, Y->n(), st)); }
+        }
         if (!Y->gi) return 0;
         {
           ProfScope ps(P_T_ACT_BWD, st);
-          if (act == CQVAD_ACT_RELU) CQ_TRY(act_bwd<T>(Y->g, Y->p, CQVAD_ACT_RELU, Y->n(), st));
+          if (act == CQVAD_ACT_RELU && !Y->gmasked) CQ_TRY(act_bwd<T>(Y->g, Y->p, CQVAD_ACT_RELU, Y->n(), st));
           if (res && res->hg) CQ_TRY(axpby<T>(res->g, Y->g, beta(res), Y->n(), st));
         }
         if (X->hg) {
@@ -184,6 +205,10 @@ struct Trainer {
           Epilogue e;
           const float b = beta(X);
           if (b != 0.f) { e.res = X->g; e.ldr = Kd; }
+          if (X->gact) {
+            if (b != 0.f) return set_error(CQVAD_E_INVALID_ARG, "backward: an activation output with two consumers is not supported");
+            e.mul_aux = X->gref; e.mul_mode = X->gact; X->gmasked = true;   // dX = (dY . W) * act'(.) in the epilogue
+          }
           CQ_TRY(gemm<T>(Y->g, Nout, Wt, X->g, Kd, X->rows, Kd, Nout, e, nullptr, st));
         }
         if (G(widx) || G(widx + 1)) {
@@ -450,8 +475,8 @@ int Trainer<T>::run() {
     for (int blk = 0; blk < 3; ++blk) {   // the same ConvBlock three times (:1017-1018, :1055-1056)
       Ten<T>* Z = conv(X, cls(l, C_CONV1), &rc);
       Ten<T>* Xn = ln(Z, nullptr, cls(l, C_CBNORM), 1e-6f, &rc);
-      Ten<T>* Hpre = lin(Xn, cls(l, C_CONV2), 4 * kC, 0, nullptr, 0, 0, &rc);
-      Ten<T>* A = gelu(Hpre, &rc);
+      lin(Xn, cls(l, C_CONV2), 4 * kC, 0, nullptr, 0, 0, &rc, CQVAD_ACT_GELU);   // pre-activation kept + gelu in one epilogue
+      Ten<T>* A = last_c2;
       X = lin(A, cls(l, C_CONV3), kC, 0, X, Sp, S, &rc);
     }
     Ten<T>* X3 = X;
