@@ -1,20 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- decoder clips/s of the class-query decoder hot path (BASELINE.json metric).
+"""bench.py -- decoder clips/s of the class-query decoder hot path (BASELINE.json metric, configs[1]).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--mode train|infer] [--impl ours|reference]
 
-A step = one pass of TransformerDecoder.forward + DETR heads (cqvad_decoder_forward) over one batch of synthetic clips
-(AVA22_ViT-B shapes: nq 15, S 14x14, K 80, 6 layers, F 2048), bf16 tensor-core path.
+A step (default --mode train = BASELINE.json configs[1] "full decoder fwd+bwd bf16, batch 32") = one
+TransformerDecoder.forward (cqvad_decoder_train_forward) + its backward (cqvad_decoder_backward: gradients of every decoder
+parameter, memory, tgt and refpoints_unsigmoid) over one batch of synthetic clips (AVA22_ViT-B shapes: nq 15, S 14x14, K 80,
+6 layers, F 2048), bf16 tensor-core path, loss = sum(w_hs*hs) + sum(w_cls*cls_hs) + sum(w_refs*refs) (SURVEY.md section 8d
+Config 2; dropout = identity).  --mode infer times the inference forward + DETR heads (cqvad_decoder_forward); the default
+run reports it under "inference_forward".
   value : whole-job clips/s with inputs already resident in HBM (CUDA events, max over ranks)
-  e2e   : same metric through the public API (DecoderEngine.forward) with pinned-HOST inputs: H2D copy of the step's
-          inputs and D2H read of the detections inside the timed region
-  roofline     : the dominant kernel (tcgen05 implicit-GEMM 3x3 conv + LN), timed live with CUDA events on the launch
-                 stream (library profiler scopes), algorithmic FLOPs / duration vs the measured bf16 peak
-  cpu_baseline : the numpy oracle port of the reference decoder on the host cores, bounded sample (rank 0, N=1 only)
-`--impl reference` times the CPU oracle port of the reference path (the reference is Python and cannot travel to the GPU
-box; /root/reference is never read here).
-Multi-GPU: one process per GPU (torchrun), clips sharded across ranks (weak scaling: --batch clips per GPU), one NCCL
-all-gather of the per-clip detections per step.
+  e2e   : same metric through the public API (DecoderEngine.forward_train/backward) with pinned-HOST inputs: H2D copy of the
+          step's inputs and D2H read of the step's result (refs + last-layer hs) inside the timed region
+  roofline     : the dominant kernel (tcgen05 implicit-GEMM 3x3 conv: forward and data-gradient launches), timed live with
+                 CUDA events on the launch stream (library profiler scopes), algorithmic FLOPs / duration vs the measured peak
+  cpu_baseline : oracle/decoder_torch.py (torch-CPU restatement of the reference decoder, autograd backward) on the host
+                 cores, bounded sample (rank 0, N=1 only)
+`--impl reference` times that same host path (the reference is Python/torch and cannot travel to the GPU box;
+/root/reference is never read here).
+Multi-GPU: one process per GPU (torchrun), clips sharded across ranks (weak scaling: --batch clips per GPU); train mode
+all-reduces the decoder gradients once per step (NCCL), infer mode all-gathers the per-clip detections.
 """
 import argparse
 import ctypes
@@ -32,6 +37,7 @@ import numpy as np  # noqa: E402
 
 CFG = "ava_vitb"
 FWD_GFLOP_PER_CLIP = 148.18            # BASELINE.md section 3 (reference flop count, AVA22_ViT-B decoder forward)
+TRAIN_GFLOP_PER_CLIP = 444.5           # fwd + bwd
 
 
 def load_peaks():
@@ -88,37 +94,56 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_oracle_clips_per_s(max_seconds=25.0, min_reps=1):
-    """The oracle port (numpy restatement of the reference decoder) on one AVA22_ViT-B clip, host cores."""
-    from oracle import synth, decoder_np
+def _host_case():
+    from oracle import synth
     cfg = synth.CONFIGS[CFG]
     W = synth.make_decoder_weights(cfg["K"], cfg["layers"], cfg["F"], seed=0)
     inp = synth.make_decoder_inputs(CFG, 1, seed=0)
-    times = []
-    t_all = time.time()
-    while len(times) < min_reps or (time.time() - t_all < max_seconds and len(times) < 5):
-        t0 = time.time()
-        hs, cls_hs, refs = decoder_np.decoder_forward(W, inp["tgt"], inp["memory"], inp["mask"], inp["pos"],
-                                                      inp["refpoints_unsigmoid"], inp["orig_res"], cfg["layers"])
-        decoder_np.detr_heads(W, hs, cls_hs, refs)
-        times.append(time.time() - t0)
-    return 1.0 / float(np.median(times)), len(times)
+    lw = synth.make_loss_weights(cfg, 1, seed=0)
+    return cfg, W, inp, lw
 
 
-def run_reference(args, rank):
-    """--impl reference: the reference's CPU path = the oracle port, all host threads (numpy BLAS), bounded sample."""
-    if rank != 0:
-        return
-    from oracle import synth, decoder_np
-    cfg = synth.CONFIGS[CFG]
-    W = synth.make_decoder_weights(cfg["K"], cfg["layers"], cfg["F"], seed=0)
-    inp = synth.make_decoder_inputs(CFG, 1, seed=0)
+def host_step_fn(mode):
+    """One clip of the workload on the host cores: train = torch-CPU restatement fwd + autograd bwd (all threads),
+    infer = numpy oracle forward + heads."""
+    cfg, W, inp, lw = _host_case()
+    if mode == "train":
+        from oracle import decoder_torch
+        import torch
+        torch.set_num_threads(os.cpu_count() or 1)
+        return lambda: decoder_torch.train_step(W, inp, lw, cfg["layers"])
+    from oracle import decoder_np
 
     def step():
         hs, cls_hs, refs = decoder_np.decoder_forward(W, inp["tgt"], inp["memory"], inp["mask"], inp["pos"],
                                                       inp["refpoints_unsigmoid"], inp["orig_res"], cfg["layers"])
         decoder_np.detr_heads(W, hs, cls_hs, refs)
+    return step
 
+
+def cpu_oracle_clips_per_s(mode, max_seconds=25.0, min_reps=1):
+    step = host_step_fn(mode)
+    times = []
+    t_all = time.time()
+    while len(times) < min_reps or (time.time() - t_all < max_seconds and len(times) < 5):
+        t0 = time.time()
+        step()
+        times.append(time.time() - t0)
+    return 1.0 / float(np.median(times)), len(times)
+
+
+WORK = {"train": "AVA22_ViT-B class-query decoder fwd + bwd (6 layers, nq 15, S 196, K 80, F 2048; gradients of all parameters, "
+                 "memory, tgt, refpoints)",
+        "infer": "AVA22_ViT-B class-query decoder forward + heads (6 layers, nq 15, S 196, K 80, F 2048)"}
+HOST_KIND = {"train": "fp32 torch-CPU restatement of the reference decoder (oracle/decoder_torch.py), autograd backward",
+             "infer": "fp32 numpy oracle port (oracle/decoder_np.py)"}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path = the oracle port, all host threads, bounded sample (1 clip per step)."""
+    if rank != 0:
+        return
+    step = host_step_fn(args.mode)
     for _ in range(min(args.warmup, 1)):
         step()
     steps = min(args.steps, 5)          # bounded: each step is one clip (~seconds of CPU work)
@@ -128,12 +153,12 @@ def run_reference(args, rank):
     dt = time.time() - t0
     v = steps / dt
     cores = os.cpu_count()
-    sample = f"{steps} steps x 1 clip (AVA22_ViT-B decoder forward + heads, fp32 numpy oracle port), median-free wall clock"
+    sample = f"{steps} steps x 1 clip ({WORK[args.mode]}), {HOST_KIND[args.mode]}, wall clock"
     print(json.dumps({
         "impl": "reference", "metric": "decoder clips/s", "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "AVA22_ViT-B class-query decoder forward + heads, 6 layers, nq 15, S 196, K 80; 1 clip per step on host CPU"},
+        "config": {"workload": WORK[args.mode] + "; 1 clip per step on the host CPU", "mode": args.mode},
         "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -146,6 +171,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -189,14 +215,30 @@ def main():
     det_local = torch.empty((B, nq, K + 4 + 3), dtype=torch.float32, device=dev)
     det_all = torch.empty((world * B, nq, K + 4 + 3), dtype=torch.float32, device=dev) if world > 1 else det_local
     det_host = torch.empty((B, nq, K + 4 + 3), dtype=torch.float32).pin_memory()
+    from class_query_vad_b200.dist import allreduce_gradients
+    lw = synth.make_loss_weights(cfg, B, seed=1)
+    g_hs = torch.from_numpy(lw["w_hs"]).to(dev).bfloat16()
+    g_cls = torch.from_numpy(lw["w_cls"]).to(dev).bfloat16()
+    g_refs = torch.from_numpy(lw["w_refs"]).to(dev)
+    res_host = torch.empty((Lr * B * nq * 4 + B * nq * 256,), dtype=torch.float32).pin_memory()
+    launches = {"n": 0}
 
-    def step(inp):
+    def infer_step(inp):
         out = eng.forward(inp["tgt"], inp["memory"], inp["mask"], inp["pos"], inp["refpoints_unsigmoid"], orig_res,
                           heads=True, skip_cls_hs=False)
         # detections of the last layer: [B, nq, K | 4 | 3] (the row format of utils/video_action_recognition.py:234)
         torch.cat([out["pred_logits"][-1], out["pred_boxes"][-1], out["pred_logits_b"][-1]], dim=-1, out=det_local)
         if world > 1:
             dist.all_gather_into_tensor(det_all, det_local)
+        launches["n"] = eng.last_launches + 1 + (1 if world > 1 else 0)
+        return out
+
+    def train_step(inp):
+        out = eng.forward_train(inp["tgt"], inp["memory"], inp["mask"], inp["pos"], inp["refpoints_unsigmoid"], orig_res)
+        eng.backward(g_hs, g_cls, g_refs, zero=True, named=False)
+        if world > 1:
+            allreduce_gradients(eng)
+        launches["n"] = eng.last_launches + eng.last_launches_bwd + (1 if world > 1 else 0)
         return out
 
     def sync_all():
@@ -218,39 +260,63 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- warm-up ----
-    for i in range(args.warmup):
-        step(dev_sets[i % NSETS])
-    sync_all()
+    def read_profile(steps):
+        prof = {}
+        for c in range(lib.cqvad_profile_num_classes()):
+            tot, sc, ln = ctypes.c_double(), ctypes.c_long(), ctypes.c_long()
+            lib.cqvad_profile_read(c, ctypes.byref(tot), ctypes.byref(sc), ctypes.byref(ln))
+            if sc.value:
+                prof[lib.cqvad_profile_class_name(c).decode()] = dict(ms_per_step=tot.value / steps, scopes=sc.value // max(steps, 1),
+                                                                     launches=ln.value // max(steps, 1))
+        return prof
 
-    # ---- timed: device-resident inputs ----
+    def measure(step, steps, result_to_host):
+        """(device-resident ms, profile, launches per step, e2e ms) of `step`."""
+        for i in range(args.warmup):
+            step(dev_sets[i % NSETS])
+        sync_all()
+        ms = timed(lambda i: step(dev_sets[i % NSETS]), steps)
+        n_launch = launches["n"]
+        # per-kernel-class breakdown (and the roofline kernel's launch time) from a separate short pass: the event scopes
+        # cost a few % and must not sit inside the timed region
+        psteps = min(steps, 5)
+        lib.cqvad_profile_enable(1)
+        timed(lambda i: step(dev_sets[i % NSETS]), psteps)
+        prof = read_profile(psteps)
+        lib.cqvad_profile_enable(0)
+
+        def e2e_step(i):
+            hp = host_sets[i % NSETS]
+            inp = {k: v.to(dev, non_blocking=True) for k, v in hp.items()}
+            out = step(inp)
+            result_to_host(out)
+        for i in range(2):
+            e2e_step(i)
+        ms_e2e = timed(e2e_step, steps)
+        return ms, prof, n_launch, ms_e2e
+
+    def train_result(out):
+        n1 = Lr * B * nq * 4
+        res_host[:n1].copy_(out["refs"].reshape(-1), non_blocking=True)
+        res_host[n1:].copy_(out["hs"][-1].reshape(-1).float(), non_blocking=True)
+
+    def infer_result(out):
+        det_host.copy_(det_local, non_blocking=True)
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    lib.cqvad_profile_enable(1)
-    ms = timed(lambda i: step(dev_sets[i % NSETS]), args.steps)
-    prof = {}
-    for c in range(lib.cqvad_profile_num_classes()):
-        tot, sc, ln = ctypes.c_double(), ctypes.c_long(), ctypes.c_long()
-        lib.cqvad_profile_read(c, ctypes.byref(tot), ctypes.byref(sc), ctypes.byref(ln))
-        prof[lib.cqvad_profile_class_name(c).decode()] = dict(ms_per_step=tot.value / args.steps, scopes=sc.value // max(args.steps, 1),
-                                                             launches=ln.value // max(args.steps, 1))
-    lib.cqvad_profile_enable(0)
-    launches_per_step = eng.last_launches + 1 + (1 if world > 1 else 0)     # + torch.cat (+ NCCL all-gather)
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- timed: end to end through the public API with pinned host inputs ----
     h2d = sum(host_sets[0][k].numel() * host_sets[0][k].element_size() for k in host_sets[0])
-    d2h = det_host.numel() * 4
-
-    def e2e_step(i):
-        hp = host_sets[i % NSETS]
-        inp = {k: v.to(dev, non_blocking=True) for k, v in hp.items()}
-        step(inp)
-        det_host.copy_(det_local, non_blocking=True)
-    for i in range(2):
-        e2e_step(i)
-    ms_e2e = timed(e2e_step, args.steps)
+    main_mode = args.mode
+    if main_mode == "train":
+        ms, prof, n_launch, ms_e2e = measure(train_step, args.steps, train_result)
+        d2h = res_host.numel() * 4
+        isteps = max(3, min(args.steps, 10))
+        ims, iprof, in_launch, ims_e2e = measure(infer_step, isteps, infer_result)
+    else:
+        ms, prof, n_launch, ms_e2e = measure(infer_step, args.steps, infer_result)
+        d2h = det_host.numel() * 4
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
         if world > 1:
@@ -260,40 +326,53 @@ def main():
     clips = world * B * args.steps
     value = clips / (ms / 1e3)
     peaks = load_peaks()
-    # ---- roofline of the dominant kernel: implicit-GEMM conv3x3 (+bias+LN epilogue), 3 launches per layer ----
+    # ---- roofline of the dominant kernel: tcgen05 implicit-GEMM 3x3 conv; 2*N*S*C^2*9 FLOPs per launch ----
     S = cfg["h"] * cfg["w"]
-    Nrows = B * nq * S                                   # algorithmic output pixels per launch
-    conv = prof["conv3x3_ln (tcgen05 implicit GEMM)"]
-    conv_launch_ms = conv["ms_per_step"] / max(conv["scopes"], 1)
-    conv_flops = 2.0 * Nrows * 256 * 2304               # 2*N*S*C^2*9 per ConvBlock conv
+    conv_flops = 2.0 * (B * nq * S) * 256 * 2304
+    if main_mode == "train":
+        cf, cd = prof["train fwd: conv3x3 (tcgen05 implicit GEMM)"], prof["train bwd: conv3x3 dgrad (tcgen05 implicit GEMM)"]
+        conv_launch_ms = (cf["ms_per_step"] + cd["ms_per_step"]) / max(cf["scopes"] + cd["scopes"], 1)
+        kname = "gemm_tc_kernel (conv mode: forward + data-gradient launches, 36 per step)"
+    else:
+        conv = prof["conv3x3_ln (tcgen05 implicit GEMM)"]
+        conv_launch_ms = conv["ms_per_step"] / max(conv["scopes"], 1)
+        kname = "gemm_tc_kernel (conv mode)"
     achieved = conv_flops / (conv_launch_ms * 1e-3) / 1e12
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("conv3x3_ln_bytes_per_launch")
-    roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (conv mode)", "achieved": achieved, "peak": peaks["tf_sust"],
+        traffic = json.load(open(tp)).get("conv3x3_bytes_per_launch")
+    roof = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peaks["tf_sust"],
             "unit": "TFLOP/s", "frac": achieved / peaks["tf_sust"], "traffic": traffic, "peak_source": peaks["src"] + " sustained bf16",
             "launch_ms": conv_launch_ms, "flops_per_launch": conv_flops}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        v, reps = cpu_oracle_clips_per_s()
+        v, reps = cpu_oracle_clips_per_s(main_mode)
         cpu = {"value": v, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"{reps} x 1 clip, same workload shape (AVA22_ViT-B decoder forward + heads), fp32 numpy oracle port"}
+               "sample": f"{reps} x 1 clip, same workload shape ({WORK[main_mode]}), {HOST_KIND[main_mode]}"}
+    gflop = TRAIN_GFLOP_PER_CLIP if main_mode == "train" else FWD_GFLOP_PER_CLIP
     line = {
         "metric": "decoder clips/s", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"AVA22_ViT-B class-query decoder FORWARD + heads (6 layers, nq 15, S 196, K 80, F 2048), "
-                               f"{B} clips/GPU; backward not implemented yet (BASELINE configs[1] names fwd+bwd)",
-                   "batch_per_gpu": B, "parallelism": f"clip-sharded x{world}", "l2": "4 input sets cycled (128 MB) + ~0.8 GB of intermediates per step >> 126 MB L2",
-                   "decoder_tflops": value * FWD_GFLOP_PER_CLIP / 1e3 / world},
+        "config": {"workload": WORK[main_mode] + f", {B} clips/GPU, dropout = identity", "mode": main_mode,
+                   "batch_per_gpu": B, "parallelism": f"clip-sharded x{world}" + (", 1 gradient all-reduce/step" if main_mode == "train" and world > 1 else ""),
+                   "l2": "4 input sets cycled (128 MB) + GBs of intermediates per step >> 126 MB L2",
+                   "decoder_tflops": value * gflop / 1e3 / world},
         "clocks": clocks,
         "e2e": {"value": clips / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": int(launches_per_step * args.steps),
+        "gpu_launches": int(n_launch * args.steps),
         "roofline": roof,
         "cpu_baseline": cpu,
         "breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in prof.items()},
     }
+    if main_mode == "train":
+        iclips = world * B * isteps
+        line["inference_forward"] = {
+            "workload": WORK["infer"], "value": iclips / (ims / 1e3), "unit": "clips/s", "ms_per_step": ims / isteps, "steps": isteps,
+            "e2e": iclips / (ims_e2e / 1e3), "gpu_launches_per_step": int(in_launch),
+            "decoder_tflops": iclips / (ims / 1e3) * FWD_GFLOP_PER_CLIP / 1e3 / world,
+            "breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in iprof.items()}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -5,6 +5,7 @@ parameter names); all arithmetic runs in hand-written CUDA behind the C ABI of i
 """
 from . import _lib
 from .engine import DecoderEngine, pack_decoder_weights
+from .functions.decoder_func import DecoderFunction
 from .functions.ms_deform_attn_func import MSDeformAttnFunction, ms_deform_attn_indices
 from .modules.ms_deform_attn import MSDeformAttn3D
 from .modules.attention import MultiheadAttention
@@ -12,7 +13,7 @@ from .modules.position_encoding import PositionEmbeddingSine_3D, build_position_
 from .modules.decoder import (MLP, ConvBlock, TransformerDecoderLayer, TransformerClassDecoderLayer, TransformerDecoder,
                               build_decoder)
 
-__all__ = ["DecoderEngine", "pack_decoder_weights", "MSDeformAttnFunction", "ms_deform_attn_indices", "MSDeformAttn3D",
+__all__ = ["DecoderEngine", "DecoderFunction", "pack_decoder_weights", "MSDeformAttnFunction", "ms_deform_attn_indices", "MSDeformAttn3D",
            "MultiheadAttention", "PositionEmbeddingSine_3D", "build_position_encoding", "gen_sineembed_for_position",
            "MLP", "ConvBlock", "TransformerDecoderLayer", "TransformerClassDecoderLayer", "TransformerDecoder",
            "build_decoder"]

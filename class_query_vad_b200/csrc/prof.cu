@@ -15,7 +15,8 @@ const char* kNames[P_COUNT] = {"conv3x3_ln (tcgen05 implicit GEMM)", "convblock_
                                "output LN / heads", "small-row ops (prologue, loc SA, FFNs, box head)", "input conversion",
                                "train fwd: GEMM / conv", "train fwd: LN, attention, elementwise", "train bwd: dgrad GEMM / conv",
                                "train bwd: wgrad", "train bwd: activation / residual", "train bwd: LayerNorm", "train bwd: attention",
-                               "train bwd: misc"};
+                               "train bwd: misc", "train fwd: conv3x3 (tcgen05 implicit GEMM)", "train bwd: conv3x3 dgrad (tcgen05 implicit GEMM)",
+                               "train bwd: conv3x3 wgrad (tcgen05 MN-major)"};
 }  // namespace
 long launch_count_now();
 bool prof_enabled() { return g_on; }

@@ -5,7 +5,8 @@
 namespace cqvad {
 enum ProfClass { P_CONV = 0, P_CONV_MLP, P_CLS_FFN, P_BIG_PROJ, P_CLS_XATTN, P_CLS_SATTN, P_CLS_OPROJ, P_LOC_QSK, P_LVLMIX,
                  P_ADDLN, P_OUT_LN, P_SMALL, P_INPUT,
-                 P_T_FWD_GEMM, P_T_FWD_OTHER, P_T_DGRAD, P_T_WGRAD, P_T_ACT_BWD, P_T_LN_BWD, P_T_ATTN_BWD, P_T_MISC_BWD, P_COUNT };
+                 P_T_FWD_GEMM, P_T_FWD_OTHER, P_T_DGRAD, P_T_WGRAD, P_T_ACT_BWD, P_T_LN_BWD, P_T_ATTN_BWD, P_T_MISC_BWD,
+                 P_T_CONV_FWD, P_T_CONV_DGRAD, P_T_CONV_WGRAD, P_COUNT };
 bool prof_enabled();
 void prof_begin(int cls, cudaStream_t st);
 void prof_end(int cls, cudaStream_t st);

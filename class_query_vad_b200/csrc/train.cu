@@ -272,7 +272,7 @@ struct Trainer {
       Epilogue e;
       e.bias = Wf(widx + 1);
       int r;
-      { ProfScope ps(P_T_FWD_GEMM, st); r = gemm<T>(X->p, kC, Wm(widx), Z->p, kC, X->rows, kC, 9 * kC, e, &cg, st); }
+      { ProfScope ps(P_T_CONV_FWD, st); r = gemm<T>(X->p, kC, Wm(widx), Z->p, kC, X->rows, kC, 9 * kC, e, &cg, st); }
       if (r == 0) r = dbg("conv", widx);
       if (r != 0 && *rc == 0) *rc = r;
     }
@@ -280,15 +280,15 @@ struct Trainer {
       tape.push_back([=]() -> int {
         if (!Z->gi) return 0;
         if (X->hg) {
-          ProfScope ps(P_T_DGRAD, st);
           CQ_TRY(build_wt(widx, 0, 0, true));
+          ProfScope ps(P_T_CONV_DGRAD, st);
           Epilogue e;
           e.zero_period = Sp; e.zero_valid = S;
           const float b = beta(X);
           if (b != 0.f) { e.res = X->g; e.ldr = kC; }
           CQ_TRY(gemm<T>(Z->g, kC, Wd, X->g, kC, X->rows, kC, 9 * kC, e, &cg, st));
         }
-        ProfScope ps(P_T_WGRAD, st);
+        ProfScope ps(P_T_CONV_WGRAD, st);
         return wgrad<T>(Z->g, kC, X->p, kC, G(widx), 9 * kC, G(widx + 1), X->rows, kC, kC, &cg, st);
       });
     }

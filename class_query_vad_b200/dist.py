@@ -49,3 +49,15 @@ def gather_detections(det_local, n_clips_total=None, group=None):
     if all(c == bmax for c in counts):
         return out
     return torch.cat([out[r * bmax: r * bmax + counts[r]] for r in range(world)], dim=0)
+
+
+def allreduce_gradients(engine, group=None, average=True):
+    """Training: ONE all-reduce over the engine's flat fp32 gradient buffer (all decoder parameters, ~133 MB for the 6-layer
+    AVA decoder) per optimizer step -- what DDP does per bucket in the reference (utils/model_utils.py:113-121).  Parameters
+    the reference never uses (q_proj, cls_norm) are not in the buffer, which is what static_graph=True DDP skips."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return engine._gflat
+    dist.all_reduce(engine._gflat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        engine._gflat.div_(dist.get_world_size(group))
+    return engine._gflat

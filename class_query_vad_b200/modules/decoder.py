@@ -245,10 +245,22 @@ class TransformerDecoder(nn.Module):
                 memory_key_padding_mask=None, pos=None, refpoints_unsigmoid=None, orig_res=None):
         if tgt_mask is not None or memory_mask is not None or tgt_key_padding_mask is not None:
             raise NotImplementedError("tgt_mask / memory_mask / tgt_key_padding_mask are never passed (dab_transformer.py:395)")
-        if self.training:
-            raise NotImplementedError("training-mode (dropout) forward is not implemented; call .eval()")
         eng = self._get_engine(tgt.device)
         eng.nq = tgt.shape[0]
+        named = [(n, p) for n, p in self.named_parameters()]
+        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for _, p in named) or tgt.requires_grad or
+                                                  memory.requires_grad or refpoints_unsigmoid.requires_grad)
+        if needs_grad:
+            # training step: native forward that keeps the backward's intermediates + native backward behind autograd.
+            # Dropout is the identity on this path (the reference trains with p = 0.1 / 0.5: DESIGN.md "divergences").
+            if self.training and not getattr(self, "_warned_dropout", False):
+                import warnings
+                warnings.warn("class_query_vad_b200: dropout is the identity in the native training path")
+                self._warned_dropout = True
+            from ..functions.decoder_func import DecoderFunction
+            hs, cls_hs, refs = DecoderFunction.apply(eng, [n for n, _ in named], memory_key_padding_mask, pos, orig_res, tgt,
+                                                     memory, refpoints_unsigmoid, *[p for _, p in named])
+            return [hs, cls_hs, refs]
         out = eng.forward(tgt, memory, memory_key_padding_mask, pos, refpoints_unsigmoid, orig_res, heads=False)
         return [out["hs"], out["cls_hs"], out["refs"]]
 

@@ -130,8 +130,9 @@ def test_decoder_module_drop_in_fp32():
     dec = dec.cuda().eval()
     dec.compute_dtype = torch.float32
     t = lambda a: torch.from_numpy(a).cuda()
-    hs, cls_hs, refs = dec(t(inp["tgt"]), t(inp["memory"]), memory_key_padding_mask=t(inp["mask"]), pos=t(inp["pos"]),
-                           refpoints_unsigmoid=t(inp["refpoints_unsigmoid"]), orig_res=inp["orig_res"])
+    with torch.no_grad():     # inference path (with grad enabled the module runs the native training step: test_train_gpu.py)
+        hs, cls_hs, refs = dec(t(inp["tgt"]), t(inp["memory"]), memory_key_padding_mask=t(inp["mask"]), pos=t(inp["pos"]),
+                               refpoints_unsigmoid=t(inp["refpoints_unsigmoid"]), orig_res=inp["orig_res"])
     assert rel_err(hs.cpu().numpy(), g["hs"]) < TOL_FP32
     assert rel_err(cls_hs.cpu().numpy(), g["cls_hs"]) < TOL_FP32
     assert rel_err(refs.cpu().numpy(), g["refs"]) < TOL_FP32

@@ -64,3 +64,33 @@ def test_gather_detections_world2_gloo(n_clips):
 def test_gather_is_identity_without_process_group():
     x = torch.randn(3, 2, 5)
     assert gather_detections(x) is x
+
+
+def _allreduce_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from class_query_vad_b200.dist import allreduce_gradients
+
+    class FakeEngine:      # the engine contract allreduce_gradients relies on: one flat fp32 gradient buffer
+        _gflat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    out = allreduce_gradients(FakeEngine())
+    q.put((rank, out.tolist()))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    expect = [1.5 * i for i in range(10)]      # mean of (1x, 2x)
+    assert res[0] == expect and res[1] == expect

@@ -83,3 +83,27 @@ def test_msda_indices_properties():
     loc[..., 0] = (1 + 0.5) / 4; loc[..., 1] = (2 + 0.5) / 3; loc[..., 2] = (0 + 0.5) / 2
     tl, hl, wl, mask = msda_np.msda3d_indices(np.array([(2, 3, 4)]), loc)
     assert (tl.item(), hl.item(), wl.item()) == (0, 2, 1)
+
+
+@pytest.mark.parametrize("name", ["grad_tiny", "grad_tiny_masked", "grad_small_masked"])
+def test_torch_restatement_gradients_match_reference_autograd(name):
+    """oracle/decoder_torch.py (the host baseline of the TRAINING step) against gradients of the unmodified reference."""
+    from oracle import decoder_torch
+    g = load_golden(name)
+    cfg, B, W, inp = case_from_meta(g["meta"])
+    seed = int(g["meta"][8])
+    lw = synth.make_loss_weights(cfg, B, seed=seed)
+    loss, grads, gmem, gtgt, gref = decoder_torch.train_step(W, inp, lw, cfg["layers"])
+    assert abs(loss - float(g["loss"])) < 1e-4 * max(1.0, abs(float(g["loss"])))
+    G = float(np.median([np.abs(g[k]).max() for k in g if k.startswith(("g.", "gs."))]))
+    for nm, got in (("memory", gmem), ("tgt", gtgt), ("refpoints_unsigmoid", gref)):
+        if "gin." + nm in g:
+            assert np.abs(got - g["gin." + nm]).max() <= 1e-4 * max(np.abs(g["gin." + nm]).max(), 1e-2 * G), nm
+    for k in g:
+        if k.startswith("g."):
+            nm = k[2:]
+            assert np.abs(grads[nm] - g[k]).max() <= 1e-4 * max(np.abs(g[k]).max(), 1e-2 * G), nm
+        elif k.startswith("gs."):
+            nm = k[3:]
+            idx = synth.grad_sample_index(grads[nm].size, seed)
+            assert np.abs(grads[nm].reshape(-1)[idx] - g[k]).max() <= 1e-4 * max(np.abs(g[k]).max(), 1e-2 * G), nm

@@ -165,3 +165,37 @@ def test_backward_is_linear_in_the_output_gradients():
         ref = 2.0 * ga[k] - 0.5 * gb[k]
         scale = max(float(ref.abs().max()), 1e-3 * G)
         assert float((gc[k] - ref).abs().max()) / scale < 1e-3, k
+
+
+def test_module_autograd_drop_in():
+    """nn.Module boundary in training: loss.backward() through build_decoder()'s TransformerDecoder fills .grad of the
+    reference-named parameters (fp32 path, against the reference-autograd fixture)."""
+    from class_query_vad_b200 import build_decoder
+    g = load_golden("grad_tiny_masked")
+    cfg, B, W, inp = case_from_meta(g["meta"])
+    seed = int(g["meta"][8])
+    dec = build_decoder(cfg["nq"], cfg["K"], cfg["layers"], cfg["F"])
+    dec.load_state_dict({k: torch.from_numpy(v) for k, v in W.items() if not k.startswith("heads.")}, strict=True)
+    dec = dec.cuda().train()
+    dec.compute_dtype = torch.float32
+    t = lambda a: torch.from_numpy(a).cuda()
+    memory = t(inp["memory"]).requires_grad_(True)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        hs, cls_hs, refs = dec(t(inp["tgt"]), memory, memory_key_padding_mask=t(inp["mask"]), pos=t(inp["pos"]),
+                               refpoints_unsigmoid=t(inp["refpoints_unsigmoid"]), orig_res=inp["orig_res"])
+    lw = synth.make_loss_weights(cfg, B, seed=seed)
+    loss = (t(lw["w_hs"]) * hs).sum() + (t(lw["w_cls"]) * cls_hs).sum() + (t(lw["w_refs"]) * refs).sum()
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 1e-3 * max(1.0, abs(float(g["loss"])))
+    assert rel_err(memory.grad.cpu().numpy(), g["gin.memory"]) < TOL_FP32
+    P = dict(dec.named_parameters())
+    assert P["cls_layers.0.q_proj.weight"].grad is None and P["cls_norm.weight"].grad is None     # unused in the reference too
+    for nm in ("norm.weight", "cls_norm2.bias", "layers.1.norm3.weight", "cls_layers.1.conv_blocks.0.norm.bias",
+               "ref_anchor_head.layers.1.weight", "bbox_embed.layers.2.weight", "layers.0.lvl_w_embed.weight"):
+        assert rel_err(P[nm].grad.cpu().numpy(), g["g." + nm]) < TOL_FP32, nm
+    w = P["cls_layers.0.conv_blocks.0.conv1.weight"].grad.cpu().numpy()
+    idx = synth.grad_sample_index(w.size, seed)
+    ref_s = g["gs.cls_layers.0.conv_blocks.0.conv1.weight"]
+    assert np.abs(w.reshape(-1)[idx] - ref_s).max() / np.abs(ref_s).max() < TOL_FP32
