@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "bwd.cuh"
 #include "kernels_mem.cuh"
+#include "tc_common.cuh"
 
 namespace cqvad {
 
@@ -18,7 +19,7 @@ constexpr int kThreads = kWarps * 32;
 inline unsigned row_grid(long rows) { return (unsigned)cdiv(rows, kWarps); }
 inline unsigned persist_grid(long rows) {
   long b = cdiv(rows, kWarps);
-  return (unsigned)(b < 148 * 4 ? (b < 1 ? 1 : b) : 148 * 4);
+  return (unsigned)(b < 148 * 8 ? (b < 1 ? 1 : b) : 148 * 8);
 }
 
 __device__ __forceinline__ float half_sum_lo(float v, int lane) { return warp_sum(lane < 16 ? v : 0.f); }
@@ -476,26 +477,42 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 __device__ __forceinline__ float gelu_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
 }
+constexpr int EW_UNROLL = 4;   // 16-byte vectors in flight per thread
 template <typename T>
-__global__ void act_bwd_kernel(T* dH, const T* __restrict__ ref, int act, long n8) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n8) return;
-  float d[8], r[8];
-  load8(dH + i * 8, d);
-  load8(ref + i * 8, r);
+__global__ void __launch_bounds__(256) act_bwd_kernel(T* dH, const T* __restrict__ ref, int act, long n8) {
+  const long base = ((long)blockIdx.x * blockDim.x) * EW_UNROLL + threadIdx.x;
+  float d[EW_UNROLL][8], r[EW_UNROLL][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) d[j] = act == CQVAD_ACT_RELU ? (r[j] > 0.f ? d[j] : 0.f) : d[j] * gelu_grad(r[j]);
-  store8(dH + i * 8, d);
+  for (int u = 0; u < EW_UNROLL; ++u) {
+    const long i = base + (long)u * blockDim.x;
+    if (i < n8) { load8(dH + i * 8, d[u]); load8(ref + i * 8, r[u]); }
+  }
+#pragma unroll
+  for (int u = 0; u < EW_UNROLL; ++u) {
+    const long i = base + (long)u * blockDim.x;
+    if (i >= n8) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[u][j] = act == CQVAD_ACT_RELU ? (r[u][j] > 0.f ? d[u][j] : 0.f) : d[u][j] * (DT<T>::id == CQVAD_BF16 ? tc::gelu_grad_fast(r[u][j]) : gelu_grad(r[u][j]));
+    store8(dH + i * 8, d[u]);
+  }
 }
 template <typename T>
-__global__ void gelu_fwd_kernel(const T* __restrict__ pre, T* __restrict__ out, long n8) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n8) return;
-  float v[8];
-  load8(pre + i * 8, v);
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const T* __restrict__ pre, T* __restrict__ out, long n8) {
+  const long base = ((long)blockIdx.x * blockDim.x) * EW_UNROLL + threadIdx.x;
+  float v[EW_UNROLL][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-  store8(out + i * 8, v);
+  for (int u = 0; u < EW_UNROLL; ++u) {
+    const long i = base + (long)u * blockDim.x;
+    if (i < n8) load8(pre + i * 8, v[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < EW_UNROLL; ++u) {
+    const long i = base + (long)u * blockDim.x;
+    if (i >= n8) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[u][j] = DT<T>::id == CQVAD_BF16 ? tc::gelu_fast(v[u][j]) : gelu_erf(v[u][j]);
+    store8(out + i * 8, v[u]);
+  }
 }
 template <typename D, typename S>
 __global__ void axpby_kernel(D* dst, const S* __restrict__ src, float beta, long n8) {
@@ -683,7 +700,7 @@ template <typename T>
 int act_bwd(T* dH, const T* ref, int act, long n, cudaStream_t st) {
   CQ_CHECK_SHAPE(n % 8 == 0, "act_bwd: element count must be a multiple of 8");
   if (n == 0) return 0;
-  act_bwd_kernel<T><<<(unsigned)cdiv(n / 8, 256), 256, 0, st>>>(dH, ref, act, n / 8);
+  act_bwd_kernel<T><<<(unsigned)cdiv(n / 8, 256 * EW_UNROLL), 256, 0, st>>>(dH, ref, act, n / 8);
   CQ_LAUNCH_CHECK();
   return 0;
 }
@@ -694,7 +711,7 @@ template <typename T>
 int gelu_fwd(const T* pre, T* out, long n, cudaStream_t st) {
   CQ_CHECK_SHAPE(n % 8 == 0, "gelu: element count must be a multiple of 8");
   if (n == 0) return 0;
-  gelu_fwd_kernel<T><<<(unsigned)cdiv(n / 8, 256), 256, 0, st>>>(pre, out, n / 8);
+  gelu_fwd_kernel<T><<<(unsigned)cdiv(n / 8, 256 * EW_UNROLL), 256, 0, st>>>(pre, out, n / 8);
   CQ_LAUNCH_CHECK();
   return 0;
 }

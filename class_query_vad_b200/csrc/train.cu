@@ -162,6 +162,9 @@ struct Trainer {
 
   // ---- ops -------------------------------------------------------------------------------------------------------
   // Y = act(X.W^T + b) (+ res)   [rows, Nout];  zero_period/valid: rows written as zeros (y-padded layout)
+  // Fusing gelu / act' into the GEMM epilogue (one thread per output row) measured SLOWER on B200 than a plain epilogue plus
+  // a full-occupancy elementwise pass (245 us vs 65 + 65 us on the [94 080 x 1024] ConvBlock hidden): off by default.
+  const bool fuse_act = getenv("CQVAD_TRAIN_FUSE_ACT") != nullptr;
   Ten<T>* last_c2 = nullptr;   // second output of the last lin(..., c2_act)
   Ten<T>* lin(Ten<T>* X, int widx, int Nout, int act = CQVAD_ACT_NONE, Ten<T>* res = nullptr, int zp = 0, int zv = 0,
               int* rc = nullptr, int c2_act = CQVAD_ACT_NONE) {
@@ -180,9 +183,10 @@ struct Trainer {
     if (fwd()) {
       Epilogue e;
       e.bias = Wf(widx + 1); e.act = act; e.res = res ? res->p : nullptr; e.ldr = Nout; e.zero_period = zp; e.zero_valid = zv;
-      if (A2) { e.c2 = A2->p; e.c2_act = c2_act; }
+      if (A2 && fuse_act) { e.c2 = A2->p; e.c2_act = c2_act; }
       int r;
       { ProfScope ps(P_T_FWD_GEMM, st); r = gemm<T>(X->p, Kd, Wm(widx), Y->p, Nout, X->rows, Nout, Kd, e, nullptr, st); }
+      if (r == 0 && A2 && !fuse_act) { ProfScope ps(P_T_FWD_OTHER, st); r = gelu_fwd<T>(Y->p, A2->p, Y->n(), st); }
       if (r == 0) r = dbg("lin", widx);
       if (r != 0 && rc && *rc == 0) *rc = r;
     }
@@ -205,7 +209,7 @@ struct Trainer {
           Epilogue e;
           const float b = beta(X);
           if (b != 0.f) { e.res = X->g; e.ldr = Kd; }
-          if (X->gact) {
+          if (X->gact && fuse_act) {
             if (b != 0.f) return set_error(CQVAD_E_INVALID_ARG, "backward: an activation output with two consumers is not supported");
             e.mul_aux = X->gref; e.mul_mode = X->gact; X->gmasked = true;   // dX = (dY . W) * act'(.) in the epilogue
           }
