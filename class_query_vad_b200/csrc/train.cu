@@ -98,7 +98,11 @@ struct Trainer {
   int BT, nq, h, wd, S, Sp, Sq, K, F, Lr;
   long N, NS, NSq, Rp, NK;
   std::deque<Ten<T>> tens;
-  std::vector<std::function<int()>> tape;
+  struct TapeEntry { std::function<int()> fn; int branch; };
+  struct Tape {
+    std::vector<TapeEntry> v; int* cur;
+    void push_back(std::function<int()> f) { v.push_back(TapeEntry{std::move(f), *cur}); }
+  } tape;
   std::vector<T*> wt;   // transposed / flipped weight copies for the data-gradient GEMMs, by weight index
   std::vector<char> wt_alloc, wt_built;
 
@@ -107,6 +111,10 @@ struct Trainer {
     BT = d.BT; nq = d.nq; h = d.h; wd = d.w; S = h * wd; Sp = (h + 1) * wd; K = d.K; F = d.F; Lr = d.layers;
     Sq = (S + 7) & ~7;
     N = (long)nq * BT; NS = N * S; NSq = N * Sq; Rp = N * Sp; NK = N * K;
+    tape.cur = &cur_branch;
+    static const bool one = [] { const char* e = getenv("CQVAD_TRAIN_STREAMS"); return e && atoi(e) == 1; }();
+    two_streams = !one && mode != PLAN && side_stream() != nullptr;
+    streams[0] = st; streams[1] = two_streams ? side_stream() : st;
     const size_t nw = (size_t)Lr * (LOC_COUNT + CLS_COUNT) + GLOB_COUNT;
     wt.assign(nw, nullptr); wt_alloc.assign(nw, 0); wt_built.assign(nw, 0);
   }
@@ -118,6 +126,37 @@ struct Trainer {
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) fprintf(stderr, "train[%s] after %s #%d (arena %zu): %s\n", mode == FWD ? "fwd" : "bwd", what, idx, a.off, cudaGetErrorString(e));
     if (e != cudaSuccess) return set_error(CQVAD_E_CUDA, "train[%s] after %s #%d (arena %zu): %s", mode == FWD ? "fwd" : "bwd", what, idx, a.off, cudaGetErrorString(e));
+    return 0;
+  }
+  // Two-stream schedule.  Branch 0 = localisation chain (prologue, loc layer, hs output, box refinement: mostly small-row
+  // latency-bound kernels), branch 1 = class branch (the large GEMM / conv / attention kernels).  Forward: the class branch
+  // of layer l waits for the loc layer l only, so the loc chain runs ahead; backward: the class chain runs ahead and the loc
+  // layer l waits for the class branch l.  Events fork from / join into the caller's stream; CQVAD_TRAIN_STREAMS=1 disables.
+  cudaStream_t streams[2];
+  int cur_branch = 0;
+  bool two_streams = false;
+  float* wg_scr[2] = {nullptr, nullptr};
+  static cudaStream_t side_stream() {
+    static cudaStream_t s = [] { cudaStream_t x = nullptr; cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking); return x; }();
+    return s;
+  }
+  static cudaEvent_t sync_event(int i) {
+    static cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (!ev[i]) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+    return ev[i];
+  }
+  int link(int from, int to) {   // stream `to` waits for everything enqueued on stream `from` so far
+    if (!two_streams) return 0;
+    cudaEvent_t e = sync_event(from);
+    CQ_CUDA(cudaEventRecord(e, streams[from]));
+    CQ_CUDA(cudaStreamWaitEvent(streams[to], e, 0));
+    return 0;
+  }
+  int set_branch(int b) {
+    if (b == cur_branch) return 0;
+    if (fwd() && b == 1) CQ_TRY(link(0, 1));   // forward: the class branch consumes what the loc chain has produced
+    cur_branch = b;
+    st = streams[two_streams ? b : 0];
     return 0;
   }
   bool fwd() const { return mode == FWD; }
@@ -343,7 +382,8 @@ int Trainer<T>::run() {
   T* xt = take(kC * ldxt);          // transposed class tokens of the forward self-attention kernel
   const bool use_tc = DT<T>::id == CQVAD_BF16 && !force_simt() && K <= 128 && ((S + 15) & ~15) <= 256;
   if (fwd() && use_tc) CQ_CUDA(cudaMemsetAsync(xt, 0, (size_t)kC * ldxt * sizeof(T), st));
-  float* wg_scratch = takef((long)(wgrad_scratch_bytes() / sizeof(float)));
+  wg_scr[0] = takef((long)(wgrad_scratch_bytes() / sizeof(float)));
+  wg_scr[1] = takef((long)(wgrad_scratch_bytes() / sizeof(float)));
   float* dkp32 = takef((long)S * BT * kC);           // fp32 staging of d(ca_kpos_proj(pos)) (summed over the nq actors)
   std::vector<float*> rl(Lr + 1), drl(Lr + 1);
   for (int l = 0; l <= Lr; ++l) { rl[l] = takef(N * 4); drl[l] = takef(N * 4); }
@@ -459,6 +499,7 @@ int Trainer<T>::run() {
     if (rc != 0) return rc;
     CQ_TRY(dbg("loc layer", l));
     // ---- class-query layer :1040-1079 (actor feature detached, :810) ----
+    CQ_TRY(set_branch(1));
     Ten<T>* actor_d = detach(actor);
     Ten<T>* cffn = lin(lin(actor_d, cls(l, C_L1), F, CQVAD_ACT_RELU, nullptr, 0, 0, &rc), cls(l, C_L2), kC, 0, nullptr, 0, 0, &rc);
     Ten<T>* acls = ln(cffn, actor_d, cls(l, C_NORM), 1e-5f, &rc);
@@ -578,21 +619,28 @@ int Trainer<T>::run() {
     Qprev = cls_out;
 
     // ---- outputs of this layer :826-827 ----
-    if (fwd()) {
-      CQ_TRY(layernorm_permute<T>(out2->p, Wf(glob(G_NORM)), Wf(glob(G_NORM) + 1), 1e-5f, (char*)io.hs + (size_t)l * N * kC * osz,
-                                  of32, N, nq, BT, 1, nullptr, st));
+    if (fwd())   // still on the class-branch stream
       CQ_TRY(layernorm_permute<T>(cls_out->p, Wf(glob(G_CLSNORM2)), Wf(glob(G_CLSNORM2) + 1), 1e-5f,
                                   (char*)io.cls_hs + (size_t)l * NK * kC * osz, of32, NK, nq, BT, K, nullptr, st));
-    }
     if (rec()) {
-      const int wn = glob(G_NORM), wc = glob(G_CLSNORM2);
+      const int wc = glob(G_CLSNORM2);
+      tape.push_back([=]() -> int {
+        if (io.g_cls)
+          CQ_TRY(ln_bwd<T>(cls_out->p, nullptr, Wf(wc), 1e-5f, (const char*)io.g_cls + (size_t)l * NK * kC * osz, of32, nq, BT, K,
+                           cls_out->g, beta(cls_out), nullptr, 0.f, G(wc), G(wc + 1), NK, st));
+        return 0;
+      });
+    }
+    CQ_TRY(set_branch(0));
+    if (fwd())
+      CQ_TRY(layernorm_permute<T>(out2->p, Wf(glob(G_NORM)), Wf(glob(G_NORM) + 1), 1e-5f, (char*)io.hs + (size_t)l * N * kC * osz,
+                                  of32, N, nq, BT, 1, nullptr, st));
+    if (rec()) {
+      const int wn = glob(G_NORM);
       tape.push_back([=]() -> int {
         if (io.g_hs)
           CQ_TRY(ln_bwd<T>(out2->p, nullptr, Wf(wn), 1e-5f, (const char*)io.g_hs + (size_t)l * N * kC * osz, of32, nq, BT, 1, out2->g,
                            beta(out2), nullptr, 0.f, G(wn), G(wn + 1), N, st));
-        if (io.g_cls)
-          CQ_TRY(ln_bwd<T>(cls_out->p, nullptr, Wf(wc), 1e-5f, (const char*)io.g_cls + (size_t)l * NK * kC * osz, of32, nq, BT, K,
-                           cls_out->g, beta(cls_out), nullptr, 0.f, G(wc), G(wc + 1), NK, st));
         return 0;
       });
     }
@@ -614,12 +662,24 @@ int Trainer<T>::run() {
   }
   if (rc != 0) return rc;
   if (a.overflow) return 0;   // PLAN mode / caller checks
+  if (fwd()) CQ_TRY(link(1, 0));   // join: the caller's stream waits for the class branch
   if (rec()) {
     // ---- backward: zero what is accumulated, then run the tape in reverse ----
+    st = streams[0];
     CQ_CUDA(cudaMemsetAsync(drl[0], 0, (size_t)N * 4 * sizeof(float), st));
-    set_wgrad_scratch(wg_scratch, wgrad_scratch_bytes());
-    int ti = (int)tape.size();
-    for (auto it = tape.rbegin(); it != tape.rend(); ++it) { CQ_TRY((*it)()); CQ_TRY(dbg("tape", --ti)); }
+    CQ_TRY(link(0, 1));            // fork: the class-branch stream starts after everything already on the caller's stream
+    int ti = (int)tape.v.size(), prev = 0;
+    for (auto it = tape.v.rbegin(); it != tape.v.rend(); ++it) {
+      const int b = it->branch;
+      if (b == 0 && prev == 1) CQ_TRY(link(1, 0));   // the loc layer consumes the class branch's gradients (q_memory, qse)
+      prev = b;
+      st = streams[two_streams ? b : 0];
+      set_wgrad_scratch(wg_scr[b], wgrad_scratch_bytes());
+      CQ_TRY(it->fn());
+      CQ_TRY(dbg("tape", --ti));
+    }
+    CQ_TRY(link(1, 0));            // join
+    st = streams[0];
   }
   return 0;
 }
