@@ -44,6 +44,7 @@ struct WgParams {
   int n_tiles, k_tiles;
   long rows_per_split;    // non-conv: rows (multiple of 64); conv: image rows of the padded layout (multiple of rt)
   int conv, cw, rt; long ny;
+  float* db;              // bias gradient (column sums of dY) accumulated by the otherwise idle epilogue warps, or nullptr
 };
 
 // MN-major, SWIZZLE_128B: start>>4 | LBO>>4 (one box) | SBO>>4 (8 rows x 128 B) | version 1 | layout 2
@@ -72,6 +73,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   const int valid_rows = p.conv ? p.cw * p.rt : WROWS;
   const int ksteps = (valid_rows + 15) / 16;
   const int n_slabs = (p.Nout - nt * TILE) > 128 ? 2 : 1;
+  const bool do_colsum = p.db != nullptr && kt == 0 && tap == 0;   // one (k-tile, tap) per n-tile and row range
 
   if (p.conv && valid_rows < WROWS) {   // rows the TMA boxes never write must read as zeros
     uint4* z = reinterpret_cast<uint4*>(smem_raw + (smem_base - smem_u32(smem_raw)));
@@ -81,7 +83,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmY);
     tma_prefetch_desc(&tmX);
-    for (int s = 0; s < WSTAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    // a stage is released by the MMA commit and, when this job also sums dY's columns, by the column-sum warps
+    for (int s = 0; s < WSTAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, do_colsum ? 2 : 1); }
     mbar_init(tfull_bar, 1);
     mbar_fence_init();
   }
@@ -139,6 +142,32 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     // ===== epilogue warps 2..5: TMEM lane quarter q = warp % 4 =====
     const int q = warp & 3;
     float* out = p.part + (size_t)job * TILE * TILE;
+    if (do_colsum) {
+      // db[n] += sum_rows dY[row, n]: thread e owns columns 2e, 2e+1 of the 256-column dY tile (box 2e/64, 16-byte chunk
+      // swizzled by the row): a warp reads one 128-byte box row per instruction -- bank-conflict free
+      const int e = (warp - 2) * 32 + lane;            // 0..127
+      const int col = 2 * e;
+      const uint32_t boxo = (uint32_t)(col >> 6) * BOX_BYTES, chunk = (uint32_t)((col & 63) >> 3), inner = (uint32_t)(col & 7) * 2u;
+      float s0 = 0.f, s1 = 0.f;
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(full_bar + 8 * stage, phase);
+        const uint32_t sY = smem_base + stage * STAGE_BYTES + boxo + inner;
+#pragma unroll 8
+        for (int r = 0; r < WROWS; ++r) {
+          uint32_t v;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(sY + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4)));
+          const float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+          s0 += f.x; s1 += f.y;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // all four warps are done with this stage
+        if (e == 0) mbar_arrive(empty_bar + 8 * stage);
+        if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
+      }
+      const int n = nt * TILE + col;
+      if (n < p.Nout) atomicAdd(p.db + n, s0);
+      if (n + 1 < p.Nout) atomicAdd(p.db + n + 1, s1);
+    }
     if (iters > 0) {
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
@@ -246,7 +275,7 @@ int wgrad_tc(const bf16* dY, long lddy, const bf16* X, long ldx, float* dW, long
   if (g_wg_err) return set_error(CQVAD_E_CUDA, "wgrad_tc: cannot reserve %d bytes of shared memory", WG_SMEM);
 
   WgParams p{};
-  p.part = g_scratch; p.M = M; p.Nout = Nout; p.Kin = Kin;
+  p.part = g_scratch; p.M = M; p.Nout = Nout; p.Kin = Kin; p.db = dW ? db : nullptr;
   CUtensorMap tmY, tmX;
   int tiles, splits;
   if (conv) {
@@ -299,7 +328,7 @@ int wgrad_tc(const bf16* dY, long lddy, const bf16* X, long ldx, float* dW, long
                                                                p.conv);
     CQ_LAUNCH_CHECK();
   }
-  if (db) {
+  if (db && !dW) {   // bias gradient alone (otherwise summed inside wgrad_tc_kernel)
     long gx = cdiv(M, 8 * 16);
     if (gx > 4 * sms) gx = 4 * sms;
     dim3 grid((unsigned)gx, (unsigned)cdiv(Nout, 256));
