@@ -20,12 +20,18 @@ gh, gc, gr = t(lw["w_hs"]).bfloat16(), t(lw["w_cls"]).bfloat16(), t(lw["w_refs"]
 ev = lambda: torch.cuda.Event(enable_timing=True)
 for it in range(int(os.environ.get('ITERS', '4'))):
     e0, e1, e2 = ev(), ev(), ev()
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     e0.record()
     out = eng.forward_train(d["tgt"], d["memory"], d["mask"], d["pos"], d["refpoints_unsigmoid"], (cfg["h"], cfg["w"]))
+    t1 = time.perf_counter()
     e1.record()
     g = eng.backward(gh, gc, gr, named=False)
+    t2 = time.perf_counter()
     e2.record()
     torch.cuda.synchronize()
+    print(f"   host enqueue: fwd {1e3 * (t1 - t0):.2f} ms, bwd {1e3 * (t2 - t1):.2f} ms")
     print(f"iter {it}: fwd {e0.elapsed_time(e1):.2f} ms ({eng.last_launches} launches)  bwd {e1.elapsed_time(e2):.2f} ms ({eng.last_launches_bwd} launches)"
           f"  -> {B / (e0.elapsed_time(e2) * 1e-3):.1f} clips/s", flush=True)
 import ctypes
