@@ -35,9 +35,11 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-CFG = "ava_vitb"
-FWD_GFLOP_PER_CLIP = 148.18            # BASELINE.md section 3 (reference flop count, AVA22_ViT-B decoder forward)
-TRAIN_GFLOP_PER_CLIP = 444.5           # fwd + bwd
+CFG = "ava_vitb"                       # --config: BASELINE.json configs[1] by default; configs[2..3] shapes selectable
+# decoder forward GFLOP per clip (reference flop count); fwd + bwd = 3x
+FWD_GFLOP = {"ava_vitb": 148.18, "ava_csn152": 187.98, "ucf_vitb": 2147.7, "jhmdb_vitb": 1162.8}
+DEFAULT_BATCH = {"ava_vitb": 32, "ava_csn152": 32, "ucf_vitb": 1, "jhmdb_vitb": 1}   # clips/GPU (UCF / JHMDB: 32 / 40 frames per clip)
+CFG_NAME = {"ava_vitb": "AVA22_ViT-B", "ava_csn152": "AVA22_CSN152", "ucf_vitb": "UCF_ViT-B", "jhmdb_vitb": "JHMDB_ViT-B"}
 
 
 def load_peaks():
@@ -132,9 +134,17 @@ def cpu_oracle_clips_per_s(mode, max_seconds=25.0, min_reps=1):
     return 1.0 / float(np.median(times)), len(times)
 
 
-WORK = {"train": "AVA22_ViT-B class-query decoder fwd + bwd (6 layers, nq 15, S 196, K 80, F 2048; gradients of all parameters, "
-                 "memory, tgt, refpoints)",
-        "infer": "AVA22_ViT-B class-query decoder forward + heads (6 layers, nq 15, S 196, K 80, F 2048)"}
+class _Work(dict):
+    def __getitem__(self, mode):
+        from oracle import synth
+        c = synth.CONFIGS[CFG]
+        shape = f"({c['layers']} layers, nq {c['nq']}, T' {c['tprime']}, S {c['h'] * c['w']}, K {c['K']}, F {c['F']}"
+        if mode == "train":
+            return f"{CFG_NAME[CFG]} class-query decoder fwd + bwd {shape}; gradients of all parameters, memory, tgt, refpoints)"
+        return f"{CFG_NAME[CFG]} class-query decoder forward + heads {shape})"
+
+
+WORK = _Work()
 HOST_KIND = {"train": "fp32 torch-CPU restatement of the reference decoder (oracle/decoder_torch.py), autograd backward",
              "infer": "fp32 numpy oracle port (oracle/decoder_np.py)"}
 
@@ -169,12 +179,17 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="clips per GPU (default: 32 for the AVA configs, 1 for UCF / JHMDB)")
+    ap.add_argument("--config", default="ava_vitb", choices=sorted(FWD_GFLOP))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    global CFG
+    CFG = args.config
+    if args.batch <= 0:
+        args.batch = DEFAULT_BATCH[CFG]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -197,6 +212,7 @@ def main():
 
     cfg = synth.CONFIGS[CFG]
     B = args.batch
+    BT = B * cfg["tprime"]
     nq, K, Lr, F = cfg["nq"], cfg["K"], cfg["layers"], cfg["F"]
     W = synth.make_decoder_weights(K, Lr, F, seed=0)
     eng = DecoderEngine(W, nq=nq, K=K, layers=Lr, F=F, dtype=torch.bfloat16, device=dev, out_f32=False)
@@ -212,15 +228,15 @@ def main():
         host_sets.append(hp)
         dev_sets.append({k: v.to(dev) for k, v in hp.items()})
     orig_res = (cfg["h"], cfg["w"])
-    det_local = torch.empty((B, nq, K + 4 + 3), dtype=torch.float32, device=dev)
-    det_all = torch.empty((world * B, nq, K + 4 + 3), dtype=torch.float32, device=dev) if world > 1 else det_local
-    det_host = torch.empty((B, nq, K + 4 + 3), dtype=torch.float32).pin_memory()
+    det_local = torch.empty((BT, nq, K + 4 + 3), dtype=torch.float32, device=dev)
+    det_all = torch.empty((world * BT, nq, K + 4 + 3), dtype=torch.float32, device=dev) if world > 1 else det_local
+    det_host = torch.empty((BT, nq, K + 4 + 3), dtype=torch.float32).pin_memory()
     from class_query_vad_b200.dist import allreduce_gradients
     lw = synth.make_loss_weights(cfg, B, seed=1)
     g_hs = torch.from_numpy(lw["w_hs"]).to(dev).bfloat16()
     g_cls = torch.from_numpy(lw["w_cls"]).to(dev).bfloat16()
     g_refs = torch.from_numpy(lw["w_refs"]).to(dev)
-    res_host = torch.empty((Lr * B * nq * 4 + B * nq * 256,), dtype=torch.float32).pin_memory()
+    res_host = torch.empty((Lr * BT * nq * 4 + BT * nq * 256,), dtype=torch.float32).pin_memory()
     launches = {"n": 0}
 
     def infer_step(inp):
@@ -296,7 +312,7 @@ def main():
         return ms, prof, n_launch, ms_e2e
 
     def train_result(out):
-        n1 = Lr * B * nq * 4
+        n1 = Lr * BT * nq * 4
         res_host[:n1].copy_(out["refs"].reshape(-1), non_blocking=True)
         res_host[n1:].copy_(out["hs"][-1].reshape(-1).float(), non_blocking=True)
 
@@ -328,11 +344,11 @@ def main():
     peaks = load_peaks()
     # ---- roofline of the dominant kernel: tcgen05 implicit-GEMM 3x3 conv; 2*N*S*C^2*9 FLOPs per launch ----
     S = cfg["h"] * cfg["w"]
-    conv_flops = 2.0 * (B * nq * S) * 256 * 2304
+    conv_flops = 2.0 * (BT * nq * S) * 256 * 2304
     if main_mode == "train":
         cf, cd = prof["train fwd: conv3x3 (tcgen05 implicit GEMM)"], prof["train bwd: conv3x3 dgrad (tcgen05 implicit GEMM)"]
         conv_launch_ms = (cf["ms_per_step"] + cd["ms_per_step"]) / max(cf["scopes"] + cd["scopes"], 1)
-        kname = "gemm_tc_kernel (conv mode: forward + data-gradient launches, 36 per step)"
+        kname = f"gemm_tc_kernel (conv mode: forward + data-gradient launches, {6 * Lr} per step)"
     else:
         conv = prof["conv3x3_ln (tcgen05 implicit GEMM)"]
         conv_launch_ms = conv["ms_per_step"] / max(conv["scopes"], 1)
@@ -350,12 +366,12 @@ def main():
         v, reps = cpu_oracle_clips_per_s(main_mode)
         cpu = {"value": v, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"{reps} x 1 clip, same workload shape ({WORK[main_mode]}), {HOST_KIND[main_mode]}"}
-    gflop = TRAIN_GFLOP_PER_CLIP if main_mode == "train" else FWD_GFLOP_PER_CLIP
+    gflop = 3.0 * FWD_GFLOP[CFG] if main_mode == "train" else FWD_GFLOP[CFG]
     line = {
         "metric": "decoder clips/s", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORK[main_mode] + f", {B} clips/GPU, dropout = identity", "mode": main_mode,
+        "config": {"workload": WORK[main_mode] + f", {B} clips/GPU, dropout = identity", "mode": main_mode, "config": CFG,
                    "batch_per_gpu": B, "parallelism": f"clip-sharded x{world}" + (", 1 gradient all-reduce/step" if main_mode == "train" and world > 1 else ""),
                    "l2": "4 input sets cycled (128 MB) + GBs of intermediates per step >> 126 MB L2",
                    "decoder_tflops": value * gflop / 1e3 / world},
@@ -371,7 +387,7 @@ def main():
         line["inference_forward"] = {
             "workload": WORK["infer"], "value": iclips / (ims / 1e3), "unit": "clips/s", "ms_per_step": ims / isteps, "steps": isteps,
             "e2e": iclips / (ims_e2e / 1e3), "gpu_launches_per_step": int(in_launch),
-            "decoder_tflops": iclips / (ims / 1e3) * FWD_GFLOP_PER_CLIP / 1e3 / world,
+            "decoder_tflops": iclips / (ims / 1e3) * FWD_GFLOP[CFG] / 1e3 / world,
             "breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in iprof.items()}}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -26,6 +26,8 @@ GRAD_CASES = [
     ("grad_small_masked", "small", 3, None, 2, True, True),
     ("grad_jhmdb_like", dict(nq=5, tprime=2, h=16, w=16, K=21, layers=1, F=2048), 1, None, 5, False, True),
     ("grad_ava_vitb_b1_l2", "ava_vitb", 1, 2, 0, False, True),      # BASELINE shape (nq 15, S 196, K 80, F 2048), 2 layers
+    ("grad_ava_csn_b1_l1", "ava_csn152", 1, 1, 3, True, True),      # CSN-152 grid 16x16 = 256 keys (the largest S), masked
+    ("grad_ucf_like", dict(nq=15, tprime=2, h=14, w=14, K=24, layers=1, F=2048), 1, None, 4, False, True),
 ]
 
 

@@ -11,7 +11,8 @@ from oracle import synth
 
 pytestmark = pytest.mark.gpu
 
-GRAD_CASES = ["grad_tiny", "grad_tiny_masked", "grad_small_masked", "grad_jhmdb_like", "grad_ava_vitb_b1_l2"]
+GRAD_CASES = ["grad_tiny", "grad_tiny_masked", "grad_small_masked", "grad_jhmdb_like", "grad_ava_vitb_b1_l2", "grad_ava_csn_b1_l1",
+              "grad_ucf_like"]
 UNUSED = ("q_proj.",)   # parameters the reference never uses in forward (grad None): SURVEY.md section 8c
 # Gradients that are ZERO analytically, so that the fixture holds only rounding noise (|g| ~ 1e-6 against ~1e1 elsewhere):
 #  * biases on the KEY side of a softmax attention (a constant added to every key shifts all scores of a query equally);
@@ -89,7 +90,7 @@ def test_decoder_grads_fp32_match_reference_autograd(name):
     assert not bad, f"gradient rel errors above {TOL_FP32}: {bad}"
 
 
-@pytest.mark.parametrize("name", ["grad_jhmdb_like", "grad_ava_vitb_b1_l2"])    # the BASELINE shapes (JHMDB / AVA ViT-B)
+@pytest.mark.parametrize("name", ["grad_jhmdb_like", "grad_ava_vitb_b1_l2", "grad_ava_csn_b1_l1", "grad_ucf_like"])   # BASELINE shapes
 def test_decoder_grads_bf16_match_reference_autograd(name):
     g = load_golden(name)
     cfg, B, W, inp = case_from_meta(g["meta"])
