@@ -12,9 +12,16 @@
 //   * epilogue straight out of TMEM (tcgen05.ld 32x32b: one thread = one output row): bias, ReLU / erf-GELU, residual,
 //     zero-row masking, and row LayerNorm when N == 256 (pre-norm values stashed back into TMEM with tcgen05.st so
 //     the residual is read once).
+//   * TS variant (every non-conv GEMM with a bf16-only epilogue): 3-stage ring + a 64 KB output staging area.  The epilogue
+//     warps write bf16 rows into 128-byte-swizzled shared memory (conflict-free 16-byte stores) and ONE lane per warp issues
+//     a TMA store of a [32 rows x 64 cols] box; the bf16 residual (or the activation-derivative operand) arrives the same way
+//     through a TMA load into the staging buffer.  Evidence (ncu, profiles/): with one thread per output row every global
+//     store / residual load instruction touched 32 different 128-byte lines -- the LSU data pipe was the top unit at 55%,
+//     L1->L2 write traffic was 2x the output (half-filled sectors) and the K = 256 GEMMs ran at 2.1 TB/s of 6.5.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <mutex>
+#include <stdlib.h>
 
 namespace cqvad {
 
@@ -22,13 +29,18 @@ using namespace tc;
 
 namespace {
 
-constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, STAGES = 4, UMMA_K = 16;
+constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, STAGES_DIRECT = 4, UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
-constexpr int SMEM_TILES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+constexpr int SMEM_TILES = STAGES_DIRECT * (A_STAGE_BYTES + B_STAGE_BYTES);
 // aux: barriers 256 | bias [2][256] f32 (per TMEM buffer) | gamma [256] | beta [256] | LN partial sums [2][2][128][2] f32
 constexpr int AUX_BIAS = 256, AUX_GAM = AUX_BIAS + 2048, AUX_BET = AUX_GAM + 1024, AUX_STATS = AUX_BET + 1024, AUX_BYTES = AUX_STATS + 4096;
 constexpr int SMEM_BYTES = SMEM_TILES + 1024 /*align slack*/ + AUX_BYTES;
+constexpr int STAGES_TS = 3;
+constexpr int STG_BOX_BYTES = 32 * 64 * 2;                      // one [32 rows x 64 cols] bf16 box, 128 B per row
+constexpr int STG_BYTES = 8 * 2 * STG_BOX_BYTES;                // 8 epilogue warps x 2 column halves of their 128 columns
+constexpr int SMEM_BYTES_TS = STAGES_TS * (A_STAGE_BYTES + B_STAGE_BYTES) + STG_BYTES + 1024 + AUX_BYTES;
+constexpr int AUX_RBAR = 128;                                   // 8 warps x 2 mbarriers for the TMA-loaded side input
 constexpr int NUM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter: 128 columns each)
 constexpr int TMEM_COLS = 512;
 
@@ -41,6 +53,7 @@ struct TcParams {
   // conv
   int conv; int cw; int rt;  // image width, image rows per tile
   int m_tiles, n_tiles;
+  int side;   // TS: 1 = bf16 residual, 2 = activation-derivative operand (mul_aux) arrives through tmR
 };
 
 __device__ __forceinline__ void unpack8(const uint4& r, float (&v)[8]) {
@@ -55,15 +68,18 @@ __device__ __forceinline__ float gelu_grad(float x) {
 
 // EXTRA = true: the training-path epilogue options (second activated output, activation-derivative mask); a separate
 // instantiation so that the inference epilogue carries none of their instructions.
-template <bool EXTRA>
+template <bool EXTRA, bool TS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
+  constexpr int STAGES = TS ? STAGES_TS : STAGES_DIRECT;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base, sB = smem_base + STAGES * A_STAGE_BYTES;
-  const uint32_t bars = smem_base + SMEM_TILES;
+  const uint32_t stg_base = smem_base + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);   // TS only
+  const uint32_t bars = stg_base + (TS ? STG_BYTES : 0);
   const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES, tfull_bar = bars + 16 * STAGES,
-                 tempty_bar = tfull_bar + 16, tmem_slot = tempty_bar + 16;
+                 tempty_bar = tfull_bar + 16, tmem_slot = tempty_bar + 16, rbar_base = bars + AUX_RBAR;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
   const int kblocks = p.K / BLOCK_K;
@@ -73,6 +89,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 8); }
+    if constexpr (TS) {
+      tma_prefetch_desc(&tmC);
+      if (p.side) tma_prefetch_desc(&tmR);
+      for (int i = 0; i < 16; ++i) mbar_init(rbar_base + 8 * i, 1);
+    }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -145,6 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool do_ln = p.ln_g != nullptr;
     if (do_ln) { gam_s[et] = p.ln_g[et]; bet_s[et] = p.ln_b[et]; }   // N == 256, one n-tile
     int acc = 0; uint32_t acc_phase = 0;
+    uint32_t rph0 = 0, rph1 = 0;      // TS: parities of this warp's two side-input barriers
     const int tile_rows = p.conv ? p.cw * p.rt : BLOCK_M;
     const int c0 = g * 128;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -152,6 +174,139 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = nt * BLOCK_N;
       float* bcur = bias_s + acc * 256;
       bcur[et] = (p.bias && n0 + et < p.N) ? p.bias[n0 + et] : 0.f;
+      if constexpr (TS) {
+        // ---- TMA-store epilogue (non-conv): this warp owns rows [row0, row0+32) x columns [colw, colw+128) of C as two
+        // [32 x 64] boxes; buffer hf is reused one whole tile later, so the store of the previous tile has long been read ----
+        const int row0 = mt * BLOCK_M + q * 32;
+        const int colw = n0 + c0;
+        const uint32_t stg = stg_base + (uint32_t)((warp - 2) * 2 * STG_BOX_BYTES);
+        const uint32_t rbar = rbar_base + (uint32_t)((warp - 2) * 16);
+        const uint32_t my_row = stg + (uint32_t)(lane * 128);
+        const int sw = lane & 7;                                  // 128-byte swizzle: 16-byte chunk j of row r sits at j ^ (r & 7)
+        const bool act0 = colw < p.N, act1 = colw + 64 < p.N;     // column halves inside the matrix (warp-uniform)
+        if (p.side && lane == 0) {
+          // side-input boxes (bf16 residual / activation-derivative operand) -> the staging buffers themselves
+          bulk_wait_read<1>();
+          if (act0) { mbar_arrive_expect_tx(rbar, STG_BOX_BYTES); tma_load_2d(stg, &tmR, rbar, colw, row0); }
+          bulk_wait_read<0>();
+          if (act1) { mbar_arrive_expect_tx(rbar + 8, STG_BOX_BYTES); tma_load_2d(stg + STG_BOX_BYTES, &tmR, rbar + 8, colw + 64, row0); }
+        }
+        mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        tc_fence_after();
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // bias (and gamma/beta) visible to the 8 epilogue warps
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
+        const long grow = (long)row0 + lane;
+        const bool zero_row = p.zero_period > 0 && (int)(grow % p.zero_period) >= p.zero_valid;
+        float mean = 0.f, rstd = 1.f;
+        if (do_ln) {
+          // pass 1 (N == 256): v = act(acc + bias) (+res); stash v in TMEM; partial row statistics over this warp's 128 columns
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < 128; c += 32) {
+            const int hf = c >> 6;
+            const uint32_t buf = my_row + (uint32_t)(hf * STG_BOX_BYTES);
+            if (p.side == 1 && (c & 63) == 0) mbar_wait(rbar + 8 * hf, hf ? rph1 : rph0);
+            uint32_t r[32];
+            tmem_ld32(t_addr + c, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              float rs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+              if (p.side == 1) unpack8(lds128(buf + (uint32_t)(((((c & 63) >> 3) + g8) ^ sw) << 4)), rs);
+              float bs[8];
+              load8(bcur + c0 + c + g8 * 8, bs);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float v = __uint_as_float(r[g8 * 8 + j]) + bs[j];
+                if (p.act == CQVAD_ACT_RELU) v = fmaxf(v, 0.f);
+                else if (p.act == CQVAD_ACT_GELU) v = gelu_erf(v);
+                v += rs[j];
+                s1 += v; s2 = fmaf(v, v, s2);
+                r[g8 * 8 + j] = __float_as_uint(v);
+              }
+            }
+            tmem_st32(t_addr + c, r);
+          }
+          tmem_st_wait();
+          float* st = stats_s + acc * 512;
+          st[(g * 128 + row_in_tile) * 2] = s1;
+          st[(g * 128 + row_in_tile) * 2 + 1] = s2;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const float o1 = st[((g ^ 1) * 128 + row_in_tile) * 2], o2 = st[((g ^ 1) * 128 + row_in_tile) * 2 + 1];
+          mean = (s1 + o1) * (1.0f / BLOCK_N);
+          const float var = fmaxf((s2 + o2) * (1.0f / BLOCK_N) - mean * mean, 0.f);
+          rstd = rsqrtf(var + p.ln_eps);
+        }
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          const bool active = hf ? act1 : act0;
+          const uint32_t buf = my_row + (uint32_t)(hf * STG_BOX_BYTES);
+          if (active) {
+            if (p.side) { if (!do_ln) mbar_wait(rbar + 8 * hf, hf ? rph1 : rph0); }
+            else { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }   // this buffer's store of the previous tile has been read
+#pragma unroll 1
+            for (int cc = 0; cc < 64; cc += 32) {
+              const int c = hf * 64 + cc;
+              uint32_t r[32];
+              tmem_ld32(t_addr + c, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8) {
+                const int cb = c + g8 * 8;
+                const uint32_t saddr = buf + (uint32_t)((((cc >> 3) + g8) ^ sw) << 4);
+                float v[8];
+                if (do_ln) {
+                  float gm[8], bt[8];
+                  load8(gam_s + c0 + cb, gm);
+                  load8(bet_s + c0 + cb, bt);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] = (__uint_as_float(r[g8 * 8 + j]) - mean) * rstd * gm[j] + bt[j];
+                } else {
+                  float bs[8];
+                  load8(bcur + c0 + cb, bs);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    float x = __uint_as_float(r[g8 * 8 + j]) + bs[j];
+                    if (p.act == CQVAD_ACT_RELU) x = fmaxf(x, 0.f);
+                    else if (p.act == CQVAD_ACT_GELU) x = gelu_erf(x);
+                    v[j] = x;
+                  }
+                  if (p.side) {
+                    float sx[8];
+                    unpack8(lds128(saddr), sx);
+                    if (p.side == 1) {
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) v[j] += sx[j];
+                    } else if constexpr (EXTRA) {
+                      if (p.mul_mode == 1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = sx[j] > 0.f ? v[j] : 0.f;
+                      } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] *= gelu_grad_fast(sx[j]);
+                      }
+                    }
+                  }
+                }
+                if (zero_row) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+                }
+                uint4 o;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                sts128(saddr, o);
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tma_store_2d(&tmC, stg + (uint32_t)(hf * STG_BOX_BYTES), colw + hf * 64, row0);
+          }
+          if (lane == 0) bulk_commit();     // always two groups per tile (an empty group for a half outside the matrix)
+        }
+        if (p.side) { if (act0) rph0 ^= 1; if (act1) rph1 ^= 1; }
+      } else {
       const long grow = (long)mt * tile_rows + row_in_tile;
       const bool row_ok = row_in_tile < tile_rows && grow < p.M;
       // bf16 residual fetched one 32-column step ahead (4 x 16 bytes in flight per thread)
@@ -308,12 +463,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      }   // direct-store epilogue
       // release the accumulator buffer to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if constexpr (TS) { if (lane == 0) bulk_wait_read<0>(); }   // shared memory stays valid until the last stores have read it
+    (void)rph0; (void)rph1;
   }
 
   tc_fence_before();
@@ -343,8 +501,10 @@ void init_once() {
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) g_init_err = 2;
-  if (cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
 }
 
 }  // namespace
@@ -418,8 +578,31 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
   }
   const long tiles = (long)p.m_tiles * p.n_tiles;
   const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
-  if (p.c2 || p.mul_mode) gemm_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
-  else gemm_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
+  // TMA-store epilogue: every non-conv GEMM whose epilogue reads / writes bf16 only (at most one [M,N] side input)
+  static const bool no_ts = getenv("CQVAD_GEMM_NO_TS") != nullptr;
+  const bool ts = !no_ts && !conv && !epi.c32 && !epi.res32 && !epi.c2 && N % 8 == 0 && !(epi.res && epi.mul_mode);
+  if (ts) {
+    CUtensorMap tmC, tmR;
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    const cuuint32_t box[2] = {64, 32};
+    const cuuint64_t sc[1] = {(cuuint64_t)ldc * 2};
+    CQ_TRY(make_tmap_bf16(&tmC, C, 2, dims, sc, box));
+    tmR = tmC;
+    if (epi.res) {
+      const cuuint64_t sr[1] = {(cuuint64_t)epi.ldr * 2};
+      CQ_TRY(make_tmap_bf16(&tmR, epi.res, 2, dims, sr, box));
+      p.side = 1;
+    } else if (epi.mul_mode) {
+      CQ_TRY(make_tmap_bf16(&tmR, epi.mul_aux, 2, dims, sc, box));
+      p.side = 2;
+    }
+    if (p.mul_mode) gemm_tc_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES_TS, st>>>(tmA, tmB, tmC, tmR, p);
+    else gemm_tc_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES_TS, st>>>(tmA, tmB, tmC, tmR, p);
+  } else if (p.c2 || p.mul_mode) {
+    gemm_tc_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, tmA, tmA, p);
+  } else {
+    gemm_tc_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, tmA, tmA, p);
+  }
   CQ_LAUNCH_CHECK();
   return 0;
 }

@@ -21,6 +21,16 @@ def load_golden(name):
     return {k: z[k] for k in z.files}
 
 
+def case_from_golden(g):
+    """case_from_meta + the fixture's stored bias overrides (`wb.<name>`: ReLU-kink clearing, oracle/make_golden_grads.py)."""
+    cfg, B, W, inp = case_from_meta(g["meta"])
+    for k in g:
+        if k.startswith("wb."):
+            assert W[k[3:]].shape == g[k].shape, k
+            W[k[3:]] = np.ascontiguousarray(g[k], dtype=np.float32)
+    return cfg, B, W, inp
+
+
 def case_from_meta(meta):
     B, nq, tp, h, w, K, layers, F, seed, masked, tgt_zero = (int(v) for v in meta)
     cfg = dict(nq=nq, tprime=tp, h=h, w=w, K=K, layers=layers, F=F)

@@ -1,7 +1,7 @@
 """Pins the CPU oracle (oracle/*.py) against fixtures produced by the reference itself (oracle/make_golden.py)."""
 import numpy as np
 import pytest
-from helpers import load_golden, case_from_meta, rel_err
+from helpers import load_golden, case_from_meta, case_from_golden, rel_err
 from oracle import decoder_np, posenc_np, msda_np, synth
 
 FAST = ["dec_tiny", "dec_tiny_masked", "dec_small_masked", "dec_ucf_like", "dec_jhmdb_like", "dec_ava_csn_b1_l2"]
@@ -90,7 +90,7 @@ def test_torch_restatement_gradients_match_reference_autograd(name):
     """oracle/decoder_torch.py (the host baseline of the TRAINING step) against gradients of the unmodified reference."""
     from oracle import decoder_torch
     g = load_golden(name)
-    cfg, B, W, inp = case_from_meta(g["meta"])
+    cfg, B, W, inp = case_from_golden(g)
     seed = int(g["meta"][8])
     lw = synth.make_loss_weights(cfg, B, seed=seed)
     loss, grads, gmem, gtgt, gref = decoder_torch.train_step(W, inp, lw, cfg["layers"])

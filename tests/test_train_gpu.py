@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import load_golden, case_from_meta, rel_err, TOL_FP32, TOL_BF16
+from helpers import load_golden, case_from_golden, rel_err, TOL_FP32, TOL_BF16
 from oracle import synth
 
 pytestmark = pytest.mark.gpu
@@ -81,7 +81,7 @@ def grad_errors(grads, g, seed, tgt_zero=True, want_l2=False):
 @pytest.mark.parametrize("name", GRAD_CASES)
 def test_decoder_grads_fp32_match_reference_autograd(name):
     g = load_golden(name)
-    cfg, B, W, inp = case_from_meta(g["meta"])
+    cfg, B, W, inp = case_from_golden(g)
     seed = int(g["meta"][8])
     loss, grads, _ = run_train(cfg, B, W, inp, seed, torch.float32)
     assert abs(loss - float(g["loss"])) < 1e-3 * max(1.0, abs(float(g["loss"])))
@@ -93,7 +93,7 @@ def test_decoder_grads_fp32_match_reference_autograd(name):
 @pytest.mark.parametrize("name", ["grad_jhmdb_like", "grad_ava_vitb_b1_l2", "grad_ava_csn_b1_l1", "grad_ucf_like"])   # BASELINE shapes
 def test_decoder_grads_bf16_match_reference_autograd(name):
     g = load_golden(name)
-    cfg, B, W, inp = case_from_meta(g["meta"])
+    cfg, B, W, inp = case_from_golden(g)
     seed = int(g["meta"][8])
     loss, grads, eng = run_train(cfg, B, W, inp, seed, torch.bfloat16)
     errs, l2 = grad_errors(grads, g, seed, tgt_zero=bool(int(g["meta"][10])), want_l2=True)
@@ -119,7 +119,7 @@ def test_decoder_grads_bf16_tensor_core_and_cuda_core_paths_agree():
     inputs: two bf16 pipelines that differ only in the kernels used."""
     from class_query_vad_b200 import _lib
     g = load_golden("grad_jhmdb_like")
-    cfg, B, W, inp = case_from_meta(g["meta"])
+    cfg, B, W, inp = case_from_golden(g)
     seed = int(g["meta"][8])
     _, g_tc, _ = run_train(cfg, B, W, inp, seed, torch.bfloat16)
     g_tc = {"memory": g_tc["memory"].clone(), **{k: v.clone() for k, v in g_tc["params"].items()}}
@@ -174,7 +174,7 @@ def test_module_autograd_drop_in():
     reference-named parameters (fp32 path, against the reference-autograd fixture)."""
     from class_query_vad_b200 import build_decoder
     g = load_golden("grad_tiny_masked")
-    cfg, B, W, inp = case_from_meta(g["meta"])
+    cfg, B, W, inp = case_from_golden(g)
     seed = int(g["meta"][8])
     dec = build_decoder(cfg["nq"], cfg["K"], cfg["layers"], cfg["F"])
     dec.load_state_dict({k: torch.from_numpy(v) for k, v in W.items() if not k.startswith("heads.")}, strict=True)

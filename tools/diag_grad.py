@@ -3,14 +3,14 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
-from helpers import load_golden, case_from_meta
+from helpers import load_golden, case_from_golden
 from test_train_gpu import run_train, grad_errors
 
 names = sys.argv[2:] or ["grad_tiny"]
 dtype = torch.float32 if sys.argv[1] == "f32" else torch.bfloat16
 for name in names:
     g = load_golden(name)
-    cfg, B, W, inp = case_from_meta(g["meta"])
+    cfg, B, W, inp = case_from_golden(g)
     seed = int(g["meta"][8])
     loss, grads, eng = run_train(cfg, B, W, inp, seed, dtype)
     print(name, "loss", loss, "ref", float(g["loss"]), "launches fwd", eng.last_launches, "bwd", eng.last_launches_bwd)
