@@ -31,15 +31,15 @@ namespace {
 
 constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, STAGES_DIRECT = 4, UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
-constexpr int SMEM_TILES = STAGES_DIRECT * (A_STAGE_BYTES + B_STAGE_BYTES);
+constexpr int B_STAGE_FULL = BLOCK_N * BLOCK_K * 2;  // 32 KB (a CTA pair holds half of it per CTA)
+constexpr int SMEM_TILES = STAGES_DIRECT * (A_STAGE_BYTES + B_STAGE_FULL);
 // aux: barriers 256 | bias [2][256] f32 (per TMEM buffer) | gamma [256] | beta [256] | LN partial sums [2][2][128][2] f32
 constexpr int AUX_BIAS = 256, AUX_GAM = AUX_BIAS + 2048, AUX_BET = AUX_GAM + 1024, AUX_STATS = AUX_BET + 1024, AUX_BYTES = AUX_STATS + 4096;
 constexpr int SMEM_BYTES = SMEM_TILES + 1024 /*align slack*/ + AUX_BYTES;
 constexpr int STAGES_TS = 3;
 constexpr int STG_BOX_BYTES = 32 * 64 * 2;                      // one [32 rows x 64 cols] bf16 box, 128 B per row
 constexpr int STG_BYTES = 8 * 2 * STG_BOX_BYTES;                // 8 epilogue warps x 2 column halves of their 128 columns
-constexpr int SMEM_BYTES_TS = STAGES_TS * (A_STAGE_BYTES + B_STAGE_BYTES) + STG_BYTES + 1024 + AUX_BYTES;
+constexpr int SMEM_BYTES_TS = STAGES_TS * (A_STAGE_BYTES + B_STAGE_FULL) + STG_BYTES + 1024 + AUX_BYTES;
 constexpr int AUX_RBAR = 128;                                   // 8 warps x 2 mbarriers for the TMA-loaded side input
 constexpr int NUM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter: 128 columns each)
 constexpr int TMEM_COLS = 512;
@@ -53,6 +53,8 @@ struct TcParams {
   // conv
   int conv; int cw; int rt;  // image width, image rows per tile
   int m_tiles, n_tiles;
+  long long* trace;   // dev tool (CQVAD_GEMM_TRACE=<device address>): globaltimer stamps of CTA 0's pipeline events
+  int lean;   // TS: bias + none/ReLU (+ bf16 residual) only -> branch-free epilogue
   int side;   // TS: 1 = bf16 residual, 2 = activation-derivative operand (mul_aux) arrives through tmR
 };
 
@@ -61,6 +63,14 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// trace slots: [0,256) producer stage issue, [256,512) MMA full-wait done, [512,640) MMA tempty-wait done,
+// [640,768) epilogue warp 2 tfull-wait done, [768,896) epilogue warp 2 tile done
+#define CQ_TRACE(slot, idx, lim) do { if (p.trace && blockIdx.x == 0 && (idx) < (lim)) p.trace[(slot) + (idx)] = gtimer(); } while (0)
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
@@ -68,11 +78,58 @@ __device__ __forceinline__ float gelu_grad(float x) {
 
 // EXTRA = true: the training-path epilogue options (second activated output, activation-derivative mask); a separate
 // instantiation so that the inference epilogue carries none of their instructions.
-template <bool EXTRA, bool TS>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
-  constexpr int STAGES = TS ? STAGES_TS : STAGES_DIRECT;
+// Lean TS epilogue step (bias + optional ReLU + optional bf16 residual already sitting in the staging buffer): 64 columns of one
+// row per thread, branch-free, packed fp32x2 adds.  The general epilogue spends ~210 warp instructions per 32 columns on
+// runtime option checks; the pipeline trace (tools/trace_gemm.py) showed the epilogue, at 2.8 us per 128 x 256 tile, as the
+// stage that paces the K = 256 GEMMs (MMA 1.1 us, loads hidden).
+template <bool SIDE>
+__device__ __forceinline__ void ts_lean_half(uint32_t t_addr, const float* bias, uint32_t row_base, int sw, float lo) {
+#pragma unroll
+  for (int cc = 0; cc < 64; cc += 32) {
+    uint32_t r[32];
+    tmem_ld32(t_addr + cc, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      const uint32_t saddr = row_base + (uint32_t)((((cc >> 3) + g8) ^ sw) << 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + cc + g8 * 8), b1 = *reinterpret_cast<const float4*>(bias + cc + g8 * 8 + 4);
+      uint64_t x[4];
+      x[0] = f2add(f2pack(__uint_as_float(r[g8 * 8 + 0]), __uint_as_float(r[g8 * 8 + 1])), f2pack(b0.x, b0.y));
+      x[1] = f2add(f2pack(__uint_as_float(r[g8 * 8 + 2]), __uint_as_float(r[g8 * 8 + 3])), f2pack(b0.z, b0.w));
+      x[2] = f2add(f2pack(__uint_as_float(r[g8 * 8 + 4]), __uint_as_float(r[g8 * 8 + 5])), f2pack(b1.x, b1.y));
+      x[3] = f2add(f2pack(__uint_as_float(r[g8 * 8 + 6]), __uint_as_float(r[g8 * 8 + 7])), f2pack(b1.z, b1.w));
+      uint4 sv;
+      if constexpr (SIDE) sv = lds128(saddr);
+      uint4 o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+      const uint32_t* sw32 = reinterpret_cast<const uint32_t*>(&sv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a, b;
+        f2unpack(x[j], a, b);
+        a = fmaxf(a, lo); b = fmaxf(b, lo);
+        if constexpr (SIDE) {
+          a += __uint_as_float(sw32[j] << 16);            // bf16 -> fp32: low half = first element
+          b += __uint_as_float(sw32[j] & 0xffff0000u);
+        }
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(ow[j]) : "f"(b), "f"(a));
+      }
+      sts128(saddr, o);
+    }
+  }
+}
+
+// CTA2 = true: CTA pair (cluster of 2 on one TPC, tcgen05 cta_group::2).  The pair computes two vertically adjacent
+// 128 x 256 output tiles with ONE M = 256 UMMA stream issued by the leader; each CTA loads its own A tile and only HALF of
+// the weight tile, so the weight traffic L2 -> SM halves (the conv / large-K GEMMs were bound by the ~6300 B/clk L2 slice
+// throughput, not by the tensor pipe: B re-reads were 2/3 of the conv's L2 traffic) and the ring holds 6 (TS: 4) k-blocks.
+template <bool EXTRA, bool TS, bool CTA2>
+__device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                                             const CUtensorMap& tmR, const TcParams& p) {
+  constexpr int STAGES = CTA2 ? (TS ? 4 : 6) : (TS ? STAGES_TS : STAGES_DIRECT);
+  constexpr int B_STAGE_BYTES = CTA2 ? B_STAGE_FULL / 2 : B_STAGE_FULL;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const int ncta = CTA2 ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base, sB = smem_base + STAGES * A_STAGE_BYTES;
@@ -81,14 +138,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES, tfull_bar = bars + 16 * STAGES,
                  tempty_bar = tfull_bar + 16, tmem_slot = tempty_bar + 16, rbar_base = bars + AUX_RBAR;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  // work unit = one tile (a vertical PAIR of tiles for a CTA pair: this CTA takes m-tile 2 * mpair + rank)
+  const int num_tiles = ((p.m_tiles + ncta - 1) / ncta) * p.n_tiles;
+  const int first_tile = blockIdx.x / ncta, tile_step = gridDim.x / ncta;
   const int kblocks = p.K / BLOCK_K;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 8 * ncta); }
     if constexpr (TS) {
       tma_prefetch_desc(&tmC);
       if (p.side) tma_prefetch_desc(&tmR);
@@ -96,9 +155,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) { if constexpr (CTA2) tmem_alloc_pair(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS); }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -108,47 +168,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ===== TMA producer =====
       const uint32_t a_bytes = p.conv ? (uint32_t)(p.cw * p.rt * BLOCK_K * 2) : (uint32_t)A_STAGE_BYTES;
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+      int ev = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int mt = (tile / p.n_tiles) * ncta + (int)rank, nt = tile % p.n_tiles;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-          const uint32_t fb = full_bar + 8 * stage;
-          mbar_arrive_expect_tx(fb, a_bytes + (uint32_t)B_STAGE_BYTES);
-          if (p.conv) {
-            const int tap = kb >> 2, c0 = (kb & 3) * BLOCK_K;
-            tma_load_3d(sA + stage * A_STAGE_BYTES, &tmA, fb, c0, tap % 3 - 1, mt * p.rt + tap / 3 - 1);
+          CQ_TRACE(0, ev, 256); ++ev;
+          if constexpr (CTA2) {
+            // both CTAs' bytes land on the LEADER's full barrier (the leader arms it with the pair's total)
+            const uint32_t fb = mapa_shared(full_bar + 8 * stage, 0);
+            if (rank == 0) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * (a_bytes + (uint32_t)B_STAGE_BYTES));
+            if (p.conv) {
+              const int tap = kb >> 2, c0 = (kb & 3) * BLOCK_K;
+              tma_load_3d_pair(sA + stage * A_STAGE_BYTES, &tmA, fb, c0, tap % 3 - 1, mt * p.rt + tap / 3 - 1);
+            } else {
+              tma_load_2d_pair(sA + stage * A_STAGE_BYTES, &tmA, fb, kb * BLOCK_K, mt * BLOCK_M);
+            }
+            tma_load_2d_pair(sB + stage * B_STAGE_BYTES, &tmB, fb, kb * BLOCK_K, nt * BLOCK_N + (int)rank * (BLOCK_N / 2));
           } else {
-            tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, fb, kb * BLOCK_K, mt * BLOCK_M);
+            const uint32_t fb = full_bar + 8 * stage;
+            mbar_arrive_expect_tx(fb, a_bytes + (uint32_t)B_STAGE_BYTES);
+            if (p.conv) {
+              const int tap = kb >> 2, c0 = (kb & 3) * BLOCK_K;
+              tma_load_3d(sA + stage * A_STAGE_BYTES, &tmA, fb, c0, tap % 3 - 1, mt * p.rt + tap / 3 - 1);
+            } else {
+              tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, fb, kb * BLOCK_K, mt * BLOCK_M);
+            }
+            tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, fb, kb * BLOCK_K, nt * BLOCK_N);
           }
-          tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, fb, kb * BLOCK_K, nt * BLOCK_N);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (the leader CTA of a pair) =====
+      constexpr uint32_t idesc = make_idesc_bf16(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int ev = 0, evt = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        CQ_TRACE(512, evt, 128); ++evt;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(full_bar + 8 * stage, phase);
+          CQ_TRACE(256, ev, 256); ++ev;
           tc_fence_after();
           const uint64_t a_desc = make_smem_desc_sw128(sA + stage * A_STAGE_BYTES);
           const uint64_t b_desc = make_smem_desc_sw128(sB + stage * B_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in the (addr>>4) field
-            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (CTA2) umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar + 8 * stage);  // frees this smem stage when the MMAs above have read it
+          // frees this smem stage (in both CTAs of a pair) when the MMAs above have read it
+          if constexpr (CTA2) umma_commit_pair(empty_bar + 8 * stage); else umma_commit(empty_bar + 8 * stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar + 8 * acc);      // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (CTA2) umma_commit_pair(tfull_bar + 8 * acc); else umma_commit(tfull_bar + 8 * acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -166,11 +247,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool do_ln = p.ln_g != nullptr;
     if (do_ln) { gam_s[et] = p.ln_g[et]; bet_s[et] = p.ln_b[et]; }   // N == 256, one n-tile
     int acc = 0; uint32_t acc_phase = 0;
+    int etile = 0;
     uint32_t rph0 = 0, rph1 = 0;      // TS: parities of this warp's two side-input barriers
     const int tile_rows = p.conv ? p.cw * p.rt : BLOCK_M;
     const int c0 = g * 128;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+    const uint32_t tempty_leader = CTA2 ? mapa_shared(tempty_bar, 0) : 0u;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const int mt = (tile / p.n_tiles) * ncta + (int)rank, nt = tile % p.n_tiles;
       const int n0 = nt * BLOCK_N;
       float* bcur = bias_s + acc * 256;
       bcur[et] = (p.bias && n0 + et < p.N) ? p.bias[n0 + et] : 0.f;
@@ -191,9 +274,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           bulk_wait_read<0>();
           if (act1) { mbar_arrive_expect_tx(rbar + 8, STG_BOX_BYTES); tma_load_2d(stg + STG_BOX_BYTES, &tmR, rbar + 8, colw + 64, row0); }
         }
+        if (!p.side && lane == 0) bulk_wait_read<0>();   // the stores of the previous tile have read both buffers (ordered by bar.sync below)
         mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        if (warp == 2 && lane == 0) { CQ_TRACE(640, etile, 128); }
         tc_fence_after();
         asm volatile("bar.sync 1, 256;" ::: "memory");   // bias (and gamma/beta) visible to the 8 epilogue warps
+#define CQ_TRACE_E(k) do { if (warp == 2 && lane == 0 && etile < 8) { CQ_TRACE(896 + etile * 16, (k), 16); } } while (0)
+        CQ_TRACE_E(0);
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
         const long grow = (long)row0 + lane;
         const bool zero_row = p.zero_period > 0 && (int)(grow % p.zero_period) >= p.zero_valid;
@@ -242,14 +329,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const bool active = hf ? act1 : act0;
           const uint32_t buf = my_row + (uint32_t)(hf * STG_BOX_BYTES);
           if (active) {
-            if (p.side) { if (!do_ln) mbar_wait(rbar + 8 * hf, hf ? rph1 : rph0); }
-            else { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }   // this buffer's store of the previous tile has been read
+            if (p.side && !do_ln) mbar_wait(rbar + 8 * hf, hf ? rph1 : rph0);
+            CQ_TRACE_E(1 + hf * 6);
+            if (p.lean) {
+              const float lo = p.act == CQVAD_ACT_RELU ? 0.f : -INFINITY;
+              if (p.side) ts_lean_half<true>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo);
+              else ts_lean_half<false>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo);
+            } else {
 #pragma unroll 1
             for (int cc = 0; cc < 64; cc += 32) {
               const int c = hf * 64 + cc;
               uint32_t r[32];
               tmem_ld32(t_addr + c, r);
               tmem_ld_wait();
+              CQ_TRACE_E(2 + hf * 6 + (cc >> 5) * 2);
 #pragma unroll
               for (int g8 = 0; g8 < 4; ++g8) {
                 const int cb = c + g8 * 8;
@@ -299,9 +392,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 sts128(saddr, o);
               }
             }
+            }   // general path
+            CQ_TRACE_E(5 + hf * 6);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tma_store_2d(&tmC, stg + (uint32_t)(hf * STG_BOX_BYTES), colw + hf * 64, row0);
+            CQ_TRACE_E(6 + hf * 6);
           }
           if (lane == 0) bulk_commit();     // always two groups per tile (an empty group for a half outside the matrix)
         }
@@ -465,9 +561,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       }   // direct-store epilogue
       // release the accumulator buffer to the MMA warp
+      if (warp == 2 && lane == 0) { CQ_TRACE(768, etile, 128); }
+      ++etile;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+      if (lane == 0) { if constexpr (CTA2) mbar_arrive_cluster(tempty_leader + 8 * acc); else mbar_arrive(tempty_bar + 8 * acc); }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if constexpr (TS) { if (lane == 0) bulk_wait_read<0>(); }   // shared memory stays valid until the last stores have read it
@@ -476,11 +574,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();   // the peer's MMAs / remote arrivals no longer touch this CTA's shared memory
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CTA2) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+template <bool EXTRA, bool TS>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
+  gemm_tc_body<EXTRA, TS, false>(tmA, tmB, tmC, tmR, p);
+}
+template <bool EXTRA, bool TS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
+  gemm_tc_body<EXTRA, TS, true>(tmA, tmB, tmC, tmR, p);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -505,6 +617,10 @@ void init_once() {
   if (cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) g_init_err = 2;
   if (cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
   if (cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
 }
 
 }  // namespace
@@ -550,6 +666,7 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
   p.zero_period = epi.zero_period; p.zero_valid = epi.zero_valid;
   p.c2 = (bf16*)epi.c2; p.c2_act = epi.c2_act; p.mul_aux = (const bf16*)epi.mul_aux; p.mul_mode = epi.mul_mode;
   p.n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  if (const char* tr = getenv("CQVAD_GEMM_TRACE")) p.trace = (long long*)strtoull(tr, nullptr, 0);
   CUtensorMap tmA, tmB;
   if (conv) {
     const int w = conv->w;
@@ -570,19 +687,24 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
     const cuuint32_t box[2] = {BLOCK_K, BLOCK_M};
     CQ_TRY(make_tmap_bf16(&tmA, A, 2, dims, strides, box));
   }
+  // CTA pairs (cta_group::2) for every GEMM with enough m-tiles to fill the machine pairwise
+  static const bool no_pair = getenv("CQVAD_GEMM_NO_PAIR") != nullptr;
+  const bool pair = !no_pair && p.m_tiles >= 2 * (g_num_sms / 2) && g_num_sms >= 2;
   {
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
     const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    const cuuint32_t box[2] = {BLOCK_K, BLOCK_N};
+    const cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)(pair ? BLOCK_N / 2 : BLOCK_N)};
     CQ_TRY(make_tmap_bf16(&tmB, W, 2, dims, strides, box));
   }
-  const long tiles = (long)p.m_tiles * p.n_tiles;
-  const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+  const long tiles = pair ? (long)((p.m_tiles + 1) / 2) * p.n_tiles * 2 : (long)p.m_tiles * p.n_tiles;
+  const int sms = pair ? g_num_sms / 2 * 2 : g_num_sms;
+  const int grid = (int)(tiles < sms ? tiles : sms);
   // TMA-store epilogue: every non-conv GEMM whose epilogue reads / writes bf16 only (at most one [M,N] side input)
   static const bool no_ts = getenv("CQVAD_GEMM_NO_TS") != nullptr;
   const bool ts = !no_ts && !conv && !epi.c32 && !epi.res32 && !epi.c2 && N % 8 == 0 && !(epi.res && epi.mul_mode);
+  const bool extra = p.c2 || p.mul_mode;
+  CUtensorMap tmC = tmA, tmR = tmA;
   if (ts) {
-    CUtensorMap tmC, tmR;
     const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
     const cuuint32_t box[2] = {64, 32};
     const cuuint64_t sc[1] = {(cuuint64_t)ldc * 2};
@@ -596,13 +718,20 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
       CQ_TRY(make_tmap_bf16(&tmR, epi.mul_aux, 2, dims, sc, box));
       p.side = 2;
     }
-    if (p.mul_mode) gemm_tc_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES_TS, st>>>(tmA, tmB, tmC, tmR, p);
-    else gemm_tc_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES_TS, st>>>(tmA, tmB, tmC, tmR, p);
-  } else if (p.c2 || p.mul_mode) {
-    gemm_tc_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, tmA, tmA, p);
-  } else {
-    gemm_tc_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, tmA, tmA, p);
   }
+  p.lean = ts && !epi.ln_g && epi.zero_period == 0 && !epi.mul_mode && (epi.act == CQVAD_ACT_NONE || epi.act == CQVAD_ACT_RELU) &&
+           getenv("CQVAD_GEMM_NO_LEAN") == nullptr;
+  const size_t smem = ts ? SMEM_BYTES_TS : SMEM_BYTES;
+#define CQ_LAUNCH_TC(KERN)                                                                            \
+  do {                                                                                                \
+    if (extra && ts) KERN<true, true><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);         \
+    else if (extra) KERN<true, false><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);         \
+    else if (ts) KERN<false, true><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);            \
+    else KERN<false, false><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);                   \
+  } while (0)
+  if (pair) CQ_LAUNCH_TC(gemm_tc2_kernel);
+  else CQ_LAUNCH_TC(gemm_tc_kernel);
+#undef CQ_LAUNCH_TC
   CQ_LAUNCH_CHECK();
   return 0;
 }
