@@ -30,7 +30,7 @@ size_t wgrad_scratch_bytes();
 
 // dH *= act'(.)   ReLU: ref = post-activation H (mask H > 0);  GELU: ref = pre-activation (exact erf derivative)
 template <typename T> int act_bwd(T* dH, const T* ref, int act, long n, cudaStream_t st);
-template <typename T> int gelu_fwd(const T* pre, T* out, long n, cudaStream_t st);
+template <typename T> int gelu_fwd(const T* pre, T* out, T* dact, long n, cudaStream_t st);   // dact (optional) = gelu'(pre)
 // dst = beta*dst + src
 template <typename T> int axpby(T* dst, const T* src, float beta, long n, cudaStream_t st);
 // fp32 accumulate of a T tensor: dst32 += src

@@ -496,8 +496,10 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(T* dH, const T* __restrict
     store8(dH + i * 8, d[u]);
   }
 }
+// out = gelu(pre) and (training) dact = gelu'(pre): the derivative is stored next to the activation so that the backward
+// needs no pass of its own -- the data-gradient GEMM multiplies by it in its epilogue (Epilogue::mul_mode 3)
 template <typename T>
-__global__ void __launch_bounds__(256) gelu_fwd_kernel(const T* __restrict__ pre, T* __restrict__ out, long n8) {
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const T* __restrict__ pre, T* __restrict__ out, T* __restrict__ dact, long n8) {
   const long base = ((long)blockIdx.x * blockDim.x) * EW_UNROLL + threadIdx.x;
   float v[EW_UNROLL][8];
 #pragma unroll
@@ -509,9 +511,14 @@ __global__ void __launch_bounds__(256) gelu_fwd_kernel(const T* __restrict__ pre
   for (int u = 0; u < EW_UNROLL; ++u) {
     const long i = base + (long)u * blockDim.x;
     if (i >= n8) continue;
+    float a[8], d[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[u][j] = DT<T>::id == CQVAD_BF16 ? tc::gelu_fast(v[u][j]) : gelu_erf(v[u][j]);
-    store8(out + i * 8, v[u]);
+    for (int j = 0; j < 8; ++j) {
+      a[j] = DT<T>::id == CQVAD_BF16 ? tc::gelu_fast(v[u][j]) : gelu_erf(v[u][j]);
+      d[j] = DT<T>::id == CQVAD_BF16 ? tc::gelu_grad_fast(v[u][j]) : gelu_grad(v[u][j]);
+    }
+    store8(out + i * 8, a);
+    if (dact) store8(dact + i * 8, d);
   }
 }
 template <typename D, typename S>
@@ -708,15 +715,15 @@ template int act_bwd<float>(float*, const float*, int, long, cudaStream_t);
 template int act_bwd<bf16>(bf16*, const bf16*, int, long, cudaStream_t);
 
 template <typename T>
-int gelu_fwd(const T* pre, T* out, long n, cudaStream_t st) {
+int gelu_fwd(const T* pre, T* out, T* dact, long n, cudaStream_t st) {
   CQ_CHECK_SHAPE(n % 8 == 0, "gelu: element count must be a multiple of 8");
   if (n == 0) return 0;
-  gelu_fwd_kernel<T><<<(unsigned)cdiv(n / 8, 256 * EW_UNROLL), 256, 0, st>>>(pre, out, n / 8);
+  gelu_fwd_kernel<T><<<(unsigned)cdiv(n / 8, 256 * EW_UNROLL), 256, 0, st>>>(pre, out, dact, n / 8);
   CQ_LAUNCH_CHECK();
   return 0;
 }
-template int gelu_fwd<float>(const float*, float*, long, cudaStream_t);
-template int gelu_fwd<bf16>(const bf16*, bf16*, long, cudaStream_t);
+template int gelu_fwd<float>(const float*, float*, float*, long, cudaStream_t);
+template int gelu_fwd<bf16>(const bf16*, bf16*, bf16*, long, cudaStream_t);
 
 template <typename T>
 int axpby(T* dst, const T* src, float beta, long n, cudaStream_t st) {

@@ -130,7 +130,8 @@ struct Epilogue {
   float* c32 = nullptr;
   // training path: (a) second output c2 = act2(v) next to C = v (pre-activation kept for the backward, same ldc);
   // (b) backward through an activation fused into the data-gradient GEMM: v *= act'(aux[row, col]) with aux of C's
-  //     shape / ldc -- mul_mode 1: ReLU mask (aux = post-activation, > 0), 2: exact erf-GELU derivative (aux = pre-activation)
+  //     shape / ldc -- mul_mode 1: ReLU mask (aux = post-activation, > 0), 2: exact erf-GELU derivative (aux = pre-activation),
+  //     3: aux holds the derivative itself (stored by the forward gelu pass)
   void* c2 = nullptr;
   int c2_act = CQVAD_ACT_NONE;
   const void* mul_aux = nullptr;

@@ -82,7 +82,8 @@ __device__ __forceinline__ float gelu_grad(float x) {
 // row per thread, branch-free, packed fp32x2 adds.  The general epilogue spends ~210 warp instructions per 32 columns on
 // runtime option checks; the pipeline trace (tools/trace_gemm.py) showed the epilogue, at 2.8 us per 128 x 256 tile, as the
 // stage that paces the K = 256 GEMMs (MMA 1.1 us, loads hidden).
-template <bool SIDE>
+// SIDE: 0 none, 1 += side (residual), 2 ReLU mask (side > 0), 3 *= side (stored activation derivative)
+template <int SIDE>
 __device__ __forceinline__ void ts_lean_half(uint32_t t_addr, const float* bias, uint32_t row_base, int sw, float lo) {
 #pragma unroll
   for (int cc = 0; cc < 64; cc += 32) {
@@ -99,7 +100,7 @@ __device__ __forceinline__ void ts_lean_half(uint32_t t_addr, const float* bias,
       x[2] = f2add(f2pack(__uint_as_float(r[g8 * 8 + 4]), __uint_as_float(r[g8 * 8 + 5])), f2pack(b1.x, b1.y));
       x[3] = f2add(f2pack(__uint_as_float(r[g8 * 8 + 6]), __uint_as_float(r[g8 * 8 + 7])), f2pack(b1.z, b1.w));
       uint4 sv;
-      if constexpr (SIDE) sv = lds128(saddr);
+      if constexpr (SIDE != 0) sv = lds128(saddr);
       uint4 o;
       uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
       const uint32_t* sw32 = reinterpret_cast<const uint32_t*>(&sv);
@@ -108,9 +109,11 @@ __device__ __forceinline__ void ts_lean_half(uint32_t t_addr, const float* bias,
         float a, b;
         f2unpack(x[j], a, b);
         a = fmaxf(a, lo); b = fmaxf(b, lo);
-        if constexpr (SIDE) {
-          a += __uint_as_float(sw32[j] << 16);            // bf16 -> fp32: low half = first element
-          b += __uint_as_float(sw32[j] & 0xffff0000u);
+        if constexpr (SIDE != 0) {
+          const float sa = __uint_as_float(sw32[j] << 16), sb = __uint_as_float(sw32[j] & 0xffff0000u);   // bf16 pair -> fp32
+          if constexpr (SIDE == 1) { a += sa; b += sb; }
+          else if constexpr (SIDE == 2) { a = sa > 0.f ? a : 0.f; b = sb > 0.f ? b : 0.f; }
+          else { a *= sa; b *= sb; }
         }
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(ow[j]) : "f"(b), "f"(a));
       }
@@ -196,6 +199,14 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
             }
             tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, fb, kb * BLOCK_K, nt * BLOCK_N);
           }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      if constexpr (CTA2) {
+        // tail: the leader's multicast commits keep arriving on THIS CTA's empty barriers until the last MMA has retired;
+        // wait for all of them so that the CTA cannot exit (and its shared memory be re-used) underneath a remote arrival
+        for (int s = 0; s < STAGES; ++s) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -333,8 +344,10 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
             CQ_TRACE_E(1 + hf * 6);
             if (p.lean) {
               const float lo = p.act == CQVAD_ACT_RELU ? 0.f : -INFINITY;
-              if (p.side) ts_lean_half<true>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo);
-              else ts_lean_half<false>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo);
+              if (p.side == 0) ts_lean_half<0>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo);
+              else if (p.side == 1) ts_lean_half<1>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo);
+              else if (p.mul_mode == 1) ts_lean_half<2>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo);
+              else ts_lean_half<3>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo);
             } else {
 #pragma unroll 1
             for (int cc = 0; cc < 64; cc += 32) {
@@ -374,6 +387,9 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
                       if (p.mul_mode == 1) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = sx[j] > 0.f ? v[j] : 0.f;
+                      } else if (p.mul_mode == 3) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] *= sx[j];
                       } else {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] *= gelu_grad_fast(sx[j]);
@@ -523,6 +539,9 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
                 if (p.mul_mode == 1) {
 #pragma unroll
                   for (int j = 0; j < 8; ++j) v[j] = ax[j] > 0.f ? v[j] : 0.f;
+                } else if (p.mul_mode == 3) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] *= ax[j];
                 } else {
 #pragma unroll
                   for (int j = 0; j < 8; ++j) v[j] *= gelu_grad_fast(ax[j]);
@@ -630,17 +649,25 @@ int tc_num_sms() {
   return g_num_sms;
 }
 
-// rank-2 / rank-3 bf16 tensor map with 128-byte swizzle.  dims/strides innermost first; strides in bytes for dims >= 1.
-int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                   const cuuint32_t* box) {
+// rank-2 / rank-3 tensor map with 128-byte swizzle.  dims/strides innermost first; strides in bytes for dims >= 1.
+static int make_tmap_any(CUtensorMap* m, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
+                         const cuuint64_t* strides_bytes, const cuuint32_t* box) {
   std::call_once(g_once, init_once);
   if (g_init_err) return set_error(CQVAD_E_CUDA, "tcgen05 path: initialisation failed (%d)", g_init_err);
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+  CUresult r = g_encode(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(CQVAD_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;
+}
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                   const cuuint32_t* box) {
+  return make_tmap_any(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                  const cuuint32_t* box) {
+  return make_tmap_any(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
 }
 
 int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, int N, int K, const Epilogue& epi,
@@ -719,7 +746,7 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
       p.side = 2;
     }
   }
-  p.lean = ts && !epi.ln_g && epi.zero_period == 0 && !epi.mul_mode && (epi.act == CQVAD_ACT_NONE || epi.act == CQVAD_ACT_RELU) &&
+  p.lean = ts && !epi.ln_g && epi.zero_period == 0 && epi.mul_mode != 2 && (epi.act == CQVAD_ACT_NONE || epi.act == CQVAD_ACT_RELU) &&
            getenv("CQVAD_GEMM_NO_LEAN") == nullptr;
   const size_t smem = ts ? SMEM_BYTES_TS : SMEM_BYTES;
 #define CQ_LAUNCH_TC(KERN)                                                                            \

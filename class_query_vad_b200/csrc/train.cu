@@ -72,7 +72,7 @@ struct Ten {
   bool gi = false;  // gradient buffer holds a value (first writer overwrites, later writers accumulate)
   // this tensor is act(.) of something: the gradient arriving here must be multiplied by act'(gref).  The single consumer's
   // data-gradient GEMM does it in its epilogue (gmasked = true); otherwise the producer's backward runs an elementwise pass.
-  int gact = 0;             // 0 none, 1 ReLU (gref = this tensor), 2 GELU (gref = pre-activation)
+  int gact = 0;             // 0 none, 1 ReLU (gref = this tensor), 2 GELU (gref = pre-activation), 3 stored derivative (gref = act')
   const T* gref = nullptr;
   bool gmasked = false;
   long n() const { return rows * cols; }
@@ -204,6 +204,10 @@ struct Trainer {
   // Fusing gelu / act' into the GEMM epilogue (one thread per output row) measured SLOWER on B200 than a plain epilogue plus
   // a full-occupancy elementwise pass (245 us vs 65 + 65 us on the [94 080 x 1024] ConvBlock hidden): off by default.
   const bool fuse_act = getenv("CQVAD_TRAIN_FUSE_ACT") != nullptr;
+  // Backward through an activation: the data-gradient GEMM of the single consumer multiplies by act' in its (lean, TMA-store)
+  // epilogue -- a ReLU mask read from the activation itself, or gelu'(H) that the forward gelu pass stored next to gelu(H) --
+  // so the 578 MB read-modify-write pass over the [94 080 x 1024] ConvBlock hidden gradient disappears.
+  const bool fuse_act_bwd = getenv("CQVAD_TRAIN_NO_FUSE_ACT_BWD") == nullptr;
   Ten<T>* last_c2 = nullptr;   // second output of the last lin(..., c2_act)
   Ten<T>* lin(Ten<T>* X, int widx, int Nout, int act = CQVAD_ACT_NONE, Ten<T>* res = nullptr, int zp = 0, int zv = 0,
               int* rc = nullptr, int c2_act = CQVAD_ACT_NONE) {
@@ -216,6 +220,7 @@ struct Trainer {
       A2 = &tens.back();
       A2->rows = Y->rows; A2->cols = Y->cols; A2->p = take(Y->n()); A2->g = Y->g; A2->hg = true;
       A2->gact = c2_act == CQVAD_ACT_GELU ? 2 : 1; A2->gref = Y->p;
+      if (c2_act == CQVAD_ACT_GELU && !fuse_act && fuse_act_bwd) { A2->gact = 3; A2->gref = take(Y->n()); }   // gelu'(Y) stored by gelu_fwd
       last_c2 = A2;
     }
     const T* Wt = X->hg ? WT(widx, (long)Nout * Kd) : nullptr;
@@ -225,7 +230,7 @@ struct Trainer {
       if (A2 && fuse_act) { e.c2 = A2->p; e.c2_act = c2_act; }
       int r;
       { ProfScope ps(P_T_FWD_GEMM, st); r = gemm<T>(X->p, Kd, Wm(widx), Y->p, Nout, X->rows, Nout, Kd, e, nullptr, st); }
-      if (r == 0 && A2 && !fuse_act) { ProfScope ps(P_T_FWD_OTHER, st); r = gelu_fwd<T>(Y->p, A2->p, Y->n(), st); }
+      if (r == 0 && A2 && !fuse_act) { ProfScope ps(P_T_FWD_OTHER, st); r = gelu_fwd<T>(Y->p, A2->p, A2->gact == 3 ? const_cast<T*>(A2->gref) : nullptr, Y->n(), st); }
       if (r == 0) r = dbg("lin", widx);
       if (r != 0 && rc && *rc == 0) *rc = r;
     }
@@ -248,7 +253,7 @@ struct Trainer {
           Epilogue e;
           const float b = beta(X);
           if (b != 0.f) { e.res = X->g; e.ldr = Kd; }
-          if (X->gact && fuse_act) {
+          if (X->gact && (fuse_act || fuse_act_bwd) && b == 0.f) {
             if (b != 0.f) return set_error(CQVAD_E_INVALID_ARG, "backward: an activation output with two consumers is not supported");
             e.mul_aux = X->gref; e.mul_mode = X->gact; X->gmasked = true;   // dX = (dY . W) * act'(.) in the epilogue
           }
@@ -295,7 +300,7 @@ struct Trainer {
     A->rows = Hpre->rows; A->cols = Hpre->cols;
     A->p = take(A->n());
     A->g = Hpre->g; A->hg = Hpre->hg;
-    if (fwd()) { ProfScope ps(P_T_FWD_OTHER, st); int r = gelu_fwd<T>(Hpre->p, A->p, A->n(), st); if (r != 0) *rc = r; }
+    if (fwd()) { ProfScope ps(P_T_FWD_OTHER, st); int r = gelu_fwd<T>(Hpre->p, A->p, nullptr, A->n(), st); if (r != 0) *rc = r; }
     if (rec()) {
       tape.push_back([=]() -> int {
         if (!A->gi) return 0;

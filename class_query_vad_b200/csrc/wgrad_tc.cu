@@ -13,8 +13,10 @@
 // same shifted 3-D TMA box (64 ch x w x rt image rows) the forward implicit GEMM uses, so the horizontal halo is the TMA
 // out-of-bounds zero fill and the vertical halo the zero separator rows; stage rows beyond w*rt stay zero (zeroed once).
 //
-// Split-K partial tiles are written with plain coalesced stores to a scratch buffer and summed into dW by a second
-// kernel (fp32 RED throughput, ~1.3 cycles/lane/SM, would dominate: 64 K reductions per CTA).
+// Split-K: every CTA adds its 256x256 fp32 partial tile straight into dW with TMA reduce-stores
+// (cp.reduce.async.bulk.tensor .add): the accumulators go TMEM -> registers -> 128-byte-swizzled [32 x 32] fp32 boxes staged
+// in the (by then idle) operand ring -> L2 reduction.  No scratch buffer, no second kernel (the former partial-tile write
+// + reduce pass cost 1.7 ms of a 35 ms training step), edge tiles clipped by the tensor map.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "bwd.cuh"
@@ -24,6 +26,8 @@ namespace cqvad {
 
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                    const cuuint32_t* box);
+int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                  const cuuint32_t* box);
 int tc_num_sms();
 
 using namespace tc;
@@ -39,7 +43,6 @@ constexpr int WG_THREADS = 192;
 constexpr int TILE = 256;
 
 struct WgParams {
-  float* part;            // [jobs][256][256] fp32 partial tiles
   long M; int Nout, Kin;
   int n_tiles, k_tiles;
   long rows_per_split;    // non-conv: rows (multiple of 64); conv: image rows of the padded layout (multiple of rt)
@@ -53,7 +56,8 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, const WgParams p) {
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX,
+                const __grid_constant__ CUtensorMap tmW, const WgParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + WSTAGES * STAGE_BYTES;
@@ -83,6 +87,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmY);
     tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
     // a stage is released by the MMA commit and, when this job also sums dY's columns, by the column-sum warps
     for (int s = 0; s < WSTAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, do_colsum ? 2 : 1); }
     mbar_init(tfull_bar, 1);
@@ -141,7 +146,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   } else {
     // ===== epilogue warps 2..5: TMEM lane quarter q = warp % 4 =====
     const int q = warp & 3;
-    float* out = p.part + (size_t)job * TILE * TILE;
     if (do_colsum) {
       // db[n] += sum_rows dY[row, n]: thread e owns columns 2e, 2e+1 of the 256-column dY tile (box 2e/64, 16-byte chunk
       // swizzled by the row): a warp reads one 128-byte box row per instruction -- bank-conflict free
@@ -169,24 +173,32 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
       if (n + 1 < p.Nout) atomicAdd(p.db + n + 1, s1);
     }
     if (iters > 0) {
-      mbar_wait(tfull_bar, 0);
+      mbar_wait(tfull_bar, 0);      // every MMA has retired: the accumulators are final and the operand ring is idle
       tc_fence_after();
-    }
-    for (int s = 0; s < 2; ++s) {
-      float* orow = out + (size_t)(s * 128 + q * 32 + lane) * TILE;
-      for (int c = 0; c < TILE; c += 32) {
-        uint32_t r[32];
-        if (iters > 0 && s < n_slabs) {
+      // this warp: rows [q*32, +32) of each 128-row slab, 256 fp32 columns = 8 boxes of [32 rows x 32 cols] (128 B per row),
+      // staged in 8 x 4 KB of the ring and added into dW by TMA
+      const uint32_t stg = smem_base + (uint32_t)((warp - 2) * 8 * 4096);
+      const uint32_t my_row = stg + (uint32_t)(lane * 128);
+      const int sw = lane & 7;
+      const int col0 = (p.conv ? tap * 256 : kt * TILE);
+      for (int s = 0; s < n_slabs; ++s) {
+        if (s > 0) { if (lane == 0) bulk_wait_read<0>(); __syncwarp(); }
+        const int row0 = nt * TILE + s * 128 + q * 32;
+#pragma unroll 1
+        for (int c = 0; c < TILE; c += 32) {
+          uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 256 + c), r);
           tmem_ld_wait();
-        } else {
+          const uint32_t buf = my_row + (uint32_t)((c >> 5) * 4096);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = 0u;
+          for (int j = 0; j < 8; ++j)
+            sts128(buf + (uint32_t)((j ^ sw) << 4), make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) { tma_reduce_add_2d(&tmW, stg + (uint32_t)((c >> 5) * 4096), col0 + c, row0); bulk_commit(); }
         }
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<uint4*>(orow + c + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
       }
+      if (lane == 0) bulk_wait_read<0>();
     }
   }
 
@@ -196,33 +208,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// dW[(n0+r)*ldw + tap*256 + k0 + c] += sum_split part[job][r][c]
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW, long ldw,
-                                                           int Nout, int Kin, int n_tiles, int k_tiles, int splits, int conv) {
-  const int tiles = conv ? 9 : n_tiles * k_tiles;
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;      // over tiles * 256 * 64 float4
-  if (idx >= (long)tiles * TILE * (TILE / 4)) return;
-  const int c4 = (int)(idx % (TILE / 4)), r = (int)((idx / (TILE / 4)) % TILE), t = (int)(idx / ((long)TILE * (TILE / 4)));
-  const int nt = conv ? 0 : t / k_tiles, kt = conv ? 0 : t % k_tiles, tap = conv ? t : 0;
-  const int n = nt * TILE + r, k = kt * TILE + c4 * 4;
-  if (n >= Nout || k >= Kin) return;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = 0; s < splits; ++s) {
-    const long job = (long)s * tiles + t;
-    const float4 v = *reinterpret_cast<const float4*>(part + ((size_t)job * TILE + r) * TILE + c4 * 4);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-  }
-  float* d = dW + (long)n * ldw + (long)tap * 256 + k;
-  if (k + 3 < Kin) {
-    float4 o = *reinterpret_cast<float4*>(d);
-    o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
-    *reinterpret_cast<float4*>(d) = o;
-  } else {
-    const float a[4] = {acc.x, acc.y, acc.z, acc.w};
-    for (int i = 0; i < 4 && k + i < Kin; ++i) d[i] += a[i];
   }
 }
 
@@ -259,14 +244,14 @@ size_t g_scratch_bytes = 0;
 
 }  // namespace
 
+// kept for the callers' sake: the split-K partials no longer need a scratch buffer (TMA reduce-stores straight into dW)
 void set_wgrad_scratch(float* p, size_t bytes) { g_scratch = p; g_scratch_bytes = bytes; }
-size_t wgrad_scratch_bytes() { return (size_t)160 * TILE * TILE * sizeof(float); }
+size_t wgrad_scratch_bytes() { return 256; }
 
 int wgrad_tc(const bf16* dY, long lddy, const bf16* X, long ldx, float* dW, long ldw, float* db, long M, int Nout, int Kin,
              const ConvGeom* conv, cudaStream_t st) {
   if (M < 1024 || lddy % 8 != 0 || ldx % 8 != 0 || Nout % 8 != 0 || Kin % 8 != 0 || ldw % 4 != 0) return 1;
   if ((((uintptr_t)dY) & 15) || (((uintptr_t)X) & 15) || (dW && (((uintptr_t)dW) & 15))) return 1;
-  if (g_scratch == nullptr) return 1;
   const int sms = tc_num_sms();
   if (sms <= 0) return 1;
   std::call_once(g_wg_once, [] {
@@ -275,7 +260,7 @@ int wgrad_tc(const bf16* dY, long lddy, const bf16* X, long ldx, float* dW, long
   if (g_wg_err) return set_error(CQVAD_E_CUDA, "wgrad_tc: cannot reserve %d bytes of shared memory", WG_SMEM);
 
   WgParams p{};
-  p.part = g_scratch; p.M = M; p.Nout = Nout; p.Kin = Kin; p.db = dW ? db : nullptr;
+  p.M = M; p.Nout = Nout; p.Kin = Kin; p.db = dW ? db : nullptr;
   CUtensorMap tmY, tmX;
   int tiles, splits;
   if (conv) {
@@ -319,13 +304,13 @@ int wgrad_tc(const bf16* dY, long lddy, const bf16* X, long ldx, float* dW, long
     }
   }
   const int jobs = tiles * splits;
-  if ((size_t)jobs * TILE * TILE * sizeof(float) > g_scratch_bytes) return 1;
   if (dW) {
-    wgrad_tc_kernel<<<jobs, WG_THREADS, WG_SMEM, st>>>(tmY, tmX, p);
-    CQ_LAUNCH_CHECK();
-    const long n4 = (long)tiles * TILE * (TILE / 4);
-    wgrad_reduce_kernel<<<(unsigned)cdiv(n4, 256), 256, 0, st>>>(g_scratch, dW, ldw, Nout, Kin, p.n_tiles, p.k_tiles, splits,
-                                                               p.conv);
+    CUtensorMap tmW;
+    const cuuint64_t dims[2] = {(cuuint64_t)(conv ? 9 * kC : Kin), (cuuint64_t)Nout};
+    const cuuint64_t strides[1] = {(cuuint64_t)ldw * 4};
+    const cuuint32_t box[2] = {32, 32};
+    CQ_TRY(make_tmap_f32(&tmW, dW, 2, dims, strides, box));
+    wgrad_tc_kernel<<<jobs, WG_THREADS, WG_SMEM, st>>>(tmY, tmX, tmW, p);
     CQ_LAUNCH_CHECK();
   }
   if (db && !dW) {   // bias gradient alone (otherwise summed inside wgrad_tc_kernel)
