@@ -278,13 +278,16 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         const uint32_t my_row = stg + (uint32_t)(lane * 128);
         const int sw = lane & 7;                                  // 128-byte swizzle: 16-byte chunk j of row r sits at j ^ (r & 7)
         const bool act0 = colw < p.N, act1 = colw + 64 < p.N;     // column halves inside the matrix (warp-uniform)
-        if (p.side && lane == 0) {
-          // side-input boxes (bf16 residual / activation-derivative operand) -> the staging buffers themselves
-          bulk_wait_read<1>();
-          if (act0) { mbar_arrive_expect_tx(rbar, STG_BOX_BYTES); tma_load_2d(stg, &tmR, rbar, colw, row0); }
+        // side-input boxes (bf16 residual / activation-derivative operand) -> the staging buffers themselves.  The boxes of a
+        // tile are requested at the END of the previous tile (right after its stores have read the buffers), so that their
+        // DRAM latency overlaps the wait for the next accumulator; the first tile's are requested here.
+        auto side_request = [&](int t) {
+          const int mt_ = (t / p.n_tiles) * ncta + (int)rank, colw_ = (t % p.n_tiles) * BLOCK_N + c0, row0_ = mt_ * BLOCK_M + q * 32;
           bulk_wait_read<0>();
-          if (act1) { mbar_arrive_expect_tx(rbar + 8, STG_BOX_BYTES); tma_load_2d(stg + STG_BOX_BYTES, &tmR, rbar + 8, colw + 64, row0); }
-        }
+          if (colw_ < p.N) { mbar_arrive_expect_tx(rbar, STG_BOX_BYTES); tma_load_2d(stg, &tmR, rbar, colw_, row0_); }
+          if (colw_ + 64 < p.N) { mbar_arrive_expect_tx(rbar + 8, STG_BOX_BYTES); tma_load_2d(stg + STG_BOX_BYTES, &tmR, rbar + 8, colw_ + 64, row0_); }
+        };
+        if (p.side && lane == 0 && tile == first_tile) side_request(tile);
         if (!p.side && lane == 0) bulk_wait_read<0>();   // the stores of the previous tile have read both buffers (ordered by bar.sync below)
         mbar_wait(tfull_bar + 8 * acc, acc_phase);
         if (warp == 2 && lane == 0) { CQ_TRACE(640, etile, 128); }
@@ -417,7 +420,11 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
           }
           if (lane == 0) bulk_commit();     // always two groups per tile (an empty group for a half outside the matrix)
         }
-        if (p.side) { if (act0) rph0 ^= 1; if (act1) rph1 ^= 1; }
+        if (p.side) {
+          if (act0) rph0 ^= 1;
+          if (act1) rph1 ^= 1;
+          if (lane == 0 && tile + tile_step < num_tiles) side_request(tile + tile_step);
+        }
       } else {
       const long grow = (long)mt * tile_rows + row_in_tile;
       const bool row_ok = row_in_tile < tile_rows && grow < p.M;
