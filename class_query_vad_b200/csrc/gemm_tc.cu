@@ -34,13 +34,13 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int B_STAGE_FULL = BLOCK_N * BLOCK_K * 2;  // 32 KB (a CTA pair holds half of it per CTA)
 constexpr int SMEM_TILES = STAGES_DIRECT * (A_STAGE_BYTES + B_STAGE_FULL);
 // aux: barriers 256 | bias [2][256] f32 (per TMEM buffer) | gamma [256] | beta [256] | LN partial sums [2][2][128][2] f32
-constexpr int AUX_BIAS = 256, AUX_GAM = AUX_BIAS + 2048, AUX_BET = AUX_GAM + 1024, AUX_STATS = AUX_BET + 1024, AUX_BYTES = AUX_STATS + 4096;
+constexpr int AUX_BIAS = 320, AUX_GAM = AUX_BIAS + 2048, AUX_BET = AUX_GAM + 1024, AUX_STATS = AUX_BET + 1024, AUX_BYTES = AUX_STATS + 4096;
 constexpr int SMEM_BYTES = SMEM_TILES + 1024 /*align slack*/ + AUX_BYTES;
 constexpr int STAGES_TS = 3;
 constexpr int STG_BOX_BYTES = 32 * 64 * 2;                      // one [32 rows x 64 cols] bf16 box, 128 B per row
 constexpr int STG_BYTES = 8 * 2 * STG_BOX_BYTES;                // 8 epilogue warps x 2 column halves of their 128 columns
 constexpr int SMEM_BYTES_TS = STAGES_TS * (A_STAGE_BYTES + B_STAGE_FULL) + STG_BYTES + 1024 + AUX_BYTES;
-constexpr int AUX_RBAR = 128;                                   // 8 warps x 2 mbarriers for the TMA-loaded side input
+constexpr int AUX_RBAR = 160;                                   // 8 warps x 2 mbarriers for the TMA-loaded side input
 constexpr int NUM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter: 128 columns each)
 constexpr int TMEM_COLS = 512;
 
@@ -54,6 +54,7 @@ struct TcParams {
   int conv; int cw; int rt;  // image width, image rows per tile
   int m_tiles, n_tiles;
   long long* trace;   // dev tool (CQVAD_GEMM_TRACE=<device address>): globaltimer stamps of CTA 0's pipeline events
+  int stg_single;   // TS pair without side input: one staging box per warp (two sequential stores) buys a 5th ring stage
   int lean;   // TS: bias + none/ReLU (+ bf16 residual) only -> branch-free epilogue
   int side;   // TS: 1 = bf16 residual, 2 = activation-derivative operand (mul_aux) arrives through tmR
 };
@@ -129,7 +130,10 @@ __device__ __forceinline__ void ts_lean_half(uint32_t t_addr, const float* bias,
 template <bool EXTRA, bool TS, bool CTA2>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                              const CUtensorMap& tmR, const TcParams& p) {
-  constexpr int STAGES = CTA2 ? (TS ? 4 : 6) : (TS ? STAGES_TS : STAGES_DIRECT);
+  // ring depth: pair 6 (TS: 4, or 5 with single-buffered output staging when there is no side input), single CTA 4 (TS: 3)
+  constexpr int MAX_STAGES = 6;
+  const int STAGES = CTA2 ? (TS ? (p.stg_single ? 5 : 4) : 6) : (TS ? STAGES_TS : STAGES_DIRECT);
+  const int stg_stride = (TS && p.stg_single) ? 0 : STG_BOX_BYTES;   // byte distance between a warp's two staging boxes
   constexpr int B_STAGE_BYTES = CTA2 ? B_STAGE_FULL / 2 : B_STAGE_FULL;
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
   const int ncta = CTA2 ? 2 : 1;
@@ -137,8 +141,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base, sB = smem_base + STAGES * A_STAGE_BYTES;
   const uint32_t stg_base = smem_base + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);   // TS only
-  const uint32_t bars = stg_base + (TS ? STG_BYTES : 0);
-  const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES, tfull_bar = bars + 16 * STAGES,
+  const uint32_t bars = stg_base + (TS ? (p.stg_single ? STG_BYTES / 2 : STG_BYTES) : 0);
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * MAX_STAGES, tfull_bar = bars + 16 * MAX_STAGES,
                  tempty_bar = tfull_bar + 16, tmem_slot = tempty_bar + 16, rbar_base = bars + AUX_RBAR;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // work unit = one tile (a vertical PAIR of tiles for a CTA pair: this CTA takes m-tile 2 * mpair + rank)
@@ -273,7 +277,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         // [32 x 64] boxes; buffer hf is reused one whole tile later, so the store of the previous tile has long been read ----
         const int row0 = mt * BLOCK_M + q * 32;
         const int colw = n0 + c0;
-        const uint32_t stg = stg_base + (uint32_t)((warp - 2) * 2 * STG_BOX_BYTES);
+        const uint32_t stg = stg_base + (uint32_t)((warp - 2) * (p.stg_single ? 1 : 2) * STG_BOX_BYTES);
         const uint32_t rbar = rbar_base + (uint32_t)((warp - 2) * 16);
         const uint32_t my_row = stg + (uint32_t)(lane * 128);
         const int sw = lane & 7;                                  // 128-byte swizzle: 16-byte chunk j of row r sits at j ^ (r & 7)
@@ -305,7 +309,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
 #pragma unroll 1
           for (int c = 0; c < 128; c += 32) {
             const int hf = c >> 6;
-            const uint32_t buf = my_row + (uint32_t)(hf * STG_BOX_BYTES);
+            const uint32_t buf = my_row + (uint32_t)(hf * stg_stride);
             if (p.side == 1 && (c & 63) == 0) mbar_wait(rbar + 8 * hf, hf ? rph1 : rph0);
             uint32_t r[32];
             tmem_ld32(t_addr + c, r);
@@ -341,8 +345,10 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
           const bool active = hf ? act1 : act0;
-          const uint32_t buf = my_row + (uint32_t)(hf * STG_BOX_BYTES);
+          const uint32_t buf = my_row + (uint32_t)(hf * stg_stride);
           if (active) {
+            // single staging box per warp: the store of the first half must have read it before the second half is written
+            if (p.stg_single && hf == 1) { if (lane == 0) bulk_wait_read<0>(); __syncwarp(); }
             if (p.side && !do_ln) mbar_wait(rbar + 8 * hf, hf ? rph1 : rph0);
             CQ_TRACE_E(1 + hf * 6);
             if (p.lean) {
@@ -415,7 +421,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
             CQ_TRACE_E(5 + hf * 6);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) tma_store_2d(&tmC, stg + (uint32_t)(hf * STG_BOX_BYTES), colw + hf * 64, row0);
+            if (lane == 0) tma_store_2d(&tmC, stg + (uint32_t)(hf * stg_stride), colw + hf * 64, row0);
             CQ_TRACE_E(6 + hf * 6);
           }
           if (lane == 0) bulk_commit();     // always two groups per tile (an empty group for a half outside the matrix)
@@ -755,6 +761,7 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
   }
   p.lean = ts && !epi.ln_g && epi.zero_period == 0 && epi.mul_mode != 2 && (epi.act == CQVAD_ACT_NONE || epi.act == CQVAD_ACT_RELU) &&
            getenv("CQVAD_GEMM_NO_LEAN") == nullptr;
+  p.stg_single = ts && pair && !p.side && K >= 8 * BLOCK_K && getenv("CQVAD_GEMM_NO_STG1") == nullptr;   // load-bound shapes only: measured +7..10% at K >= 512, -12% at K = 256 (epilogue-bound)
   const size_t smem = ts ? SMEM_BYTES_TS : SMEM_BYTES;
 #define CQ_LAUNCH_TC(KERN)                                                                            \
   do {                                                                                                \
