@@ -145,6 +145,30 @@ struct Trainer {
     if (!ev[i]) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
     return ev[i];
   }
+  // Third stream: the large weight-gradient GEMMs only feed the (atomically accumulated) parameter gradients, so they leave
+  // the dgrad chain's stream as soon as their dY is final and fill the SMs that chain's kernel tails leave idle; joined at
+  // the end of the backward.  CQVAD_TRAIN_WG_STREAM=0 disables.
+  static cudaStream_t wg_stream() {
+    static cudaStream_t s = [] { cudaStream_t x = nullptr; cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking); return x; }();
+    return s;
+  }
+  bool wg_used = false;
+  cudaStream_t wgrad_stream(long rows) {
+    static const bool off = [] { const char* e = getenv("CQVAD_TRAIN_WG_STREAM"); return e && atoi(e) == 0; }();
+    static cudaEvent_t ev = [] { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); return e; }();
+    if (off || prof_enabled() || !two_streams || rows < 4096 || wg_stream() == nullptr || sizeof(T) != 2) return st;   // (the profiler times on st)
+    if (cudaEventRecord(ev, st) != cudaSuccess || cudaStreamWaitEvent(wg_stream(), ev, 0) != cudaSuccess) return st;
+    wg_used = true;
+    return wg_stream();
+  }
+  int wgrad_join() {
+    if (!wg_used) return 0;
+    static cudaEvent_t ev = [] { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); return e; }();
+    CQ_CUDA(cudaEventRecord(ev, wg_stream()));
+    CQ_CUDA(cudaStreamWaitEvent(streams[0], ev, 0));
+    wg_used = false;
+    return 0;
+  }
   int link(int from, int to) {   // stream `to` waits for everything enqueued on stream `from` so far
     if (!two_streams) return 0;
     cudaEvent_t e = sync_event(from);
@@ -261,7 +285,7 @@ struct Trainer {
         }
         if (G(widx) || G(widx + 1)) {
           ProfScope ps(P_T_WGRAD, st);
-          CQ_TRY(wgrad<T>(Y->g, Nout, X->p, Kd, G(widx), Kd, G(widx + 1), X->rows, Nout, Kd, nullptr, st));
+          CQ_TRY(wgrad<T>(Y->g, Nout, X->p, Kd, G(widx), Kd, G(widx + 1), X->rows, Nout, Kd, nullptr, wgrad_stream(X->rows)));
         }
         return 0;
       });
@@ -337,7 +361,7 @@ struct Trainer {
           CQ_TRY(gemm<T>(Z->g, kC, Wd, X->g, kC, X->rows, kC, 9 * kC, e, &cg, st));
         }
         ProfScope ps(P_T_CONV_WGRAD, st);
-        return wgrad<T>(Z->g, kC, X->p, kC, G(widx), 9 * kC, G(widx + 1), X->rows, kC, kC, &cg, st);
+        return wgrad<T>(Z->g, kC, X->p, kC, G(widx), 9 * kC, G(widx + 1), X->rows, kC, kC, &cg, wgrad_stream(X->rows));
       });
     }
     return Z;
@@ -684,6 +708,7 @@ int Trainer<T>::run() {
       CQ_TRY(dbg("tape", --ti));
     }
     CQ_TRY(link(1, 0));            // join
+    CQ_TRY(wgrad_join());
     st = streams[0];
   }
   return 0;
