@@ -29,6 +29,8 @@ SYMBOLS = {
     "cqvad_msda3d_backward": (c_int, [c_int] + [c_void_p] * 9 + [c_int] * 7 + [c_void_p]),
     "cqvad_msda3d_indices": (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_void_p]),
     "cqvad_layernorm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_long, c_int, c_void_p]),
+    "cqvad_linear_gelu_train": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_void_p]),
+    "cqvad_linear_dgrad_act": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_long, c_int, c_int, c_void_p]),
     "cqvad_linear": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_void_p]),
     "cqvad_mlp": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float,
                           c_void_p, c_void_p, c_long, c_int, c_void_p]),

@@ -136,6 +136,9 @@ struct Epilogue {
   int c2_act = CQVAD_ACT_NONE;
   const void* mul_aux = nullptr;
   int mul_mode = 0;
+  // training forward of a GELU layer in ONE epilogue: C = gelu(v), c2 = gelu'(v) with v = acc + bias (act / c2_act ignored);
+  // the pre-activation itself is never written (the backward needs only gelu' -- mul_mode 3 -- and the activation)
+  bool dual_gelu = false;
 };
 struct ConvGeom {  // implicit-GEMM 3x3 conv on the y-padded NHWC layout [n_img, h+1, w, 256]
   int h = 0, w = 0;

@@ -441,6 +441,27 @@ extern "C" int cqvad_linear(int dtype, const void* A, const void* W, const float
   return set_error(CQVAD_E_INVALID_ARG, "linear: unknown dtype %d", dtype);
 }
 
+extern "C" int cqvad_linear_gelu_train(int dtype, const void* A, const void* W, const float* bias, void* act_out,
+                                       void* dact_out, long M, int N, int K, void* stream) {
+  CQ_CHECK_ARG(A && W && act_out && dact_out && M >= 0 && N >= 1 && K >= 1, "linear_gelu_train: bad argument");
+  Epilogue e;
+  e.bias = bias; e.dual_gelu = true; e.c2 = dact_out;
+  if (dtype == CQVAD_F32) return gemm<float>((const float*)A, K, (const float*)W, (float*)act_out, N, M, N, K, e, nullptr, as_stream(stream));
+  if (dtype == CQVAD_BF16) return gemm<bf16>((const bf16*)A, K, (const bf16*)W, (bf16*)act_out, N, M, N, K, e, nullptr, as_stream(stream));
+  return set_error(CQVAD_E_INVALID_ARG, "linear_gelu_train: unknown dtype %d", dtype);
+}
+
+extern "C" int cqvad_linear_dgrad_act(int dtype, const void* dY, const void* Wt, const void* aux, int mode, void* dX, long M,
+                                      int N, int K, void* stream) {
+  CQ_CHECK_ARG(dY && Wt && aux && dX && M >= 0 && N >= 1 && K >= 1, "linear_dgrad_act: bad argument");
+  CQ_CHECK_ARG(mode == 1 || mode == 3, "linear_dgrad_act: mode must be 1 (ReLU mask) or 3 (stored derivative)");
+  Epilogue e;
+  e.mul_aux = aux; e.mul_mode = mode;
+  if (dtype == CQVAD_F32) return gemm<float>((const float*)dY, K, (const float*)Wt, (float*)dX, N, M, N, K, e, nullptr, as_stream(stream));
+  if (dtype == CQVAD_BF16) return gemm<bf16>((const bf16*)dY, K, (const bf16*)Wt, (bf16*)dX, N, M, N, K, e, nullptr, as_stream(stream));
+  return set_error(CQVAD_E_INVALID_ARG, "linear_dgrad_act: unknown dtype %d", dtype);
+}
+
 template <typename T>
 static int mlp_t(const T* X, const T* W1, const float* b1, const T* W2, const float* b2, int act, const T* res,
                  const float* g, const float* b, float eps, T* Y, T* hid, long M, int F, cudaStream_t st) {

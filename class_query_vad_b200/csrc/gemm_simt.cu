@@ -109,6 +109,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
       if (c >= N) continue;
       float v = acc[i][j];
       if (epi.bias) v += epi.bias[c];
+      if (epi.dual_gelu) {
+        C[r * ldc + c] = from_f<T>(gelu_erf(v));
+        reinterpret_cast<T*>(epi.c2)[r * ldc + c] = from_f<T>(gelu_grad(v));
+        continue;
+      }
       if (epi.act == CQVAD_ACT_RELU) v = fmaxf(v, 0.f);
       else if (epi.act == CQVAD_ACT_GELU) v = gelu_erf(v);
       if (epi.mul_mode) {

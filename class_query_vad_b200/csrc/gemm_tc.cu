@@ -54,6 +54,7 @@ struct TcParams {
   int conv; int cw; int rt;  // image width, image rows per tile
   int m_tiles, n_tiles;
   long long* trace;   // dev tool (CQVAD_GEMM_TRACE=<device address>): globaltimer stamps of CTA 0's pipeline events
+  int dual;         // TS: C = gelu(v), C2 (through tmR) = gelu'(v)
   int stg_single;   // TS pair without side input: one staging box per warp (two sequential stores) buys a 5th ring stage
   int lean;   // TS: bias + none/ReLU (+ bf16 residual) only -> branch-free epilogue
   int side;   // TS: 1 = bf16 residual, 2 = activation-derivative operand (mul_aux) arrives through tmR
@@ -119,6 +120,35 @@ __device__ __forceinline__ void ts_lean_half(uint32_t t_addr, const float* bias,
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(ow[j]) : "f"(b), "f"(a));
       }
       sts128(saddr, o);
+    }
+  }
+}
+
+// Dual GELU step (training forward): A = gelu(acc + bias) -> the C box, G = gelu'(acc + bias) -> the C2 box
+__device__ __forceinline__ void ts_dual_gelu_half(uint32_t t_addr, const float* bias, uint32_t row_a, uint32_t row_g, int sw) {
+#pragma unroll 1
+  for (int cc = 0; cc < 64; cc += 32) {
+    uint32_t r[32];
+    tmem_ld32(t_addr + cc, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      const uint32_t off = (uint32_t)((((cc >> 3) + g8) ^ sw) << 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + cc + g8 * 8), b1 = *reinterpret_cast<const float4*>(bias + cc + g8 * 8 + 4);
+      const uint64_t bb[4] = {f2pack(b0.x, b0.y), f2pack(b0.z, b0.w), f2pack(b1.x, b1.y), f2pack(b1.z, b1.w)};
+      uint4 oa, og;
+      uint32_t* wa = reinterpret_cast<uint32_t*>(&oa);
+      uint32_t* wg = reinterpret_cast<uint32_t*>(&og);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t x = f2add(f2pack(__uint_as_float(r[g8 * 8 + 2 * j]), __uint_as_float(r[g8 * 8 + 2 * j + 1])), bb[j]);
+        uint64_t a2, g2;
+        gelu_dual2(x, a2, g2);
+        wa[j] = f2_to_bf16x2(a2);
+        wg[j] = f2_to_bf16x2(g2);
+      }
+      sts128(row_a + off, oa);
+      sts128(row_g + off, og);
     }
   }
 }
@@ -351,7 +381,11 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
             if (p.stg_single && hf == 1) { if (lane == 0) bulk_wait_read<0>(); __syncwarp(); }
             if (p.side && !do_ln) mbar_wait(rbar + 8 * hf, hf ? rph1 : rph0);
             CQ_TRACE_E(1 + hf * 6);
-            if (p.lean) {
+            if (p.dual) {
+              // both boxes of this warp are reused by the second half: its stores must have read them
+              if (hf == 1) { if (lane == 0) bulk_wait_read<0>(); __syncwarp(); }
+              ts_dual_gelu_half(t_addr + hf * 64, bcur + c0 + hf * 64, my_row, my_row + STG_BOX_BYTES, sw);
+            } else if (p.lean) {
               const float lo = p.act == CQVAD_ACT_RELU ? 0.f : -INFINITY;
               if (p.side == 0) ts_lean_half<0>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo);
               else if (p.side == 1) ts_lean_half<1>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo);
@@ -421,7 +455,14 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
             CQ_TRACE_E(5 + hf * 6);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) tma_store_2d(&tmC, stg + (uint32_t)(hf * stg_stride), colw + hf * 64, row0);
+            if (lane == 0) {
+              if (p.dual) {
+                tma_store_2d(&tmC, stg, colw + hf * 64, row0);
+                tma_store_2d(&tmR, stg + STG_BOX_BYTES, colw + hf * 64, row0);   // tmR carries the second output here
+              } else {
+                tma_store_2d(&tmC, stg + (uint32_t)(hf * stg_stride), colw + hf * 64, row0);
+              }
+            }
             CQ_TRACE_E(6 + hf * 6);
           }
           if (lane == 0) bulk_commit();     // always two groups per tile (an empty group for a half outside the matrix)
@@ -741,7 +782,10 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
   const int grid = (int)(tiles < sms ? tiles : sms);
   // TMA-store epilogue: every non-conv GEMM whose epilogue reads / writes bf16 only (at most one [M,N] side input)
   static const bool no_ts = getenv("CQVAD_GEMM_NO_TS") != nullptr;
-  const bool ts = !no_ts && !conv && !epi.c32 && !epi.res32 && !epi.c2 && N % 8 == 0 && !(epi.res && epi.mul_mode);
+  const bool dual = epi.dual_gelu;
+  if (dual && (!epi.c2 || epi.res || epi.mul_mode || epi.ln_g || epi.zero_period || conv)) return 1;
+  const bool ts = !no_ts && !conv && !epi.c32 && !epi.res32 && (!epi.c2 || dual) && N % 8 == 0 && !(epi.res && epi.mul_mode);
+  if (dual && !ts) return 1;
   const bool extra = p.c2 || p.mul_mode;
   CUtensorMap tmC = tmA, tmR = tmA;
   if (ts) {
@@ -757,11 +801,14 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
     } else if (epi.mul_mode) {
       CQ_TRY(make_tmap_bf16(&tmR, epi.mul_aux, 2, dims, sc, box));
       p.side = 2;
+    } else if (dual) {
+      CQ_TRY(make_tmap_bf16(&tmR, epi.c2, 2, dims, sc, box));
+      p.dual = 1;
     }
   }
   p.lean = ts && !epi.ln_g && epi.zero_period == 0 && epi.mul_mode != 2 && (epi.act == CQVAD_ACT_NONE || epi.act == CQVAD_ACT_RELU) &&
            getenv("CQVAD_GEMM_NO_LEAN") == nullptr;
-  p.stg_single = ts && pair && !p.side && K >= 8 * BLOCK_K && getenv("CQVAD_GEMM_NO_STG1") == nullptr;   // load-bound shapes only: measured +7..10% at K >= 512, -12% at K = 256 (epilogue-bound)
+  p.stg_single = ts && pair && !p.side && !dual && K >= 8 * BLOCK_K && getenv("CQVAD_GEMM_NO_STG1") == nullptr;   // load-bound shapes only: measured +7..10% at K >= 512, -12% at K = 256 (epilogue-bound)
   const size_t smem = ts ? SMEM_BYTES_TS : SMEM_BYTES;
 #define CQ_LAUNCH_TC(KERN)                                                                            \
   do {                                                                                                \

@@ -232,6 +232,9 @@ struct Trainer {
   // epilogue -- a ReLU mask read from the activation itself, or gelu'(H) that the forward gelu pass stored next to gelu(H) --
   // so the 578 MB read-modify-write pass over the [94 080 x 1024] ConvBlock hidden gradient disappears.
   const bool fuse_act_bwd = getenv("CQVAD_TRAIN_NO_FUSE_ACT_BWD") == nullptr;
+  // ... and the forward of a GELU layer writes gelu(H) and gelu'(H) from the GEMM epilogue itself (Epilogue::dual_gelu): the
+  // pre-activation H never reaches HBM (768 -> 384 MB of traffic per ConvBlock hidden layer, one launch less)
+  const bool dual_gelu = fuse_act_bwd && !fuse_act && getenv("CQVAD_TRAIN_NO_DUAL_GELU") == nullptr;
   Ten<T>* last_c2 = nullptr;   // second output of the last lin(..., c2_act)
   Ten<T>* lin(Ten<T>* X, int widx, int Nout, int act = CQVAD_ACT_NONE, Ten<T>* res = nullptr, int zp = 0, int zv = 0,
               int* rc = nullptr, int c2_act = CQVAD_ACT_NONE) {
@@ -248,13 +251,15 @@ struct Trainer {
       last_c2 = A2;
     }
     const T* Wt = X->hg ? WT(widx, (long)Nout * Kd) : nullptr;
+    const bool dual = A2 && A2->gact == 3 && dual_gelu && !res && zp == 0 && act == CQVAD_ACT_NONE;
     if (fwd()) {
       Epilogue e;
       e.bias = Wf(widx + 1); e.act = act; e.res = res ? res->p : nullptr; e.ldr = Nout; e.zero_period = zp; e.zero_valid = zv;
       if (A2 && fuse_act) { e.c2 = A2->p; e.c2_act = c2_act; }
+      if (dual) { e.dual_gelu = true; e.c2 = const_cast<T*>(A2->gref); }
       int r;
-      { ProfScope ps(P_T_FWD_GEMM, st); r = gemm<T>(X->p, Kd, Wm(widx), Y->p, Nout, X->rows, Nout, Kd, e, nullptr, st); }
-      if (r == 0 && A2 && !fuse_act) { ProfScope ps(P_T_FWD_OTHER, st); r = gelu_fwd<T>(Y->p, A2->p, A2->gact == 3 ? const_cast<T*>(A2->gref) : nullptr, Y->n(), st); }
+      { ProfScope ps(P_T_FWD_GEMM, st); r = gemm<T>(X->p, Kd, Wm(widx), dual ? A2->p : Y->p, Nout, X->rows, Nout, Kd, e, nullptr, st); }
+      if (r == 0 && A2 && !fuse_act && !dual) { ProfScope ps(P_T_FWD_OTHER, st); r = gelu_fwd<T>(Y->p, A2->p, A2->gact == 3 ? const_cast<T*>(A2->gref) : nullptr, Y->n(), st); }
       if (r == 0) r = dbg("lin", widx);
       if (r != 0 && rc && *rc == 0) *rc = r;
     }
@@ -263,7 +268,11 @@ struct Trainer {
         if (A2) {   // the gradient arrived through the activated copy
           if (!A2->gi) return 0;
           Y->gi = true;
-          if (!A2->gmasked) { ProfScope ps(P_T_ACT_BWD, st); CQ_TRY(act_bwd<T>(Y->g, Y->p, c2_act, Y->n(), st)); }
+          if (!A2->gmasked) {
+            if (dual) return set_error(CQVAD_E_INVALID_ARG, "backward: a dual-GELU activation needs a single GEMM consumer");
+            ProfScope ps(P_T_ACT_BWD, st);
+            CQ_TRY(act_bwd<T>(Y->g, Y->p, c2_act, Y->n(), st));
+          }
         }
         if (!Y->gi) return 0;
         {

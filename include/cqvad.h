@@ -70,6 +70,15 @@ int cqvad_layernorm(int dtype, const void* x, const void* res, const float* gamm
  * BF16: tcgen05 kernel when K % 64 == 0 and N % 8 == 0, CUDA-core kernel otherwise. */
 int cqvad_linear(int dtype, const void* A, const void* W, const float* bias, const void* res, void* C,
                  long M, int N, int K, int act, void* stream);
+/* Training forward of a GELU linear layer (ConvBlock conv2 + nn.GELU, dab_transformer.py:84,93-94 under autograd):
+ * act_out[M,N] = gelu(A . W^T + bias) and dact_out[M,N] = gelu'(A . W^T + bias), both written by the GEMM epilogue; the
+ * pre-activation is never stored (autograd keeps it, the backward here needs only gelu').  BF16: tcgen05 kernel. */
+int cqvad_linear_gelu_train(int dtype, const void* A, const void* W, const float* bias, void* act_out, void* dact_out,
+                            long M, int N, int K, void* stream);
+/* Data gradient through an activation in one epilogue: dX[M,N] = (dY[M,K] . Wt[N,K]^T) * aux[M,N] (mode 3: aux holds the
+ * stored derivative) or masked by aux > 0 (mode 1: aux is the ReLU output).  Wt is the transposed weight [in, out]. */
+int cqvad_linear_dgrad_act(int dtype, const void* dY, const void* Wt, const void* aux, int mode, void* dX, long M, int N,
+                           int K, void* stream);
 /* Y[M,256] = LN?( res + W2 . act(W1 . X + b1) + b2 ): the FFN blocks of the decoder (dab_transformer.py:994-996,
  * 1043-1045, 1074-1076).  X [M,256], W1 [F,256], W2 [256,F] (dtype); ln_g/ln_b may be NULL (no LayerNorm); res may be
  * NULL.  hidden [M,F] (dtype) is scratch used only when the fused tensor-core kernel does not apply (fp32, or F % 128). */

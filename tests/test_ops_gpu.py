@@ -262,3 +262,43 @@ def test_conv_wgrad_matches_torch(n_img, h, w, dt):
     ref = wt.grad.permute(0, 2, 3, 1).reshape(C, 9 * C)            # [O][ky*3+kx][I]
     assert float((dW.double() - ref).abs().max() / ref.abs().max()) < 1e-4
     assert float((db.double() - dy.double().sum((0, 1, 2))).abs().max()) / float(dy.double().sum((0, 1, 2)).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K,dt", [(20000, 1024, 256, torch.bfloat16), (300, 512, 256, torch.bfloat16), (19001, 1024, 256, torch.bfloat16),
+                                      (777, 96, 64, torch.float32)])
+def test_linear_gelu_train_dual_epilogue(M, N, K, dt):
+    """act = gelu(A W^T + b), dact = gelu'(A W^T + b) from ONE epilogue (CTA-pair / single-CTA tcgen05 and CUDA-core paths)
+    against torch (nn.GELU erf form, dab_transformer.py:84) in fp64."""
+    from class_query_vad_b200 import _lib
+    lib = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randn((M, K), device="cuda", generator=g).to(dt)
+    W = (torch.randn((N, K), device="cuda", generator=g) / K ** 0.5 * 1.5).to(dt)
+    b = torch.randn(N, device="cuda", generator=g)
+    act = torch.empty((M, N), device="cuda", dtype=dt)
+    dact = torch.empty_like(act)
+    _lib.check(lib.cqvad_linear_gelu_train(_lib.dtype_id(dt), _lib.ptr(A), _lib.ptr(W), _lib.ptr(b), _lib.ptr(act), _lib.ptr(dact),
+                                           M, N, K, _lib.stream_ptr()))
+    x = (A.double() @ W.double().t() + b.double()).requires_grad_(True)
+    y = torch.nn.functional.gelu(x)
+    y.sum().backward()
+    tol = 6e-3 if dt == torch.bfloat16 else 2e-5     # one bf16 rounding of a value <= ~5 (2^-8 relative) / fp32 accumulation
+    assert float((act.double() - y.detach()).abs().max() / y.detach().abs().max()) < tol
+    assert float((dact.double() - x.grad).abs().max()) < tol * 1.2           # |gelu'| <= 1.13
+
+
+@pytest.mark.parametrize("M,N,K,mode", [(20000, 1024, 256, 3), (20000, 2048, 256, 1), (300, 256, 256, 3), (19001, 512, 256, 1)])
+def test_linear_dgrad_act_epilogue(M, N, K, mode):
+    """dX = (dY Wt^T) * aux (stored derivative) / masked by aux > 0 (ReLU) in the TMA-store epilogue (side input by TMA)."""
+    from class_query_vad_b200 import _lib
+    lib = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(M + N + mode)
+    dY = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+    Wt = (torch.randn((N, K), device="cuda", generator=g) / K ** 0.5).bfloat16()
+    aux = torch.randn((M, N), device="cuda", generator=g).bfloat16()
+    dX = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.cqvad_linear_dgrad_act(_lib.BF16, _lib.ptr(dY), _lib.ptr(Wt), _lib.ptr(aux), mode, _lib.ptr(dX), M, N, K,
+                                          _lib.stream_ptr()))
+    ref = dY.double() @ Wt.double().t()
+    ref = ref * aux.double() if mode == 3 else ref * (aux.double() > 0)
+    assert float((dX.double() - ref).abs().max() / ref.abs().max()) < 6e-3
