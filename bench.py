@@ -348,11 +348,11 @@ def main():
     if main_mode == "train":
         cf, cd = prof["train fwd: conv3x3 (tcgen05 implicit GEMM)"], prof["train bwd: conv3x3 dgrad (tcgen05 implicit GEMM)"]
         conv_launch_ms = (cf["ms_per_step"] + cd["ms_per_step"]) / max(cf["scopes"] + cd["scopes"], 1)
-        kname = f"gemm_tc_kernel (conv mode: forward + data-gradient launches, {6 * Lr} per step)"
+        kname = f"gemm_tc2_kernel<0,0> (CTA-pair tcgen05 implicit-GEMM 3x3 conv: forward + data-gradient launches, {6 * Lr} per step)"
     else:
         conv = prof["conv3x3_ln (tcgen05 implicit GEMM)"]
         conv_launch_ms = conv["ms_per_step"] / max(conv["scopes"], 1)
-        kname = "gemm_tc_kernel (conv mode)"
+        kname = "gemm_tc2_kernel<0,0> (CTA-pair tcgen05 implicit-GEMM 3x3 conv + LN)"
     achieved = conv_flops / (conv_launch_ms * 1e-3) / 1e12
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
