@@ -1,0 +1,62 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy restatement of the deformable encoder layer around the MSDA-3D op.  Never imported by the
+product package; tests/, __graft_entry__.smoke() and bench.py's host legs only.  Pinned to the reference by
+tests/golden/enc_*.npz (oracle/make_golden_encoder.py; tests/test_oracle_golden.py).
+
+Follows models/detr/dab_transformer.py:433-452 (get_reference_points), :484-523 (DeformableTransformerEncoderLayer) and
+ops/modules/ms_deform_attn.py:167-203 (MSDeformAttn3D.forward); the sampling core is oracle/msda_np.py.
+"""
+import numpy as np
+
+from .msda_np import msda3d_forward
+
+
+def _ln(x, g, b, eps=1e-5):
+    mu = x.mean(-1, keepdims=True)
+    var = ((x - mu) ** 2).mean(-1, keepdims=True)
+    return (x - mu) / np.sqrt(var + eps) * g + b
+
+
+def reference_points(shapes, valid_ratios):
+    """dab_transformer.py:433-452: voxel centres / (valid_ratio * extent) per level, (x, y, t) order, then scaled by every
+    level's valid ratio -> [B, Len, L, 3]."""
+    out = []
+    for lvl, (T, H, W) in enumerate(np.asarray(shapes).tolist()):
+        t, y, x = np.meshgrid(np.linspace(0.5, T - 0.5, T, dtype=np.float32), np.linspace(0.5, H - 0.5, H, dtype=np.float32),
+                              np.linspace(0.5, W - 0.5, W, dtype=np.float32), indexing="ij")
+        rt = t.reshape(-1)[None] / (valid_ratios[:, None, lvl, 2] * T)
+        ry = y.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * H)
+        rx = x.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * W)
+        out.append(np.stack((rx, ry, rt), -1))
+    ref = np.concatenate(out, 1)
+    return (ref[:, :, None] * valid_ratios[:, None]).astype(np.float32)
+
+
+def msda_module(W, query, refp, src, shapes, level_start, mask=None, M=8, pre="self_attn."):
+    """ops/modules/ms_deform_attn.py:167-203.  query, src [B, Len, 256]; refp [B, Len, L, 3] -> [B, Len, 256]."""
+    B, Lq, C = query.shape
+    L = len(shapes)
+    P = W[pre + "attention_weights.bias"].shape[0] // (M * L)
+    value = src @ W[pre + "value_proj.weight"].T + W[pre + "value_proj.bias"]                       # :181
+    if mask is not None:
+        value = np.where(mask[..., None], 0.0, value)                                               # :182-183
+    value = value.reshape(B, -1, M, C // M).astype(np.float32)
+    offs = (query @ W[pre + "sampling_offsets.weight"].T + W[pre + "sampling_offsets.bias"]).reshape(B, Lq, M, L, P, 3)   # :185
+    logit = (query @ W[pre + "attention_weights.weight"].T + W[pre + "attention_weights.bias"]).reshape(B, Lq, M, L * P)  # :186
+    e = np.exp(logit - logit.max(-1, keepdims=True))
+    attn = (e / e.sum(-1, keepdims=True)).reshape(B, Lq, M, L, P)                                   # :187
+    sh = np.asarray(shapes, dtype=np.float32)
+    norm = np.stack([sh[:, 0], sh[:, 2], sh[:, 1]], -1)          # (T, W, H) against (x, y, t) offsets: reference quirk, :190
+    loc = refp[:, :, None, :, None, :] + offs / norm[None, None, None, :, None, :]                  # :191-192
+    out = msda3d_forward(value, np.asarray(shapes, dtype=np.int64), np.asarray(level_start, dtype=np.int64),
+                         loc.astype(np.float32), attn.astype(np.float32))                           # :198-199
+    out = out.reshape(B, Lq, C)
+    return out @ W[pre + "output_proj.weight"].T + W[pre + "output_proj.bias"], loc, attn           # :200
+
+
+def encoder_layer(W, src, pos, refp, shapes, level_start, mask=None):
+    """dab_transformer.py:513-523 in eval mode (dropout = identity)."""
+    src2, _, _ = msda_module(W, src + pos, refp, src, shapes, level_start, mask)                    # :515
+    x = _ln(src + src2, W["norm1.weight"], W["norm1.bias"])                                         # :516-517
+    h = np.maximum(x @ W["linear1.weight"].T + W["linear1.bias"], 0.0)                              # :508
+    x = _ln(x + h @ W["linear2.weight"].T + W["linear2.bias"], W["norm2.weight"], W["norm2.bias"])  # :509-510
+    return x.astype(np.float32), src2.astype(np.float32)

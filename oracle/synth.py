@@ -187,3 +187,49 @@ def grad_sample_index(size, seed=0, n=2048):
     """Seeded flat indices at which large gradients are sampled in tests/golden/grad_*.npz."""
     rs = np.random.RandomState(5000 + seed + size % 9973)
     return np.sort(rs.randint(0, size, size=min(n, size)))
+
+
+# ---- deformable encoder layer (dab_transformer.py:484-523, ops/modules/ms_deform_attn.py:122-203) -------------------------
+def encoder_layer_param_spec(F, L=4, P=8, M=8, C=D_MODEL):
+    """Ordered (name, shape) list of the reference DeformableTransformerEncoderLayer state_dict."""
+    return [("self_attn.sampling_offsets.weight", (M * L * P * 3, C)), ("self_attn.sampling_offsets.bias", (M * L * P * 3,)),
+            ("self_attn.attention_weights.weight", (M * L * P, C)), ("self_attn.attention_weights.bias", (M * L * P,)),
+            ("self_attn.value_proj.weight", (C, C)), ("self_attn.value_proj.bias", (C,)),
+            ("self_attn.output_proj.weight", (C, C)), ("self_attn.output_proj.bias", (C,)),
+            ("norm1.weight", (C,)), ("norm1.bias", (C,)),
+            ("linear1.weight", (F, C)), ("linear1.bias", (F,)), ("linear2.weight", (C, F)), ("linear2.bias", (C,)),
+            ("norm2.weight", (C,)), ("norm2.bias", (C,))]
+
+
+def make_encoder_layer_weights(F, L=4, P=8, seed=0):
+    """Deterministic non-degenerate weights: the reference init zeroes sampling_offsets.weight / attention_weights.* (parity would
+    be vacuous), so every tensor is random; sampling offsets are a few voxels wide (bias = ring pattern scale, weight small)."""
+    rs = np.random.RandomState(7000 + seed)
+    W = {}
+    for name, shape in encoder_layer_param_spec(F, L, P):
+        if name.startswith("norm"):
+            W[name] = (1.0 + 0.2 * rs.standard_normal(shape)).astype(np.float32) if name.endswith("weight") else \
+                (0.1 * rs.standard_normal(shape)).astype(np.float32)
+        elif name == "self_attn.sampling_offsets.bias":
+            W[name] = (1.5 * rs.standard_normal(shape)).astype(np.float32)
+        elif name == "self_attn.sampling_offsets.weight":
+            W[name] = (0.05 * rs.standard_normal(shape)).astype(np.float32)
+        elif name.endswith("bias"):
+            W[name] = (0.1 * rs.standard_normal(shape)).astype(np.float32)
+        else:
+            W[name] = (rs.standard_normal(shape) / np.sqrt(shape[1])).astype(np.float32)
+    return W
+
+
+def make_encoder_inputs(B, shapes, seed=0, masked=False):
+    """src, pos [B, Len, 256]; valid_ratios [B, L, 3] (x, y, t); mask [B, Len] bool (True = padded token)."""
+    rs = np.random.RandomState(8000 + seed)
+    Len = int(sum(t * h * w for (t, h, w) in shapes))
+    src = rs.standard_normal((B, Len, D_MODEL)).astype(np.float32)
+    pos = (0.5 * rs.standard_normal((B, Len, D_MODEL))).astype(np.float32)
+    vr = np.ones((B, len(shapes), 3), dtype=np.float32)
+    mask = np.zeros((B, Len), dtype=bool)
+    if masked:
+        vr[1::2] = (0.75 + 0.2 * rs.rand(*vr[1::2].shape)).astype(np.float32)
+        mask[1::2] = rs.rand(*mask[1::2].shape) < 0.15
+    return dict(src=src, pos=pos, valid_ratios=vr, mask=mask)

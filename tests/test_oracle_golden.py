@@ -107,3 +107,27 @@ def test_torch_restatement_gradients_match_reference_autograd(name):
             nm = k[3:]
             idx = synth.grad_sample_index(grads[nm].size, seed)
             assert np.abs(grads[nm].reshape(-1)[idx] - g[k]).max() <= 1e-4 * max(np.abs(g[k]).max(), 1e-2 * G), nm
+
+
+ENC_CASES = ["enc_tiny", "enc_small_masked", "enc_mid_f2048"]
+
+
+def enc_case(g):
+    B, F_, P, seed, masked = (int(v) for v in g["meta"])
+    shapes = [tuple(int(x) for x in r) for r in g["shapes"]]
+    W = synth.make_encoder_layer_weights(F_, len(shapes), P, seed=seed)
+    inp = synth.make_encoder_inputs(B, shapes, seed=seed, masked=bool(masked))
+    return W, inp, shapes, bool(masked)
+
+
+@pytest.mark.parametrize("name", ENC_CASES)
+def test_encoder_layer_oracle_matches_reference(name):
+    """oracle/encoder_np.py against the reference DeformableTransformerEncoderLayer + MSDeformAttn3D module + get_reference_points."""
+    from oracle import encoder_np
+    g = load_golden(name)
+    W, inp, shapes, masked = enc_case(g)
+    refp = encoder_np.reference_points(shapes, inp["valid_ratios"])
+    assert np.abs(refp - g["reference_points"]).max() < 1e-6
+    out, attn_out = encoder_np.encoder_layer(W, inp["src"], inp["pos"], refp, shapes, g["level_start"], inp["mask"] if masked else None)
+    assert np.abs(attn_out - g["attn_out"]).max() <= 2e-5 * np.abs(g["attn_out"]).max()
+    assert np.abs(out - g["out"]).max() <= 2e-5 * np.abs(g["out"]).max()
