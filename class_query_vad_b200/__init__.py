@@ -10,10 +10,13 @@ from .functions.ms_deform_attn_func import MSDeformAttnFunction, ms_deform_attn_
 from .modules.ms_deform_attn import MSDeformAttn3D
 from .modules.attention import MultiheadAttention
 from .modules.position_encoding import PositionEmbeddingSine_3D, build_position_encoding, gen_sineembed_for_position
+from .modules.encoder import (DeformableTransformerEncoderLayer, DeformableTransformerEncoder, encoder_layer_forward,
+                              pack_encoder_layer_weights)
 from .modules.decoder import (MLP, ConvBlock, TransformerDecoderLayer, TransformerClassDecoderLayer, TransformerDecoder,
                               build_decoder)
 
 __all__ = ["DecoderEngine", "DecoderFunction", "pack_decoder_weights", "MSDeformAttnFunction", "ms_deform_attn_indices", "MSDeformAttn3D",
            "MultiheadAttention", "PositionEmbeddingSine_3D", "build_position_encoding", "gen_sineembed_for_position",
            "MLP", "ConvBlock", "TransformerDecoderLayer", "TransformerClassDecoderLayer", "TransformerDecoder",
-           "build_decoder"]
+           "build_decoder", "DeformableTransformerEncoderLayer", "DeformableTransformerEncoder", "encoder_layer_forward",
+           "pack_encoder_layer_weights"]

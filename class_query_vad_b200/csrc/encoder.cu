@@ -1,0 +1,181 @@
+// Deformable encoder layer around the MSDA-3D op:
+//   DeformableTransformerEncoderLayer.forward (models/detr/dab_transformer.py:513-523) with
+//   MSDeformAttn3D.forward (ops/modules/ms_deform_attn.py:167-203) inlined:
+//     q      = src + pos                                                  (:515 with_pos_embed)
+//     value  = value_proj(src), padded tokens zeroed                      (:181-183)
+//     off    = sampling_offsets(q), logit = attention_weights(q)          (:185-186)   fp32 outputs of the tcgen05 GEMMs
+//     attn   = softmax_{L*P}(logit); loc = ref + off / (T_l, W_l, H_l)    (:187-192)   one warp per (token, head)
+//     samp   = MSDA-3D(value, loc, attn)                                  (:198)       msda.cu
+//     x1     = LN1(src + output_proj(samp))                               (:200, :516-517)  LayerNorm in the GEMM epilogue
+//     out    = LN2(x1 + linear2(relu(linear1(x1))))                       (:507-510)   fused tcgen05 MLP (hidden stays on the SM)
+// Dropout is the identity (eval / the native path's documented divergence).  Heads = 8, d_model = 256 (all shipped configs).
+#include "common.cuh"
+
+namespace cqvad {
+namespace {
+
+enum { E_OFF_W = 0, E_OFF_B, E_ATT_W, E_ATT_B, E_VAL_W, E_VAL_B, E_OUT_W, E_OUT_B, E_N1_W, E_N1_B, E_L1_W, E_L1_B, E_L2_W, E_L2_B,
+       E_N2_W, E_N2_B, E_COUNT };
+constexpr int kM = 8;   // heads
+
+template <typename T>
+__global__ void __launch_bounds__(256) add_rows_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long n8) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float x[8], y[8];
+  load8(a + i * 8, x);
+  load8(b + i * 8, y);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] += y[j];
+  store8(o + i * 8, x);
+}
+
+// value.masked_fill(padding_mask[..., None], 0): one warp per row of 256
+template <typename T>
+__global__ void __launch_bounds__(256) mask_rows_kernel(T* __restrict__ x, const uint8_t* __restrict__ mask, long rows) {
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows || !mask[row]) return;
+  const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  store8(x + row * kC + lane * 8, z);
+}
+
+// one warp per (token, head): softmax over the L*P logits and sampling locations of the L*P points.
+// off [rows, M*L*P*3], logit [rows, M*L*P] (fp32), ref [rows, L, 3] -> loc [rows, M, L, P, 3], attn [rows, M, L, P]
+__global__ void __launch_bounds__(256) msda_prepare_kernel(const float* __restrict__ off, const float* __restrict__ logit,
+                                                           const float* __restrict__ ref, const int64_t* __restrict__ shapes,
+                                                           float* __restrict__ loc, float* __restrict__ attn, long rows, int L,
+                                                           int P) {
+  const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= rows * kM) return;
+  const long row = wid / kM;
+  const int LP = L * P;
+  const float* lg = logit + wid * LP;
+  float mx = -INFINITY;
+  for (int j = lane; j < LP; j += 32) mx = fmaxf(mx, lg[j]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < LP; j += 32) sum += expf(lg[j] - mx);
+  sum = warp_sum(sum);
+  for (int j = lane; j < LP; j += 32) {
+    attn[wid * LP + j] = expf(lg[j] - mx) / sum;
+    const int l = j / P;
+    // offset normaliser stacked as (T_l, W_l, H_l) against (x, y, t) offsets: the reference's own order, ms_deform_attn.py:190
+    const float nx = (float)shapes[l * 3 + 0], ny = (float)shapes[l * 3 + 2], nt = (float)shapes[l * 3 + 1];
+    const float* o = off + (wid * LP + j) * 3;
+    const float* r = ref + (row * L + l) * 3;
+    float* d = loc + (wid * LP + j) * 3;
+    d[0] = r[0] + __fdiv_rn(o[0], nx);
+    d[1] = r[1] + __fdiv_rn(o[1], ny);
+    d[2] = r[2] + __fdiv_rn(o[2], nt);
+  }
+}
+
+struct EncWs {
+  char* base; size_t off = 0, cap;
+  EncWs(void* p, size_t c) : base((char*)p), cap(c) {}
+  void* take(size_t bytes) {
+    const size_t a = (off + 255) & ~(size_t)255;
+    off = a + bytes;
+    return (base && off <= cap) ? base + a : nullptr;
+  }
+};
+
+template <typename T>
+size_t enc_ws_bytes(long rows, int L, int P, int F) {
+  EncWs w(nullptr, 0);
+  const int LP3 = kM * L * P * 3, LP1 = kM * L * P;
+  w.take((size_t)rows * kC * sizeof(T));                        // q
+  w.take((size_t)rows * kC * sizeof(T));                        // value
+  w.take((size_t)rows * LP3 * sizeof(T));                       // offsets (dtype)
+  w.take((size_t)rows * LP1 * sizeof(T));                       // logits (dtype)
+  if (sizeof(T) == 2) { w.take((size_t)rows * LP3 * 4); w.take((size_t)rows * LP1 * 4); }   // fp32 copies of both
+  w.take((size_t)rows * LP3 * 4);                               // loc
+  w.take((size_t)rows * LP1 * 4);                               // attn
+  w.take((size_t)rows * kC * sizeof(T));                        // sampled
+  w.take((size_t)rows * kC * sizeof(T));                        // x1
+  w.take((size_t)rows * F * sizeof(T));                         // FFN hidden (only used off the fused-MLP path)
+  return w.off + 256;
+}
+
+template <typename T>
+int enc_layer_t(const void* const* W, const T* src, const T* pos, const float* refp, const int64_t* shapes, const int64_t* lsi,
+                const uint8_t* mask, T* out, T* attn_out, void* ws, size_t ws_bytes, int B, long Len, int L, int P, int F,
+                cudaStream_t st) {
+  const long rows = (long)B * Len;
+  if (rows == 0) return 0;
+  const int LP3 = kM * L * P * 3, LP1 = kM * L * P;
+  if (ws_bytes < enc_ws_bytes<T>(rows, L, P, F)) return set_error(CQVAD_E_WORKSPACE, "deform_encoder_layer: workspace too small");
+  EncWs w(ws, ws_bytes);
+  T* q = (T*)w.take((size_t)rows * kC * sizeof(T));
+  T* value = (T*)w.take((size_t)rows * kC * sizeof(T));
+  T* offT = (T*)w.take((size_t)rows * LP3 * sizeof(T));
+  T* lgT = (T*)w.take((size_t)rows * LP1 * sizeof(T));
+  float *off32 = (float*)offT, *lg32 = (float*)lgT;
+  if (sizeof(T) == 2) { off32 = (float*)w.take((size_t)rows * LP3 * 4); lg32 = (float*)w.take((size_t)rows * LP1 * 4); }
+  float* loc = (float*)w.take((size_t)rows * LP3 * 4);
+  float* attn = (float*)w.take((size_t)rows * LP1 * 4);
+  T* samp = (T*)w.take((size_t)rows * kC * sizeof(T));
+  T* x1 = (T*)w.take((size_t)rows * kC * sizeof(T));
+  T* hid = (T*)w.take((size_t)rows * F * sizeof(T));
+  auto Wm = [&](int i) { return (const T*)W[i]; };
+  auto Wf = [&](int i) { return (const float*)W[i]; };
+
+  const long n8 = rows * kC / 8;
+  add_rows_kernel<T><<<(unsigned)cdiv(n8, 256), 256, 0, st>>>(src, pos, q, n8);
+  CQ_LAUNCH_CHECK();
+  { Epilogue e; e.bias = Wf(E_VAL_B); CQ_TRY(gemm<T>(src, kC, Wm(E_VAL_W), value, kC, rows, kC, kC, e, nullptr, st)); }
+  if (mask) {
+    mask_rows_kernel<T><<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(value, mask, rows);
+    CQ_LAUNCH_CHECK();
+  }
+  // offsets / logits: fp32 straight from the accumulators (bf16: fp32 side output of the epilogue), so that the sampling
+  // locations carry no bf16 rounding of their own
+  { Epilogue e; e.bias = Wf(E_OFF_B); if (sizeof(T) == 2) e.c32 = off32; CQ_TRY(gemm<T>(q, kC, Wm(E_OFF_W), offT, LP3, rows, LP3, kC, e, nullptr, st)); }
+  { Epilogue e; e.bias = Wf(E_ATT_B); if (sizeof(T) == 2) e.c32 = lg32; CQ_TRY(gemm<T>(q, kC, Wm(E_ATT_W), lgT, LP1, rows, LP1, kC, e, nullptr, st)); }
+  msda_prepare_kernel<<<(unsigned)cdiv(rows * kM * 32, 256), 256, 0, st>>>(off32, lg32, refp, shapes, loc, attn, rows, L, P);
+  CQ_LAUNCH_CHECK();
+  CQ_TRY(cqvad_msda3d_forward(DT<T>::id, value, shapes, lsi, loc, attn, samp, B, (int)Len, kM, kC / kM, L, (int)Len, P, (void*)st));
+  if (attn_out) {   // the module's own output (tests): output_proj(samp)
+    Epilogue e; e.bias = Wf(E_OUT_B);
+    CQ_TRY(gemm<T>(samp, kC, Wm(E_OUT_W), attn_out, kC, rows, kC, kC, e, nullptr, st));
+  }
+  { Epilogue e; e.bias = Wf(E_OUT_B); e.res = src; e.ldr = kC; e.ln_g = Wf(E_N1_W); e.ln_b = Wf(E_N1_B); e.ln_eps = 1e-5f;
+    CQ_TRY(gemm<T>(samp, kC, Wm(E_OUT_W), x1, kC, rows, kC, kC, e, nullptr, st)); }
+  return cqvad_mlp(DT<T>::id, x1, Wm(E_L1_W), Wf(E_L1_B), Wm(E_L2_W), Wf(E_L2_B), CQVAD_ACT_RELU, x1, Wf(E_N2_W), Wf(E_N2_B), 1e-5f,
+                   out, hid, rows, F, (void*)st);
+}
+
+}  // namespace
+}  // namespace cqvad
+
+using namespace cqvad;
+
+extern "C" int cqvad_deform_encoder_layer_num_weights(void) { return E_COUNT; }
+
+extern "C" size_t cqvad_deform_encoder_layer_workspace_bytes(int dtype, int B, long Len, int L, int P, int F) {
+  if (B < 0 || Len < 0 || L < 1 || P < 1 || F < 1) return 0;
+  return dtype == CQVAD_F32 ? enc_ws_bytes<float>((long)B * Len, L, P, F) : enc_ws_bytes<bf16>((long)B * Len, L, P, F);
+}
+
+extern "C" int cqvad_deform_encoder_layer_forward(int dtype, const void* const* weights, const void* src, const void* pos,
+                                                  const float* reference_points, const int64_t* shapes,
+                                                  const int64_t* level_start, const uint8_t* padding_mask, void* out,
+                                                  void* attn_out, void* workspace, size_t workspace_bytes, int B, long Len, int L,
+                                                  int P, int F, void* stream) {
+  CQ_CHECK_ARG(B >= 0 && Len >= 0 && L >= 1 && P >= 1 && F >= 1, "deform_encoder_layer: bad dimensions");
+  if ((long)B * Len == 0) return 0;
+  CQ_CHECK_ARG(weights && src && pos && reference_points && shapes && level_start && out && workspace,
+               "deform_encoder_layer: null pointer");
+  for (int i = 0; i < E_COUNT; ++i) CQ_CHECK_ARG(weights[i] != nullptr, "deform_encoder_layer: weight %d is null", i);
+  CQ_CHECK_SHAPE(F % 8 == 0 && (kM * L * P) % 8 == 0, "deform_encoder_layer: F and heads*levels*points must be multiples of 8");
+  CQ_CHECK_SHAPE(Len < (1L << 31) / kC, "deform_encoder_layer: Len*256 must fit int32 (as the MSDA op requires)");
+  if (dtype == CQVAD_F32)
+    return enc_layer_t<float>(weights, (const float*)src, (const float*)pos, reference_points, shapes, level_start, padding_mask,
+                              (float*)out, (float*)attn_out, workspace, workspace_bytes, B, Len, L, P, F, as_stream(stream));
+  if (dtype == CQVAD_BF16)
+    return enc_layer_t<bf16>(weights, (const bf16*)src, (const bf16*)pos, reference_points, shapes, level_start, padding_mask,
+                             (bf16*)out, (bf16*)attn_out, workspace, workspace_bytes, B, Len, L, P, F, as_stream(stream));
+  return set_error(CQVAD_E_INVALID_ARG, "deform_encoder_layer: unknown dtype %d", dtype);
+}

@@ -1,0 +1,123 @@
+"""Drop-ins for the reference `DeformableTransformerEncoderLayer` / `DeformableTransformerEncoder`
+(models/detr/dab_transformer.py:425-523): same constructors, forward signatures and parameter names (a reference state_dict
+loads with strict=True); one layer = ONE C-ABI call, cqvad_deform_encoder_layer_forward (csrc/encoder.cu).  Inference path
+(dropout = identity); no torch arithmetic on the activation path -- `get_reference_points` (a [B, Len, L, 3] meshgrid of the
+level shapes and valid ratios, computed once per forward) is host-side glue written with torch like the reference's."""
+import ctypes
+import copy
+
+import torch
+from torch import nn
+
+from .. import _lib
+from .ms_deform_attn import MSDeformAttn3D
+
+ENC_WEIGHT_ORDER = ("self_attn.sampling_offsets", "self_attn.attention_weights", "self_attn.value_proj", "self_attn.output_proj",
+                    "norm1", "linear1", "linear2", "norm2")
+_MATRICES = {"self_attn.sampling_offsets", "self_attn.attention_weights", "self_attn.value_proj", "self_attn.output_proj",
+             "linear1", "linear2"}
+
+
+def pack_encoder_layer_weights(state, dtype, device, prefix=""):
+    """[(tensor kept alive)], ctypes pointer table in the order include/cqvad.h documents."""
+    keep = []
+    for base in ENC_WEIGHT_ORDER:
+        for leaf in ("weight", "bias"):
+            t = state[f"{prefix}{base}.{leaf}"]
+            t = t if isinstance(t, torch.Tensor) else torch.as_tensor(t)
+            dt = dtype if (leaf == "weight" and base in _MATRICES) else torch.float32
+            keep.append(t.detach().to(device=device, dtype=dt).contiguous())
+    tab = (ctypes.c_void_p * len(keep))(*[k.data_ptr() for k in keep])
+    return keep, tab
+
+
+def encoder_layer_forward(packed, src, pos, reference_points, shapes, level_start, padding_mask, n_points, d_ffn, want_attn=False):
+    """packed = pack_encoder_layer_weights(...).  src/pos [B, Len, 256]; returns out (and the attention module's output)."""
+    keep, tab = packed
+    _lib.require_cuda(src, pos, reference_points, shapes, level_start)
+    lib = _lib.lib()
+    dt = src.dtype
+    B, Len, C = src.shape
+    if C != 256:
+        raise ValueError("d_model must be 256")
+    L = int(shapes.shape[0])
+    src_c, pos_c = src.contiguous(), pos.to(dt).contiguous()
+    refp = reference_points.to(torch.float32).contiguous()
+    if tuple(refp.shape) != (B, Len, L, 3):
+        raise ValueError("reference_points must be [B, Len, n_levels, 3]")
+    sh, ls = shapes.to(torch.int64).contiguous(), level_start.to(torch.int64).contiguous()
+    m8 = None
+    if padding_mask is not None:
+        m8 = padding_mask.to(src.device).contiguous()
+        m8 = m8.view(torch.uint8) if m8.dtype == torch.bool else m8.to(torch.uint8)
+    need = lib.cqvad_deform_encoder_layer_workspace_bytes(_lib.dtype_id(dt), B, Len, L, n_points, d_ffn)
+    ws = torch.empty(need, dtype=torch.uint8, device=src.device)
+    out = torch.empty_like(src_c)
+    attn_out = torch.empty_like(src_c) if want_attn else None
+    p = _lib.ptr
+    _lib.check(lib.cqvad_deform_encoder_layer_forward(_lib.dtype_id(dt), tab, p(src_c), p(pos_c), p(refp), p(sh), p(ls), p(m8), p(out),
+                                                      p(attn_out), p(ws), need, B, Len, L, n_points, d_ffn, _lib.stream_ptr()))
+    return (out, attn_out) if want_attn else out
+
+
+class DeformableTransformerEncoderLayer(nn.Module):
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4):
+        super().__init__()
+        if d_model != 256 or n_heads != 8 or activation != "relu":
+            raise ValueError("libcqvad encoder layer: d_model 256, 8 heads, relu (every shipped configuration)")
+        self.self_attn = MSDeformAttn3D(d_model, n_levels, n_heads, n_points)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.dropout2 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout3 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.n_points, self.d_ffn = n_points, d_ffn
+        self._packed = None
+
+    def _pack(self, dtype, device):
+        ver = tuple(p._version for p in self.parameters()) + (dtype, str(device))
+        if self._packed is None or self._packed[0] != ver:
+            self._packed = (ver, pack_encoder_layer_weights(self.state_dict(), dtype, device))
+        return self._packed[1]
+
+    def forward(self, src, pos, reference_points, spatio_temporal_shapes, level_start_index, padding_mask=None):
+        if self.training and (self.dropout1.p > 0 or self.dropout2.p > 0):
+            import warnings
+            warnings.warn("libcqvad encoder layer applies no dropout (inference semantics)", stacklevel=2)
+        if pos is None:
+            pos = torch.zeros_like(src)
+        return encoder_layer_forward(self._pack(src.dtype, src.device), src, pos, reference_points, spatio_temporal_shapes,
+                                     level_start_index, padding_mask, self.n_points, self.d_ffn)
+
+
+class DeformableTransformerEncoder(nn.Module):
+    def __init__(self, encoder_layer, num_layers, gradient_checkpointing=False):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+        self.gradient_checkpointing = gradient_checkpointing
+
+    @staticmethod
+    def get_reference_points(spatio_temporal_shapes, valid_ratios, device):
+        # dab_transformer.py:433-452
+        reference_points_list = []
+        for lvl, (T_, H_, W_) in enumerate(spatio_temporal_shapes.tolist() if torch.is_tensor(spatio_temporal_shapes)
+                                           else spatio_temporal_shapes):
+            ref_t, ref_y, ref_x = torch.meshgrid(torch.linspace(0.5, T_ - 0.5, T_, dtype=torch.float32, device=device),
+                                                 torch.linspace(0.5, H_ - 0.5, H_, dtype=torch.float32, device=device),
+                                                 torch.linspace(0.5, W_ - 0.5, W_, dtype=torch.float32, device=device), indexing="ij")
+            ref_t = ref_t.reshape(-1)[None] / (valid_ratios[:, None, lvl, 2] * T_)
+            ref_y = ref_y.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * H_)
+            ref_x = ref_x.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * W_)
+            reference_points_list.append(torch.stack((ref_x, ref_y, ref_t), -1))
+        reference_points = torch.cat(reference_points_list, 1)
+        return reference_points[:, :, None] * valid_ratios[:, None]
+
+    def forward(self, src, spatio_temporal_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None):
+        output = src
+        reference_points = self.get_reference_points(spatio_temporal_shapes, valid_ratios, device=src.device)
+        for layer in self.layers:
+            output = layer(output, pos, reference_points, spatio_temporal_shapes, level_start_index, padding_mask)
+        return output

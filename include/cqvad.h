@@ -79,6 +79,22 @@ int cqvad_linear_gelu_train(int dtype, const void* A, const void* W, const float
  * stored derivative) or masked by aux > 0 (mode 1: aux is the ReLU output).  Wt is the transposed weight [in, out]. */
 int cqvad_linear_dgrad_act(int dtype, const void* dY, const void* Wt, const void* aux, int mode, void* dX, long M, int N,
                            int K, void* stream);
+/* One deformable encoder layer around the MSDA-3D op:
+ * DeformableTransformerEncoderLayer.forward (models/detr/dab_transformer.py:513-523) with MSDeformAttn3D.forward
+ * (ops/modules/ms_deform_attn.py:167-203) inlined, eval semantics (dropout = identity), 8 heads, d_model 256.
+ *   src, pos, out [B, Len, 256] (dtype); reference_points [B, Len, L, 3] fp32 ((x,y,t), get_reference_points :433-452);
+ *   shapes [L,3] (T,H,W) / level_start [L] int64 ON THE DEVICE (as for cqvad_msda3d_forward); padding_mask [B, Len] u8 or NULL;
+ *   weights: 16 device pointers in state_dict order -- self_attn.{sampling_offsets,attention_weights,value_proj,output_proj}
+ *   .{weight,bias}, norm1.{weight,bias}, linear1.{weight,bias}, linear2.{weight,bias}, norm2.{weight,bias}; matrices in
+ *   `dtype`, biases / LayerNorm vectors fp32.  attn_out (optional, [B, Len, 256]) receives the attention module's own output
+ *   (output_proj of the sampled values, before the residual).  The offsets / logits GEMMs hand fp32 values to the location /
+ *   softmax kernel in both dtypes. */
+int cqvad_deform_encoder_layer_num_weights(void);
+size_t cqvad_deform_encoder_layer_workspace_bytes(int dtype, int B, long Len, int L, int P, int F);
+int cqvad_deform_encoder_layer_forward(int dtype, const void* const* weights, const void* src, const void* pos,
+                                       const float* reference_points, const int64_t* shapes, const int64_t* level_start,
+                                       const uint8_t* padding_mask, void* out, void* attn_out, void* workspace,
+                                       size_t workspace_bytes, int B, long Len, int L, int P, int F, void* stream);
 /* Y[M,256] = LN?( res + W2 . act(W1 . X + b1) + b2 ): the FFN blocks of the decoder (dab_transformer.py:994-996,
  * 1043-1045, 1074-1076).  X [M,256], W1 [F,256], W2 [256,F] (dtype); ln_g/ln_b may be NULL (no LayerNorm); res may be
  * NULL.  hidden [M,F] (dtype) is scratch used only when the fused tensor-core kernel does not apply (fp32, or F % 128). */
