@@ -271,6 +271,90 @@ __global__ void __launch_bounds__(kWarps * 32) msda_bwd_kernel(const T* __restri
   }
 }
 
+// Backward, channel-vectorised (same conditions and lane mapping as msda_fwd_vec_kernel): lane = (point slot g, 8-channel
+// chunk ch).  Per corner one 16-byte (bf16) value load, an 8-term dot with the lane's slice of grad_out, and two
+// red.global.add.v4.f32 into grad_value; the four scalar gradients of a point are folded over the D/8 lanes of its slot only
+// (2 shuffle steps at D = 32) and written by the slot's first lane.  The scalar kernel recomputed the point geometry on all 32
+// lanes and paid four full warp reductions per point.
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+template <typename T>
+__global__ void __launch_bounds__(kWarps * 32) msda_bwd_vec_kernel(const T* __restrict__ value,
+                                                                   const int64_t* __restrict__ shapes,
+                                                                   const int64_t* __restrict__ lsi,
+                                                                   const float* __restrict__ loc,
+                                                                   const float* __restrict__ attn,
+                                                                   const T* __restrict__ grad_out,
+                                                                   float* __restrict__ grad_value,
+                                                                   float* __restrict__ grad_loc,
+                                                                   float* __restrict__ grad_attn, long n_warps_total,
+                                                                   int Len, int M, int D, int L, int Lq, int P) {
+  const long wid = (long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= n_warps_total) return;
+  const int m = (int)(wid % M);
+  const long bq = wid / M;
+  const int b = (int)(bq / Lq);
+  const int LP = L * P;
+  const long row_stride = (long)M * D;
+  const int lpp = D >> 3, G = 32 / lpp;
+  const int g = lane / lpp, ch = lane % lpp;
+  const long voff = (long)b * Len * row_stride + (long)m * D + ch * 8;
+  const T* vbase = value + voff;
+  float* gvbase = grad_value + voff;
+  const float* locp = loc + wid * LP * 3;
+  const float* attp = attn + wid * LP;
+  float go[8];
+  load8(grad_out + wid * D + ch * 8, go);
+  for (int p0 = 0; p0 < LP; p0 += G) {
+    const int pt = p0 + g;
+    float g_w = 0.f, g_h = 0.f, g_t = 0.f, g_a = 0.f;
+    if (pt < LP) {
+      const int l = pt / P;
+      const int T_ = (int)shapes[l * 3], H = (int)shapes[l * 3 + 1], W = (int)shapes[l * 3 + 2];
+      int tl, hl, wl; unsigned mk; float lt, lh, lw;
+      point_geometry(locp[pt * 3], locp[pt * 3 + 1], locp[pt * 3 + 2], T_, H, W, tl, hl, wl, mk, lt, lh, lw);
+      if (mk != 0) {
+        const float a = attp[pt];
+        const int base = (int)lsi[l] + (tl * H + hl) * W + wl;
+        const int hs = W, ts = H * W;
+        const float ht = 1.f - lt, hh = 1.f - lh, hw = 1.f - lw;
+        const float ft[2] = {ht, lt}, fh[2] = {hh, lh}, fw[2] = {hw, lw};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (!(mk & (1u << k))) continue;
+          const int kt = k >> 2, kh = (k >> 1) & 1, kw = k & 1;
+          const long row = (long)(base + kt * ts + kh * hs + kw) * row_stride;
+          const float wgt = ft[kt] * fh[kh] * fw[kw];
+          float v[8];
+          load8(vbase + row, v);
+          float dot = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dot = fmaf(v[e], go[e], dot);
+          const float s = a * wgt;
+          red_add_v4(gvbase + row, s * go[0], s * go[1], s * go[2], s * go[3]);
+          red_add_v4(gvbase + row + 4, s * go[4], s * go[5], s * go[6], s * go[7]);
+          g_a = fmaf(wgt, dot, g_a);
+          g_w = fmaf((kw ? 1.f : -1.f) * ft[kt] * fh[kh], dot, g_w);
+          g_h = fmaf((kh ? 1.f : -1.f) * ft[kt] * fw[kw], dot, g_h);
+          g_t = fmaf((kt ? 1.f : -1.f) * fh[kh] * fw[kw], dot, g_t);
+        }
+        g_w *= a * (float)W; g_h *= a * (float)H; g_t *= a * (float)T_;
+      }
+    }
+    for (int o = 1; o < lpp; o <<= 1) {      // fold the slot's D/8 channel chunks
+      g_a += __shfl_xor_sync(0xffffffffu, g_a, o); g_w += __shfl_xor_sync(0xffffffffu, g_w, o);
+      g_h += __shfl_xor_sync(0xffffffffu, g_h, o); g_t += __shfl_xor_sync(0xffffffffu, g_t, o);
+    }
+    if (ch == 0 && pt < LP) {
+      grad_attn[wid * LP + pt] = g_a;
+      float* gl = grad_loc + (wid * LP + pt) * 3;
+      gl[0] = g_w; gl[1] = g_h; gl[2] = g_t;
+    }
+  }
+}
+
 template <typename T>
 int msda_fwd_t(const void* value, const int64_t* shapes, const int64_t* lsi, const float* loc, const float* attn, void* out,
                int N, int Len, int M, int D, int L, int Lq, int P, cudaStream_t st) {
@@ -302,6 +386,14 @@ int msda_bwd_t(const void* value, const int64_t* shapes, const int64_t* lsi, con
   const long nw = (long)N * Lq * M;
   if (nw == 0) return 0;
   const unsigned grid = (unsigned)cdiv(nw, kWarps);
+  static const bool no_vec = getenv("CQVAD_MSDA_NO_VEC") != nullptr;
+  const int lpp = D >> 3;
+  if (!no_vec && D % 8 == 0 && lpp >= 1 && lpp <= 32 && (lpp & (lpp - 1)) == 0 && (((uintptr_t)value) & 15) == 0 &&
+      (((uintptr_t)go) & 15) == 0 && (((uintptr_t)gv) & 15) == 0) {
+    msda_bwd_vec_kernel<T><<<grid, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, loc, attn, (const T*)go, gv, gl, ga, nw, Len, M, D, L, Lq, P);
+    CQ_LAUNCH_CHECK();
+    return 0;
+  }
   if (D <= 32)
     msda_bwd_kernel<T, 1><<<grid, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, loc, attn, (const T*)go, gv, gl, ga, nw, Len, M, D, L, Lq, P);
   else if (D <= 64)
