@@ -124,12 +124,17 @@ __global__ void __launch_bounds__(kWarps * 32) msda_fwd_kernel(const T* __restri
 // corner instead of one 2-byte load per lane, i.e. 32 wide loads per warp where the scalar kernel issued 256 narrow ones --
 // and the G partial sums are folded with xor-shuffles at the end.  ncu launch list of the encoder layer (B = 4, ViT-B/224
 // pyramid): the scalar kernel took 6.5 ms of an 8.0 ms layer (17.5 GB of 64-byte gathers through L2, LSU-issue bound).
-template <typename T>
+// FUSED = true (the encoder layer): `loc` holds the raw sampling OFFSETS and `attn` the raw LOGITS
+// (fp32 outputs of the two query projections), `ref` the reference points [B*Lq, L, 3]; the softmax over the L*P logits and
+// loc = ref + off / (T_l, W_l, H_l) (ops/modules/ms_deform_attn.py:187-192, reference normaliser order) happen in phase 1, so
+// the 102 MB/clip sampling_locations and the attention weights never exist in memory.
+template <typename T, bool FUSED>
 __global__ void __launch_bounds__(kWarps * 32) msda_fwd_vec_kernel(const T* __restrict__ value,
                                                                    const int64_t* __restrict__ shapes,
                                                                    const int64_t* __restrict__ lsi,
                                                                    const float* __restrict__ loc,
-                                                                   const float* __restrict__ attn, T* __restrict__ out,
+                                                                   const float* __restrict__ attn,
+                                                                   const float* __restrict__ ref, T* __restrict__ out,
                                                                    long n_warps_total, int Len, int M, int D, int L, int Lq,
                                                                    int P) {
   const long wid = (long)blockIdx.x * kWarps + (threadIdx.x >> 5);
@@ -147,6 +152,15 @@ __global__ void __launch_bounds__(kWarps * 32) msda_fwd_vec_kernel(const T* __re
   const float* locp = loc + wid * LP * 3;
   const float* attp = attn + wid * LP;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float sm_max = 0.f, sm_sum = 1.f;
+  if constexpr (FUSED) {   // softmax statistics over the head's L*P logits (same arithmetic as msda_prepare_kernel)
+    sm_max = -INFINITY;
+    for (int j = lane; j < LP; j += 32) sm_max = fmaxf(sm_max, attp[j]);
+    sm_max = warp_max(sm_max);
+    sm_sum = 0.f;
+    for (int j = lane; j < LP; j += 32) sm_sum += expf(attp[j] - sm_max);
+    sm_sum = warp_sum(sm_sum);
+  }
 
   for (int p0 = 0; p0 < LP; p0 += 32) {
     const int pt = p0 + lane;
@@ -155,10 +169,15 @@ __global__ void __launch_bounds__(kWarps * 32) msda_fwd_vec_kernel(const T* __re
       const int l = pt / P;
       const int Tt = (int)shapes[l * 3], H = (int)shapes[l * 3 + 1], W = (int)shapes[l * 3 + 2];
       int tl, hl, wl;
-      point_geometry(locp[pt * 3], locp[pt * 3 + 1], locp[pt * 3 + 2], Tt, H, W, tl, hl, wl, g_mask, g_lt, g_lh, g_lw);
+      float lx = locp[pt * 3], ly = locp[pt * 3 + 1], lz = locp[pt * 3 + 2];
+      if constexpr (FUSED) {
+        const float* r = ref + (bq * L + l) * 3;
+        lx = r[0] + __fdiv_rn(lx, (float)Tt); ly = r[1] + __fdiv_rn(ly, (float)W); lz = r[2] + __fdiv_rn(lz, (float)H);
+      }
+      point_geometry(lx, ly, lz, Tt, H, W, tl, hl, wl, g_mask, g_lt, g_lh, g_lw);
       g_hs = W; g_ts = H * W;
       g_base = (int)lsi[l] + (tl * H + hl) * W + wl;
-      g_a = attp[pt];
+      g_a = FUSED ? expf(attp[pt] - sm_max) / sm_sum : attp[pt];
     }
     const int np = min(32, LP - p0);
     for (int j0 = 0; j0 < np; j0 += G) {
@@ -365,7 +384,7 @@ int msda_fwd_t(const void* value, const int64_t* shapes, const int64_t* lsi, con
   const int lpp = D >> 3;
   if (!no_vec && D % 8 == 0 && lpp >= 1 && lpp <= 32 && (lpp & (lpp - 1)) == 0 && (((uintptr_t)value) & 15) == 0 &&
       (((uintptr_t)out) & 15) == 0) {
-    msda_fwd_vec_kernel<T><<<grid, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, loc, attn, (T*)out, nw, Len, M, D, L, Lq, P);
+    msda_fwd_vec_kernel<T, false><<<grid, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, loc, attn, nullptr, (T*)out, nw, Len, M, D, L, Lq, P);
     CQ_LAUNCH_CHECK();
     return 0;
   }
@@ -404,6 +423,19 @@ int msda_bwd_t(const void* value, const int64_t* shapes, const int64_t* lsi, con
   return 0;
 }
 
+template <typename T>
+int msda_fwd_fused_t(const void* value, const int64_t* shapes, const int64_t* lsi, const float* off, const float* logit,
+                     const float* ref, void* out, int N, int Len, int M, int D, int L, int Lq, int P, cudaStream_t st) {
+  const long nw = (long)N * Lq * M;
+  if (nw == 0) return 0;
+  const int lpp = D >> 3;
+  if (D % 8 != 0 || lpp < 1 || lpp > 32 || (lpp & (lpp - 1)) != 0 || (((uintptr_t)value) & 15) || (((uintptr_t)out) & 15)) return 1;
+  msda_fwd_vec_kernel<T, true><<<(unsigned)cdiv(nw, kWarps), kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, off, logit, ref,
+                                                                                  (T*)out, nw, Len, M, D, L, Lq, P);
+  CQ_LAUNCH_CHECK();
+  return 0;
+}
+
 int check_dims(int N, int Len, int M, int D, int L, int Lq, int P) {
   CQ_CHECK_ARG(N >= 0 && Len >= 0 && M >= 1 && D >= 1 && L >= 1 && Lq >= 0 && P >= 1, "msda3d: bad dimensions");
   CQ_CHECK_SHAPE(D <= 128, "msda3d: head dim D=%d > 128 not supported", D);
@@ -412,6 +444,14 @@ int check_dims(int N, int Len, int M, int D, int L, int Lq, int P) {
 }
 
 }  // namespace
+
+// offsets + logits + reference points -> sampled values (encoder.cu); returns 1 when the vectorised kernel does not apply
+int msda_fwd_fused(int dtype, const void* value, const int64_t* shapes, const int64_t* lsi, const float* off, const float* logit,
+                   const float* ref, void* out, int N, int Len, int M, int D, int L, int Lq, int P, cudaStream_t st) {
+  CQ_TRY(check_dims(N, Len, M, D, L, Lq, P));
+  if (dtype == CQVAD_F32) return msda_fwd_fused_t<float>(value, shapes, lsi, off, logit, ref, out, N, Len, M, D, L, Lq, P, st);
+  return msda_fwd_fused_t<bf16>(value, shapes, lsi, off, logit, ref, out, N, Len, M, D, L, Lq, P, st);
+}
 }  // namespace cqvad
 
 using namespace cqvad;

@@ -82,3 +82,18 @@ def test_encoder_layer_full_pyramid_batch_independence():
     assert src.shape[1] == 33320
     assert torch.isfinite(both.float()).all()
     assert torch.equal(both[1:2], one)
+
+
+def test_encoder_layer_fused_sampling_variant_matches_reference():
+    """CQVAD_ENC_FUSED=1 (softmax + sampling locations inside the sampling kernel; read once per process, hence a subprocess)."""
+    import os, subprocess, sys
+    code = ("import sys, torch; sys.path.insert(0, 'tests'); "
+            "from helpers import load_golden, rel_err; from test_encoder_gpu import _run; "
+            "g = load_golden('enc_small_masked'); "
+            "o32, a32 = _run(g, torch.float32); o16, a16 = _run(g, torch.bfloat16); "
+            "assert rel_err(o32.cpu().numpy(), g['out']) < 1e-3 and rel_err(a32.cpu().numpy(), g['attn_out']) < 1e-3; "
+            "assert rel_err(o16.float().cpu().numpy(), g['out']) < 2e-2; print('fused ok')")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, CQVAD_ENC_FUSED="1"), capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "fused ok" in r.stdout, r.stderr[-2000:]
