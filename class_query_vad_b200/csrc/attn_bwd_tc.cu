@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "bwd.cuh"
+#include <stdlib.h>
 
 namespace cqvad {
 
@@ -29,7 +30,7 @@ int tc_num_sms();
 
 namespace {
 
-constexpr int AB_THREADS = 160;
+constexpr int AB_THREADS = 288;   // warp 0: TMA + MMA; warps 1-8: softmax (two per TMEM lane quarter, half of the keys each); warps 1-4: epilogue
 constexpr int TILE16K = 16384;
 
 struct AbParams {
@@ -42,7 +43,10 @@ struct AbParams {
   int halves;                     // 128-key halves (1 or 2)
   float scale, scale_log2;
   uint32_t off_k, off_v, off_do, off_p, off_ds, off_bar;
+  long long* trace;               // dev tool (CQVAD_ATTN_TRACE=<device address>): globaltimer stamps of CTA (0,0)'s phases
 };
+#define AB_TRACE(k, tid) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == (tid)) { long long t_; \
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.trace[k] = t_; } } while (0)
 
 __device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -54,6 +58,14 @@ __device__ __forceinline__ void tmem_ld16b(uint32_t taddr, uint32_t (&r)[16]) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16b(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 __device__ __forceinline__ uint32_t pk(float a, float b) {
@@ -96,10 +108,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x;
   const long i = blockIdx.y;
+  AB_TRACE(0, 0);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
-    mbar_init(bar_in, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 4); mbar_init(bar_o, 1);
+    mbar_init(bar_in, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 8); mbar_init(bar_o, 1);
     mbar_fence_init();
   }
   if (warp == 1) { __syncwarp(); tmem_alloc(tmem_slot, 512); }
@@ -108,6 +121,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  AB_TRACE(1, 0);
   const uint32_t t_s = tmem_base, t_dp = tmem_base + 256;
   const uint32_t t_dv = tmem_base, t_dq = tmem_base + 128, t_dk = tmem_base + 192;   // reuse once S / dP are consumed
   const int off32 = (h * 32) & 63;            // the head's 32 value columns inside their 64-column block
@@ -122,6 +136,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_load_2d(sV, &tmV, bar_in, vcol0, (int)(i * p.v_rows));
       tma_load_2d(sDO, &tmDO, bar_in, vcol0, (int)(i * p.K));
       mbar_wait(bar_in, 0);
+      AB_TRACE(2, 0);
       tc_fence_after();
       {
         const uint32_t idesc = make_idesc_bf16(128, p.Sp16);
@@ -158,38 +173,61 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else {
+    // Softmax / dS phase on 8 warps.  The phase trace (tools/trace_attn_bwd.py) of the 4-warp, 3-pass version showed 16 us of a
+    // 23.7 us CTA here (exp2f twice per element, one exposed warp per TMEM lane quarter): now each lane quarter has two warps
+    // (key halves), the exponentials are computed ONCE (ex2.approx) and parked in TMEM over S, and the row statistics of the
+    // two halves are exchanged through shared memory.
     const int q = warp & 3;
+    const int sh = (warp - 1) >> 2;                 // key half of this warp
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const bool vrow = row < p.K;
     const int S = p.S, Sp16 = p.Sp16;
+    const int nch = Sp16 >> 4, ch0 = sh ? (nch + 1) >> 1 : 0, ch1 = sh ? nch : (nch + 1) >> 1;
+    // [3][2][128] partials, aliased onto the (still unused) dS tile: S = 256 leaves no spare shared memory (224 KB of tiles)
+    float* xch = reinterpret_cast<float*>(smem_raw + (sDS - smem_u32(smem_raw)));
     mbar_wait(bar_s, 0);
+    AB_TRACE(4, 32);
     tc_fence_after();
     float mx = -INFINITY;
-    for (int c = 0; c < Sp16; c += 16) {
+    for (int c = ch0 * 16; c < ch1 * 16; c += 16) {
       uint32_t r[16];
       tmem_ld16b(t_s + lane_off + c, r);
       tmem_ld_wait();
 #pragma unroll
       for (int e = 0; e < 16; ++e) if (c + e < S) mx = fmaxf(mx, __uint_as_float(r[e]));
     }
+    xch[sh * 128 + row] = mx;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    mx = fmaxf(mx, xch[(sh ^ 1) * 128 + row]);
+    AB_TRACE(5, 32);
     const float sc = p.scale_log2, mxs = mx * sc;
     float sum = 0.f, sdp = 0.f;
-    for (int c = 0; c < Sp16; c += 16) {
+    for (int c = ch0 * 16; c < ch1 * 16; c += 16) {
       uint32_t r[16], d[16];
       tmem_ld16b(t_s + lane_off + c, r);
       tmem_ld16b(t_dp + lane_off + c, d);
       tmem_ld_wait();
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        const float x = (c + e < S) ? exp2f(fmaf(__uint_as_float(r[e]), sc, -mxs)) : 0.f;
+        const float x = (c + e < S) ? ex2_approx(fmaf(__uint_as_float(r[e]), sc, -mxs)) : 0.f;
         sum += x;
-        sdp = fmaf(x, (c + e < S) ? __uint_as_float(d[e]) : 0.f, sdp);
+        sdp = fmaf(x, __uint_as_float(d[e]), sdp);
+        r[e] = __float_as_uint(x);
       }
+      tmem_st16b(t_s + lane_off + c, r);          // exp values parked over S: the last pass does not recompute them
     }
-    const float inv = 1.0f / sum;
+    tmem_st_wait();
+    xch[256 + sh * 128 + row] = sum;
+    xch[512 + sh * 128 + row] = sdp;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    sum += xch[256 + (sh ^ 1) * 128 + row];
+    sdp += xch[512 + (sh ^ 1) * 128 + row];
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // every partial has been read: the dS tile may be written
+    AB_TRACE(6, 32);
+    const float inv = vrow ? 1.0f / sum : 0.f;
     const float D = sdp * inv;
-    for (int c = 0; c < Sp16; c += 16) {
+    for (int c = ch0 * 16; c < ch1 * 16; c += 16) {
       uint32_t r[16], d[16];
       tmem_ld16b(t_s + lane_off + c, r);
       tmem_ld16b(t_dp + lane_off + c, d);
@@ -197,10 +235,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float pv[16], dsv[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        const bool ok = vrow && (c + e < S);
-        const float x = ok ? exp2f(fmaf(__uint_as_float(r[e]), sc, -mxs)) * inv : 0.f;
+        const float x = __uint_as_float(r[e]) * inv;          // 0 for keys >= S (exp parked as 0) and class rows >= K (inv = 0)
         pv[e] = x;
-        dsv[e] = ok ? p.scale * x * (__uint_as_float(d[e]) - D) : 0.f;
+        dsv[e] = p.scale * x * (__uint_as_float(d[e]) - D);
       }
 #pragma unroll
       for (int g8 = 0; g8 < 2; ++g8) {
@@ -211,13 +248,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         st_tile8(sDS, row, c + g8 * 8, b);
       }
     }
+    AB_TRACE(7, 32);
     tc_fence_before();
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_p);
+    if (sh == 0) {
     mbar_wait(bar_o, 0);
+    AB_TRACE(8, 32);
     tc_fence_after();
-    // ---- epilogue ----
+    // ---- epilogue (warps 1-4: one TMEM lane quarter each) ----
     uint32_t rq[32], rk[32], rv[32];
     if (p.fused) {   // self-attention: keys == queries, one output row per thread
       tmem_ld32(t_dq + lane_off + qoff, rq);
@@ -248,7 +288,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
     }
+    }   // sh == 0: epilogue warps
   }
+  AB_TRACE(9, 32);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -256,6 +298,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  AB_TRACE(10, 0);
 }
 
 // heads 4-7 of the class cross-attention: one block per actor instance, warp = head
@@ -407,6 +450,7 @@ int launch_attn_bwd(const bf16* q, long q_total, const bf16* kmat, long k_total,
   }
   p.dQ = dQ; p.dK = dK; p.dV = dV; p.beta_q = bq; p.beta_k = bk; p.beta_v = bv;
   p.K = K; p.S = S; p.Sp16 = Sp16; p.q_rows = q_rows; p.k_rows = k_rows; p.v_rows = v_rows; p.hd = hd; p.fused = fused;
+  if (const char* tr = getenv("CQVAD_ATTN_TRACE")) p.trace = (long long*)strtoull(tr, nullptr, 0) + (fused ? 16 : 0);
   p.scale = 1.0f / sqrtf((float)hd); p.scale_log2 = 1.4426950408889634f * p.scale;
   dim3 grid((unsigned)heads, (unsigned)N);
   attn_bwd_tc_kernel<<<grid, AB_THREADS, smem_bytes, st>>>(tmQ, tmK, tmV, tmDO, p);

@@ -248,23 +248,25 @@ __device__ __forceinline__ uint64_t f2add(uint64_t a, uint64_t b) {
 //   gelu(x) = 0.5 x (1 + erf(x / sqrt 2)),  erf(z) ~ z * Q(z^2) on |z| <= 3 (degree-8 minimax Q, |erf error| <= 2.4e-5,
 //   saturating beyond: 1 - erf(3) = 2.2e-5)  =>  |gelu error| <= 5.1e-5, 40x below one bf16 rounding of the result.
 // 13 packed + 4 scalar instructions per pair, against ~30 per value for erff().
+// Estrin evaluation of Q(u), u = z^2 (dependency depth 4 instead of Horner's 8: the epilogues that use it are latency bound)
+__device__ __forceinline__ uint64_t erf_q2(uint64_t u) {
+#define CQ_P2(c) f2pack(c, c)
+  const uint64_t u2 = f2mul(u, u), u4 = f2mul(u2, u2);
+  const uint64_t p01 = f2fma(CQ_P2(-3.753148729e-01f), u, CQ_P2(1.128268425e+00f));
+  const uint64_t p23 = f2fma(CQ_P2(-2.510285923e-02f), u, CQ_P2(1.110793319e-01f));
+  const uint64_t p45 = f2fma(CQ_P2(-5.110367538e-04f), u, CQ_P2(4.235426778e-03f));
+  const uint64_t p67 = f2fma(CQ_P2(-1.944822197e-06f), u, CQ_P2(4.106051334e-05f));
+  const uint64_t lo = f2fma(p23, u2, p01), hi = f2fma(p67, u2, p45);
+  return f2fma(f2fma(CQ_P2(4.074209625e-08f), u4, hi), u4, lo);
+#undef CQ_P2
+}
 __device__ __forceinline__ uint64_t gelu2(uint64_t x2) {
   float z0, z1;
   f2unpack(f2mul(x2, f2pack(0.70710678118654752f, 0.70710678118654752f)), z0, z1);
   z0 = fminf(fmaxf(z0, -3.0f), 3.0f);
   z1 = fminf(fmaxf(z1, -3.0f), 3.0f);
   const uint64_t z2 = f2pack(z0, z1);
-  const uint64_t u2 = f2mul(z2, z2);
-  uint64_t q = f2pack(4.074209625e-08f, 4.074209625e-08f);
-  q = f2fma(q, u2, f2pack(-1.944822197e-06f, -1.944822197e-06f));
-  q = f2fma(q, u2, f2pack(4.106051334e-05f, 4.106051334e-05f));
-  q = f2fma(q, u2, f2pack(-5.110367538e-04f, -5.110367538e-04f));
-  q = f2fma(q, u2, f2pack(4.235426778e-03f, 4.235426778e-03f));
-  q = f2fma(q, u2, f2pack(-2.510285923e-02f, -2.510285923e-02f));
-  q = f2fma(q, u2, f2pack(1.110793319e-01f, 1.110793319e-01f));
-  q = f2fma(q, u2, f2pack(-3.753148729e-01f, -3.753148729e-01f));
-  q = f2fma(q, u2, f2pack(1.128268425e+00f, 1.128268425e+00f));
-  const uint64_t e2 = f2mul(z2, q);
+  const uint64_t e2 = f2mul(z2, erf_q2(f2mul(z2, z2)));
   const uint64_t hx = f2mul(x2, f2pack(0.5f, 0.5f));
   return f2fma(hx, e2, hx);
 }
@@ -282,17 +284,7 @@ __device__ __forceinline__ void gelu_dual2(uint64_t x2, uint64_t& a2, uint64_t& 
   z1 = fminf(fmaxf(z1, -3.0f), 3.0f);
   const uint64_t z2 = f2pack(z0, z1);
   const uint64_t u = f2mul(z2, z2);
-  // Estrin evaluation of the degree-8 polynomial Q(u) (the epilogue is latency bound: dependency depth 4 instead of 8)
-#define CQ_P2(c) f2pack(c, c)
-  const uint64_t u2 = f2mul(u, u), u4 = f2mul(u2, u2);
-  const uint64_t p01 = f2fma(CQ_P2(-3.753148729e-01f), u, CQ_P2(1.128268425e+00f));
-  const uint64_t p23 = f2fma(CQ_P2(-2.510285923e-02f), u, CQ_P2(1.110793319e-01f));
-  const uint64_t p45 = f2fma(CQ_P2(-5.110367538e-04f), u, CQ_P2(4.235426778e-03f));
-  const uint64_t p67 = f2fma(CQ_P2(-1.944822197e-06f), u, CQ_P2(4.106051334e-05f));
-  const uint64_t lo = f2fma(p23, u2, p01), hi = f2fma(p67, u2, p45);
-  const uint64_t hi8 = f2fma(CQ_P2(4.074209625e-08f), u4, hi);
-  const uint64_t q = f2fma(hi8, u4, lo);
-#undef CQ_P2
+  const uint64_t q = erf_q2(u);
   const uint64_t half2 = f2pack(0.5f, 0.5f);
   const uint64_t cdf = f2fma(f2mul(z2, q), half2, half2);
   a2 = f2mul(x2, cdf);
