@@ -133,6 +133,9 @@ __global__ void __launch_bounds__(256) mha_qsk_kernel(const T* __restrict__ q, c
 //   score[h,s] = ( qc_h . (kc_h[i,s] + first*kp_h[s,b]) + qs_h . kp_h[s,b] ) / sqrt(64);  masked by mask[b,s]
 //   o_h = sum_s softmax_s(score)[s] * v_h[i,s]
 // kc, v: rows (i*S + s) with row stride ldkv (k at column 0.., v given as its own pointer); kp rows (s*BT + b).
+// Channel-vectorised: warp = head, lane = (key slot g = lane / 4, 8-channel chunk ch = lane % 4): eight keys per step, one
+// 16-byte load per operand and lane, scores folded over the 4 lanes of a slot; the PV pass accumulates 8 channels per lane over
+// its key slot and folds the 8 slots at the end (the lane-per-channel version issued 2-byte loads key by key: 73 us per launch).
 template <typename T>
 __global__ void __launch_bounds__(256) dec_qsk_kernel(const T* __restrict__ qc, const T* __restrict__ qs,
                                                       const T* __restrict__ kc, const T* __restrict__ v, long ldkv,
@@ -142,39 +145,42 @@ __global__ void __launch_bounds__(256) dec_qsk_kernel(const T* __restrict__ qc, 
   const long i = blockIdx.x;
   const int bb = (int)(i % BT);
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, ch = lane & 3;
   float* my_sc = smem + (size_t)h * S;
-  const int c = h * 32 + lane;
-  const float qcv = to_f(qc[i * kC + c]) * 0.125f;
-  const float qsv = to_f(qs[i * kC + c]) * 0.125f;
-  const float qk = first ? qcv + qsv : qsv;  // coefficient of kp: first layer adds kp to the content key too (:964-967)
+  const int c = h * 32 + ch * 8;
+  float qcv[8], qk[8];
+  {
+    float qsv[8];
+    load8(qc + i * kC + c, qcv);
+    load8(qs + i * kC + c, qsv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      qcv[e] *= 0.125f;
+      qk[e] = first ? qcv[e] + qsv[e] * 0.125f : qsv[e] * 0.125f;  // coefficient of kp: the first layer adds kp to the content key too (:964-967)
+    }
+  }
   const T* kcb = kc + i * Sq * ldkv + c;
   const T* kpb = kp + (long)bb * kC + c;
   float mx = -INFINITY;
-  int s = 0;
-  for (; s + 4 <= S; s += 4) {  // 4 keys in flight per lane
-    float a[4];
+  for (int s0 = 0; s0 < S; s0 += 8) {
+    const int s = s0 + g;
+    float r = 0.f;
+    if (s < S) {
+      float a[8], b[8];
+      load8(kcb + (long)s * ldkv, a);
+      load8(kpb + (long)s * BT * kC, b);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float kcv = to_f(kcb[(long)(s + u) * ldkv]);
-      const float kpv = to_f(kpb[(long)(s + u) * BT * kC]);
-      a[u] = fmaf(qcv, kcv, qk * kpv);
+      for (int e = 0; e < 8; ++e) r = fmaf(qcv[e], a[e], fmaf(qk[e], b[e], r));
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float r = warp_sum(a[u]);
-      if (mask && mask[(long)bb * S + s + u]) r = -INFINITY;
-      if (lane == 0) my_sc[s + u] = r;
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    if (s < S) {
+      if (mask && mask[(long)bb * S + s]) r = -INFINITY;
+      if (ch == 0) my_sc[s] = r;
       mx = fmaxf(mx, r);
     }
   }
-  for (; s < S; ++s) {
-    const float kcv = to_f(kcb[(long)s * ldkv]);
-    const float kpv = to_f(kpb[(long)s * BT * kC]);
-    float r = warp_sum(fmaf(qcv, kcv, qk * kpv));
-    if (mask && mask[(long)bb * S + s]) r = -INFINITY;
-    if (lane == 0) my_sc[s] = r;
-    mx = fmaxf(mx, r);
-  }
+  mx = warp_max(mx);
   __syncwarp();
   float sum = 0.f;
   for (int m = lane; m < S; m += 32) {
@@ -185,10 +191,27 @@ __global__ void __launch_bounds__(256) dec_qsk_kernel(const T* __restrict__ qc, 
   sum = warp_sum(sum);
   __syncwarp();
   const T* vb = v + i * Sq * ldkv + c;
-  float acc = 0.f;
-#pragma unroll 4
-  for (int m = 0; m < S; ++m) acc = fmaf(my_sc[m], to_f(vb[(long)m * ldkv]), acc);
-  o[i * kC + c] = from_f<T>(acc / sum);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int s0 = 0; s0 < S; s0 += 8) {
+    const int s = s0 + g;
+    if (s >= S) continue;
+    float w[8];
+    load8(vb + (long)s * ldkv, w);
+    const float pr = my_sc[s];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = fmaf(pr, w[e], acc[e]);
+  }
+#pragma unroll
+  for (int of = 4; of < 32; of <<= 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], of);
+  }
+  if (g == 0) {
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= inv;
+    store8(o + i * kC + c, acc);
+  }
 }
 
 template <typename K>
