@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(256) dec_qsk_kernel(const T* __restrict__ qc, 
   const T* kcb = kc + i * Sq * ldkv + c;
   const T* kpb = kp + (long)bb * kC + c;
   float mx = -INFINITY;
-  for (int s0 = 0; s0 < S; s0 += 8) {
+#pragma unroll 4
+  for (int s0 = 0; s0 < S; s0 += 8) {   // unrolled: four key groups of loads in flight per lane
     const int s = s0 + g;
     float r = 0.f;
     if (s < S) {
@@ -192,7 +193,8 @@ __global__ void __launch_bounds__(256) dec_qsk_kernel(const T* __restrict__ qc, 
   __syncwarp();
   const T* vb = v + i * Sq * ldkv + c;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int s0 = 0; s0 < S; s0 += 8) {
+#pragma unroll 4
+  for (int s0 = 0; s0 < S; s0 += 8) {   // unrolled: four key groups of loads in flight per lane
     const int s = s0 + g;
     if (s >= S) continue;
     float w[8];

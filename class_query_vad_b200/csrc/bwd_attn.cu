@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(256) dec_qsk_bwd_kernel(const T* __restrict__ 
   const T* vb = v + i * Sq * ldkv + c;
   const T* kpb = kp + (long)bb * kC + c;
   float mx = -INFINITY;
-  for (int s0 = 0; s0 < S; s0 += 8) {
+#pragma unroll 4
+  for (int s0 = 0; s0 < S; s0 += 8) {   // unrolled: four key groups of loads in flight per lane
     const int s = s0 + g;
     float r = 0.f, dp = 0.f;
     if (s < S) {
@@ -228,7 +229,8 @@ __global__ void __launch_bounds__(256) dec_qsk_bwd_kernel(const T* __restrict__ 
   T* dkcb = dkc + i * Sq * ldkv + c;
   T* dvb = dv + i * Sq * ldkv + c;
   float* dkpb = dkp32 + (long)bb * kC + c;
-  for (int s0 = 0; s0 < S; s0 += 8) {
+#pragma unroll 4
+  for (int s0 = 0; s0 < S; s0 += 8) {   // unrolled: four key groups of loads in flight per lane
     const int s = s0 + g;
     if (s >= S) continue;
     const float ds = my_ds[s], p = my_p[s];

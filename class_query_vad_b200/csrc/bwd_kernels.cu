@@ -141,12 +141,7 @@ __global__ void __launch_bounds__(kThreads) ln_bwd_kernel(const T* __restrict__ 
 }
 
 // ---- level mix + norm_ backward ----------------------------------------------------------------------------------
-// warp per (s, b, actor group): the four memory rows are loaded once and reused by the group's actors.  One warp per (s, b)
-// looping over all nq actors left the kernel at 6 272 warps (0.7 of a wave) with a 15-deep serial chain: 150 us for 190 MB;
-// blockIdx.y splits the actors into groups, d(memory) is then accumulated with vector reductions.
-__device__ __forceinline__ void red_add_v4f(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
+// warp per (s, b): the four memory rows are loaded once and reused by the nq actors that share them
 template <typename T>
 __global__ void __launch_bounds__(kThreads) lvlmix_ln_bwd_kernel(const T* __restrict__ mem, const float* __restrict__ lvlw,
                                                                  const float* __restrict__ g, const T* __restrict__ dqm,
@@ -159,8 +154,6 @@ __global__ void __launch_bounds__(kThreads) lvlmix_ln_bwd_kernel(const T* __rest
   float gm[8];
   load8(g + lane * 8, gm);
   const long rows = (long)S * BT;
-  const int per = (nq + (int)gridDim.y - 1) / (int)gridDim.y;
-  const int n_begin = (int)blockIdx.y * per, n_end = min(nq, n_begin + per);
   for (long row = (long)blockIdx.x * kWarps + warp; row < rows; row += (long)gridDim.x * kWarps) {
     const int s = (int)(row / BT), bb = (int)(row % BT);
     float m[kL][8], dm[kL][8];
@@ -170,7 +163,7 @@ __global__ void __launch_bounds__(kThreads) lvlmix_ln_bwd_kernel(const T* __rest
 #pragma unroll
       for (int j = 0; j < 8; ++j) dm[l][j] = 0.f;
     }
-    for (int n = n_begin; n < n_end; ++n) {
+    for (int n = 0; n < nq; ++n) {
       const long i = (long)n * BT + bb;
       const float4 w4 = *reinterpret_cast<const float4*>(lvlw + i * 4);
       const float w[4] = {w4.x, w4.y, w4.z, w4.w};
@@ -194,8 +187,11 @@ __global__ void __launch_bounds__(kThreads) lvlmix_ln_bwd_kernel(const T* __rest
 #pragma unroll
     for (int l = 0; l < kL; ++l) {
       float* p = dmem32 + (((long)l * S + s) * BT + bb) * kC + lane * 8;
-      red_add_v4f(p, dm[l][0], dm[l][1], dm[l][2], dm[l][3]);
-      red_add_v4f(p + 4, dm[l][4], dm[l][5], dm[l][6], dm[l][7]);
+      float o[8];
+      load8(p, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += dm[l][j];
+      store8(p, o);
     }
   }
   flush_gb(ag, ab, dg, db, red);
@@ -782,8 +778,7 @@ template <typename T>
 int lvlmix_ln_bwd(const T* mem, const float* lvlw, const float* g, const T* dqm, float* dmem32, float* dlvlw, float* dg,
                   float* db, long N, int nq, int S, int Sq, int BT, cudaStream_t st) {
   if (N == 0) return 0;
-  const dim3 grid(persist_grid((long)S * BT), (unsigned)(nq >= 12 ? 4 : (nq >= 4 ? 2 : 1)));
-  lvlmix_ln_bwd_kernel<T><<<grid, kThreads, 0, st>>>(mem, lvlw, g, dqm, dmem32, dlvlw, dg, db, nq, S, Sq, BT);
+  lvlmix_ln_bwd_kernel<T><<<persist_grid((long)S * BT), kThreads, 0, st>>>(mem, lvlw, g, dqm, dmem32, dlvlw, dg, db, nq, S, Sq, BT);
   CQ_LAUNCH_CHECK();
   return 0;
 }
