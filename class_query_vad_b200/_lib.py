@@ -31,6 +31,11 @@ SYMBOLS = {
     "cqvad_layernorm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_long, c_int, c_void_p]),
     "cqvad_linear_gelu_train": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_void_p]),
     "cqvad_linear_dgrad_act": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_long, c_int, c_int, c_void_p]),
+    "cqvad_deform_encoder_layer_train_workspace_bytes": (c_size_t, [c_int, c_int, c_long, c_int, c_int, c_int]),
+    "cqvad_deform_encoder_layer_train_forward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                          c_void_p, c_void_p, c_size_t, c_int, c_long, c_int, c_int, c_int, c_void_p]),
+    "cqvad_deform_encoder_layer_backward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                     c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_long, c_int, c_int, c_int, c_void_p]),
     "cqvad_deform_encoder_layer_num_weights": (c_int, []),
     "cqvad_deform_encoder_layer_workspace_bytes": (c_size_t, [c_int, c_int, c_long, c_int, c_int, c_int]),
     "cqvad_deform_encoder_layer_forward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -10,6 +10,7 @@
 //     out    = LN2(x1 + linear2(relu(linear1(x1))))                       (:507-510)   fused tcgen05 MLP (hidden stays on the SM)
 // Dropout is the identity (eval / the native path's documented divergence).  Heads = 8, d_model = 256 (all shipped configs).
 #include "common.cuh"
+#include "bwd.cuh"
 
 #include <stdlib.h>
 
@@ -160,6 +161,136 @@ int enc_layer_t(const void* const* W, const T* src, const T* pos, const float* r
                    out, hid, rows, F, (void*)st);
 }
 
+// ---- training: forward that keeps what the backward needs, and the backward ------------------------------------------------
+// backward of msda_prepare: dlogit = attn * (dattn - sum_j attn_j dattn_j)  (softmax), doff = dloc / (T_l, W_l, H_l); written in
+// the GEMM operand type T (they feed the weight- and data-gradient GEMMs of the two query projections)
+template <typename T>
+__global__ void __launch_bounds__(256) msda_prepare_bwd_kernel(const float* __restrict__ attn, const float* __restrict__ dattn,
+                                                               const float* __restrict__ dloc, const int64_t* __restrict__ shapes,
+                                                               T* __restrict__ doff, T* __restrict__ dlogit, long rows, int L,
+                                                               int P) {
+  const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= rows * kM) return;
+  const int LP = L * P;
+  float dot = 0.f;
+  for (int j = lane; j < LP; j += 32) dot = fmaf(attn[wid * LP + j], dattn[wid * LP + j], dot);
+  dot = warp_sum(dot);
+  for (int j = lane; j < LP; j += 32) {
+    dlogit[wid * LP + j] = from_f<T>(attn[wid * LP + j] * (dattn[wid * LP + j] - dot));
+    const int l = j / P;
+    const float nx = (float)shapes[l * 3 + 0], ny = (float)shapes[l * 3 + 2], nt = (float)shapes[l * 3 + 1];
+    const float* g = dloc + (wid * LP + j) * 3;
+    T* d = doff + (wid * LP + j) * 3;
+    d[0] = from_f<T>(g[0] / nx); d[1] = from_f<T>(g[1] / ny); d[2] = from_f<T>(g[2] / nt);
+  }
+}
+
+// one layout for both passes: [saved by the forward | scratch of the backward]
+template <typename T>
+struct EncTrainWs {
+  T *q, *value, *offT, *lgT, *samp, *z1, *x1, *h, *z2;
+  float *off32, *lg32, *loc, *attn;
+  T *dz2, *dh, *dx1, *dz1, *dsamp, *doffT, *dlgT, *dq, *dvalT, *wt;
+  float *dval32, *dloc, *dattn;
+  size_t bytes;
+  EncTrainWs(void* base, size_t cap, long rows, int L, int P, int F) {
+    EncWs w(base, cap);
+    const size_t LP3 = (size_t)kM * L * P * 3, LP1 = (size_t)kM * L * P, R = (size_t)rows, C = kC;
+    auto tk = [&](size_t n) { return (T*)w.take(n * sizeof(T)); };
+    auto tf = [&](size_t n) { return (float*)w.take(n * 4); };
+    q = tk(R * C); value = tk(R * C); offT = tk(R * LP3); lgT = tk(R * LP1);
+    off32 = (float*)offT; lg32 = (float*)lgT;
+    if (sizeof(T) == 2) { off32 = tf(R * LP3); lg32 = tf(R * LP1); }
+    loc = tf(R * LP3); attn = tf(R * LP1);
+    samp = tk(R * C); z1 = tk(R * C); x1 = tk(R * C); h = tk(R * F); z2 = tk(R * C);
+    dz2 = tk(R * C); dh = tk(R * F); dx1 = tk(R * C); dz1 = tk(R * C); dsamp = tk(R * C);
+    doffT = tk(R * LP3); dlgT = tk(R * LP1); dq = tk(R * C); dvalT = tk(R * C);
+    dval32 = tf(R * C); dloc = tf(R * LP3); dattn = tf(R * LP1);
+    wt = tk(2 * C * C + LP3 * C + LP1 * C + 2 * (size_t)F * C);      // transposed weights for the data gradients
+    bytes = w.off + 256;
+  }
+};
+
+template <typename T>
+int enc_train_fwd_t(const void* const* W, const T* src, const T* pos, const float* refp, const int64_t* shapes, const int64_t* lsi,
+                    const uint8_t* mask, T* out, void* ws, size_t ws_bytes, int B, long Len, int L, int P, int F, cudaStream_t st) {
+  const long rows = (long)B * Len;
+  if (rows == 0) return 0;
+  const int LP3 = kM * L * P * 3, LP1 = kM * L * P;
+  EncTrainWs<T> w(ws, ws_bytes, rows, L, P, F);
+  if (ws_bytes < w.bytes) return set_error(CQVAD_E_WORKSPACE, "deform_encoder_layer (training): workspace too small");
+  auto Wm = [&](int i) { return (const T*)W[i]; };
+  auto Wf = [&](int i) { return (const float*)W[i]; };
+  const long n8 = rows * kC / 8;
+  add_rows_kernel<T><<<(unsigned)cdiv(n8, 256), 256, 0, st>>>(src, pos, w.q, n8);
+  CQ_LAUNCH_CHECK();
+  { Epilogue e; e.bias = Wf(E_VAL_B); CQ_TRY(gemm<T>(src, kC, Wm(E_VAL_W), w.value, kC, rows, kC, kC, e, nullptr, st)); }
+  if (mask) { mask_rows_kernel<T><<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(w.value, mask, rows); CQ_LAUNCH_CHECK(); }
+  { Epilogue e; e.bias = Wf(E_OFF_B); if (sizeof(T) == 2) e.c32 = w.off32; CQ_TRY(gemm<T>(w.q, kC, Wm(E_OFF_W), w.offT, LP3, rows, LP3, kC, e, nullptr, st)); }
+  { Epilogue e; e.bias = Wf(E_ATT_B); if (sizeof(T) == 2) e.c32 = w.lg32; CQ_TRY(gemm<T>(w.q, kC, Wm(E_ATT_W), w.lgT, LP1, rows, LP1, kC, e, nullptr, st)); }
+  msda_prepare_kernel<<<(unsigned)cdiv(rows * kM * 32, 256), 256, 0, st>>>(w.off32, w.lg32, refp, shapes, w.loc, w.attn, rows, L, P);
+  CQ_LAUNCH_CHECK();
+  CQ_TRY(cqvad_msda3d_forward(DT<T>::id, w.value, shapes, lsi, w.loc, w.attn, w.samp, B, (int)Len, kM, kC / kM, L, (int)Len, P, (void*)st));
+  { Epilogue e; e.bias = Wf(E_OUT_B); e.res = src; e.ldr = kC; CQ_TRY(gemm<T>(w.samp, kC, Wm(E_OUT_W), w.z1, kC, rows, kC, kC, e, nullptr, st)); }
+  CQ_TRY(layernorm_rows<T>(w.z1, nullptr, Wf(E_N1_W), Wf(E_N1_B), 1e-5f, w.x1, false, rows, st));
+  { Epilogue e; e.bias = Wf(E_L1_B); e.act = CQVAD_ACT_RELU; CQ_TRY(gemm<T>(w.x1, kC, Wm(E_L1_W), w.h, F, rows, F, kC, e, nullptr, st)); }
+  { Epilogue e; e.bias = Wf(E_L2_B); e.res = w.x1; e.ldr = kC; CQ_TRY(gemm<T>(w.h, F, Wm(E_L2_W), w.z2, kC, rows, kC, F, e, nullptr, st)); }
+  return layernorm_rows<T>(w.z2, nullptr, Wf(E_N2_W), Wf(E_N2_B), 1e-5f, out, false, rows, st);
+}
+
+template <typename T>
+int enc_train_bwd_t(const void* const* W, const T* src, const int64_t* shapes, const int64_t* lsi, const uint8_t* mask,
+                    const T* gout, T* gsrc, T* gpos, float* const* G, void* ws, size_t ws_bytes, int B, long Len, int L, int P, int F,
+                    cudaStream_t st) {
+  const long rows = (long)B * Len;
+  if (rows == 0) return 0;
+  const int LP3 = kM * L * P * 3, LP1 = kM * L * P;
+  EncTrainWs<T> w(ws, ws_bytes, rows, L, P, F);
+  if (ws_bytes < w.bytes) return set_error(CQVAD_E_WORKSPACE, "deform_encoder_layer (training): workspace too small");
+  auto Wm = [&](int i) { return (const T*)W[i]; };
+  auto Wf = [&](int i) { return (const float*)W[i]; };
+  // transposed weights [in][out] for dX = dY . W
+  T* wt_val = w.wt; T* wt_out = wt_val + kC * kC; T* wt_off = wt_out + kC * kC; T* wt_att = wt_off + (size_t)LP3 * kC;
+  T* wt_l1 = wt_att + (size_t)LP1 * kC; T* wt_l2 = wt_l1 + (size_t)F * kC;
+  CQ_TRY(transpose_w<T>(Wm(E_VAL_W), wt_val, kC, kC, st));
+  CQ_TRY(transpose_w<T>(Wm(E_OUT_W), wt_out, kC, kC, st));
+  CQ_TRY(transpose_w<T>(Wm(E_OFF_W), wt_off, LP3, kC, st));
+  CQ_TRY(transpose_w<T>(Wm(E_ATT_W), wt_att, LP1, kC, st));
+  CQ_TRY(transpose_w<T>(Wm(E_L1_W), wt_l1, F, kC, st));
+  CQ_TRY(transpose_w<T>(Wm(E_L2_W), wt_l2, kC, F, st));
+  // out = LN2(z2)
+  CQ_TRY(ln_bwd<T>(w.z2, nullptr, Wf(E_N2_W), 1e-5f, gout, false, 0, 0, 0, w.dz2, 0.f, nullptr, 0.f, G[E_N2_W], G[E_N2_B], rows, st));
+  // z2 = x1 + linear2(h), h = relu(linear1(x1))
+  CQ_TRY(wgrad<T>(w.dz2, kC, w.h, F, G[E_L2_W], F, G[E_L2_B], rows, kC, F, nullptr, st));
+  { Epilogue e; e.mul_aux = w.h; e.mul_mode = 1; CQ_TRY(gemm<T>(w.dz2, kC, wt_l2, w.dh, F, rows, F, kC, e, nullptr, st)); }
+  CQ_TRY(wgrad<T>(w.dh, F, w.x1, kC, G[E_L1_W], kC, G[E_L1_B], rows, F, kC, nullptr, st));
+  { Epilogue e; e.res = w.dz2; e.ldr = kC; CQ_TRY(gemm<T>(w.dh, F, wt_l1, w.dx1, kC, rows, kC, F, e, nullptr, st)); }
+  // x1 = LN1(z1), z1 = src + output_proj(samp)
+  CQ_TRY(ln_bwd<T>(w.z1, nullptr, Wf(E_N1_W), 1e-5f, w.dx1, false, 0, 0, 0, w.dz1, 0.f, nullptr, 0.f, G[E_N1_W], G[E_N1_B], rows, st));
+  CQ_TRY(wgrad<T>(w.dz1, kC, w.samp, kC, G[E_OUT_W], kC, G[E_OUT_B], rows, kC, kC, nullptr, st));
+  { Epilogue e; CQ_TRY(gemm<T>(w.dz1, kC, wt_out, w.dsamp, kC, rows, kC, kC, e, nullptr, st)); }
+  // sampling
+  CQ_CUDA(cudaMemsetAsync(w.dval32, 0, (size_t)rows * kC * 4, st));
+  CQ_TRY(cqvad_msda3d_backward(DT<T>::id, w.value, shapes, lsi, w.loc, w.attn, w.dsamp, w.dval32, w.dloc, w.dattn, B, (int)Len, kM,
+                               kC / kM, L, (int)Len, P, (void*)st));
+  msda_prepare_bwd_kernel<T><<<(unsigned)cdiv(rows * kM * 32, 256), 256, 0, st>>>(w.attn, w.dattn, w.dloc, shapes, w.doffT, w.dlgT,
+                                                                                 rows, L, P);
+  CQ_LAUNCH_CHECK();
+  // the two query projections: dq = doff . Woff + dlogit . Watt  (written straight into grad_pos: q = src + pos)
+  CQ_TRY(wgrad<T>(w.doffT, LP3, w.q, kC, G[E_OFF_W], kC, G[E_OFF_B], rows, LP3, kC, nullptr, st));
+  CQ_TRY(wgrad<T>(w.dlgT, LP1, w.q, kC, G[E_ATT_W], kC, G[E_ATT_B], rows, LP1, kC, nullptr, st));
+  { Epilogue e; CQ_TRY(gemm<T>(w.doffT, LP3, wt_off, w.dq, kC, rows, kC, LP3, e, nullptr, st)); }
+  { Epilogue e; e.res = w.dq; e.ldr = kC; CQ_TRY(gemm<T>(w.dlgT, LP1, wt_att, gpos, kC, rows, kC, LP1, e, nullptr, st)); }
+  // value projection (padded tokens: value was overwritten with zeros, so no gradient flows through them)
+  CQ_TRY(f32_to_t<T>(w.dval32, w.dvalT, 0.f, rows * kC, st));
+  if (mask) { mask_rows_kernel<T><<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(w.dvalT, mask, rows); CQ_LAUNCH_CHECK(); }
+  CQ_TRY(wgrad<T>(w.dvalT, kC, src, kC, G[E_VAL_W], kC, G[E_VAL_B], rows, kC, kC, nullptr, st));
+  // grad_src = dz1 (residual) + dvalue . Wv + dq
+  { Epilogue e; e.res = w.dz1; e.ldr = kC; CQ_TRY(gemm<T>(w.dvalT, kC, wt_val, gsrc, kC, rows, kC, kC, e, nullptr, st)); }
+  return axpby<T>(gsrc, gpos, 1.f, rows * kC, st);
+}
+
 }  // namespace
 }  // namespace cqvad
 
@@ -191,4 +322,51 @@ extern "C" int cqvad_deform_encoder_layer_forward(int dtype, const void* const* 
     return enc_layer_t<bf16>(weights, (const bf16*)src, (const bf16*)pos, reference_points, shapes, level_start, padding_mask,
                              (bf16*)out, (bf16*)attn_out, workspace, workspace_bytes, B, Len, L, P, F, as_stream(stream));
   return set_error(CQVAD_E_INVALID_ARG, "deform_encoder_layer: unknown dtype %d", dtype);
+}
+
+extern "C" size_t cqvad_deform_encoder_layer_train_workspace_bytes(int dtype, int B, long Len, int L, int P, int F) {
+  if (B < 0 || Len < 0 || L < 1 || P < 1 || F < 1) return 0;
+  return dtype == CQVAD_F32 ? EncTrainWs<float>(nullptr, 0, (long)B * Len, L, P, F).bytes
+                            : EncTrainWs<bf16>(nullptr, 0, (long)B * Len, L, P, F).bytes;
+}
+
+extern "C" int cqvad_deform_encoder_layer_train_forward(int dtype, const void* const* weights, const void* src, const void* pos,
+                                                        const float* reference_points, const int64_t* shapes,
+                                                        const int64_t* level_start, const uint8_t* padding_mask, void* out,
+                                                        void* workspace, size_t workspace_bytes, int B, long Len, int L, int P,
+                                                        int F, void* stream) {
+  CQ_CHECK_ARG(B >= 0 && Len >= 0 && L >= 1 && P >= 1 && F >= 1, "deform_encoder_layer: bad dimensions");
+  if ((long)B * Len == 0) return 0;
+  CQ_CHECK_ARG(weights && src && pos && reference_points && shapes && level_start && out && workspace,
+               "deform_encoder_layer: null pointer");
+  for (int i = 0; i < E_COUNT; ++i) CQ_CHECK_ARG(weights[i] != nullptr, "deform_encoder_layer: weight %d is null", i);
+  CQ_CHECK_SHAPE(F % 8 == 0 && (kM * L * P) % 8 == 0, "deform_encoder_layer: F and heads*levels*points must be multiples of 8");
+  if (dtype == CQVAD_F32)
+    return enc_train_fwd_t<float>(weights, (const float*)src, (const float*)pos, reference_points, shapes, level_start, padding_mask,
+                                  (float*)out, workspace, workspace_bytes, B, Len, L, P, F, as_stream(stream));
+  if (dtype == CQVAD_BF16)
+    return enc_train_fwd_t<bf16>(weights, (const bf16*)src, (const bf16*)pos, reference_points, shapes, level_start, padding_mask,
+                                 (bf16*)out, workspace, workspace_bytes, B, Len, L, P, F, as_stream(stream));
+  return set_error(CQVAD_E_INVALID_ARG, "deform_encoder_layer: unknown dtype %d", dtype);
+}
+
+extern "C" int cqvad_deform_encoder_layer_backward(int dtype, const void* const* weights, const void* src, const int64_t* shapes,
+                                                   const int64_t* level_start, const uint8_t* padding_mask, const void* grad_out,
+                                                   void* grad_src, void* grad_pos, float* const* grad_weights, void* workspace,
+                                                   size_t workspace_bytes, int B, long Len, int L, int P, int F, void* stream) {
+  CQ_CHECK_ARG(B >= 0 && Len >= 0 && L >= 1 && P >= 1 && F >= 1, "deform_encoder_layer: bad dimensions");
+  if ((long)B * Len == 0) return 0;
+  CQ_CHECK_ARG(weights && src && shapes && level_start && grad_out && grad_src && grad_pos && grad_weights && workspace,
+               "deform_encoder_layer_backward: null pointer");
+  for (int i = 0; i < E_COUNT; ++i)
+    CQ_CHECK_ARG(weights[i] != nullptr && grad_weights[i] != nullptr, "deform_encoder_layer_backward: weight / gradient %d is null", i);
+  if (dtype == CQVAD_F32)
+    return enc_train_bwd_t<float>(weights, (const float*)src, shapes, level_start, padding_mask, (const float*)grad_out,
+                                  (float*)grad_src, (float*)grad_pos, grad_weights, workspace, workspace_bytes, B, Len, L, P, F,
+                                  as_stream(stream));
+  if (dtype == CQVAD_BF16)
+    return enc_train_bwd_t<bf16>(weights, (const bf16*)src, shapes, level_start, padding_mask, (const bf16*)grad_out,
+                                 (bf16*)grad_src, (bf16*)grad_pos, grad_weights, workspace, workspace_bytes, B, Len, L, P, F,
+                                 as_stream(stream));
+  return set_error(CQVAD_E_INVALID_ARG, "deform_encoder_layer_backward: unknown dtype %d", dtype);
 }

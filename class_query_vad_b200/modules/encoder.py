@@ -1,7 +1,8 @@
 """Drop-ins for the reference `DeformableTransformerEncoderLayer` / `DeformableTransformerEncoder`
 (models/detr/dab_transformer.py:425-523): same constructors, forward signatures and parameter names (a reference state_dict
-loads with strict=True); one layer = ONE C-ABI call, cqvad_deform_encoder_layer_forward (csrc/encoder.cu).  Inference path
-(dropout = identity); no torch arithmetic on the activation path -- `get_reference_points` (a [B, Len, L, 3] meshgrid of the
+loads with strict=True); one layer = ONE C-ABI call, cqvad_deform_encoder_layer_forward (csrc/encoder.cu); with gradients
+enabled the layer goes through EncoderLayerFunction (cqvad_deform_encoder_layer_train_forward / _backward).  Dropout =
+identity; no torch arithmetic on the activation path -- `get_reference_points` (a [B, Len, L, 3] meshgrid of the
 level shapes and valid ratios, computed once per forward) is host-side glue written with torch like the reference's."""
 import ctypes
 import copy
@@ -60,6 +61,50 @@ def encoder_layer_forward(packed, src, pos, reference_points, shapes, level_star
     return (out, attn_out) if want_attn else out
 
 
+class EncoderLayerFunction(torch.autograd.Function):
+    """loss.backward() through one encoder layer: cqvad_deform_encoder_layer_train_forward / _backward.
+    apply(src, pos, reference_points, shapes, level_start, padding_mask, n_points, d_ffn, *16 parameters in state_dict order)."""
+
+    @staticmethod
+    def forward(ctx, src, pos, reference_points, shapes, level_start, padding_mask, n_points, d_ffn, *params):
+        _lib.require_cuda(src, pos, reference_points, shapes, level_start)
+        lib = _lib.lib()
+        dt = src.dtype
+        B, Len, C = src.shape
+        L = int(shapes.shape[0])
+        names = [f"{b}.{l}" for b in ENC_WEIGHT_ORDER for l in ("weight", "bias")]
+        keep, tab = pack_encoder_layer_weights(dict(zip(names, params)), dt, src.device)
+        src_c, pos_c = src.detach().contiguous(), pos.detach().to(dt).contiguous()
+        refp = reference_points.detach().to(torch.float32).contiguous()
+        sh, ls = shapes.to(torch.int64).contiguous(), level_start.to(torch.int64).contiguous()
+        m8 = None
+        if padding_mask is not None:
+            m8 = padding_mask.to(src.device).contiguous()
+            m8 = m8.view(torch.uint8) if m8.dtype == torch.bool else m8.to(torch.uint8)
+        need = lib.cqvad_deform_encoder_layer_train_workspace_bytes(_lib.dtype_id(dt), B, Len, L, n_points, d_ffn)
+        ws = torch.empty(need, dtype=torch.uint8, device=src.device)
+        out = torch.empty_like(src_c)
+        p = _lib.ptr
+        _lib.check(lib.cqvad_deform_encoder_layer_train_forward(_lib.dtype_id(dt), tab, p(src_c), p(pos_c), p(refp), p(sh), p(ls), p(m8),
+                                                                p(out), p(ws), need, B, Len, L, n_points, d_ffn, _lib.stream_ptr()))
+        ctx.saved = (keep, tab, src_c, sh, ls, m8, ws, need, (B, Len, L, n_points, d_ffn), [q.dtype for q in params])
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        keep, tab, src_c, sh, ls, m8, ws, need, (B, Len, L, n_points, d_ffn), pdt = ctx.saved
+        lib = _lib.lib()
+        dt = src_c.dtype
+        go = grad_out.to(dt).contiguous()
+        gsrc, gpos = torch.empty_like(src_c), torch.empty_like(src_c)
+        gw = [torch.zeros(k.shape, dtype=torch.float32, device=src_c.device) for k in keep]
+        gtab = (ctypes.c_void_p * len(gw))(*[g.data_ptr() for g in gw])
+        p = _lib.ptr
+        _lib.check(lib.cqvad_deform_encoder_layer_backward(_lib.dtype_id(dt), tab, p(src_c), p(sh), p(ls), p(m8), p(go), p(gsrc), p(gpos),
+                                                           gtab, p(ws), need, B, Len, L, n_points, d_ffn, _lib.stream_ptr()))
+        return (gsrc, gpos, None, None, None, None, None, None) + tuple(g.to(d) for g, d in zip(gw, pdt))
+
+
 class DeformableTransformerEncoderLayer(nn.Module):
     def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4):
         super().__init__()
@@ -88,6 +133,11 @@ class DeformableTransformerEncoderLayer(nn.Module):
             warnings.warn("libcqvad encoder layer applies no dropout (inference semantics)", stacklevel=2)
         if pos is None:
             pos = torch.zeros_like(src)
+        if torch.is_grad_enabled() and (src.requires_grad or any(p.requires_grad for p in self.parameters())):
+            sd = dict(self.named_parameters())
+            params = [sd[f"{b}.{l}"] for b in ENC_WEIGHT_ORDER for l in ("weight", "bias")]
+            return EncoderLayerFunction.apply(src, pos, reference_points, spatio_temporal_shapes, level_start_index, padding_mask,
+                                              self.n_points, self.d_ffn, *params)
         return encoder_layer_forward(self._pack(src.dtype, src.device), src, pos, reference_points, spatio_temporal_shapes,
                                      level_start_index, padding_mask, self.n_points, self.d_ffn)
 

@@ -95,6 +95,22 @@ int cqvad_deform_encoder_layer_forward(int dtype, const void* const* weights, co
                                        const float* reference_points, const int64_t* shapes, const int64_t* level_start,
                                        const uint8_t* padding_mask, void* out, void* attn_out, void* workspace,
                                        size_t workspace_bytes, int B, long Len, int L, int P, int F, void* stream);
+/* Training pair of the encoder layer (the reference differentiates DeformableTransformerEncoderLayer.forward with autograd,
+ * train.py:151; the sampling gradient is the mathematical one, see cqvad_msda3d_backward).  train_forward = the same result as
+ * cqvad_deform_encoder_layer_forward with unfused LayerNorms / FFN, keeping q, value, locations, attention weights, the
+ * sampled values, both pre-norm sums and the FFN hidden in `workspace`; backward consumes that workspace (same pointer, same
+ * size, untouched in between), writes grad_src / grad_pos [B, Len, 256] (dtype) and ACCUMULATES the 16 parameter gradients
+ * (fp32, state_dict order, caller zero-fills).  Dropout = identity.  reference_points get no gradient (derived from shapes). */
+size_t cqvad_deform_encoder_layer_train_workspace_bytes(int dtype, int B, long Len, int L, int P, int F);
+int cqvad_deform_encoder_layer_train_forward(int dtype, const void* const* weights, const void* src, const void* pos,
+                                             const float* reference_points, const int64_t* shapes,
+                                             const int64_t* level_start, const uint8_t* padding_mask, void* out,
+                                             void* workspace, size_t workspace_bytes, int B, long Len, int L, int P, int F,
+                                             void* stream);
+int cqvad_deform_encoder_layer_backward(int dtype, const void* const* weights, const void* src, const int64_t* shapes,
+                                        const int64_t* level_start, const uint8_t* padding_mask, const void* grad_out,
+                                        void* grad_src, void* grad_pos, float* const* grad_weights, void* workspace,
+                                        size_t workspace_bytes, int B, long Len, int L, int P, int F, void* stream);
 /* Y[M,256] = LN?( res + W2 . act(W1 . X + b1) + b2 ): the FFN blocks of the decoder (dab_transformer.py:994-996,
  * 1043-1045, 1074-1076).  X [M,256], W1 [F,256], W2 [256,F] (dtype); ln_g/ln_b may be NULL (no LayerNorm); res may be
  * NULL.  hidden [M,F] (dtype) is scratch used only when the fused tensor-core kernel does not apply (fp32, or F % 128). */
