@@ -156,7 +156,8 @@ struct Trainer {
   cudaStream_t wgrad_stream(long rows) {
     static const bool off = [] { const char* e = getenv("CQVAD_TRAIN_WG_STREAM"); return e && atoi(e) == 0; }();
     static cudaEvent_t ev = [] { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); return e; }();
-    if (off || prof_enabled() || !two_streams || rows < 4096 || wg_stream() == nullptr || sizeof(T) != 2) return st;   // (the profiler times on st)
+    static const long min_rows = [] { const char* e = getenv("CQVAD_TRAIN_WG_MIN_ROWS"); return e ? atol(e) : 1L; }();   // small-row wgrads too: 124 launches of ~8 us leave the loc chain
+    if (off || prof_enabled() || !two_streams || rows < min_rows || wg_stream() == nullptr || sizeof(T) != 2) return st;   // (the profiler times on st)
     if (cudaEventRecord(ev, st) != cudaSuccess || cudaStreamWaitEvent(wg_stream(), ev, 0) != cudaSuccess) return st;
     wg_used = true;
     return wg_stream();

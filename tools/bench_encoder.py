@@ -32,3 +32,27 @@ ms = sorted(ts)[len(ts) // 2]
 rows = B * Len
 gflop = 2.0 * rows * 256 * (256 + 768 + 256 + 256 + 2 * F_) / 1e9          # linears only (the sampling is a gather)
 print(f"B={B} Len={Len}: {ms:.3f} ms per layer  ({B / ms * 1e3:.1f} clips/s/layer, {gflop / ms:.1f} TFLOP/s of GEMM work, {gflop / B:.1f} GFLOP/clip)")
+
+# ---- training step of the layer (forward keeping activations + backward) through the autograd Function ----
+from class_query_vad_b200 import DeformableTransformerEncoderLayer
+layer = DeformableTransformerEncoderLayer(d_model=256, d_ffn=F_, n_levels=4, n_heads=8, n_points=P)
+layer.load_state_dict({k: torch.from_numpy(v) for k, v in W.items()}, strict=True)
+layer = layer.to(dev).eval()
+srcg = src.clone().requires_grad_(True)
+posg = pos.clone().requires_grad_(True)
+go = torch.randn_like(src)
+tf, tb = [], []
+for it in range(iters):
+    for p_ in layer.parameters():
+        p_.grad = None
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    out = layer(srcg, posg, refp, sh, ls, None)
+    e1.record()
+    out.backward(go)
+    e2.record()
+    torch.cuda.synchronize()
+    tf.append(e0.elapsed_time(e1)); tb.append(e1.elapsed_time(e2))
+mf, mb = sorted(tf)[len(tf) // 2], sorted(tb)[len(tb) // 2]
+print(f"B={B} training step of one layer: fwd {mf:.3f} ms + bwd {mb:.3f} ms = {mf + mb:.3f} ms  ({B / (mf + mb) * 1e3:.1f} clips/s/layer, "
+      f"{3 * gflop / (mf + mb):.1f} TFLOP/s of GEMM work)")
