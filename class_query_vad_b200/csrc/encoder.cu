@@ -291,6 +291,77 @@ int enc_train_bwd_t(const void* const* W, const T* src, const int64_t* shapes, c
   return axpby<T>(gsrc, gpos, 1.f, rows * kC, st);
 }
 
+// ---- encoder -> decoder data format ------------------------------------------------------------
+// Transformer.forward (models/detr/dab_transformer.py:349-393) between the encoder and the decoder: un-flatten per level,
+// make_interpolated_features (:239-294: F.grid_sample, align_corners = False, zeros padding) onto the (num_frames, H, W) grid of
+// level -2, key-frame slice (`eff`, :378-382), rearrange to the decoder's "L (H W) (B T) C".  The reference materialises every
+// level at every frame as [B, C, T, H, W] (+ two permuted copies) and then keeps ONE frame; here one warp produces one row of the
+// decoder memory straight from the token-major encoder output: channels are the contiguous axis, so the <= 8 corner reads are
+// 512-byte coalesced segments and only consumed frames are computed.
+__device__ __forceinline__ float lin_m11(int i, int n) {   // torch.linspace(-1, 1, n)[i] (symmetric evaluation, RangeFactories.cu)
+  if (n == 1) return -1.f;
+  const float step = 2.f / (float)(n - 1);
+  return i < n / 2 ? -1.f + step * (float)i : 1.f - step * (float)(n - 1 - i);
+}
+__device__ __forceinline__ float unnorm(float c, int size) { return ((c + 1.f) * (float)size - 1.f) * 0.5f; }
+
+template <typename T>
+__global__ void __launch_bounds__(256) interp_to_decoder_kernel(const T* __restrict__ tok, const T* __restrict__ postok,
+                                                                const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
+                                                                T* __restrict__ mem, T* __restrict__ pos0, int L, int B, long Len,
+                                                                int Tt, int H, int W, int nf, int eff) {
+  const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int Tp = eff ? 1 : nf;
+  const long BT = (long)B * Tp, S = (long)H * W;
+  if (wid >= (long)L * S * BT) return;
+  const long bt = wid % BT;
+  const long s = (wid / BT) % S;
+  const int l = (int)(wid / (BT * S));
+  const int b = (int)(bt / Tp), fr = eff ? nf / 2 : (int)(bt % Tp);
+  const int i = (int)(s / W), j = (int)(s % W);
+  const int Tl = (int)shapes[l * 3], Hl = (int)shapes[l * 3 + 1], Wl = (int)shapes[l * 3 + 2];
+  const T* base = tok + ((long)b * Len + lsi[l]) * kC + lane * 8;
+  float x, y, lt = 0.f;
+  int t0 = fr, nt = 1;
+  if (Tt == nf) {   // per-frame 2-D sampling; the reference stacks the grid as (meshy, meshx): row coordinate -> x, column -> y
+    x = unnorm(lin_m11(i, H), Wl); y = unnorm(lin_m11(j, W), Hl);
+  } else {          // trilinear, grid (x, y, t) = (dw[j], dh[i], dt[fr])
+    x = unnorm(lin_m11(j, W), Wl); y = unnorm(lin_m11(i, H), Hl);
+    const float t = unnorm(lin_m11(fr, nf), Tl);
+    t0 = (int)floorf(t); lt = t - (float)t0; nt = 2;
+  }
+  const int x0 = (int)floorf(x), y0 = (int)floorf(y);
+  const float lx = x - (float)x0, ly = y - (float)y0;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int kt = 0; kt < nt; ++kt) {
+    const int tz = t0 + kt;
+    const float wt = nt == 1 ? 1.f : (kt ? lt : 1.f - lt);
+    if (tz < 0 || tz >= Tl) continue;
+#pragma unroll
+    for (int ky = 0; ky < 2; ++ky) {
+      const int yz = y0 + ky;
+      if (yz < 0 || yz >= Hl) continue;
+#pragma unroll
+      for (int kx = 0; kx < 2; ++kx) {
+        const int xz = x0 + kx;
+        if (xz < 0 || xz >= Wl) continue;
+        const float wgt = wt * (ky ? ly : 1.f - ly) * (kx ? lx : 1.f - lx);
+        float v[8];
+        load8(base + ((long)(tz * Hl + yz) * Wl + xz) * kC, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, v[e], acc[e]);
+      }
+    }
+  }
+  store8(mem + wid * kC + lane * 8, acc);
+  if (pos0 && l == L - 2) {   // pos of level -2, repeated in time (:285), no resampling
+    float v[8];
+    load8(postok + ((long)b * Len + lsi[l] + ((long)(fr % Tt) * H + i) * W + j) * kC + lane * 8, v);
+    store8(pos0 + (s * BT + bt) * kC + lane * 8, v);
+  }
+}
+
 }  // namespace
 }  // namespace cqvad
 
@@ -369,4 +440,27 @@ extern "C" int cqvad_deform_encoder_layer_backward(int dtype, const void* const*
                                  (bf16*)grad_src, (bf16*)grad_pos, grad_weights, workspace, workspace_bytes, B, Len, L, P, F,
                                  as_stream(stream));
   return set_error(CQVAD_E_INVALID_ARG, "deform_encoder_layer_backward: unknown dtype %d", dtype);
+}
+
+extern "C" int cqvad_encoder_to_decoder_memory(int dtype, const void* tokens, const void* pos_tokens, const int64_t* shapes,
+                                               const int64_t* level_start, int L, int B, long Len, int Tt, int H, int W,
+                                               int num_frames, int eff, void* memory, void* pos0, void* stream) {
+  CQ_CHECK_ARG(L >= 2 && B >= 0 && Len >= 0 && Tt >= 1 && H >= 1 && W >= 1 && num_frames >= 1, "encoder_to_decoder_memory: bad dimensions");
+  const long rows = (long)L * H * W * B * (eff ? 1 : num_frames);
+  if (rows == 0) return 0;
+  CQ_CHECK_ARG(tokens && shapes && level_start && memory && (pos0 == nullptr || pos_tokens != nullptr),
+               "encoder_to_decoder_memory: null pointer");
+  const unsigned grid = (unsigned)cdiv(rows * 32, 256);
+  if (dtype == CQVAD_F32)
+    interp_to_decoder_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)tokens, (const float*)pos_tokens, shapes,
+                                                                         level_start, (float*)memory, (float*)pos0, L, B, Len, Tt, H,
+                                                                         W, num_frames, eff ? 1 : 0);
+  else if (dtype == CQVAD_BF16)
+    interp_to_decoder_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16*)tokens, (const bf16*)pos_tokens, shapes,
+                                                                        level_start, (bf16*)memory, (bf16*)pos0, L, B, Len, Tt, H, W,
+                                                                        num_frames, eff ? 1 : 0);
+  else
+    return set_error(CQVAD_E_INVALID_ARG, "encoder_to_decoder_memory: unknown dtype %d", dtype);
+  CQ_LAUNCH_CHECK();
+  return 0;
 }

@@ -171,3 +171,23 @@ class DeformableTransformerEncoder(nn.Module):
         for layer in self.layers:
             output = layer(output, pos, reference_points, spatio_temporal_shapes, level_start_index, padding_mask)
         return output
+
+
+def encoder_to_decoder_memory(tokens, pos_tokens, shapes, level_start, num_frames, eff=True):
+    """The encoder -> decoder step of Transformer.forward (dab_transformer.py:349-393) through cqvad_encoder_to_decoder_memory:
+    tokens / pos_tokens [B, Len, 256] -> (memory [L, H*W, B*T', 256], pos0 [H*W, B*T', 256]) with (T, H, W) = shapes[-2]."""
+    _lib.require_cuda(tokens, shapes, level_start)
+    dt = tokens.dtype
+    B, Len, C = tokens.shape
+    L = int(shapes.shape[0])
+    Tt, H, W = (int(v) for v in shapes[L - 2].tolist())
+    Tp = 1 if eff else int(num_frames)
+    tok = tokens.contiguous()
+    ptok = None if pos_tokens is None else pos_tokens.to(dt).contiguous()
+    sh, ls = shapes.to(torch.int64).contiguous(), level_start.to(torch.int64).contiguous()
+    memory = torch.empty((L, H * W, B * Tp, C), dtype=dt, device=tokens.device)
+    pos0 = None if ptok is None else torch.empty((H * W, B * Tp, C), dtype=dt, device=tokens.device)
+    p = _lib.ptr
+    _lib.check(_lib.lib().cqvad_encoder_to_decoder_memory(_lib.dtype_id(dt), p(tok), p(ptok), p(sh), p(ls), L, B, Len, Tt, H, W,
+                                                         int(num_frames), 1 if eff else 0, p(memory), p(pos0), _lib.stream_ptr()))
+    return memory, pos0

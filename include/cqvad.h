@@ -111,6 +111,16 @@ int cqvad_deform_encoder_layer_backward(int dtype, const void* const* weights, c
                                         const int64_t* level_start, const uint8_t* padding_mask, const void* grad_out,
                                         void* grad_src, void* grad_pos, float* const* grad_weights, void* workspace,
                                         size_t workspace_bytes, int B, long Len, int L, int P, int F, void* stream);
+/* Encoder output -> decoder memory: the part of Transformer.forward between the two
+ * (models/detr/dab_transformer.py:349-393): per-level un-flatten, make_interpolated_features (:239-294, grid_sample with
+ * align_corners = False and zeros padding onto the (num_frames, H, W) grid of level -2, including the reference's (meshy, meshx)
+ * grid order in the T == num_frames branch), key-frame slice when `eff`, and the "L (H W) (B T) C" rearrange, in ONE pass that
+ * computes only the consumed frames.  tokens / pos_tokens [B, Len, 256] (dtype; pos_tokens = lvl_pos_embed_flatten, may be
+ * NULL with pos0); shapes [L,3] (T,H,W) / level_start [L] int64 on the device; (Tt, H, W) = shapes[L-2] passed by value;
+ * memory [L, H*W, B*T', 256], pos0 [H*W, B*T', 256] (T' = 1 if eff else num_frames). */
+int cqvad_encoder_to_decoder_memory(int dtype, const void* tokens, const void* pos_tokens, const int64_t* shapes,
+                                    const int64_t* level_start, int L, int B, long Len, int Tt, int H, int W, int num_frames,
+                                    int eff, void* memory, void* pos0, void* stream);
 /* Y[M,256] = LN?( res + W2 . act(W1 . X + b1) + b2 ): the FFN blocks of the decoder (dab_transformer.py:994-996,
  * 1043-1045, 1074-1076).  X [M,256], W1 [F,256], W2 [256,F] (dtype); ln_g/ln_b may be NULL (no LayerNorm); res may be
  * NULL.  hidden [M,F] (dtype) is scratch used only when the fused tensor-core kernel does not apply (fp32, or F % 128). */

@@ -158,3 +158,24 @@ def test_encoder_layer_grads_bf16_match_reference_autograd(name):
           for k, v in grads.items()}
     assert float(np.median(list(l2.values()))) < 2.0 * TOL_BF16, l2
     assert max(l2.values()) < 5 * TOL_BF16, l2
+
+
+from test_oracle_golden import interp_case, INTERP_CASES
+
+
+@pytest.mark.parametrize("name", INTERP_CASES)
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, TOL_FP32), (torch.bfloat16, TOL_BF16)])
+def test_encoder_to_decoder_memory_matches_reference(name, dtype, tol):
+    """cqvad_encoder_to_decoder_memory against the reference's make_interpolated_features + stack / key-frame slice / rearrange
+    (both grid_sample branches, eff and all-frames); pos0 is a pure gather: exact."""
+    from class_query_vad_b200 import encoder_to_decoder_memory
+    g = load_golden(name)
+    tokens, pos_tokens, shapes, nf, eff = interp_case(g)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    mem, pos0 = encoder_to_decoder_memory(t(tokens).to(dtype), t(pos_tokens).to(dtype), t(g["shapes"]), t(g["level_start"]), nf, eff)
+    torch.cuda.synchronize()
+    assert tuple(mem.shape) == g["memory"].shape
+    assert rel_err(mem.float().cpu().numpy(), g["memory"]) < tol
+    ref_pos = torch.from_numpy(g["pos0"]).to(dtype).float().numpy()
+    assert np.array_equal(pos0.float().cpu().numpy(), ref_pos)

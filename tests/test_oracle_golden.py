@@ -131,3 +131,29 @@ def test_encoder_layer_oracle_matches_reference(name):
     out, attn_out = encoder_np.encoder_layer(W, inp["src"], inp["pos"], refp, shapes, g["level_start"], inp["mask"] if masked else None)
     assert np.abs(attn_out - g["attn_out"]).max() <= 2e-5 * np.abs(g["attn_out"]).max()
     assert np.abs(out - g["out"]).max() <= 2e-5 * np.abs(g["out"]).max()
+
+
+INTERP_CASES = ["interp_2d_eff", "interp_2d_all", "interp_3d_eff", "interp_3d_all"]
+
+
+def interp_case(g):
+    B, nf, eff, seed = (int(v) for v in g["meta"])
+    shapes = [tuple(int(x) for x in r) for r in g["shapes"]]
+    rs = np.random.RandomState(6000 + seed)
+    Len = sum(t * h * w for t, h, w in shapes)
+    tokens = rs.standard_normal((B, Len, 256)).astype(np.float32)
+    pos_tokens = rs.standard_normal((B, Len, 256)).astype(np.float32)
+    return tokens, pos_tokens, shapes, nf, bool(eff)
+
+
+@pytest.mark.parametrize("name", INTERP_CASES)
+def test_interp_oracle_matches_reference(name):
+    """oracle/interp_np.py against the reference's make_interpolated_features + the stack / slice / rearrange of Transformer.forward."""
+    from oracle import interp_np
+    g = load_golden(name)
+    tokens, pos_tokens, shapes, nf, eff = interp_case(g)
+    mem = interp_np.interp_to_decoder(tokens, shapes, g["level_start"], nf, eff)
+    assert mem.shape == g["memory"].shape
+    assert np.abs(mem - g["memory"]).max() <= 2e-5 * np.abs(g["memory"]).max()
+    pos0 = interp_np.pos_to_decoder(pos_tokens, shapes, g["level_start"], nf, eff)
+    assert np.array_equal(pos0, g["pos0"])
