@@ -179,3 +179,40 @@ def test_encoder_to_decoder_memory_matches_reference(name, dtype, tol):
     assert rel_err(mem.float().cpu().numpy(), g["memory"]) < tol
     ref_pos = torch.from_numpy(g["pos0"]).to(dtype).float().numpy()
     assert np.array_equal(pos0.float().cpu().numpy(), ref_pos)
+
+
+def test_transformer_forward_composition_matches_reference():
+    """Integration: flatten + level_embed (test-side glue) -> drop-in DeformableTransformerEncoder (1 layer) ->
+    cqvad_encoder_to_decoder_memory -> DecoderEngine, against the UNMODIFIED reference Transformer.forward
+    (tests/golden/transformer_tiny.npz, oracle/make_golden_transformer.py), fp32 at 1e-3."""
+    from class_query_vad_b200 import (DeformableTransformerEncoderLayer, DeformableTransformerEncoder, encoder_to_decoder_memory,
+                                      DecoderEngine)
+    from oracle.make_golden_transformer import CFG as c, make_inputs
+    g = load_golden("transformer_tiny")
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    srcs, poss, level_embed, refpoint = make_inputs(c)
+    We = synth.make_encoder_layer_weights(c["F"], 4, c["P"], seed=c["seed"])
+    Wd = synth.make_decoder_weights(c["K"], c["layers"], c["F"], seed=c["seed"])
+    B, T = c["B"], c["T"]
+    # dab_transformer.py:310-327 (host-side glue of Transformer.forward: flatten, level embedding, shapes)
+    src_flat = torch.cat([t(s).flatten(2).transpose(1, 2) for s in srcs], 1).contiguous()
+    pos_flat = torch.cat([t(p).flatten(2).transpose(1, 2) + t(level_embed[l]).view(1, 1, -1) for l, p in enumerate(poss)], 1).contiguous()
+    sh = torch.tensor(c["shapes"], dtype=torch.int64, device=dev)
+    ls = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+    valid = torch.ones((B, 4, 3), device=dev)
+    layer = DeformableTransformerEncoderLayer(d_model=256, d_ffn=c["F"], n_levels=4, n_heads=8, n_points=c["P"])
+    layer.load_state_dict({k: torch.from_numpy(v) for k, v in We.items()}, strict=True)
+    enc = DeformableTransformerEncoder(layer, 1).to(dev).eval()
+    with torch.no_grad():
+        memory = enc(src_flat, sh, ls, valid, pos=pos_flat, padding_mask=None)
+    mem_l, pos0 = encoder_to_decoder_memory(memory, pos_flat, sh, ls, num_frames=T, eff=True)
+    Tt, H, W = c["shapes"][-2]
+    nq = c["nq"]
+    refp = t(refpoint)[:, None].expand(-1, B, -1, -1).flatten(1, 2).contiguous()        # :371  [nq, B*T', 4]
+    eng = DecoderEngine(Wd, nq=nq, K=c["K"], layers=c["layers"], F=c["F"], dtype=torch.float32, device=dev)
+    out = eng.forward(torch.zeros((nq, B, 256), device=dev), mem_l, torch.zeros((B, H * W), dtype=torch.bool, device=dev),
+                      pos0[None].expand(4, -1, -1, -1), refp, (H, W))
+    torch.cuda.synchronize()
+    for name in ("hs", "cls_hs", "refs"):
+        assert rel_err(out[name].float().cpu().numpy(), g[name]) < TOL_FP32, name
