@@ -362,6 +362,32 @@ __global__ void __launch_bounds__(256) interp_to_decoder_kernel(const T* __restr
   }
 }
 
+// ---- pyramid level -> encoder tokens (Transformer.forward, dab_transformer.py:310-327) --------------------------------------
+// src.flatten(2).transpose(1, 2) (+ level_embed[lvl] for the position embedding): channel-first [B, 256, N] -> token-major
+// rows [B, level_start + n, 256] of the concatenated sequence, through a 32 x 33 shared-memory tile (coalesced on both sides).
+template <typename T>
+__global__ void __launch_bounds__(256) level_to_tokens_kernel(const T* __restrict__ x, const float* __restrict__ add, T* __restrict__ out,
+                                                              long N, long Len, long level_start) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const long n0 = (long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const T* xb = x + (long)b * kC * N;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {                          // rows = channels, columns = positions (contiguous in x)
+    const long n = n0 + tx;
+    tile[r][tx] = n < N ? to_f(xb[(long)(c0 + r) * N + n]) : 0.f;
+  }
+  __syncthreads();
+  T* ob = out + ((long)b * Len + level_start) * kC;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {                          // rows = positions, columns = channels (contiguous in out)
+    const long n = n0 + r;
+    if (n < N) ob[n * kC + c0 + tx] = from_f<T>(tile[tx][r] + (add ? add[c0 + tx] : 0.f));
+  }
+}
+
 }  // namespace
 }  // namespace cqvad
 
@@ -461,6 +487,23 @@ extern "C" int cqvad_encoder_to_decoder_memory(int dtype, const void* tokens, co
                                                                         num_frames, eff ? 1 : 0);
   else
     return set_error(CQVAD_E_INVALID_ARG, "encoder_to_decoder_memory: unknown dtype %d", dtype);
+  CQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cqvad_level_to_tokens(int dtype, const void* x, const float* add, void* tokens, int B, long N, long Len,
+                                     long level_start, void* stream) {
+  CQ_CHECK_ARG(B >= 0 && N >= 0 && Len >= N && level_start >= 0 && level_start + N <= Len, "level_to_tokens: bad dimensions");
+  if ((long)B * N == 0) return 0;
+  CQ_CHECK_ARG(x && tokens, "level_to_tokens: null pointer");
+  CQ_CHECK_SHAPE(B <= 65535, "level_to_tokens: batch %d > 65535", B);
+  const dim3 grid((unsigned)cdiv(N, 32), kC / 32, (unsigned)B);
+  if (dtype == CQVAD_F32)
+    level_to_tokens_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)x, add, (float*)tokens, N, Len, level_start);
+  else if (dtype == CQVAD_BF16)
+    level_to_tokens_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16*)x, add, (bf16*)tokens, N, Len, level_start);
+  else
+    return set_error(CQVAD_E_INVALID_ARG, "level_to_tokens: unknown dtype %d", dtype);
   CQ_LAUNCH_CHECK();
   return 0;
 }

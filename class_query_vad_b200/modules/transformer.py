@@ -1,0 +1,86 @@
+"""Drop-in for the reference `Transformer` (models/detr/dab_transformer.py:100-397) in its shipped configuration
+(deformable 'attention' encoder, class-query decoder, no two-stage): same parameter names (`level_embed`, `encoder.layers.*`,
+`decoder.*`: a reference state_dict loads with strict=True) and the same forward signature.  Every activation-sized step runs
+in libcqvad.so: cqvad_level_to_tokens (flatten + level embedding), cqvad_deform_encoder_layer_forward, cqvad_encoder_to_decoder_memory
+(un-flatten + make_interpolated_features + key-frame slice + rearrange) and the decoder engine.  Mask bookkeeping (valid ratios,
+the flattened padding mask) is the reference's own few lines on boolean tensors."""
+import torch
+from torch import nn
+
+from .. import _lib
+from .decoder import build_decoder
+from .encoder import DeformableTransformerEncoderLayer, DeformableTransformerEncoder, encoder_to_decoder_memory
+
+
+def flatten_levels(srcs, pos_embeds, level_embed):
+    """dab_transformer.py:310-327: per level [B, 256, T, H, W] -> (src_flatten, lvl_pos_embed_flatten) [B, Len, 256], shapes
+    [L, 3], level_start [L] through cqvad_level_to_tokens."""
+    _lib.require_cuda(*srcs)
+    lib = _lib.lib()
+    dt, dev = srcs[0].dtype, srcs[0].device
+    B = srcs[0].shape[0]
+    shapes = [tuple(int(v) for v in s.shape[2:]) for s in srcs]
+    ns = [t * h * w for t, h, w in shapes]
+    Len = sum(ns)
+    src_flat = torch.empty((B, Len, 256), dtype=dt, device=dev)
+    pos_flat = torch.empty((B, Len, 256), dtype=dt, device=dev)
+    le = level_embed.detach().to(device=dev, dtype=torch.float32).contiguous()
+    p = _lib.ptr
+    start = 0
+    for l, (s, pe) in enumerate(zip(srcs, pos_embeds)):
+        if s.shape[1] != 256:
+            raise ValueError("d_model must be 256")
+        sc, pc = s.contiguous(), pe.to(dt).contiguous()
+        _lib.check(lib.cqvad_level_to_tokens(_lib.dtype_id(dt), p(sc), None, p(src_flat), B, ns[l], Len, start, _lib.stream_ptr()))
+        _lib.check(lib.cqvad_level_to_tokens(_lib.dtype_id(dt), p(pc), p(le[l]), p(pos_flat), B, ns[l], Len, start, _lib.stream_ptr()))
+        start += ns[l]
+    sh = torch.tensor(shapes, dtype=torch.int64, device=dev)
+    ls = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+    return src_flat, pos_flat, sh, ls
+
+
+class Transformer(nn.Module):
+    def __init__(self, d_model=256, nhead=8, num_queries=15, num_encoder_layers=6, num_decoder_layers=6, dim_feedforward=2048,
+                 dropout=0.1, num_feature_levels=4, enc_n_points=8, num_classes=80, temp_len=16):
+        super().__init__()
+        if d_model != 256 or nhead != 8:
+            raise ValueError("libcqvad Transformer: d_model 256, 8 heads (every shipped configuration)")
+        layer = DeformableTransformerEncoderLayer(d_model, dim_feedforward, dropout, "relu", num_feature_levels, nhead, enc_n_points)
+        self.encoder = DeformableTransformerEncoder(layer, num_encoder_layers)
+        self.decoder = build_decoder(num_queries=num_queries, num_classes=num_classes, num_layers=num_decoder_layers,
+                                     dim_feedforward=dim_feedforward, d_model=d_model, nhead=nhead, dropout=dropout, temp_len=temp_len)
+        self.level_embed = nn.Parameter(torch.randn(num_feature_levels, d_model))
+        self.temp_len = temp_len
+        self.num_feature_levels = num_feature_levels
+        self.d_model = d_model
+        self.eff = True          # models/model.py:52 (single-frame decoding)
+
+    @staticmethod
+    def get_valid_ratio(mask):
+        # dab_transformer.py:228-237
+        _, T, H, W = mask.shape
+        valid_T = torch.sum(~mask[:, :, 0, 0], 1)
+        valid_H = torch.sum(~mask[:, 0, :, 0], 1)
+        valid_W = torch.sum(~mask[:, 0, 0, :], 1)
+        return torch.stack([valid_W.float() / W, valid_H.float() / H, valid_T.float() / T], -1)
+
+    def forward(self, srcs, masks, pos_embeds, refpoint_embed=None):
+        assert refpoint_embed is not None
+        bs = srcs[0].shape[0]
+        src_flat, pos_flat, sh, ls = flatten_levels(srcs, pos_embeds, self.level_embed)
+        mask_flat = torch.cat([m.flatten(1) for m in masks], 1)
+        valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
+        memory = self.encoder(src_flat, sh, ls, valid_ratios, pos=pos_flat, padding_mask=mask_flat if bool(mask_flat.any()) else None)
+        L = self.num_feature_levels
+        Tt, H, W = (int(v) for v in sh[L - 2].tolist())
+        mem_l, pos0 = encoder_to_decoder_memory(memory, pos_flat, sh, ls, num_frames=self.temp_len, eff=self.eff)
+        # mask of level -2 repeated in time (:250-252), key-frame slice, "(B T) (H W)" (:393)
+        m = masks[L - 2].repeat(1, self.temp_len // masks[L - 2].size(1), 1, 1)
+        if self.eff:
+            t = m.size(1)
+            m = m[:, t // 2:t // 2 + 1]
+        mask = m.flatten(2).flatten(0, 1)
+        refp = refpoint_embed[:, None].expand(-1, bs, -1, -1).flatten(1, 2)          # :371
+        tgt = torch.zeros((refp.shape[0], mask.shape[0], self.d_model), device=src_flat.device, dtype=src_flat.dtype)
+        return self.decoder(tgt, mem_l, memory_key_padding_mask=mask, pos=pos0[None].expand(L, -1, -1, -1),
+                            refpoints_unsigmoid=refp, orig_res=(H, W))

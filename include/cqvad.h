@@ -111,6 +111,11 @@ int cqvad_deform_encoder_layer_backward(int dtype, const void* const* weights, c
                                         const int64_t* level_start, const uint8_t* padding_mask, const void* grad_out,
                                         void* grad_src, void* grad_pos, float* const* grad_weights, void* workspace,
                                         size_t workspace_bytes, int B, long Len, int L, int P, int F, void* stream);
+/* One pyramid level into the encoder's token sequence (Transformer.forward, models/detr/dab_transformer.py:310-327):
+ * tokens[b, level_start + n, c] = x[b, c, n] (+ add[c]) for x [B, 256, N = T*H*W] channel-first (dtype), add = level_embed[lvl]
+ * (fp32, for the position embedding; NULL for the features), tokens [B, Len, 256]. */
+int cqvad_level_to_tokens(int dtype, const void* x, const float* add, void* tokens, int B, long N, long Len, long level_start,
+                          void* stream);
 /* Encoder output -> decoder memory: the part of Transformer.forward between the two
  * (models/detr/dab_transformer.py:349-393): per-level un-flatten, make_interpolated_features (:239-294, grid_sample with
  * align_corners = False and zeros padding onto the (num_frames, H, W) grid of level -2, including the reference's (meshy, meshx)

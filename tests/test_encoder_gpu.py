@@ -216,3 +216,32 @@ def test_transformer_forward_composition_matches_reference():
     torch.cuda.synchronize()
     for name in ("hs", "cls_hs", "refs"):
         assert rel_err(out[name].float().cpu().numpy(), g[name]) < TOL_FP32, name
+
+
+def test_transformer_drop_in_module_matches_reference():
+    """class_query_vad_b200.Transformer (flatten + level_embed, encoder, inter-stage resample, decoder: all in libcqvad.so) loaded with
+    the reference-named state_dict (strict) against the unmodified reference Transformer.forward."""
+    from class_query_vad_b200 import Transformer
+    from oracle.make_golden_transformer import CFG as c, make_inputs
+    g = load_golden("transformer_tiny")
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    srcs, poss, level_embed, refpoint = make_inputs(c)
+    We = synth.make_encoder_layer_weights(c["F"], 4, c["P"], seed=c["seed"])
+    Wd = synth.make_decoder_weights(c["K"], c["layers"], c["F"], seed=c["seed"])
+    tr = Transformer(num_queries=c["nq"], num_encoder_layers=1, num_decoder_layers=c["layers"], dim_feedforward=c["F"],
+                     enc_n_points=c["P"], num_classes=c["K"], temp_len=c["T"])
+    sd = {"level_embed": torch.from_numpy(level_embed)}
+    sd.update({"encoder.layers.0." + k: torch.from_numpy(v) for k, v in We.items()})
+    sd.update({"decoder." + k: torch.from_numpy(v) for k, v in Wd.items() if not k.startswith("heads.")})
+    tr.load_state_dict(sd, strict=True)
+    tr = tr.to(dev).eval()
+    masks = [torch.zeros((c["B"],) + s, dtype=torch.bool, device=dev) for s in c["shapes"]]
+    # the decoder module computes in bf16 on the tensor cores by default (compute_dtype); fp32 is the 1e-3 parity mode
+    for cdt, tol in ((torch.float32, TOL_FP32), (torch.bfloat16, TOL_BF16)):
+        tr.decoder.compute_dtype = cdt
+        with torch.no_grad():
+            hs, cls_hs, refs = tr([t(s) for s in srcs], masks, [t(p) for p in poss], t(refpoint))
+        torch.cuda.synchronize()
+        for name, got in (("hs", hs), ("cls_hs", cls_hs), ("refs", refs)):
+            assert rel_err(got.float().cpu().numpy(), g[name]) < tol, (name, cdt)
