@@ -389,9 +389,60 @@ def main():
             "e2e": iclips / (ims_e2e / 1e3), "gpu_launches_per_step": int(in_launch),
             "decoder_tflops": iclips / (ims / 1e3) * FWD_GFLOP[CFG] / 1e3 / world,
             "breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in iprof.items()}}
+    if main_mode == "train" and world == 1 and CFG == "ava_vitb":
+        try:
+            line["encoder_layer"] = encoder_layer_numbers(dev)
+        except Exception as e:                      # the headline never depends on the extra measurement
+            line["encoder_layer"] = {"error": str(e)[:200]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def encoder_layer_numbers(dev, B=4, iters=5):
+    """SURVEY.md section 8f row 1, reported next to the headline: one deformable encoder layer (forward, and forward + backward) on
+    the ViT-B/224 pyramid (Len = 33 320 tokens per clip), bf16, inputs resident, CUDA events, median of `iters`."""
+    import numpy as np
+    import torch
+    from class_query_vad_b200 import DeformableTransformerEncoderLayer, DeformableTransformerEncoder
+    from oracle import synth
+    shapes = [(8, 56, 56), (8, 28, 28), (8, 14, 14), (8, 7, 7)]
+    F_, P = 2048, 8
+    W = synth.make_encoder_layer_weights(F_, 4, P, seed=5)
+    inp = synth.make_encoder_inputs(1, shapes, seed=5)
+    layer = DeformableTransformerEncoderLayer(d_model=256, d_ffn=F_, n_levels=4, n_heads=8, n_points=P)
+    layer.load_state_dict({k: torch.from_numpy(v) for k, v in W.items()}, strict=True)
+    layer = layer.to(dev).eval()
+    sh = torch.tensor(shapes, dtype=torch.int64, device=dev)
+    ls = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+    refp = DeformableTransformerEncoder.get_reference_points(sh, torch.ones((B, 4, 3), device=dev), dev)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev).bfloat16().repeat(B, 1, 1).contiguous()
+    src, pos = t(inp["src"]), t(inp["pos"])
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    tf, tt = [], []
+    for _ in range(iters + 1):
+        e0, e1 = ev(), ev()
+        e0.record()
+        with torch.no_grad():
+            layer(src, pos, refp, sh, ls, None)
+        e1.record()
+        torch.cuda.synchronize()
+        tf.append(e0.elapsed_time(e1))
+    srcg, posg = src.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+    go = torch.randn_like(src)
+    for _ in range(iters + 1):
+        for p_ in layer.parameters():
+            p_.grad = None
+        e0, e1 = ev(), ev()
+        e0.record()
+        layer(srcg, posg, refp, sh, ls, None).backward(go)
+        e1.record()
+        torch.cuda.synchronize()
+        tt.append(e0.elapsed_time(e1))
+    mf, mt = float(np.median(tf[1:])), float(np.median(tt[1:]))
+    return {"workload": f"one DeformableTransformerEncoderLayer, ViT-B/224 pyramid (33 320 tokens/clip), F 2048, 8 points, bf16, {B} clips",
+            "forward_ms": round(mf, 3), "forward_clips_per_s": round(B / mf * 1e3, 1),
+            "train_step_ms": round(mt, 3), "train_step_clips_per_s": round(B / mt * 1e3, 1), "gemm_gflop_per_clip_forward": 96.1}
 
 
 if __name__ == "__main__":
