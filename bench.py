@@ -8,7 +8,8 @@ TransformerDecoder.forward (cqvad_decoder_train_forward) + its backward (cqvad_d
 parameter, memory, tgt and refpoints_unsigmoid) over one batch of synthetic clips (AVA22_ViT-B shapes: nq 15, S 14x14, K 80,
 6 layers, F 2048), bf16 tensor-core path, loss = sum(w_hs*hs) + sum(w_cls*cls_hs) + sum(w_refs*refs) (SURVEY.md section 8d
 Config 2; dropout = identity).  --mode infer times the inference forward + DETR heads (cqvad_decoder_forward); the default
-run reports it under "inference_forward".
+run reports it under "inference_forward"; at N=1 the line also carries "encoder_layer" (one
+deformable encoder layer, forward and forward + backward, on the ViT-B/224 pyramid).
   value : whole-job clips/s with inputs already resident in HBM (CUDA events, max over ranks)
   e2e   : same metric through the public API (DecoderEngine.forward_train/backward) with pinned-HOST inputs: H2D copy of the
           step's inputs and D2H read of the step's result (refs + last-layer hs) inside the timed region
