@@ -1,10 +1,13 @@
 // tcgen05 GEMM for sm_100a:  C[M,N] = epilogue( A[M,K] . W[N,K]^T ),  bf16 operands, fp32 accumulation in TMEM.
 //
-//   * persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator), warps 2-5 =
-//     epilogue (one TMEM lane quarter each).  Three pipelines: smem ring (TMA <-> MMA, 4 stages of
-//     128x64 A + 256x64 B, 128-byte swizzle), TMEM accumulator double buffer (MMA <-> epilogue, 2 x 256 columns),
-//     and the static tile scheduler.
-//   * UMMA shape 128 x 256 x 16 (cta_group::1): 128 cycles per instruction = the tensor-pipe floor.
+//   * persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator), warps 2-9 =
+//     epilogue (two per TMEM lane quarter, 128 columns each).  Three pipelines: smem ring (TMA <-> MMA, 128-byte swizzle),
+//     TMEM accumulator double buffer (MMA <-> epilogue, 2 x 256 columns), and the static tile scheduler.
+//   * two launch forms of the same body: single CTA (UMMA 128 x 256 x 16, cta_group::1; ring of 4 x (128x64 A + 256x64 B),
+//     TS: 3) for the small-row GEMMs, and CTA PAIRS (gemm_tc2_kernel: cluster of 2 on one TPC, UMMA 256 x 256 x 16,
+//     cta_group::2) whenever there are >= 148 m-tiles: each CTA loads its own A tile and HALF of the weight tile, the leader
+//     issues the MMAs for both, commits are multicast to both CTAs' barriers, both CTAs' TMA bytes complete on the leader's
+//     full barrier; ring of 6 x 32 KB (TS: 4, or 5 with single-buffered output staging for K >= 512).
 //   * the A operand is either a 2-D row-major matrix or, for the 3x3 convolution of ConvBlock
 //     (models/detr/dab_transformer.py:81,90), a 3-D view [256 ch, w, N*(h+1) rows] of the y-padded NHWC activation:
 //     every k-block of a filter tap is ONE TMA box (64 ch x w x RT rows) shifted by (dx,dy); the horizontal halo is
@@ -12,12 +15,14 @@
 //   * epilogue straight out of TMEM (tcgen05.ld 32x32b: one thread = one output row): bias, ReLU / erf-GELU, residual,
 //     zero-row masking, and row LayerNorm when N == 256 (pre-norm values stashed back into TMEM with tcgen05.st so
 //     the residual is read once).
-//   * TS variant (every non-conv GEMM with a bf16-only epilogue): 3-stage ring + a 64 KB output staging area.  The epilogue
+//   * TS variant (every non-conv GEMM with a bf16-only epilogue): a 64 KB output staging area next to the ring.  The epilogue
 //     warps write bf16 rows into 128-byte-swizzled shared memory (conflict-free 16-byte stores) and ONE lane per warp issues
 //     a TMA store of a [32 rows x 64 cols] box; the bf16 residual (or the activation-derivative operand) arrives the same way
 //     through a TMA load into the staging buffer.  Evidence (ncu, profiles/): with one thread per output row every global
 //     store / residual load instruction touched 32 different 128-byte lines -- the LSU data pipe was the top unit at 55%,
 //     L1->L2 write traffic was 2x the output (half-filled sectors) and the K = 256 GEMMs ran at 2.1 TB/s of 6.5.
+//     Lean (branch-free) and dual-GELU forms of that epilogue: ts_lean_half / ts_dual_gelu_half below.
+//   * every mbarrier wait carries a watchdog (tc_common.cuh::mbar_wait_slow): a stuck pipeline traps instead of hanging.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <mutex>
