@@ -225,7 +225,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     sdp += xch[512 + (sh ^ 1) * 128 + row];
     asm volatile("bar.sync 1, 256;" ::: "memory");   // every partial has been read: the dS tile may be written
     AB_TRACE(6, 32);
-    const float inv = vrow ? 1.0f / sum : 0.f;
+    const float inv = 1.0f / sum;
     const float D = sdp * inv;
     for (int c = ch0 * 16; c < ch1 * 16; c += 16) {
       uint32_t r[16], d[16];
@@ -235,9 +235,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float pv[16], dsv[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        const float x = __uint_as_float(r[e]) * inv;          // 0 for keys >= S (exp parked as 0) and class rows >= K (inv = 0)
+        const float x = vrow ? __uint_as_float(r[e]) * inv : 0.f;   // 0 for keys >= S (exp parked as 0) and class rows >= K
         pv[e] = x;
-        dsv[e] = p.scale * x * (__uint_as_float(d[e]) - D);
+        dsv[e] = vrow ? p.scale * x * (__uint_as_float(d[e]) - D) : 0.f;
       }
 #pragma unroll
       for (int g8 = 0; g8 < 2; ++g8) {
