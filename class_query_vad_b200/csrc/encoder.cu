@@ -367,25 +367,95 @@ __global__ void __launch_bounds__(256) interp_to_decoder_kernel(const T* __restr
 // rows [B, level_start + n, 256] of the concatenated sequence, through a 32 x 33 shared-memory tile (coalesced on both sides).
 template <typename T>
 __global__ void __launch_bounds__(256) level_to_tokens_kernel(const T* __restrict__ x, const float* __restrict__ add, T* __restrict__ out,
-                                                              long N, long Len, long level_start) {
+                                                              long N, long Len, long level_start, int C = kC) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const long n0 = (long)blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-  const T* xb = x + (long)b * kC * N;
+  const T* xb = x + (long)b * C * N;
 #pragma unroll
   for (int r = ty; r < 32; r += 8) {                          // rows = channels, columns = positions (contiguous in x)
     const long n = n0 + tx;
     tile[r][tx] = n < N ? to_f(xb[(long)(c0 + r) * N + n]) : 0.f;
   }
   __syncthreads();
-  T* ob = out + ((long)b * Len + level_start) * kC;
+  T* ob = out + ((long)b * Len + level_start) * C;
 #pragma unroll
   for (int r = ty; r < 32; r += 8) {                          // rows = positions, columns = channels (contiguous in out)
     const long n = n0 + r;
-    if (n < N) ob[n * kC + c0 + tx] = from_f<T>(tile[tx][r] + (add ? add[c0 + tx] : 0.f));
+    if (n < N) ob[n * C + c0 + tx] = from_f<T>(tile[tx][r] + (add ? add[c0 + tx] : 0.f));
   }
+}
+
+// ---- input projection of a backbone level (CSN configurations) ----------------------------------
+// models/model.py:64-71,162-164: input_proj[l] = Conv3d(C_in, 256, kernel_size = 1) -> GroupNorm(32, 256).  The 1x1x1 conv is a
+// GEMM over the level's positions; GroupNorm(32 groups of 8 channels) normalises over (8 channels x T*H*W) per clip: in the
+// token-major layout a lane's 8 channels ARE one group, so the statistics are per-lane sums over rows (no cross-lane traffic
+// until the block reduction) and the normalised rows land directly in the encoder's token sequence (conv + norm + flatten).
+template <typename T>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ y, float* __restrict__ stats, long N, int rows_per_block) {
+  __shared__ float red[8][32][2];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long r0 = (long)blockIdx.x * rows_per_block, r1 = min(N, r0 + rows_per_block);
+  float s = 0.f, q = 0.f;
+  for (long r = r0 + warp; r < r1; r += 8) {
+    float v[8];
+    load8(y + ((long)b * N + r) * kC + lane * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s += v[e]; q = fmaf(v[e], v[e], q); }
+  }
+  red[warp][lane][0] = s; red[warp][lane][1] = q;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x >> 1, k = threadIdx.x & 1;
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += red[w][g][k];
+    atomicAdd(stats + ((long)b * 32 + g) * 2 + k, a);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ y, const float* __restrict__ stats,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                       T* __restrict__ tokens, long N, long Len, long level_start, int B) {
+  const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= (long)B * N) return;
+  const int b = (int)(wid / N);
+  const long n = wid % N;
+  const float cnt = (float)N * 8.f;
+  const float mean = stats[((long)b * 32 + lane) * 2] / cnt;
+  const float var = fmaxf(stats[((long)b * 32 + lane) * 2 + 1] / cnt - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  float v[8], g[8], bt[8];
+  load8(y + wid * kC + lane * 8, v);
+  load8(gamma + lane * 8, g);
+  load8(beta + lane * 8, bt);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = (v[e] - mean) * rstd * g[e] + bt[e];
+  store8(tokens + ((long)b * Len + level_start + n) * kC + lane * 8, v);
+}
+
+template <typename T>
+int input_proj_t(const T* x, const T* W, const float* bias, const float* gamma, const float* beta, float eps, T* tokens, void* ws,
+                 size_t ws_bytes, int B, int Cin, long N, long Len, long level_start, cudaStream_t st) {
+  const long rows = (long)B * N;
+  EncWs w(ws, ws_bytes);
+  T* xt = (T*)w.take((size_t)rows * Cin * sizeof(T));
+  T* y = (T*)w.take((size_t)rows * kC * sizeof(T));
+  float* stats = (float*)w.take((size_t)B * 64 * 4);
+  if (!xt || !y || !stats) return set_error(CQVAD_E_WORKSPACE, "input_proj: workspace too small");
+  const dim3 tg((unsigned)cdiv(N, 32), (unsigned)(Cin / 32), (unsigned)B);
+  level_to_tokens_kernel<T><<<tg, 256, 0, st>>>(x, nullptr, xt, N, N, 0, Cin);      // [B, Cin, N] -> [B*N, Cin]
+  CQ_LAUNCH_CHECK();
+  { Epilogue e; e.bias = bias; CQ_TRY(gemm<T>(xt, Cin, W, y, kC, rows, kC, Cin, e, nullptr, st)); }
+  CQ_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * 64 * 4, st));
+  const int rpb = 256;
+  gn_stats_kernel<T><<<dim3((unsigned)cdiv(N, rpb), (unsigned)B), 256, 0, st>>>(y, stats, N, rpb);
+  CQ_LAUNCH_CHECK();
+  gn_apply_kernel<T><<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(y, stats, gamma, beta, eps, tokens, N, Len, level_start, B);
+  CQ_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace
@@ -506,4 +576,25 @@ extern "C" int cqvad_level_to_tokens(int dtype, const void* x, const float* add,
     return set_error(CQVAD_E_INVALID_ARG, "level_to_tokens: unknown dtype %d", dtype);
   CQ_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" size_t cqvad_input_proj_workspace_bytes(int dtype, int B, int Cin, long N) {
+  const size_t es = dtype == CQVAD_F32 ? 4 : 2;
+  return (size_t)B * N * Cin * es + (size_t)B * N * kC * es + (size_t)B * 64 * 4 + 4 * 256 + 256;
+}
+
+extern "C" int cqvad_input_proj_1x1_gn(int dtype, const void* x, const void* weight, const float* bias, const float* gn_weight,
+                                       const float* gn_bias, float eps, void* tokens, void* workspace, size_t workspace_bytes,
+                                       int B, int Cin, long N, long Len, long level_start, void* stream) {
+  CQ_CHECK_ARG(B >= 0 && Cin >= 32 && N >= 0 && Len >= N && level_start >= 0 && level_start + N <= Len, "input_proj: bad dimensions");
+  if ((long)B * N == 0) return 0;
+  CQ_CHECK_ARG(x && weight && gn_weight && gn_bias && tokens && workspace, "input_proj: null pointer");
+  CQ_CHECK_SHAPE(Cin % 32 == 0 && B <= 65535, "input_proj: C_in must be a multiple of 32 (got %d), batch <= 65535", Cin);
+  if (dtype == CQVAD_F32)
+    return input_proj_t<float>((const float*)x, (const float*)weight, bias, gn_weight, gn_bias, eps, (float*)tokens, workspace,
+                               workspace_bytes, B, Cin, N, Len, level_start, as_stream(stream));
+  if (dtype == CQVAD_BF16)
+    return input_proj_t<bf16>((const bf16*)x, (const bf16*)weight, bias, gn_weight, gn_bias, eps, (bf16*)tokens, workspace,
+                              workspace_bytes, B, Cin, N, Len, level_start, as_stream(stream));
+  return set_error(CQVAD_E_INVALID_ARG, "input_proj: unknown dtype %d", dtype);
 }

@@ -84,3 +84,36 @@ class Transformer(nn.Module):
         tgt = torch.zeros((refp.shape[0], mask.shape[0], self.d_model), device=src_flat.device, dtype=src_flat.dtype)
         return self.decoder(tgt, mem_l, memory_key_padding_mask=mask, pos=pos0[None].expand(L, -1, -1, -1),
                             refpoints_unsigmoid=refp, orig_res=(H, W))
+
+
+def input_proj_levels(feats, convs, norms):
+    """models/model.py:162-164 for the backbone levels of the CSN configurations: per level Conv3d(C_in, 256, 1) + GroupNorm(32, 256)
+    written straight into the encoder's token sequence through cqvad_input_proj_1x1_gn.  feats: list of [B, C_in, T, H, W];
+    convs / norms: the nn.Conv3d / nn.GroupNorm modules of input_proj[l].  Returns (src_flatten [B, Len, 256], shapes, level_start)."""
+    _lib.require_cuda(*feats)
+    lib = _lib.lib()
+    dt, dev = feats[0].dtype, feats[0].device
+    B = feats[0].shape[0]
+    shapes = [tuple(int(v) for v in f.shape[2:]) for f in feats]
+    ns = [t * h * w for t, h, w in shapes]
+    Len = sum(ns)
+    tokens = torch.empty((B, Len, 256), dtype=dt, device=dev)
+    p = _lib.ptr
+    start = 0
+    for l, (f, conv, gn) in enumerate(zip(feats, convs, norms)):
+        Cin = f.shape[1]
+        if tuple(conv.kernel_size) != (1, 1, 1) or gn.num_groups != 32 or conv.out_channels != 256:
+            raise ValueError("input_proj_levels covers Conv3d(kernel_size=1) -> GroupNorm(32, 256)")
+        w = conv.weight.detach().reshape(256, Cin).to(device=dev, dtype=dt).contiguous()
+        b = None if conv.bias is None else conv.bias.detach().to(device=dev, dtype=torch.float32).contiguous()
+        g = gn.weight.detach().to(device=dev, dtype=torch.float32).contiguous()
+        be = gn.bias.detach().to(device=dev, dtype=torch.float32).contiguous()
+        need = lib.cqvad_input_proj_workspace_bytes(_lib.dtype_id(dt), B, Cin, ns[l])
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        fc = f.contiguous()
+        _lib.check(lib.cqvad_input_proj_1x1_gn(_lib.dtype_id(dt), p(fc), p(w), p(b), p(g), p(be), float(gn.eps), p(tokens), p(ws), need,
+                                               B, Cin, ns[l], Len, start, _lib.stream_ptr()))
+        start += ns[l]
+    sh = torch.tensor(shapes, dtype=torch.int64, device=dev)
+    ls = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+    return tokens, sh, ls

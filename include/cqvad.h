@@ -111,6 +111,16 @@ int cqvad_deform_encoder_layer_backward(int dtype, const void* const* weights, c
                                         const int64_t* level_start, const uint8_t* padding_mask, const void* grad_out,
                                         void* grad_src, void* grad_pos, float* const* grad_weights, void* workspace,
                                         size_t workspace_bytes, int B, long Len, int L, int P, int F, void* stream);
+/* Input projection of one backbone level (CSN configurations, models/model.py:64-71,162-164):
+ * tokens[b, level_start + n, :] = GroupNorm(32, 256)( Conv3d(C_in, 256, kernel_size = 1)(x) )[b, :, n] for x [B, C_in, N = T*H*W]
+ * channel-first (dtype): transpose to token-major, tcgen05 GEMM with W [256, C_in] (dtype) + bias, per-clip group statistics
+ * over (8 channels x N), normalise + affine (gn_weight / gn_bias fp32 [256]) straight into the encoder's token sequence
+ * [B, Len, 256] (conv + norm + flatten in one call).  C_in % 32 == 0 (bf16 tensor-core path: % 64).  The extra stride-2 level
+ * (Conv3d kernel 3, models/model.py:72-76) is not covered. */
+size_t cqvad_input_proj_workspace_bytes(int dtype, int B, int Cin, long N);
+int cqvad_input_proj_1x1_gn(int dtype, const void* x, const void* weight, const float* bias, const float* gn_weight,
+                            const float* gn_bias, float eps, void* tokens, void* workspace, size_t workspace_bytes, int B, int Cin,
+                            long N, long Len, long level_start, void* stream);
 /* One pyramid level into the encoder's token sequence (Transformer.forward, models/detr/dab_transformer.py:310-327):
  * tokens[b, level_start + n, c] = x[b, c, n] (+ add[c]) for x [B, 256, N = T*H*W] channel-first (dtype), add = level_embed[lvl]
  * (fp32, for the position embedding; NULL for the features), tokens [B, Len, 256]. */

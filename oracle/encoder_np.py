@@ -60,3 +60,17 @@ def encoder_layer(W, src, pos, refp, shapes, level_start, mask=None):
     h = np.maximum(x @ W["linear1.weight"].T + W["linear1.bias"], 0.0)                              # :508
     x = _ln(x + h @ W["linear2.weight"].T + W["linear2.bias"], W["norm2.weight"], W["norm2.bias"])  # :509-510
     return x.astype(np.float32), src2.astype(np.float32)
+
+
+def input_proj_1x1_gn(x, w, b, gamma, beta, eps=1e-5, groups=32):
+    """models/model.py:64-71,162-164: Conv3d(C_in, 256, kernel_size=1) -> GroupNorm(32, 256) on x [B, C_in, T, H, W]; returned
+    token-major [B, T*H*W, 256] (= .flatten(2).transpose(1, 2) of the reference's output, dab_transformer.py:317)."""
+    B, Cin = x.shape[:2]
+    xt = x.reshape(B, Cin, -1).transpose(0, 2, 1).astype(np.float64)              # [B, N, Cin]
+    y = xt @ w.reshape(w.shape[0], Cin).T.astype(np.float64) + b                      # [B, N, 256]
+    C = y.shape[-1]
+    yg = y.reshape(B, -1, groups, C // groups)
+    mu = yg.mean(axis=(1, 3), keepdims=True)
+    var = yg.var(axis=(1, 3), keepdims=True)
+    out = ((yg - mu) / np.sqrt(var + eps)).reshape(B, -1, C) * gamma + beta
+    return out.astype(np.float32)

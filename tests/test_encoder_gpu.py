@@ -245,3 +245,24 @@ def test_transformer_drop_in_module_matches_reference():
         torch.cuda.synchronize()
         for name, got in (("hs", hs), ("cls_hs", cls_hs), ("refs", refs)):
             assert rel_err(got.float().cpu().numpy(), g[name]) < tol, (name, cdt)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, TOL_FP32), (torch.bfloat16, TOL_BF16)])
+def test_input_proj_1x1_gn_matches_reference_modules(tag, dtype, tol):
+    """cqvad_input_proj_1x1_gn (transpose + GEMM + GroupNorm + flatten) against the reference's input_proj modules."""
+    from torch import nn
+    from class_query_vad_b200 import input_proj_levels
+    from oracle.make_golden_inputproj import CASES, make_case
+    g = load_golden("inputproj")
+    kw = CASES[tag]
+    x, w, b, gm, be = make_case(kw)
+    dev = torch.device("cuda:0")
+    conv, gn = nn.Conv3d(kw["Cin"], 256, kernel_size=1), nn.GroupNorm(32, 256)
+    with torch.no_grad():
+        conv.weight.copy_(torch.from_numpy(w)); conv.bias.copy_(torch.from_numpy(b))
+        gn.weight.copy_(torch.from_numpy(gm)); gn.bias.copy_(torch.from_numpy(be))
+    tokens, sh, ls = input_proj_levels([torch.from_numpy(x).to(dev).to(dtype)], [conv], [gn])
+    torch.cuda.synchronize()
+    assert sh.tolist() == [list(kw["shape"])] and ls.tolist() == [0]
+    assert rel_err(tokens.float().cpu().numpy(), g[tag + "_tokens"]) < tol

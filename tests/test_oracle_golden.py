@@ -157,3 +157,14 @@ def test_interp_oracle_matches_reference(name):
     assert np.abs(mem - g["memory"]).max() <= 2e-5 * np.abs(g["memory"]).max()
     pos0 = interp_np.pos_to_decoder(pos_tokens, shapes, g["level_start"], nf, eff)
     assert np.array_equal(pos0, g["pos0"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_input_proj_oracle_matches_torch_modules(tag):
+    """oracle/encoder_np.input_proj_1x1_gn against nn.Conv3d(k=1) + nn.GroupNorm(32) as models/model.py:64-71 builds them."""
+    from oracle import encoder_np
+    from oracle.make_golden_inputproj import CASES, make_case
+    g = load_golden("inputproj")
+    x, w, b, gm, be = make_case(CASES[tag])
+    got = encoder_np.input_proj_1x1_gn(x, w, b, gm, be)
+    assert np.abs(got - g[tag + "_tokens"]).max() <= 2e-5 * np.abs(g[tag + "_tokens"]).max()
