@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 #include "common.cuh"
+#include <stdlib.h>
 #include "kernels_mem.cuh"
 #include "attention.cuh"
 #include "prof.cuh"
@@ -121,7 +122,11 @@ int Decoder<bf16>::mlp(const bf16* X, long M, int Fh, int w1, int w2, int act, c
   if (y32) y32_valid = false;
   // the fused kernel walks the hidden dimension serially per 128-row tile: with few row tiles (small-row FFNs, M = nq*BT)
   // two plain GEMMs spread the F dimension over more SMs
-  if (!force_simt() && M > 2048) {
+  // CQVAD_INFER_UNFUSED_MLP=1 (experiment, measured SLOWER: 2 829 vs 2 898 clips/s inference at B = 32): the ConvBlock MLP as two
+  // CTA-pair GEMMs (GELU in the lean TMA-store epilogue) instead of the fused kernel that keeps the hidden activation on the SM
+  static const bool unfused_big = getenv("CQVAD_INFER_UNFUSED_MLP") != nullptr;
+  const bool skip_fused = unfused_big && act == CQVAD_ACT_GELU && !emit_qt && !y32 && M >= 148 * 128;
+  if (!force_simt() && M > 2048 && !skip_fused) {
     int r = mlp_tc(X, Wm(w1), Wf(w1 + 1), Wm(w2), Wf(w2 + 1), act, res, ln_idx >= 0 ? Wf(ln_idx) : nullptr,
                    ln_idx >= 0 ? Wf(ln_idx + 1) : nullptr, eps, Y, M, kC, Fh, zero_period, zero_valid, st,
                    emit_qt ? qt : nullptr, ldqt, K, K8, res32, y32);

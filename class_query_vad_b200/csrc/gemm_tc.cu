@@ -91,7 +91,7 @@ __device__ __forceinline__ float gelu_grad(float x) {
 // stage that paces the K = 256 GEMMs (MMA 1.1 us, loads hidden).
 // SIDE: 0 none, 1 += side (residual), 2 ReLU mask (side > 0), 3 *= side (stored activation derivative)
 template <int SIDE>
-__device__ __forceinline__ void ts_lean_half(uint32_t t_addr, const float* bias, uint32_t row_base, int sw, float lo) {
+__device__ __forceinline__ void ts_lean_half(uint32_t t_addr, const float* bias, uint32_t row_base, int sw, float lo, bool gelu) {
 #pragma unroll
   for (int cc = 0; cc < 64; cc += 32) {
     uint32_t r[32];
@@ -106,6 +106,10 @@ __device__ __forceinline__ void ts_lean_half(uint32_t t_addr, const float* bias,
       x[1] = f2add(f2pack(__uint_as_float(r[g8 * 8 + 2]), __uint_as_float(r[g8 * 8 + 3])), f2pack(b0.z, b0.w));
       x[2] = f2add(f2pack(__uint_as_float(r[g8 * 8 + 4]), __uint_as_float(r[g8 * 8 + 5])), f2pack(b1.x, b1.y));
       x[3] = f2add(f2pack(__uint_as_float(r[g8 * 8 + 6]), __uint_as_float(r[g8 * 8 + 7])), f2pack(b1.z, b1.w));
+      if (gelu) {   // erf-form GELU on the packed polynomial (warp-uniform branch)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = gelu2(x[j]);
+      }
       uint4 sv;
       if constexpr (SIDE != 0) sv = lds128(saddr);
       uint4 o;
@@ -392,10 +396,11 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
               ts_dual_gelu_half(t_addr + hf * 64, bcur + c0 + hf * 64, my_row, my_row + STG_BOX_BYTES, sw);
             } else if (p.lean) {
               const float lo = p.act == CQVAD_ACT_RELU ? 0.f : -INFINITY;
-              if (p.side == 0) ts_lean_half<0>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo);
-              else if (p.side == 1) ts_lean_half<1>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo);
-              else if (p.mul_mode == 1) ts_lean_half<2>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo);
-              else ts_lean_half<3>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo);
+              const bool ge = p.act == CQVAD_ACT_GELU;
+              if (p.side == 0) ts_lean_half<0>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge);
+              else if (p.side == 1) ts_lean_half<1>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge);
+              else if (p.mul_mode == 1) ts_lean_half<2>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge);
+              else ts_lean_half<3>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge);
             } else {
 #pragma unroll 1
             for (int cc = 0; cc < 64; cc += 32) {
@@ -811,7 +816,7 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
       p.dual = 1;
     }
   }
-  p.lean = ts && !epi.ln_g && epi.zero_period == 0 && epi.mul_mode != 2 && (epi.act == CQVAD_ACT_NONE || epi.act == CQVAD_ACT_RELU) &&
+  p.lean = ts && !epi.ln_g && epi.zero_period == 0 && epi.mul_mode != 2 &&
            getenv("CQVAD_GEMM_NO_LEAN") == nullptr;
   p.stg_single = ts && pair && !p.side && !dual && K >= 8 * BLOCK_K && getenv("CQVAD_GEMM_NO_STG1") == nullptr;   // load-bound shapes only: measured +7..10% at K >= 512, -12% at K = 256 (epilogue-bound)
   const size_t smem = ts ? SMEM_BYTES_TS : SMEM_BYTES;
