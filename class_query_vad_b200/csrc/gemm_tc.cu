@@ -816,9 +816,9 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
       p.dual = 1;
     }
   }
-  p.lean = ts && !epi.ln_g && epi.zero_period == 0 && epi.mul_mode != 2 &&
-           getenv("CQVAD_GEMM_NO_LEAN") == nullptr;
-  p.stg_single = ts && pair && !p.side && !dual && K >= 8 * BLOCK_K && getenv("CQVAD_GEMM_NO_STG1") == nullptr;   // load-bound shapes only: measured +7..10% at K >= 512, -12% at K = 256 (epilogue-bound)
+  static const bool no_lean = getenv("CQVAD_GEMM_NO_LEAN") != nullptr, no_stg1 = getenv("CQVAD_GEMM_NO_STG1") != nullptr;
+  p.lean = ts && !epi.ln_g && epi.zero_period == 0 && epi.mul_mode != 2 && !no_lean;
+  p.stg_single = ts && pair && !p.side && !dual && K >= 8 * BLOCK_K && !no_stg1;   // load-bound shapes only: measured +7..10% at K >= 512, -12% at K = 256 (epilogue-bound)
   const size_t smem = ts ? SMEM_BYTES_TS : SMEM_BYTES;
 #define CQ_LAUNCH_TC(KERN)                                                                            \
   do {                                                                                                \
