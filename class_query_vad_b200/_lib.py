@@ -39,6 +39,7 @@ SYMBOLS = {
     "cqvad_input_proj_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_long]),
     "cqvad_input_proj_1x1_gn": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t,
                                          c_int, c_int, c_long, c_long, c_long, c_void_p]),
+    "cqvad_msda3d_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_void_p]),
     "cqvad_level_to_tokens": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_long, c_long, c_long, c_void_p]),
     "cqvad_encoder_to_decoder_memory": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_long, c_int, c_int, c_int,
                                                  c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -598,3 +598,14 @@ extern "C" int cqvad_input_proj_1x1_gn(int dtype, const void* x, const void* wei
                               workspace_bytes, B, Cin, N, Len, level_start, as_stream(stream));
   return set_error(CQVAD_E_INVALID_ARG, "input_proj: unknown dtype %d", dtype);
 }
+
+extern "C" int cqvad_msda3d_prepare(const float* offsets, const float* logits, const float* reference_points, const int64_t* shapes,
+                                    float* loc, float* attn, long rows, int L, int P, void* stream) {
+  CQ_CHECK_ARG(rows >= 0 && L >= 1 && P >= 1, "msda3d_prepare: bad dimensions");
+  if (rows == 0) return 0;
+  CQ_CHECK_ARG(offsets && logits && reference_points && shapes && loc && attn, "msda3d_prepare: null pointer");
+  msda_prepare_kernel<<<(unsigned)cdiv(rows * kM * 32, 256), 256, 0, as_stream(stream)>>>(offsets, logits, reference_points, shapes, loc,
+                                                                                         attn, rows, L, P);
+  CQ_LAUNCH_CHECK();
+  return 0;
+}

@@ -9,7 +9,7 @@ from torch import nn
 from torch.nn.init import xavier_uniform_, constant_
 
 from ..functions.ms_deform_attn_func import MSDeformAttnFunction
-from .ops import linear, softmax_lastdim
+from .ops import linear
 
 
 def _is_power_of_2(n):
@@ -61,22 +61,27 @@ class MSDeformAttn3D(nn.Module):
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
-        offs = linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias) \
-            .view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 3)
-        attw = linear(query, self.attention_weights.weight, self.attention_weights.bias) \
-            .view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
-        attw = softmax_lastdim(attw).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
-        if reference_points.shape[-1] == 3:
-            # normaliser stacked as (T_l, W_l, H_l) against (x,y,t) offsets: reference quirk kept (ms_deform_attn.py:192)
-            offset_normalizer = torch.stack([input_spatial_shapes[..., 0], input_spatial_shapes[..., 2],
-                                             input_spatial_shapes[..., 1]], -1)
-            sampling_locations = reference_points[:, :, None, :, None, :] \
-                + offs / offset_normalizer[None, None, None, :, None, :]
-        elif reference_points.shape[-1] == 6:
-            sampling_locations = reference_points[:, :, None, :, None, :3] \
-                + offs / self.n_points * reference_points[:, :, None, :, None, 3:] * 0.5
-        else:
+        if reference_points.shape[-1] != 3:
+            # the 6-vector (reference box) form of ops/modules/ms_deform_attn.py:193-195 is only reached by the two-stage
+            # variant, which no shipped configuration enables
             raise ValueError('Last dim of reference_points must be 3, but get {} instead.'.format(reference_points.shape[-1]))
+        if self.n_heads != 8:
+            raise ValueError("libcqvad MSDeformAttn3D: 8 heads (every shipped configuration)")
+        offs = linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias)
+        attw = linear(query, self.attention_weights.weight, self.attention_weights.bias)
+        # softmax over the L*P logits + sampling locations (reference quirk kept: normaliser stacked as (T_l, W_l, H_l) against
+        # (x, y, t) offsets, ms_deform_attn.py:190) in one kernel: cqvad_msda3d_prepare
+        from .. import _lib
+        rows = N * Len_q
+        off32, lg32 = offs.float().contiguous(), attw.float().contiguous()
+        ref32 = reference_points.float().contiguous()
+        sampling_locations = torch.empty((N, Len_q, self.n_heads, self.n_levels, self.n_points, 3), dtype=torch.float32,
+                                         device=query.device)
+        attw = torch.empty((N, Len_q, self.n_heads, self.n_levels, self.n_points), dtype=torch.float32, device=query.device)
+        p = _lib.ptr
+        _lib.check(_lib.lib().cqvad_msda3d_prepare(p(off32), p(lg32), p(ref32), p(input_spatial_shapes.to(torch.int64).contiguous()),
+                                                  p(sampling_locations), p(attw), rows, self.n_levels, self.n_points,
+                                                  _lib.stream_ptr()))
         output = MSDeformAttnFunction.apply(value.contiguous(), input_spatial_shapes, input_level_start_index,
                                             sampling_locations.contiguous(), attw.contiguous(), self.im2col_step)
         return linear(output, self.output_proj.weight, self.output_proj.bias)

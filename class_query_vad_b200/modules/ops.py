@@ -61,11 +61,6 @@ def ffn(x, w1, b1, w2, b2, act=_lib.ACT_RELU, res=None, ln_weight=None, ln_bias=
     return out.view(x.shape)
 
 
-def softmax_lastdim(x):
-    # glue for the encoder-side module (attention weights over L*P = 32 points); the decoder path never uses it
-    return torch.softmax(x, -1)
-
-
 def mha_core(q, k, v, num_heads, key_padding_mask=None, query_specific_key=False):
     """Attention core (attention.py:336-414) through cqvad_mha_core.  Returns [L, Nb, Ev] before out_proj."""
     _lib.require_cuda(q, k, v)

@@ -79,6 +79,12 @@ int cqvad_linear_gelu_train(int dtype, const void* A, const void* W, const float
  * stored derivative) or masked by aux > 0 (mode 1: aux is the ReLU output).  Wt is the transposed weight [in, out]. */
 int cqvad_linear_dgrad_act(int dtype, const void* dY, const void* Wt, const void* aux, int mode, void* dX, long M, int N,
                            int K, void* stream);
+/* attention_weights = softmax over the L*P logits of a head; sampling_locations = reference_points + offsets / (T_l, W_l, H_l)
+ * (ops/modules/ms_deform_attn.py:187-192, the reference's normaliser order against (x, y, t) offsets), 8 heads:
+ * offsets [rows, 8, L, P, 3], logits [rows, 8, L*P], reference_points [rows, L, 3] (all fp32), shapes [L,3] int64 on the device
+ * -> loc [rows, 8, L, P, 3], attn [rows, 8, L, P] (fp32), the inputs of cqvad_msda3d_forward.  rows = N * Len_q. */
+int cqvad_msda3d_prepare(const float* offsets, const float* logits, const float* reference_points, const int64_t* shapes,
+                         float* loc, float* attn, long rows, int L, int P, void* stream);
 /* One deformable encoder layer around the MSDA-3D op:
  * DeformableTransformerEncoderLayer.forward (models/detr/dab_transformer.py:513-523) with MSDeformAttn3D.forward
  * (ops/modules/ms_deform_attn.py:167-203) inlined, eval semantics (dropout = identity), 8 heads, d_model 256.

@@ -266,3 +266,22 @@ def test_input_proj_1x1_gn_matches_reference_modules(tag, dtype, tol):
     torch.cuda.synchronize()
     assert sh.tolist() == [list(kw["shape"])] and ls.tolist() == [0]
     assert rel_err(tokens.float().cpu().numpy(), g[tag + "_tokens"]) < tol
+
+
+@pytest.mark.parametrize("name", ["enc_tiny", "enc_small_masked"])
+def test_msdeformattn3d_module_matches_reference(name):
+    """The stand-alone drop-in module (four cqvad_linear calls + cqvad_msda3d_prepare + MSDeformAttnFunction) against the reference
+    module's output kept in the encoder fixtures (`attn_out`)."""
+    from class_query_vad_b200 import MSDeformAttn3D
+    g = load_golden(name)
+    W, inp, shapes, masked = enc_case(g)
+    B, F_, P, seed, _ = (int(v) for v in g["meta"])
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    m = MSDeformAttn3D(256, len(shapes), 8, P)
+    m.load_state_dict({k[len("self_attn."):]: torch.from_numpy(v) for k, v in W.items() if k.startswith("self_attn.")}, strict=True)
+    m = m.to(dev).eval()
+    with torch.no_grad():
+        out = m(t(inp["src"] + inp["pos"]), t(g["reference_points"]), t(inp["src"]), t(g["shapes"]), t(g["level_start"]),
+                t(inp["mask"]) if masked else None)
+    assert rel_err(out.cpu().numpy(), g["attn_out"]) < TOL_FP32
