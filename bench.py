@@ -308,13 +308,19 @@ def main():
         # computes (one event per step orders them); the first step's copy is exposed.
         copy_stream = torch.cuda.Stream(device=dev)
         pending = {}
+        bufs = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host_sets[0].items()} for _ in range(2)]
+        done = [None, None]          # "the step that used this buffer has finished" events
 
         def stage(i):
+            b = i % 2
             with torch.cuda.stream(copy_stream):
-                inp = {k: v.to(dev, non_blocking=True) for k, v in host_sets[i % NSETS].items()}
+                if done[b] is not None:
+                    copy_stream.wait_event(done[b])
+                for k, v in host_sets[i % NSETS].items():
+                    bufs[b][k].copy_(v, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
-            return inp, ev
+            return bufs[b], ev
 
         def e2e_step(i):
             inp, ev = pending.pop(i) if i in pending else stage(i)
@@ -323,8 +329,9 @@ def main():
             pending[i + 1] = stage(i + 1)
             out = step(inp)
             result_to_host(out)
-            for t_ in inp.values():
-                t_.record_stream(cur)
+            d = torch.cuda.Event()
+            d.record(cur)
+            done[i % 2] = d
         for i in range(2):
             e2e_step(i)
         pending.clear()
