@@ -36,6 +36,9 @@ SYMBOLS = {
                                                           c_void_p, c_void_p, c_size_t, c_int, c_long, c_int, c_int, c_int, c_void_p]),
     "cqvad_deform_encoder_layer_backward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                      c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_long, c_int, c_int, c_int, c_void_p]),
+    "cqvad_input_proj_3x3s2_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "cqvad_input_proj_3x3s2_gn": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t,
+                                           c_int, c_int, c_int, c_int, c_int, c_long, c_long, c_void_p]),
     "cqvad_input_proj_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_long]),
     "cqvad_input_proj_1x1_gn": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t,
                                          c_int, c_int, c_long, c_long, c_long, c_void_p]),

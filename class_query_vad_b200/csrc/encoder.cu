@@ -458,6 +458,48 @@ int input_proj_t(const T* x, const T* W, const float* bias, const float* gamma, 
   return 0;
 }
 
+// extra pyramid level of the non-ViT configurations (models/model.py:72-76,166-170): Conv3d(C_in, 256, kernel_size = 3,
+// stride = (1, 2, 2), padding = 1) -> GroupNorm(32, 256).  The level is tiny (7x7 -> 4x4 per frame): an im2col gather (27 taps,
+// zero padding) into a [rows, 27 * C_in] matrix, then the same tcgen05 GEMM + group-norm kernels as the 1x1x1 levels.
+// col[(b, t, yo, xo), tap * C_in + ci] = x[b, ci, t + kt - 1, 2 yo + ky - 1, 2 xo + kx - 1]
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_3x3s2_kernel(const T* __restrict__ x, T* __restrict__ col, int Cin, int Tn, int H, int W,
+                                                           int Ho, int Wo, long rows) {
+  const long row = blockIdx.x;
+  const int tap = blockIdx.y;
+  if (row >= rows) return;
+  const int kt = tap / 9, ky = (tap / 3) % 3, kx = tap % 3;
+  const int xo = (int)(row % Wo), yo = (int)((row / Wo) % Ho), t = (int)((row / ((long)Wo * Ho)) % Tn);
+  const long b = row / ((long)Wo * Ho * Tn);
+  const int ti = t + kt - 1, yi = 2 * yo + ky - 1, xi = 2 * xo + kx - 1;
+  const bool ok = ti >= 0 && ti < Tn && yi >= 0 && yi < H && xi >= 0 && xi < W;
+  const long plane = (long)Tn * H * W;
+  const T* src = x + b * Cin * plane + ((long)ti * H + yi) * W + xi;
+  T* dst = col + (row * 27 + tap) * Cin;
+  for (int ci = threadIdx.x; ci < Cin; ci += 256) dst[ci] = ok ? src[(long)ci * plane] : from_f<T>(0.f);
+}
+
+template <typename T>
+int input_proj3_t(const T* x, const T* Wr, const float* bias, const float* gamma, const float* beta, float eps, T* tokens, void* ws,
+                  size_t ws_bytes, int B, int Cin, int Tn, int H, int W, long Len, long level_start, cudaStream_t st) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long N = (long)Tn * Ho * Wo, rows = (long)B * N;
+  EncWs w(ws, ws_bytes);
+  T* col = (T*)w.take((size_t)rows * 27 * Cin * sizeof(T));
+  T* y = (T*)w.take((size_t)rows * kC * sizeof(T));
+  float* stats = (float*)w.take((size_t)B * 64 * 4);
+  if (!col || !y || !stats) return set_error(CQVAD_E_WORKSPACE, "input_proj (3x3x3): workspace too small");
+  im2col_3x3s2_kernel<T><<<dim3((unsigned)rows, 27), 256, 0, st>>>(x, col, Cin, Tn, H, W, Ho, Wo, rows);
+  CQ_LAUNCH_CHECK();
+  { Epilogue e; e.bias = bias; CQ_TRY(gemm<T>(col, 27L * Cin, Wr, y, kC, rows, kC, 27 * Cin, e, nullptr, st)); }
+  CQ_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * 64 * 4, st));
+  gn_stats_kernel<T><<<dim3((unsigned)cdiv(N, 256), (unsigned)B), 256, 0, st>>>(y, stats, N, 256);
+  CQ_LAUNCH_CHECK();
+  gn_apply_kernel<T><<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(y, stats, gamma, beta, eps, tokens, N, Len, level_start, B);
+  CQ_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 }  // namespace cqvad
 
@@ -608,4 +650,28 @@ extern "C" int cqvad_msda3d_prepare(const float* offsets, const float* logits, c
                                                                                          attn, rows, L, P);
   CQ_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" size_t cqvad_input_proj_3x3s2_workspace_bytes(int dtype, int B, int Cin, int T, int H, int W) {
+  const size_t es = dtype == CQVAD_F32 ? 4 : 2;
+  const size_t rows = (size_t)B * T * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1);
+  return rows * 27 * Cin * es + rows * kC * es + (size_t)B * 64 * 4 + 4 * 256 + 256;
+}
+
+extern "C" int cqvad_input_proj_3x3s2_gn(int dtype, const void* x, const void* weight_taps, const float* bias, const float* gn_weight,
+                                         const float* gn_bias, float eps, void* tokens, void* workspace, size_t workspace_bytes,
+                                         int B, int Cin, int T, int H, int W, long Len, long level_start, void* stream) {
+  CQ_CHECK_ARG(B >= 0 && Cin >= 1 && T >= 1 && H >= 1 && W >= 1 && level_start >= 0, "input_proj (3x3x3): bad dimensions");
+  const long N = (long)T * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1);
+  CQ_CHECK_ARG(level_start + N <= Len, "input_proj (3x3x3): level does not fit the token sequence");
+  if ((long)B * N == 0) return 0;
+  CQ_CHECK_ARG(x && weight_taps && gn_weight && gn_bias && tokens && workspace, "input_proj (3x3x3): null pointer");
+  CQ_CHECK_SHAPE(Cin % 8 == 0 && (long)B * N <= 2147483647L, "input_proj (3x3x3): C_in must be a multiple of 8 (got %d)", Cin);
+  if (dtype == CQVAD_F32)
+    return input_proj3_t<float>((const float*)x, (const float*)weight_taps, bias, gn_weight, gn_bias, eps, (float*)tokens, workspace,
+                                workspace_bytes, B, Cin, T, H, W, Len, level_start, as_stream(stream));
+  if (dtype == CQVAD_BF16)
+    return input_proj3_t<bf16>((const bf16*)x, (const bf16*)weight_taps, bias, gn_weight, gn_bias, eps, (bf16*)tokens, workspace,
+                               workspace_bytes, B, Cin, T, H, W, Len, level_start, as_stream(stream));
+  return set_error(CQVAD_E_INVALID_ARG, "input_proj (3x3x3): unknown dtype %d", dtype);
 }

@@ -87,32 +87,52 @@ class Transformer(nn.Module):
 
 
 def input_proj_levels(feats, convs, norms):
-    """models/model.py:162-164 for the backbone levels of the CSN configurations: per level Conv3d(C_in, 256, 1) + GroupNorm(32, 256)
-    written straight into the encoder's token sequence through cqvad_input_proj_1x1_gn.  feats: list of [B, C_in, T, H, W];
-    convs / norms: the nn.Conv3d / nn.GroupNorm modules of input_proj[l].  Returns (src_flatten [B, Len, 256], shapes, level_start)."""
+    """models/model.py:162-170 for the non-ViT (CSN) configurations: input_proj[l] = Conv3d + GroupNorm(32, 256) per level, written
+    straight into the encoder's token sequence.  feats: the backbone levels [B, C_in, T, H, W]; convs / norms: the nn.Conv3d /
+    nn.GroupNorm modules of input_proj in order -- the first len(feats) are the 1x1x1 projections (cqvad_input_proj_1x1_gn), any
+    further one is the extra stride-(1,2,2) kernel-3 level applied to the LAST backbone feature (cqvad_input_proj_3x3s2_gn; the
+    reference feeds a second extra level from the first one's output, which needs the channel-first tensor and is not covered).
+    Returns (src_flatten [B, Len, 256], shapes [L, 3], level_start [L])."""
     _lib.require_cuda(*feats)
     lib = _lib.lib()
     dt, dev = feats[0].dtype, feats[0].device
     B = feats[0].shape[0]
+    if len(convs) > len(feats) + 1:
+        raise ValueError("input_proj_levels: at most one extra (stride-2) level")
     shapes = [tuple(int(v) for v in f.shape[2:]) for f in feats]
+    if len(convs) == len(feats) + 1:
+        t, h, w = shapes[-1]
+        shapes.append((t, (h - 1) // 2 + 1, (w - 1) // 2 + 1))
     ns = [t * h * w for t, h, w in shapes]
     Len = sum(ns)
     tokens = torch.empty((B, Len, 256), dtype=dt, device=dev)
     p = _lib.ptr
+    f32 = lambda t_: None if t_ is None else t_.detach().to(device=dev, dtype=torch.float32).contiguous()
     start = 0
-    for l, (f, conv, gn) in enumerate(zip(feats, convs, norms)):
-        Cin = f.shape[1]
-        if tuple(conv.kernel_size) != (1, 1, 1) or gn.num_groups != 32 or conv.out_channels != 256:
-            raise ValueError("input_proj_levels covers Conv3d(kernel_size=1) -> GroupNorm(32, 256)")
-        w = conv.weight.detach().reshape(256, Cin).to(device=dev, dtype=dt).contiguous()
-        b = None if conv.bias is None else conv.bias.detach().to(device=dev, dtype=torch.float32).contiguous()
-        g = gn.weight.detach().to(device=dev, dtype=torch.float32).contiguous()
-        be = gn.bias.detach().to(device=dev, dtype=torch.float32).contiguous()
-        need = lib.cqvad_input_proj_workspace_bytes(_lib.dtype_id(dt), B, Cin, ns[l])
-        ws = torch.empty(need, dtype=torch.uint8, device=dev)
-        fc = f.contiguous()
-        _lib.check(lib.cqvad_input_proj_1x1_gn(_lib.dtype_id(dt), p(fc), p(w), p(b), p(g), p(be), float(gn.eps), p(tokens), p(ws), need,
-                                               B, Cin, ns[l], Len, start, _lib.stream_ptr()))
+    for l, (conv, gn) in enumerate(zip(convs, norms)):
+        if gn.num_groups != 32 or conv.out_channels != 256:
+            raise ValueError("input_proj_levels covers Conv3d -> GroupNorm(32, 256)")
+        g, be, b = f32(gn.weight), f32(gn.bias), f32(conv.bias)
+        if l < len(feats):
+            f = feats[l].contiguous()
+            Cin = f.shape[1]
+            if tuple(conv.kernel_size) != (1, 1, 1):
+                raise ValueError("backbone levels are projected with kernel_size 1")
+            w = conv.weight.detach().reshape(256, Cin).to(device=dev, dtype=dt).contiguous()
+            need = lib.cqvad_input_proj_workspace_bytes(_lib.dtype_id(dt), B, Cin, ns[l])
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            _lib.check(lib.cqvad_input_proj_1x1_gn(_lib.dtype_id(dt), p(f), p(w), p(b), p(g), p(be), float(gn.eps), p(tokens), p(ws), need,
+                                                   B, Cin, ns[l], Len, start, _lib.stream_ptr()))
+        else:
+            f = feats[-1].contiguous()
+            Cin, (T, H, W) = f.shape[1], f.shape[2:]
+            if tuple(conv.kernel_size) != (3, 3, 3) or tuple(conv.stride) != (1, 2, 2) or tuple(conv.padding) != (1, 1, 1):
+                raise ValueError("the extra level is Conv3d(kernel_size=3, stride=(1, 2, 2), padding=1)")
+            w = conv.weight.detach().permute(0, 2, 3, 4, 1).reshape(256, 27 * Cin).to(device=dev, dtype=dt).contiguous()
+            need = lib.cqvad_input_proj_3x3s2_workspace_bytes(_lib.dtype_id(dt), B, Cin, T, H, W)
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            _lib.check(lib.cqvad_input_proj_3x3s2_gn(_lib.dtype_id(dt), p(f), p(w), p(b), p(g), p(be), float(gn.eps), p(tokens), p(ws), need,
+                                                     B, Cin, T, H, W, Len, start, _lib.stream_ptr()))
         start += ns[l]
     sh = torch.tensor(shapes, dtype=torch.int64, device=dev)
     ls = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))

@@ -122,11 +122,19 @@ int cqvad_deform_encoder_layer_backward(int dtype, const void* const* weights, c
  * channel-first (dtype): transpose to token-major, tcgen05 GEMM with W [256, C_in] (dtype) + bias, per-clip group statistics
  * over (8 channels x N), normalise + affine (gn_weight / gn_bias fp32 [256]) straight into the encoder's token sequence
  * [B, Len, 256] (conv + norm + flatten in one call).  C_in % 32 == 0 (bf16 tensor-core path: % 64).  The extra stride-2 level
- * (Conv3d kernel 3, models/model.py:72-76) is not covered. */
+ * (Conv3d kernel 3, models/model.py:72-76) is cqvad_input_proj_3x3s2_gn. */
 size_t cqvad_input_proj_workspace_bytes(int dtype, int B, int Cin, long N);
 int cqvad_input_proj_1x1_gn(int dtype, const void* x, const void* weight, const float* bias, const float* gn_weight,
                             const float* gn_bias, float eps, void* tokens, void* workspace, size_t workspace_bytes, int B, int Cin,
                             long N, long Len, long level_start, void* stream);
+/* The extra pyramid level of the non-ViT configurations (models/model.py:72-76,166-170): Conv3d(C_in, 256, kernel_size = 3,
+ * stride = (1, 2, 2), padding = 1) -> GroupNorm(32, 256) -> flatten, written at level_start of the token sequence.
+ * x [B, C_in, T, H, W] channel-first (dtype); weight_taps [256, 27, C_in] (dtype) = conv.weight.permute(0, 2, 3, 4, 1) flattened
+ * (tap = (kt * 3 + ky) * 3 + kx).  Output positions: T x ((H-1)/2+1) x ((W-1)/2+1).  im2col gather + tcgen05 GEMM + group norm. */
+size_t cqvad_input_proj_3x3s2_workspace_bytes(int dtype, int B, int Cin, int T, int H, int W);
+int cqvad_input_proj_3x3s2_gn(int dtype, const void* x, const void* weight_taps, const float* bias, const float* gn_weight,
+                              const float* gn_bias, float eps, void* tokens, void* workspace, size_t workspace_bytes, int B, int Cin,
+                              int T, int H, int W, long Len, long level_start, void* stream);
 /* One pyramid level into the encoder's token sequence (Transformer.forward, models/detr/dab_transformer.py:310-327):
  * tokens[b, level_start + n, c] = x[b, c, n] (+ add[c]) for x [B, 256, N = T*H*W] channel-first (dtype), add = level_embed[lvl]
  * (fp32, for the position embedding; NULL for the features), tokens [B, Len, 256]. */

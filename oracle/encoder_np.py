@@ -74,3 +74,24 @@ def input_proj_1x1_gn(x, w, b, gamma, beta, eps=1e-5, groups=32):
     var = yg.var(axis=(1, 3), keepdims=True)
     out = ((yg - mu) / np.sqrt(var + eps)).reshape(B, -1, C) * gamma + beta
     return out.astype(np.float32)
+
+
+def input_proj_3x3s2_gn(x, w, b, gamma, beta, eps=1e-5, groups=32):
+    """models/model.py:72-76,166-170: Conv3d(C_in, 256, kernel_size=3, stride=(1, 2, 2), padding=1) -> GroupNorm(32, 256) on
+    x [B, C_in, T, H, W], w [256, C_in, 3, 3, 3]; returned token-major [B, T*Ho*Wo, 256]."""
+    B, Cin, T, H, W = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    xp = np.zeros((B, Cin, T + 2, H + 2, W + 2), dtype=np.float64)
+    xp[:, :, 1:-1, 1:-1, 1:-1] = x
+    y = np.zeros((B, T, Ho, Wo, w.shape[0]), dtype=np.float64)
+    for kt in range(3):
+        for ky in range(3):
+            for kx in range(3):
+                patch = xp[:, :, kt:kt + T, ky:ky + 2 * Ho - 1:2, kx:kx + 2 * Wo - 1:2]        # [B, Cin, T, Ho, Wo]
+                y += np.einsum("bcthw,oc->bthwo", patch, w[:, :, kt, ky, kx].astype(np.float64))
+    y = (y + b).reshape(B, -1, w.shape[0])
+    C = y.shape[-1]
+    yg = y.reshape(B, -1, groups, C // groups)
+    mu = yg.mean(axis=(1, 3), keepdims=True)
+    var = yg.var(axis=(1, 3), keepdims=True)
+    return (((yg - mu) / np.sqrt(var + eps)).reshape(B, -1, C) * gamma + beta).astype(np.float32)

@@ -285,3 +285,33 @@ def test_msdeformattn3d_module_matches_reference(name):
         out = m(t(inp["src"] + inp["pos"]), t(g["reference_points"]), t(inp["src"]), t(g["shapes"]), t(g["level_start"]),
                 t(inp["mask"]) if masked else None)
     assert rel_err(out.cpu().numpy(), g["attn_out"]) < TOL_FP32
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, TOL_FP32), (torch.bfloat16, TOL_BF16)])
+def test_input_proj_with_extra_stride2_level_matches_reference_modules(dtype, tol):
+    """One backbone level through the 1x1x1 projection AND the extra stride-(1,2,2) kernel-3 level (models/model.py:166-170 applies it
+    to the last backbone feature), both landing in one token sequence: cqvad_input_proj_1x1_gn + cqvad_input_proj_3x3s2_gn."""
+    from torch import nn
+    from class_query_vad_b200 import input_proj_levels
+    from oracle.make_golden_inputproj import CASES3, make_case3
+    from oracle import encoder_np
+    g = load_golden("inputproj")
+    dev = torch.device("cuda:0")
+    for tag in ("d", "e"):
+        kw = CASES3[tag]
+        x, w, b, gm, be = make_case3(kw)
+        c3, gn3 = nn.Conv3d(kw["Cin"], 256, kernel_size=3, stride=(1, 2, 2), padding=1), nn.GroupNorm(32, 256)
+        c1, gn1 = nn.Conv3d(kw["Cin"], 256, kernel_size=1), nn.GroupNorm(32, 256)
+        with torch.no_grad():
+            c3.weight.copy_(torch.from_numpy(w)); c3.bias.copy_(torch.from_numpy(b))
+            gn3.weight.copy_(torch.from_numpy(gm)); gn3.bias.copy_(torch.from_numpy(be))
+            w1 = (np.random.RandomState(5).standard_normal((256, kw["Cin"], 1, 1, 1)) / np.sqrt(kw["Cin"])).astype(np.float32)
+            c1.weight.copy_(torch.from_numpy(w1)); c1.bias.zero_()
+        tokens, sh, ls = input_proj_levels([torch.from_numpy(x).to(dev).to(dtype)], [c1, c3], [gn1, gn3])
+        torch.cuda.synchronize()
+        n0 = int(np.prod(kw["shape"]))
+        assert sh.tolist() == [list(kw["shape"]), g[tag + "_shape"].tolist()] and ls.tolist() == [0, n0]
+        ref1 = encoder_np.input_proj_1x1_gn(x, w1, np.zeros(256, np.float32), np.ones(256, np.float32), np.zeros(256, np.float32))
+        got = tokens.float().cpu().numpy()
+        assert rel_err(got[:, :n0], ref1) < tol
+        assert rel_err(got[:, n0:], g[tag + "_tokens"]) < tol

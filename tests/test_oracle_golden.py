@@ -168,3 +168,15 @@ def test_input_proj_oracle_matches_torch_modules(tag):
     x, w, b, gm, be = make_case(CASES[tag])
     got = encoder_np.input_proj_1x1_gn(x, w, b, gm, be)
     assert np.abs(got - g[tag + "_tokens"]).max() <= 2e-5 * np.abs(g[tag + "_tokens"]).max()
+
+
+@pytest.mark.parametrize("tag", ["d", "e"])
+def test_input_proj_extra_level_oracle_matches_torch_modules(tag):
+    """oracle/encoder_np.input_proj_3x3s2_gn against nn.Conv3d(k=3, stride=(1,2,2), padding=1) + nn.GroupNorm(32) (model.py:72-76)."""
+    from oracle import encoder_np
+    from oracle.make_golden_inputproj import CASES3, make_case3
+    g = load_golden("inputproj")
+    x, w, b, gm, be = make_case3(CASES3[tag])
+    got = encoder_np.input_proj_3x3s2_gn(x, w, b, gm, be)
+    assert got.shape == g[tag + "_tokens"].shape
+    assert np.abs(got - g[tag + "_tokens"]).max() <= 2e-5 * np.abs(g[tag + "_tokens"]).max()
