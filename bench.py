@@ -16,10 +16,12 @@ deformable encoder layer, forward and forward + backward, on the ViT-B/224 pyram
           is issued on a copy stream while step i computes (double-buffered loader; every step still copies its own inputs)
   roofline     : the dominant kernel (tcgen05 implicit-GEMM 3x3 conv: forward and data-gradient launches), timed live with
                  CUDA events on the launch stream (library profiler scopes), algorithmic FLOPs / duration vs the measured peak
-  cpu_baseline : oracle/decoder_torch.py (torch-CPU restatement of the reference decoder, autograd backward) on the host
-                 cores, bounded sample (rank 0, N=1 only)
-`--impl reference` times that same host path (the reference is Python/torch and cannot travel to the GPU box;
-/root/reference is never read here).
+  cpu_baseline : the unmodified reference decoder (baseline/_ref) on the host cores, torch-CPU all threads, bounded sample
+                 (rank 0, N=1 only); kind "port" (oracle restatement) only if that install is missing
+`--impl reference` times the UNMODIFIED reference decoder on the host cores (byte-for-byte install under the git-ignored
+baseline/_ref, oracle/install_ref.py -- it travels to the GPU box; /root/reference is never read here), exactly --warmup +
+--steps steps of one clip each.  "reference_gpu_eager" (N=1): the same unmodified reference run eagerly on the B200 itself
+(fp32 with TF32 off = the parity oracle's arithmetic, and bf16 autocast) -- BASELINE.md section 5.1.
 Multi-GPU: one process per GPU (torchrun), clips sharded across ranks (weak scaling: --batch clips per GPU); train mode
 all-reduces the decoder gradients once per step (NCCL), infer mode all-gathers the per-clip detections.
 """
@@ -108,32 +110,41 @@ def _host_case():
 
 
 def host_step_fn(mode):
-    """One clip of the workload on the host cores: train = torch-CPU restatement fwd + autograd bwd (all threads),
-    infer = numpy oracle forward + heads."""
+    """One clip of the workload on the host cores, all threads.  Returns (step, kind, description):
+    kind "reference" = the UNMODIFIED reference decoder (+ restated head lines) imported from the git-ignored install
+    baseline/_ref (oracle/install_ref.py); only when that install is absent, kind "port" = the oracle
+    restatement (torch-CPU for the training step, numpy for inference)."""
+    from oracle import ref_runner
+    if ref_runner.available():
+        n = ref_runner.cpu_threads()
+        step = ref_runner.step_fn(CFG, mode, B=1, device="cpu")
+        what = "decoder forward + autograd backward" if mode == "train" else "decoder forward + heads"
+        return step, "reference", f"unmodified reference TransformerDecoder (baseline/_ref, fp32, eval, torch-CPU {n} threads), {what}"
     cfg, W, inp, lw = _host_case()
     if mode == "train":
         from oracle import decoder_torch
         import torch
         torch.set_num_threads(os.cpu_count() or 1)
-        return lambda: decoder_torch.train_step(W, inp, lw, cfg["layers"])
+        return (lambda: decoder_torch.train_step(W, inp, lw, cfg["layers"])), "port", HOST_KIND["train"]
     from oracle import decoder_np
 
     def step():
         hs, cls_hs, refs = decoder_np.decoder_forward(W, inp["tgt"], inp["memory"], inp["mask"], inp["pos"],
                                                       inp["refpoints_unsigmoid"], inp["orig_res"], cfg["layers"])
         decoder_np.detr_heads(W, hs, cls_hs, refs)
-    return step
+    return step, "port", HOST_KIND["infer"]
 
 
 def cpu_oracle_clips_per_s(mode, max_seconds=25.0, min_reps=1):
-    step = host_step_fn(mode)
+    step, kind, desc = host_step_fn(mode)
+    step()                                   # warm-up (allocator, thread pool)
     times = []
     t_all = time.time()
-    while len(times) < min_reps or (time.time() - t_all < max_seconds and len(times) < 5):
+    while len(times) < min_reps or (time.time() - t_all < max_seconds and len(times) < 10):
         t0 = time.time()
         step()
         times.append(time.time() - t0)
-    return 1.0 / float(np.median(times)), len(times)
+    return 1.0 / float(np.median(times)), len(times), kind, desc
 
 
 class _Work(dict):
@@ -151,27 +162,37 @@ HOST_KIND = {"train": "fp32 torch-CPU restatement of the reference decoder (orac
              "infer": "fp32 numpy oracle port (oracle/decoder_np.py)"}
 
 
+def bench_config(mode, B, world):
+    """The `config` object of the JSON line -- identical for both arms (the reference arm measures a bounded sample of it)."""
+    return {"workload": WORK[mode] + f", {B} clips/GPU", "mode": mode, "config": CFG, "batch_per_gpu": B,
+            "parallelism": f"clip-sharded x{world}" + (", bucketed gradient all-reduce overlapped with the backward" if mode == "train" and world > 1 else ""),
+            "l2": "4 input sets cycled (128 MB) + GBs of intermediates per step >> 126 MB L2"}
+
+
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU path = the oracle port, all host threads, bounded sample (1 clip per step)."""
+    """--impl reference: the reference's own CPU implementation of the path (the unmodified reference decoder from
+    baseline/_ref), all host threads, EXACTLY --warmup + --steps steps; each step is a bounded sample of the workload: ONE clip
+    (our arm's step is `batch_per_gpu` clips), stated in cpu_baseline.sample.  Rank 0 only."""
     if rank != 0:
         return
-    step = host_step_fn(args.mode)
-    for _ in range(min(args.warmup, 1)):
+    step, kind, desc = host_step_fn(args.mode)
+    for _ in range(args.warmup):
         step()
-    steps = min(args.steps, 5)          # bounded: each step is one clip (~seconds of CPU work)
     t0 = time.time()
-    for _ in range(steps):
+    for _ in range(args.steps):
         step()
     dt = time.time() - t0
-    v = steps / dt
+    v = args.steps / dt
     cores = os.cpu_count()
-    sample = f"{steps} steps x 1 clip ({WORK[args.mode]}), {HOST_KIND[args.mode]}, wall clock"
+    sample = (f"{args.steps} timed steps x 1 clip per step (bounded sample: the GPU arm's step is {args.batch} clips/GPU); {desc}; "
+              f"wall clock, {args.warmup} warm-up steps")
     print(json.dumps({
-        "impl": "reference", "metric": "decoder clips/s", "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": "decoder clips/s", "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORK[args.mode] + "; 1 clip per step on the host CPU", "mode": args.mode},
-        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": bench_config(args.mode, args.batch, max(args.gpus, 1)),
+        "clips_per_step": 1,
+        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -391,18 +412,16 @@ def main():
             "launch_ms": conv_launch_ms, "flops_per_launch": conv_flops}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        v, reps = cpu_oracle_clips_per_s(main_mode)
-        cpu = {"value": v, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"{reps} x 1 clip, same workload shape ({WORK[main_mode]}), {HOST_KIND[main_mode]}"}
+        v, reps, kind, desc = cpu_oracle_clips_per_s(main_mode)
+        cpu = {"value": v, "unit": "clips/s", "cores": os.cpu_count(), "kind": kind,
+               "sample": f"median of {reps} x 1 clip, same workload shape ({WORK[main_mode]}); {desc}"}
     gflop = 3.0 * FWD_GFLOP[CFG] if main_mode == "train" else FWD_GFLOP[CFG]
     line = {
         "metric": "decoder clips/s", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORK[main_mode] + f", {B} clips/GPU, dropout = identity", "mode": main_mode, "config": CFG,
-                   "batch_per_gpu": B, "parallelism": f"clip-sharded x{world}" + (", 1 gradient all-reduce/step" if main_mode == "train" and world > 1 else ""),
-                   "l2": "4 input sets cycled (128 MB) + GBs of intermediates per step >> 126 MB L2",
-                   "decoder_tflops": value * gflop / 1e3 / world},
+        "config": bench_config(main_mode, B, world),
+        "decoder_tflops_per_gpu": value * gflop / 1e3 / world,
         "clocks": clocks,
         "e2e": {"value": clips / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(n_launch * args.steps),
@@ -417,6 +436,11 @@ def main():
             "e2e": iclips / (ims_e2e / 1e3), "gpu_launches_per_step": int(in_launch),
             "decoder_tflops": iclips / (ims / 1e3) * FWD_GFLOP[CFG] / 1e3 / world,
             "breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in iprof.items()}}
+    if world == 1:
+        try:
+            line["reference_gpu_eager"] = reference_gpu_eager(dev, main_mode, B)
+        except Exception as e:
+            line["reference_gpu_eager"] = {"error": str(e)[:200]}
     if main_mode == "train" and world == 1 and CFG == "ava_vitb":
         try:
             line["encoder_layer"] = encoder_layer_numbers(dev)
@@ -425,6 +449,41 @@ def main():
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def reference_gpu_eager(dev, mode, B, iters=5):
+    """the UNMODIFIED reference decoder (baseline/_ref) run eagerly by PyTorch (cuBLAS / cuDNN / ATen
+    kernels) on the same B200, same workload (B clips per step): fp32 with TF32 disabled (the parity oracle's arithmetic) and
+    bf16 autocast (the reference's fastest stock path).  CUDA events, median of `iters` after 2 warm-ups.  A reported baseline."""
+    import torch
+    from oracle import ref_runner
+    if not ref_runner.available():
+        return {"unavailable": "baseline/_ref not installed (python oracle/install_ref.py)"}
+    tf = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    out = {"workload": WORK[mode] + f", {B} clips per step, unmodified reference modules, eager PyTorch on cuda"}
+    try:
+        for tag, ac in (("fp32_tf32_off", False), ("bf16_autocast", True)):
+            try:
+                step = ref_runner.step_fn(CFG, mode, B=B, device=dev, autocast_bf16=ac)
+                ts = []
+                for i in range(iters + 2):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    step()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                ms = float(np.median(ts[2:]))
+                out[tag] = {"ms_per_step": round(ms, 3), "clips_per_s": round(B / ms * 1e3, 2)}
+                del step
+            except Exception as e:          # e.g. out of memory at this batch in fp32
+                out[tag] = {"error": str(e)[:160]}
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf
+    return out
 
 
 def encoder_layer_numbers(dev, B=4, iters=5):

@@ -36,6 +36,8 @@ GRAD_CASES = [
     ("grad_ava_vitb_b1_l2", "ava_vitb", 1, 2, 0, False, True),      # BASELINE shape (nq 15, S 196, K 80, F 2048), 2 layers
     ("grad_ava_csn_b1_l1", "ava_csn152", 1, 1, 3, True, True),      # CSN-152 grid 16x16 = 256 keys (the largest S), masked
     ("grad_ucf_like", dict(nq=15, tprime=2, h=14, w=14, K=24, layers=1, F=2048), 1, None, 4, False, True),
+    # the benchmarked depth: full 6-layer AVA22_ViT-B decoder (BASELINE configs[1] shape), 2 clips
+    ("grad_ava_vitb_b2_l6", "ava_vitb", 2, None, 0, False, True),
 ]
 
 
@@ -43,9 +45,13 @@ GRAD_CASES = [
 RELU_FEEDERS = re.compile(r"(^|\.)(linear1|cls_linear1|cls_linear1_)$|^(query_scale|ref_point_head|ref_anchor_head)\.layers\.0$"
                           r"|^bbox_embed\.layers\.[01]$")
 KINK_MARGIN = 2e-4
+# 6 layers x 2 clips have 3e7 ReLU pre-activations: a 2e-4 margin cannot be cleared by bias nudges (every hidden unit has rows
+# inside it).  This fixture anchors the bf16 tolerance (2e-2) and relative-L2 figures, so only pre-activations within fp32
+# rounding of zero are moved.
+KINK_MARGIN_BY_CASE = {"grad_ava_vitb_b2_l6": 4e-6}
 
 
-def clear_relu_kinks(dec, forward, max_iter=40):
+def clear_relu_kinks(dec, forward, max_iter=40, margin=None):
     """Nudges ReLU-feeding biases until no pre-activation is within KINK_MARGIN * rms of zero.  Returns {bias name: vector}."""
     feeders = {n: m for n, m in dec.named_modules() if RELU_FEEDERS.search(n)}
     assert len(feeders) >= 8, sorted(feeders)
@@ -63,7 +69,7 @@ def clear_relu_kinks(dec, forward, max_iter=40):
             if not outs:      # e.g. query_scale in a 1-layer decoder (dab_transformer.py:752: layer 0 uses scale 1)
                 continue
             o = torch.cat([x.reshape(-1, x.shape[-1]) for x in outs], 0)
-            thr = KINK_MARGIN * float(o.pow(2).mean().sqrt())
+            thr = (margin or KINK_MARGIN) * float(o.pow(2).mean().sqrt())
             bad = (o.abs() < thr).any(0).nonzero().flatten().numpy()
             if bad.size:
                 bad_total += int((o.abs() < thr).sum())
@@ -87,7 +93,8 @@ def run_case(ref, name, cfg, B, layers, seed, masked, tgt_zero):
     t = lambda a: torch.from_numpy(a.copy())
     nudged = clear_relu_kinks(dec, lambda: dec(t(inp["tgt"]), t(inp["memory"]), memory_key_padding_mask=t(inp["mask"]),
                                                pos=t(inp["pos"]), refpoints_unsigmoid=t(inp["refpoints_unsigmoid"]),
-                                               orig_res=inp["orig_res"]))
+                                               orig_res=inp["orig_res"]),
+                              margin=KINK_MARGIN_BY_CASE.get(name))
     tgt = t(inp["tgt"]).requires_grad_(True)
     memory = t(inp["memory"]).requires_grad_(True)
     ref_u = t(inp["refpoints_unsigmoid"]).requires_grad_(True)

@@ -1,8 +1,9 @@
-"""TEST INFRASTRUCTURE ONLY -- imports the *unmodified* reference decoder from /root/reference.
+"""TEST / BASELINE INFRASTRUCTURE ONLY -- imports the *unmodified* reference decoder.
 
-Used solely by oracle/make_golden.py (run in the build container, where /root/reference is mounted)
-to produce the fixtures under tests/golden/.  Nothing in the product package, bench.py or the `-m gpu`
-tests may import this module: /root/reference does not exist on the GPU box.
+Root of the reference tree: $CQVAD_REF, else the git-ignored install `baseline/_ref/` (oracle/install_ref.py: a byte-for-byte
+copy that travels to the GPU box), else /root/reference (build container only).  Users: the fixture generators
+oracle/make_golden*.py, `bench.py --impl reference` / its `cpu_baseline` and `reference_gpu_eager` legs (the reference timed
+beside the product, never as the product), and tests/test_msda_ref_gpu.py.  Nothing in the product package imports this module.
 
 The reference's `models.detr.dab_transformer` cannot be imported as shipped because of four imports that are
 unrelated to the decoder arithmetic:
@@ -18,7 +19,38 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("CQVAD_REF", "/root/reference")
+_HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    for c in (os.environ.get("CQVAD_REF"), os.path.join(_HERE, "baseline", "_ref"), "/root/reference"):
+        if c and os.path.isdir(os.path.join(c, "models", "detr")):
+            return c
+    return os.environ.get("CQVAD_REF", "/root/reference")
+
+
+REF_ROOT = _find_root()
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_ROOT, "models", "detr"))
+
+
+def import_reference_msda():
+    """The reference's own compiled CUDA extension (ops/src built by oracle/install_ref.py with the value.scalar_type() shim);
+    returns the module with ms_deform_attn_forward / ms_deform_attn_backward, or None when it was not built."""
+    import importlib
+    import torch  # noqa: F401  (libtorch must be loaded first)
+    so = os.path.join(REF_ROOT, "MultiScaleDeformableAttention.so")
+    if not os.path.exists(so):
+        return None
+    m = sys.modules.get("MultiScaleDeformableAttention")
+    if m is not None and getattr(m, "__file__", None):
+        return m
+    sys.modules.pop("MultiScaleDeformableAttention", None)
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    return importlib.import_module("MultiScaleDeformableAttention")
 
 
 def _mod(name, **attrs):
@@ -37,7 +69,8 @@ def import_reference():
     def _raise(*a, **k):
         raise RuntimeError("MultiScaleDeformableAttention is a stub (CUDA-only in the reference)")
 
-    if "MultiScaleDeformableAttention" not in sys.modules:
+    if "MultiScaleDeformableAttention" not in sys.modules and (
+            os.environ.get("CQVAD_REF_STUB_MSDA", "1") == "1" or import_reference_msda() is None):
         _mod("MultiScaleDeformableAttention", ms_deform_attn_forward=_raise, ms_deform_attn_backward=_raise)
     if "timm" not in sys.modules:
         class DropPath(nn.Identity):
