@@ -8,7 +8,10 @@
 // sampling point p (L*P points spread over the lanes, coalesced 12-byte/4-byte loads of loc/attn), then the warp
 // walks the points, broadcasting them by shuffle, and each lane gathers its channel(s): a corner read is one
 // coalesced D*sizeof(T) segment.  Index arithmetic follows the kernel contract bit-exactly:
-//   x_im = fl32(fl32(loc * dim) - 0.5)   (__fmul_rn then __fsub_rn: no FMA contraction; cuh:424-426)
+//   x_im = fl32(loc * dim - 0.5)   (__fmaf_rn: ONE rounding.  The reference source reads `loc * dim - 0.5` with a double
+//   literal, cuh:424-426, but nvcc narrows and contracts it: the compiled reference kernel executes FFMA R, loc, dim, -0.5 --
+//   verified in its SASS and by the one-hot index probe of tests/test_msda_ref_gpu.py, which the round-1 "product rounded
+//   first" reading failed on locations within half an ulp of a voxel centre)
 //   low = (int)floorf(x_im); point used iff -1 < x_im < dim on all axes (cuh:428); corner validity cuh:63-109.
 #include "common.cuh"
 #include <stdlib.h>
@@ -19,9 +22,9 @@ namespace {
 
 __device__ __forceinline__ void point_geometry(float loc_x, float loc_y, float loc_t, int T, int H, int W, int& tl,
                                                int& hl, int& wl, unsigned& mask, float& lt, float& lh, float& lw) {
-  const float t_im = __fsub_rn(__fmul_rn(loc_t, (float)T), 0.5f);
-  const float h_im = __fsub_rn(__fmul_rn(loc_y, (float)H), 0.5f);
-  const float w_im = __fsub_rn(__fmul_rn(loc_x, (float)W), 0.5f);
+  const float t_im = __fmaf_rn(loc_t, (float)T, -0.5f);
+  const float h_im = __fmaf_rn(loc_y, (float)H, -0.5f);
+  const float w_im = __fmaf_rn(loc_x, (float)W, -0.5f);
   tl = (int)floorf(t_im); hl = (int)floorf(h_im); wl = (int)floorf(w_im);
   lt = t_im - (float)tl; lh = h_im - (float)hl; lw = w_im - (float)wl;
   const bool inside = t_im > -1.f && h_im > -1.f && w_im > -1.f && t_im < (float)T && h_im < (float)H && w_im < (float)W;
@@ -214,6 +217,158 @@ __global__ void __launch_bounds__(kWarps * 32) msda_fwd_vec_kernel(const T* __re
   if (g == 0) store8(out + wid * D + ch * 8, acc);
 }
 
+
+// ---- Forward, query-tile kernel (round 2) -----------------------------------------------------------------------------
+// ncu on msda_fwd_vec_kernel (B = 4, ViT-B/224 pyramid): 1.89 G warp instructions (1 770 per (b,q,m)), sm__throughput 71 %,
+// lts__throughput 22 %, 10.7 GB of L2->L1 sectors for 0.68 GB of algorithmic bytes: issue-bound first, L1-miss traffic second.
+// This kernel attacks both:
+//  * a CTA owns TQ consecutive queries of ONE head (the vec kernel gave a CTA the 8 heads of one query, which share no value
+//    bytes): neighbouring queries sample overlapping voxels of the same head, so the 8 warps -- and the CTA's later
+//    iterations -- hit in L1 what the first toucher brought in;
+//  * bf16 values are consumed by the mixed-precision FMA `fma.rn.f32.bf16` (SASS FHFMA.BF16: bf16 x bf16 + f32 -> f32, the
+//    product is exact, one fp32 rounding per accumulate), straight from the packed registers of the 16-byte load: the
+//    8 bf16->f32 conversions per corner are gone.  The trilinear corner weight is rounded to bf16 for that product (relative
+//    2^-9 per term, unbiased; the attention weight stays fp32 and multiplies the per-point sum in fp32); fp32 values keep
+//    fp32 weights;
+//  * invalid corners are predicated loads into zeroed registers instead of branches: one straight-line body per step.
+// Index contract (point_geometry) unchanged.
+constexpr int kTileQ = 64;   // queries per CTA (8 per warp)
+
+__device__ __forceinline__ float fma_bf16(unsigned short a, unsigned short b, float c) {
+  float d;
+  asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) {
+  unsigned r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint4 ldg16_or_zero(const void* p, bool valid) {
+  uint4 r = make_uint4(0u, 0u, 0u, 0u);
+  if (valid) r = __ldg(reinterpret_cast<const uint4*>(p));
+  return r;
+}
+
+constexpr int kMaxLevels = 16;
+
+// one step of the tile kernel: this lane's point (already broadcast) against its 8-channel chunk.  ALLVALID: every corner of
+// every lane's point is inside the volume (warp-uniform fast path, no predicates); otherwise invalid corners are predicated
+// loads into zeroed registers.
+template <typename T, bool ALLVALID>
+__device__ __forceinline__ void tile_step(const char* __restrict__ ubase, unsigned b0, unsigned dw, unsigned dh, unsigned dt,
+                                          unsigned mk, float lt, float lh, float lw, float a, float (&acc)[8]) {
+  const float ht = 1.f - lt, hh = 1.f - lh, hw = 1.f - lw;
+  const float thh = ht * hh, thl = ht * lh, tlh = lt * hh, tll = lt * lh;
+  const float wgt[8] = {thh * hw, thh * lw, thl * hw, thl * lw, tlh * hw, tlh * lw, tll * hw, tll * lw};
+  const unsigned off[8] = {b0, b0 + dw, b0 + dh, b0 + dh + dw, b0 + dt, b0 + dt + dw, b0 + dt + dh, b0 + dt + dh + dw};
+  float val[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if constexpr (sizeof(T) == 2) {
+    uint4 r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {   // all 8 loads in flight before the first use
+      if constexpr (ALLVALID) r[k] = __ldg(reinterpret_cast<const uint4*>(ubase + off[k]));
+      else r[k] = ldg16_or_zero(ubase + off[k], (mk >> k) & 1u);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+      const unsigned wp = pack_bf16x2(wgt[k], wgt[k + 1]);
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const unsigned short wb = kk ? (unsigned short)(wp >> 16) : (unsigned short)(wp & 0xffffu);
+        const unsigned rr[4] = {r[k + kk].x, r[k + kk].y, r[k + kk].z, r[k + kk].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          val[2 * e] = fma_bf16((unsigned short)(rr[e] & 0xffffu), wb, val[2 * e]);
+          val[2 * e + 1] = fma_bf16((unsigned short)(rr[e] >> 16), wb, val[2 * e + 1]);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      uint4 r0, r1;
+      if constexpr (ALLVALID) {
+        r0 = __ldg(reinterpret_cast<const uint4*>(ubase + off[k]));
+        r1 = __ldg(reinterpret_cast<const uint4*>(ubase + off[k]) + 1);
+      } else {
+        const bool ok = (mk >> k) & 1u;
+        r0 = ldg16_or_zero(ubase + off[k], ok); r1 = ldg16_or_zero(ubase + off[k] + 16, ok);
+      }
+      const float w = wgt[k];
+      val[0] = fmaf(w, __uint_as_float(r0.x), val[0]); val[1] = fmaf(w, __uint_as_float(r0.y), val[1]);
+      val[2] = fmaf(w, __uint_as_float(r0.z), val[2]); val[3] = fmaf(w, __uint_as_float(r0.w), val[3]);
+      val[4] = fmaf(w, __uint_as_float(r1.x), val[4]); val[5] = fmaf(w, __uint_as_float(r1.y), val[5]);
+      val[6] = fmaf(w, __uint_as_float(r1.z), val[6]); val[7] = fmaf(w, __uint_as_float(r1.w), val[7]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = fmaf(val[e], a, acc[e]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarps * 32) msda_fwd_tile_kernel(const T* __restrict__ value,
+                                                                    const int64_t* __restrict__ shapes,
+                                                                    const int64_t* __restrict__ lsi,
+                                                                    const float* __restrict__ loc,
+                                                                    const float* __restrict__ attn, T* __restrict__ out,
+                                                                    int n_tiles, int Len, int M, int D, int L, int Lq, int P) {
+  __shared__ int s_T[kMaxLevels], s_H[kMaxLevels], s_W[kMaxLevels], s_ls[kMaxLevels];
+  if (threadIdx.x < L) {
+    s_T[threadIdx.x] = (int)shapes[threadIdx.x * 3]; s_H[threadIdx.x] = (int)shapes[threadIdx.x * 3 + 1];
+    s_W[threadIdx.x] = (int)shapes[threadIdx.x * 3 + 2]; s_ls[threadIdx.x] = (int)lsi[threadIdx.x];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tile = blockIdx.x % n_tiles;
+  const int bm = blockIdx.x / n_tiles;           // (batch, head)
+  const int m = bm % M, b = bm / M;
+  const int LP = L * P;
+  const unsigned rsb = (unsigned)(M * D) * (unsigned)sizeof(T);   // bytes between consecutive tokens (Len*M*D*sizeof(T) < 2^32 checked)
+  const int lpp = D >> 3, G = 32 / lpp;
+  const int g = lane / lpp, ch = lane % lpp;
+  // warp-uniform base of this (batch, head); per-lane 32-bit byte offsets below
+  const char* ubase = reinterpret_cast<const char*>(value + (long)b * Len * ((long)M * D) + (long)m * D);
+  const unsigned choff = (unsigned)ch * 8u * (unsigned)sizeof(T);
+  const int q_end = min(Lq, (tile + 1) * kTileQ);
+  for (int q = tile * kTileQ + warp; q < q_end; q += kWarps) {
+    const long wid = ((long)b * Lq + q) * M + m;
+    const float* locp = loc + wid * LP * 3;
+    const float* attp = attn + wid * LP;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p0 = 0; p0 < LP; p0 += 32) {
+      const int pt = p0 + lane;
+      unsigned g_b0 = 0, g_dh = 0, g_dt = 0, g_mask = 0; float g_lt = 0, g_lh = 0, g_lw = 0, g_a = 0;
+      if (pt < LP) {
+        const int l = pt / P;
+        const int Tt = s_T[l], H = s_H[l], W = s_W[l];
+        int tl, hl, wl;
+        point_geometry(locp[pt * 3], locp[pt * 3 + 1], locp[pt * 3 + 2], Tt, H, W, tl, hl, wl, g_mask, g_lt, g_lh, g_lw);
+        g_dh = (unsigned)W * rsb; g_dt = (unsigned)(H * W) * rsb;
+        g_b0 = (unsigned)(s_ls[l] + (tl * H + hl) * W + wl) * rsb;   // wraps for invalid low corners; those are never read
+        g_a = attp[pt];
+      }
+      const int np = min(32, LP - p0);
+      for (int j0 = 0; j0 < np; j0 += G) {
+        const int src = min(j0 + g, 31);
+        unsigned mk = __shfl_sync(0xffffffffu, g_mask, src);
+        const unsigned b0 = __shfl_sync(0xffffffffu, g_b0, src) + choff;
+        const unsigned dh = __shfl_sync(0xffffffffu, g_dh, src), dt = __shfl_sync(0xffffffffu, g_dt, src);
+        const float lt = __shfl_sync(0xffffffffu, g_lt, src), lh = __shfl_sync(0xffffffffu, g_lh, src);
+        const float lw = __shfl_sync(0xffffffffu, g_lw, src), a = __shfl_sync(0xffffffffu, g_a, src);
+        if (j0 + g >= np) mk = 0;
+        if (__all_sync(0xffffffffu, mk == 0xffu)) tile_step<T, true>(ubase, b0, rsb, dh, dt, mk, lt, lh, lw, a, acc);
+        else if (__any_sync(0xffffffffu, mk != 0u)) tile_step<T, false>(ubase, b0, rsb, dh, dt, mk, lt, lh, lw, a, acc);
+      }
+    }
+    for (int o = lpp; o < 32; o <<= 1) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+    }
+    if (g == 0) store8(out + wid * D + ch * 8, acc);
+  }
+}
+
 // Backward (mathematical gradient of the forward).  Same warp mapping; grad_value via red.global.add.f32 (one
 // coalesced 128-byte reduction per corner), grad_loc / grad_attn reduced over the head's channels by shuffle and
 // written once by the owning warp (no atomics).
@@ -381,9 +536,19 @@ int msda_fwd_t(const void* value, const int64_t* shapes, const int64_t* lsi, con
   if (nw == 0) return 0;
   const unsigned grid = (unsigned)cdiv(nw, kWarps);
   static const bool no_vec = getenv("CQVAD_MSDA_NO_VEC") != nullptr;
+  static const bool old_vec = getenv("CQVAD_MSDA_OLD_FWD") != nullptr;   // A/B switch: the round-1 warp-per-(b,q,m) kernel
   const int lpp = D >> 3;
-  if (!no_vec && D % 8 == 0 && lpp >= 1 && lpp <= 32 && (lpp & (lpp - 1)) == 0 && (((uintptr_t)value) & 15) == 0 &&
-      (((uintptr_t)out) & 15) == 0) {
+  const bool vec_ok = !no_vec && D % 8 == 0 && lpp >= 1 && lpp <= 32 && (lpp & (lpp - 1)) == 0 && (((uintptr_t)value) & 15) == 0 &&
+                      (((uintptr_t)out) & 15) == 0;
+  if (vec_ok && !old_vec && L <= kMaxLevels && (long)Len * M * D * (long)sizeof(T) < (1L << 32)) {
+    const int n_tiles = (int)cdiv(Lq, kTileQ);
+    const long n_cta = (long)n_tiles * N * M;
+    CQ_CHECK_SHAPE(n_cta < (1L << 31), "msda3d: grid too large");
+    msda_fwd_tile_kernel<T><<<(unsigned)n_cta, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, loc, attn, (T*)out, n_tiles, Len, M, D, L, Lq, P);
+    CQ_LAUNCH_CHECK();
+    return 0;
+  }
+  if (vec_ok) {
     msda_fwd_vec_kernel<T, false><<<grid, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, loc, attn, nullptr, (T*)out, nw, Len, M, D, L, Lq, P);
     CQ_LAUNCH_CHECK();
     return 0;

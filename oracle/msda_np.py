@@ -1,10 +1,12 @@
 """TEST INFRASTRUCTURE -- numpy restatement of the reference 3-D multi-scale deformable attention op.
 
-PARITY UNPINNED by the reference's own tests: ops/test.py is the stale 2-D Deformable-DETR script and the shipped
-kernel has no CPU implementation (ops/src/cpu/ms_deform_attn_cpu.cpp:26,39 throw).  This restatement follows the
-CUDA kernel's arithmetic line by line and is cross-checked against torch's 5-D F.grid_sample (the 3-D analogue of
-the reference's own ms_deform_attn_core_pytorch, ops/functions/ms_deform_attn_func.py:48-68) in
-tests/test_oracle_golden.py, and against tests/golden/msda_*.npz generated by oracle/make_golden.py.
+The reference's own tests do not pin this op (ops/test.py is the stale 2-D Deformable-DETR script, and the shipped kernel has
+no CPU implementation: ops/src/cpu/ms_deform_attn_cpu.cpp:26,39 throw).  PINNED HERE in two ways: (1) on the GPU against the
+REFERENCE KERNEL ITSELF, compiled from ops/src for sm_100a (oracle/install_ref.py -> baseline/_ref; tests/test_msda_ref_gpu.py:
+values <= 1e-5 and the read pattern / low-corner indices bit-exact through a one-hot coordinate probe); (2) on the CPU against
+torch's 5-D F.grid_sample (the 3-D analogue of the reference's own ms_deform_attn_core_pytorch,
+ops/functions/ms_deform_attn_func.py:48-68) in tests/test_oracle_golden.py and tests/golden/msda.npz.  This restatement
+follows the CUDA kernel's arithmetic line by line, including the coordinate rounding the COMPILED kernel performs (below).
 
   msda3d_indices / msda3d_forward   <- ops/src/cuda/ms_deform_im2col_cuda_t.cuh:33-115 (trilinear), :374-439 (kernel)
   msda3d_backward                   <- the mathematical gradient of that forward (autograd spec).  The reference
@@ -15,17 +17,25 @@ import numpy as np
 
 
 def _coords(loc, shapes, dt):
-    """cuh:412-426.  loc [...,L,P,3] (x,y,t); shapes [L,3] (T,H,W).  The kernel computes
-    `loc_T * spatial_T - 0.5` with an fp32 product rounded BEFORE the subtraction (the literal is a double, so
-    no FMA contraction): fl32(fl32(loc*dim) - 0.5)."""
-    T = shapes[:, 0].astype(dt)[:, None]
-    H = shapes[:, 1].astype(dt)[:, None]
-    Wd = shapes[:, 2].astype(dt)[:, None]
-    half = dt(0.5)
-    w_im = (loc[..., 0].astype(dt) * Wd).astype(dt) - half
-    h_im = (loc[..., 1].astype(dt) * H).astype(dt) - half
-    t_im = (loc[..., 2].astype(dt) * T).astype(dt) - half
-    return t_im.astype(dt), h_im.astype(dt), w_im.astype(dt)
+    """cuh:412-426.  loc [...,L,P,3] (x,y,t); shapes [L,3] (T,H,W).  The source reads `loc_T * spatial_T - 0.5` (float
+    product, double literal); nvcc narrows the subtraction back to fp32 (it is exact either way) and CONTRACTS it with the
+    product: the compiled kernel executes `FFMA R, loc, dim, -0.5` (cuobjdump -sass of the reference extension built for
+    sm_100a, profiles/r02_sass_summary.txt) -- ONE rounding: fl32(loc*dim - 0.5).  The round-1 reading of the source
+    (product rounded first) picked a different voxel on locations that sit within half an ulp of a voxel centre; the
+    one-hot index probe against the reference kernel (tests/test_msda_ref_gpu.py) caught it.  In numpy the fused result is
+    the float64 evaluation (24-bit x <= 11-bit product and the subtraction are exact in double) rounded once to fp32."""
+    if dt != np.float32:            # float64 mode (grid_sample cross-checks): plain arithmetic
+        T = shapes[:, 0].astype(dt)[:, None]; H = shapes[:, 1].astype(dt)[:, None]; Wd = shapes[:, 2].astype(dt)[:, None]
+        return (loc[..., 2].astype(dt) * T - dt(0.5), loc[..., 1].astype(dt) * H - dt(0.5), loc[..., 0].astype(dt) * Wd - dt(0.5))
+    f8 = np.float64
+    T = shapes[:, 0].astype(f8)[:, None]
+    H = shapes[:, 1].astype(f8)[:, None]
+    Wd = shapes[:, 2].astype(f8)[:, None]
+    loc32 = loc.astype(np.float32)
+    w_im = (loc32[..., 0].astype(f8) * Wd - 0.5).astype(np.float32)
+    h_im = (loc32[..., 1].astype(f8) * H - 0.5).astype(np.float32)
+    t_im = (loc32[..., 2].astype(f8) * T - 0.5).astype(np.float32)
+    return t_im, h_im, w_im
 
 
 def msda3d_indices(shapes, loc, dt=np.float32):

@@ -9,8 +9,9 @@ baseline/_ref/) runs on the same GPU, on the same inputs, beside cqvad_msda3d_fo
     one level, one point, attention weight 1).  Output channel i of the t-section is then the summed trilinear weight of the
     corners the kernel actually READ at t == i: the non-zero pattern of the output IS the set of (valid) corner indices.
     The patterns of the two kernels must be identical, on locations that sit exactly on voxel centres / borders (where
-    fl32(fl32(loc*dim) - 0.5) lands on an integer and an FMA-contracted or double-precision evaluation picks another voxel),
-    and the low corner decoded from the reference output must equal cqvad_msda3d_indices.
+    loc*dim - 0.5 lands within an ulp of an integer, so that a product-rounded-first, an FMA-contracted and a double-precision
+    evaluation pick different voxels), and the low corner decoded from the reference output must equal cqvad_msda3d_indices.
+    (This probe is what established the contract: the compiled reference kernel evaluates FFMA(loc, dim, -0.5).)
   * the reference BACKWARD is not a gradient -- it is timed in bench.py, never compared.
 """
 import numpy as np

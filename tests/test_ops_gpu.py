@@ -44,7 +44,7 @@ def test_msda_indices_bit_exact_and_vit_shape():
     shapes = [(8, 56, 56), (8, 28, 28), (8, 14, 14), (8, 7, 7)]
     d = synth.make_msda_inputs(1, shapes, M=8, D=32, Lq=3000, P=8, seed=4, spread=0.4)
     loc = d["loc"]
-    # adversarial locations: exact voxel centres / borders, where fl32(loc*dim)-0.5 sits on an integer
+    # adversarial locations: exact voxel centres / borders, where loc*dim - 0.5 sits on an integer
     T, H, W = 8, 56, 56
     loc[0, :50, 0, 0, :, 0] = (np.arange(50)[:, None] % W + 0.5) / W
     loc[0, :50, 0, 0, :, 1] = (np.arange(50)[:, None] % H + 0.5) / H

@@ -40,6 +40,51 @@ def summary(tag, l2):
         print(f"        {e:10.3e}  {k}")
 
 
+def global_l2(fa, fb, tz):
+    """relative L2 of the whole parameter gradient (all tensors concatenated) and its cosine."""
+    num = den = dot = na = 0.0
+    for k in fb:
+        if k.startswith("in.") or k not in fa:
+            continue
+        a, b = fa[k], fb[k]
+        num += float((a - b).pow(2).sum()); den += float(b.pow(2).sum()); dot += float((a * b).sum()); na += float(a.pow(2).sum())
+    return (num / den) ** 0.5, dot / (na * den) ** 0.5
+
+
+def reference_bf16_errors(g, cfg, B, W, inp, seed, tz):
+    from oracle import ref_import, synth
+    from oracle.make_golden import build_reference_decoder
+    ref = ref_import.import_reference()
+    dev = torch.device("cuda:0")
+    lw = synth.make_loss_weights(cfg, B, seed=seed)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = {}
+    for tag in ("autocast(bf16) over the fp32 reference module", "reference module .bfloat16() (weights + activations bf16)"):
+      try:
+            dec = build_reference_decoder(ref, cfg, W).to(dev)
+            pure = tag.startswith("reference module")
+            if pure:
+                dec = dec.bfloat16()
+            cast = (lambda x: x.bfloat16()) if pure else (lambda x: x)
+            tgt = cast(t(inp["tgt"])).requires_grad_(True)
+            mem = cast(t(inp["memory"])).requires_grad_(True)
+            refu = cast(t(inp["refpoints_unsigmoid"])).requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=not pure):
+                hs, cls_hs, refs = dec(tgt, mem, memory_key_padding_mask=t(inp["mask"]), pos=cast(t(inp["pos"])),
+                                       refpoints_unsigmoid=refu, orig_res=inp["orig_res"])
+            loss = (t(lw["w_hs"]) * hs.float()).sum() + (t(lw["w_cls"]) * cls_hs.float()).sum() + (t(lw["w_refs"]) * refs.float()).sum()
+            loss.backward()
+            params = {k: (torch.zeros_like(p_) if p_.grad is None else p_.grad).float() for k, p_ in dec.named_parameters()}
+            grads = dict(memory=mem.grad.float(), tgt=tgt.grad.float(), refpoints_unsigmoid=refu.grad.float(), params=params)
+            _, l2 = grad_errors(grads, g, seed, tgt_zero=tz, want_l2=True)
+            out[tag] = l2
+            del dec
+            torch.cuda.empty_cache()
+      except Exception as e:
+        print(f"  [D {tag}] does not run: {str(e)[:160]}")
+    return out
+
+
 def flat(grads):
     d = {"in.memory": grads["memory"], "in.tgt": grads["tgt"], "in.refpoints_unsigmoid": grads["refpoints_unsigmoid"]}
     d.update(grads["params"])
@@ -71,5 +116,21 @@ for name in sys.argv[1:] or ["grad_ava_vitb_b1_l2"]:
         if n > 0 and float(fB[k].abs().max()) > 1e-4 * Gmed:
             l2C[k] = float((fA[k] - fB[k]).norm()) / n
     summary("C bf16 path vs fp32 path on the SAME bf16-representable matrices (arithmetic/storage error alone)", l2C)
+    gl, cs = global_l2(fA, fB, tz)
+    print(f"  whole parameter gradient, bf16 path vs fp32 path on the same matrices: rel-L2 {gl:.3e}, cosine {cs:.6f}")
+    for k in ("in.memory", "in.tgt", "in.refpoints_unsigmoid"):
+        print(f"  {k}: A {l2A.get(k, float('nan')):.3e}  B {l2B.get(k, float('nan')):.3e}  C {l2C.get(k, float('nan')):.3e}")
+    cls = {"conv (GELU ConvBlock)": "conv_blocks", "ReLU FFN linear1": "linear1", "loc chain sa_/ca_": ".sa_", "norm": "norm"}
+    for tag, pat in cls.items():
+        va = [v for k, v in l2A.items() if pat in k]; vb = [v for k, v in l2B.items() if pat in k]; vc = [v for k, v in l2C.items() if pat in k]
+        if va:
+            print(f"  class {tag:28s} median A {np.median(va):.3e}  B {np.median(vb):.3e}  C {np.median(vc):.3e}  (n={len(va)})")
     del engB
     torch.cuda.empty_cache()
+    # (D) the UNMODIFIED reference itself evaluated in bf16 on this GPU: (D1) torch autocast(bf16) around the fp32 module,
+    # (D2) the module cast to bf16 (weights and activations bf16) -- same fixture, same metric
+    try:
+        for tag, l2D in reference_bf16_errors(g, cfg, B, W, inp, seed, tz).items():
+            summary(f"D {tag} vs reference fp32 fixture", l2D)
+    except Exception as e:
+        print("  [D] reference bf16 evaluation failed:", str(e)[:200])
