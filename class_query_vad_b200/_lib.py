@@ -75,6 +75,7 @@ SYMBOLS = {
     "cqvad_profile_num_classes": (c_int, []),
     "cqvad_profile_class_name": (c_char_p, [c_int]),
     "cqvad_profile_read": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(c_long), POINTER(c_long)]),
+    "cqvad_profile_read_work": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double)]),
     "cqvad_debug_force_simt": (None, [c_int]),
 }
 

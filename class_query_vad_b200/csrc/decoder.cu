@@ -215,7 +215,9 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
   CQ_TRY(sigmoid4(ref_u, r_cur, refs, N, nq, BT, st));               // :735; refs[0]
   delete ps;
 #define PROF(c) { delete ps; ps = new ProfScope(c, st); }
+#define WORK(c, fl, by) { if (prof_enabled()) prof_work(c, fl, by); }
   ps = nullptr;
+  const double eb = sizeof(T), NSd = (double)N * S;   // algorithmic work: valid rows only, operands once, result once
 
   for (int l = 0; l < Lr; ++l) {
     const bool first = (l == 0);
@@ -250,6 +252,7 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
     CQ_TRY(lvlmix_ln<T>(memc, lvlw, Wf(loc(l, NORMU)), Wf(loc(l, NORMU) + 1), qm, N, S, Sq, BT, st));
     // ---- cross-attention with per-actor keys :951-988 ----
     PROF(P_BIG_PROJ);
+    WORK(P_BIG_PROJ, 2.0 * NSd * 512 * kC + 2.0 * S * BT * kC * kC, eb * (NSd * (kC + 512) + (double)S * BT * 2 * kC + 3.0 * kC * kC));
     if (w[loc(l, CA_KV)] != nullptr) {
       CQ_TRY(lin(qm, NSq, kC, loc(l, CA_KV), kv, 2 * kC));          // [k | v] in one pass over q_memory
     } else {
@@ -281,8 +284,10 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
       e.ln_g = Wf(cls(l, C_CBNORM)); e.ln_b = Wf(cls(l, C_CBNORM) + 1); e.ln_eps = 1e-6f;
       ConvGeom cg; cg.h = h; cg.w = wd;
       PROF(P_CONV);
+      WORK(P_CONV, 2.0 * NSd * kC * 9 * kC, eb * (2.0 * NSd * kC + 9.0 * kC * kC));
       CQ_TRY(gemm<T>(xin, kC, Wm(cls(l, C_CONV1)), Xn, kC, Rp, kC, 9 * kC, e, &cg, st));
       PROF(P_CONV_MLP);
+      WORK(P_CONV_MLP, 2.0 * NSd * kC * 4 * kC * 2, eb * (3.0 * NSd * kC + 8.0 * kC * kC));
       CQ_TRY(mlp(Xn, Rp, 4 * kC, cls(l, C_CONV2), cls(l, C_CONV3), CQVAD_ACT_GELU, xin, -1, 0.f, xout, Hc, Sp, S));
       T* t = xin; xin = xout; xout = t;
     }
@@ -309,6 +314,7 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
       CQ_TRY(gemm<T>(caoc, kC, Wm(cls(l, C_CA_O)), cls0, kC, NK, kC, kC, e, nullptr, st));
     }
     PROF(P_CLS_FFN);
+    WORK(P_CLS_FFN, 2.0 * (double)NK * kC * F * 2, eb * (2.0 * (double)NK * kC + 2.0 * (double)F * kC));
     T* cls_out = Qc[l & 1];   // Qin is dead after the attention; reuse its buffer for the layer output / next query
     CQ_TRY(mlp(cls0, NK, F, cls(l, C_L1_), cls(l, C_L2_), CQVAD_ACT_RELU, cls0, cls(l, C_NORM_), 1e-5f, cls_out, Hf, 0, 0,
                /*emit_qt=*/l + 1 < Lr, cls0_32, clsout_32));
@@ -346,6 +352,7 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
   }
   delete ps;
 #undef PROF
+#undef WORK
   return 0;
 }
 

@@ -252,67 +252,89 @@ __device__ __forceinline__ uint4 ldg16_or_zero(const void* p, bool valid) {
 
 constexpr int kMaxLevels = 16;
 
-// one step of the tile kernel: this lane's point (already broadcast) against its 8-channel chunk.  ALLVALID: every corner of
-// every lane's point is inside the volume (warp-uniform fast path, no predicates); otherwise invalid corners are predicated
-// loads into zeroed registers.
-template <typename T, bool ALLVALID>
+// 32-byte load (SASS LDG.E.ENL2.256): 16 bf16 channels per lane
+struct U8 { unsigned v[8]; };
+__device__ __forceinline__ U8 ldg32(const void* p) {
+  U8 r;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+
+// one step of the tile kernel: this lane's point (already broadcast) against its channel chunk (NW 32-bit words per corner:
+// 4 = 8 bf16, 8 = 16 bf16 or 8 fp32).  ALLVALID: every corner of every lane's point is inside the volume (warp-uniform fast
+// path, no predicates); otherwise invalid corners are predicated loads into zeroed registers.
+template <typename T, int NW, bool ALLVALID>
 __device__ __forceinline__ void tile_step(const char* __restrict__ ubase, unsigned b0, unsigned dw, unsigned dh, unsigned dt,
-                                          unsigned mk, float lt, float lh, float lw, float a, float (&acc)[8]) {
+                                          unsigned mk, float lt, float lh, float lw, float a, float (&acc)[NW * (4 / sizeof(T)) * 1]) {
+  constexpr int NC = NW * (4 / sizeof(T));          // channels per lane
   const float ht = 1.f - lt, hh = 1.f - lh, hw = 1.f - lw;
   const float thh = ht * hh, thl = ht * lh, tlh = lt * hh, tll = lt * lh;
   const float wgt[8] = {thh * hw, thh * lw, thl * hw, thl * lw, tlh * hw, tlh * lw, tll * hw, tll * lw};
   const unsigned off[8] = {b0, b0 + dw, b0 + dh, b0 + dh + dw, b0 + dt, b0 + dt + dw, b0 + dt + dh, b0 + dt + dh + dw};
-  float val[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if constexpr (sizeof(T) == 2) {
-    uint4 r[8];
+  float val[NC];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {   // all 8 loads in flight before the first use
-      if constexpr (ALLVALID) r[k] = __ldg(reinterpret_cast<const uint4*>(ubase + off[k]));
-      else r[k] = ldg16_or_zero(ubase + off[k], (mk >> k) & 1u);
-    }
+  for (int e = 0; e < NC; ++e) val[e] = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; k += 2) {
-      const unsigned wp = pack_bf16x2(wgt[k], wgt[k + 1]);
+  for (int k0 = 0; k0 < 8; k0 += 4) {   // 4 corners in flight at a time
+    unsigned r[4][NW];
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const unsigned short wb = kk ? (unsigned short)(wp >> 16) : (unsigned short)(wp & 0xffffu);
-        const unsigned rr[4] = {r[k + kk].x, r[k + kk].y, r[k + kk].z, r[k + kk].w};
+    for (int kk = 0; kk < 4; ++kk) {
+      const int k = k0 + kk;
+      const bool ok = ALLVALID || ((mk >> k) & 1u);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          val[2 * e] = fma_bf16((unsigned short)(rr[e] & 0xffffu), wb, val[2 * e]);
-          val[2 * e + 1] = fma_bf16((unsigned short)(rr[e] >> 16), wb, val[2 * e + 1]);
+      for (int e = 0; e < NW; ++e) r[kk][e] = 0u;
+      if (ok) {
+        if constexpr (NW == 8 && sizeof(T) == 2) {   // 16 bf16 channels: one 32-byte load (measured slower than 2 lanes x 16 B: opt-in)
+          const U8 u = ldg32(ubase + off[k]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[kk][e] = u.v[e];
+        } else if constexpr (NW == 8) {                // 8 fp32 channels: two 16-byte loads
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(ubase + off[k]));
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(ubase + off[k]) + 1);
+          r[kk][0] = u.x; r[kk][1] = u.y; r[kk][2] = u.z; r[kk][3] = u.w; r[kk][4] = v.x; r[kk][5] = v.y; r[kk][6] = v.z; r[kk][7] = v.w;
+        } else {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(ubase + off[k]));
+          r[kk][0] = u.x; r[kk][1] = u.y; r[kk][2] = u.z; r[kk][3] = u.w;
         }
       }
     }
-  } else {
+    if constexpr (sizeof(T) == 2) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      uint4 r0, r1;
-      if constexpr (ALLVALID) {
-        r0 = __ldg(reinterpret_cast<const uint4*>(ubase + off[k]));
-        r1 = __ldg(reinterpret_cast<const uint4*>(ubase + off[k]) + 1);
-      } else {
-        const bool ok = (mk >> k) & 1u;
-        r0 = ldg16_or_zero(ubase + off[k], ok); r1 = ldg16_or_zero(ubase + off[k] + 16, ok);
+      for (int kk = 0; kk < 4; kk += 2) {
+        const unsigned wp = pack_bf16x2(wgt[k0 + kk], wgt[k0 + kk + 1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const unsigned short wb = h ? (unsigned short)(wp >> 16) : (unsigned short)(wp & 0xffffu);
+#pragma unroll
+          for (int e = 0; e < NW; ++e) {
+            val[2 * e] = fma_bf16((unsigned short)(r[kk + h][e] & 0xffffu), wb, val[2 * e]);
+            val[2 * e + 1] = fma_bf16((unsigned short)(r[kk + h][e] >> 16), wb, val[2 * e + 1]);
+          }
+        }
       }
-      const float w = wgt[k];
-      val[0] = fmaf(w, __uint_as_float(r0.x), val[0]); val[1] = fmaf(w, __uint_as_float(r0.y), val[1]);
-      val[2] = fmaf(w, __uint_as_float(r0.z), val[2]); val[3] = fmaf(w, __uint_as_float(r0.w), val[3]);
-      val[4] = fmaf(w, __uint_as_float(r1.x), val[4]); val[5] = fmaf(w, __uint_as_float(r1.y), val[5]);
-      val[6] = fmaf(w, __uint_as_float(r1.z), val[6]); val[7] = fmaf(w, __uint_as_float(r1.w), val[7]);
+    } else {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int e = 0; e < NW; ++e) val[e] = fmaf(wgt[k0 + kk], __uint_as_float(r[kk][e]), val[e]);
+      }
     }
   }
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = fmaf(val[e], a, acc[e]);
+  for (int e = 0; e < NC; ++e) acc[e] = fmaf(val[e], a, acc[e]);
 }
 
-template <typename T>
+// NW: 32-bit words per lane and corner.  bf16: NW = 8 (16 channels, D % 16 == 0) or 4 (8 channels); fp32: NW = 8 (8 channels).
+template <typename T, int NW>
 __global__ void __launch_bounds__(kWarps * 32) msda_fwd_tile_kernel(const T* __restrict__ value,
                                                                     const int64_t* __restrict__ shapes,
                                                                     const int64_t* __restrict__ lsi,
                                                                     const float* __restrict__ loc,
                                                                     const float* __restrict__ attn, T* __restrict__ out,
                                                                     int n_tiles, int Len, int M, int D, int L, int Lq, int P) {
+  constexpr int NC = NW * (4 / sizeof(T));   // channels per lane
   __shared__ int s_T[kMaxLevels], s_H[kMaxLevels], s_W[kMaxLevels], s_ls[kMaxLevels];
   if (threadIdx.x < L) {
     s_T[threadIdx.x] = (int)shapes[threadIdx.x * 3]; s_H[threadIdx.x] = (int)shapes[threadIdx.x * 3 + 1];
@@ -325,17 +347,19 @@ __global__ void __launch_bounds__(kWarps * 32) msda_fwd_tile_kernel(const T* __r
   const int m = bm % M, b = bm / M;
   const int LP = L * P;
   const unsigned rsb = (unsigned)(M * D) * (unsigned)sizeof(T);   // bytes between consecutive tokens (Len*M*D*sizeof(T) < 2^32 checked)
-  const int lpp = D >> 3, G = 32 / lpp;
+  const int lpp = D / NC, G = 32 / lpp;          // lanes per point, points per step
   const int g = lane / lpp, ch = lane % lpp;
   // warp-uniform base of this (batch, head); per-lane 32-bit byte offsets below
   const char* ubase = reinterpret_cast<const char*>(value + (long)b * Len * ((long)M * D) + (long)m * D);
-  const unsigned choff = (unsigned)ch * 8u * (unsigned)sizeof(T);
+  const unsigned choff = (unsigned)ch * (unsigned)(NC * sizeof(T));
   const int q_end = min(Lq, (tile + 1) * kTileQ);
   for (int q = tile * kTileQ + warp; q < q_end; q += kWarps) {
     const long wid = ((long)b * Lq + q) * M + m;
     const float* locp = loc + wid * LP * 3;
     const float* attp = attn + wid * LP;
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float acc[NC];
+#pragma unroll
+    for (int e = 0; e < NC; ++e) acc[e] = 0.f;
     for (int p0 = 0; p0 < LP; p0 += 32) {
       const int pt = p0 + lane;
       unsigned g_b0 = 0, g_dh = 0, g_dt = 0, g_mask = 0; float g_lt = 0, g_lh = 0, g_lw = 0, g_a = 0;
@@ -357,15 +381,23 @@ __global__ void __launch_bounds__(kWarps * 32) msda_fwd_tile_kernel(const T* __r
         const float lt = __shfl_sync(0xffffffffu, g_lt, src), lh = __shfl_sync(0xffffffffu, g_lh, src);
         const float lw = __shfl_sync(0xffffffffu, g_lw, src), a = __shfl_sync(0xffffffffu, g_a, src);
         if (j0 + g >= np) mk = 0;
-        if (__all_sync(0xffffffffu, mk == 0xffu)) tile_step<T, true>(ubase, b0, rsb, dh, dt, mk, lt, lh, lw, a, acc);
-        else if (__any_sync(0xffffffffu, mk != 0u)) tile_step<T, false>(ubase, b0, rsb, dh, dt, mk, lt, lh, lw, a, acc);
+        if (__all_sync(0xffffffffu, mk == 0xffu)) tile_step<T, NW, true>(ubase, b0, rsb, dh, dt, mk, lt, lh, lw, a, acc);
+        else if (__any_sync(0xffffffffu, mk != 0u)) tile_step<T, NW, false>(ubase, b0, rsb, dh, dt, mk, lt, lh, lw, a, acc);
       }
     }
     for (int o = lpp; o < 32; o <<= 1) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+      for (int e = 0; e < NC; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
     }
-    if (g == 0) store8(out + wid * D + ch * 8, acc);
+    if (g == 0) {
+#pragma unroll
+      for (int e0 = 0; e0 < NC; e0 += 8) {
+        float o8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o8[e] = acc[e0 + e];
+        store8(out + wid * D + ch * NC + e0, o8);
+      }
+    }
   }
 }
 
@@ -540,11 +572,20 @@ int msda_fwd_t(const void* value, const int64_t* shapes, const int64_t* lsi, con
   const int lpp = D >> 3;
   const bool vec_ok = !no_vec && D % 8 == 0 && lpp >= 1 && lpp <= 32 && (lpp & (lpp - 1)) == 0 && (((uintptr_t)value) & 15) == 0 &&
                       (((uintptr_t)out) & 15) == 0;
-  if (vec_ok && !old_vec && L <= kMaxLevels && (long)Len * M * D * (long)sizeof(T) < (1L << 32)) {
+  if (vec_ok && !old_vec && L <= kMaxLevels && (long)Len * M * D * (long)sizeof(T) < (1L << 32) &&
+      true) {
     const int n_tiles = (int)cdiv(Lq, kTileQ);
     const long n_cta = (long)n_tiles * N * M;
     CQ_CHECK_SHAPE(n_cta < (1L << 31), "msda3d: grid too large");
-    msda_fwd_tile_kernel<T><<<(unsigned)n_cta, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, loc, attn, (T*)out, n_tiles, Len, M, D, L, Lq, P);
+    const int lpp16 = D >> 4;
+    const bool wide = sizeof(T) == 2 && D % 16 == 0 && lpp16 >= 1 && (lpp16 & (lpp16 - 1)) == 0 && (((uintptr_t)value) & 31) == 0 &&
+                      ((size_t)M * D * sizeof(T)) % 32 == 0 && getenv("CQVAD_MSDA_WIDE") != nullptr;   // LDG.256 variant: 1.85 ms vs 1.40 ms (112 registers), opt-in
+    if (sizeof(T) == 4)       // 8 fp32 channels = one 32-byte load
+      msda_fwd_tile_kernel<T, 8><<<(unsigned)n_cta, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, loc, attn, (T*)out, n_tiles, Len, M, D, L, Lq, P);
+    else if (wide)            // 16 bf16 channels per lane
+      msda_fwd_tile_kernel<T, 8><<<(unsigned)n_cta, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, loc, attn, (T*)out, n_tiles, Len, M, D, L, Lq, P);
+    else if constexpr (sizeof(T) == 2)
+      msda_fwd_tile_kernel<T, 4><<<(unsigned)n_cta, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, loc, attn, (T*)out, n_tiles, Len, M, D, L, Lq, P);
     CQ_LAUNCH_CHECK();
     return 0;
   }

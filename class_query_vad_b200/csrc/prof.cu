@@ -5,7 +5,7 @@
 namespace cqvad {
 namespace {
 struct Pair { cudaEvent_t a, b; };
-struct ClassState { std::vector<Pair> pool; size_t used = 0; long launches_at_begin = 0; long launches = 0; };
+struct ClassState { std::vector<Pair> pool; size_t used = 0; long launches_at_begin = 0; long launches = 0; double flops = 0, bytes = 0; };
 ClassState g_cls[P_COUNT];
 bool g_on = false;
 const char* kNames[P_COUNT] = {"conv3x3_ln (tcgen05 implicit GEMM)", "convblock_mlp (tcgen05 fused MLP)",
@@ -16,7 +16,9 @@ const char* kNames[P_COUNT] = {"conv3x3_ln (tcgen05 implicit GEMM)", "convblock_
                                "train fwd: GEMM / conv", "train fwd: LN, attention, elementwise", "train bwd: dgrad GEMM / conv",
                                "train bwd: wgrad", "train bwd: activation / residual", "train bwd: LayerNorm", "train bwd: attention",
                                "train bwd: misc", "train fwd: conv3x3 (tcgen05 implicit GEMM)", "train bwd: conv3x3 dgrad (tcgen05 implicit GEMM)",
-                               "train bwd: conv3x3 wgrad (tcgen05 MN-major)"};
+                               "train bwd: conv3x3 wgrad (tcgen05 MN-major)",
+                               "train fwd: GELU GEMM (conv2, gelu + gelu' epilogue)", "train bwd: dgrad GEMM x act' (epilogue multiply)",
+                               "train fwd: small-row GEMMs (< 8192 rows)", "train bwd: small-row dgrad GEMMs", "train bwd: small-row wgrad"};
 }  // namespace
 long launch_count_now();
 bool prof_enabled() { return g_on; }
@@ -31,6 +33,7 @@ void prof_begin(int cls, cudaStream_t st) {
   c.launches_at_begin = launch_count_now();
   cudaEventRecord(c.pool[c.used].a, st);
 }
+void prof_work(int cls, double flops, double bytes) { g_cls[cls].flops += flops; g_cls[cls].bytes += bytes; }
 void prof_end(int cls, cudaStream_t st) {
   ClassState& c = g_cls[cls];
   cudaEventRecord(c.pool[c.used].b, st);
@@ -42,7 +45,7 @@ void prof_end(int cls, cudaStream_t st) {
 using namespace cqvad;
 extern "C" void cqvad_profile_enable(int on) {
   g_on = on != 0;
-  for (int i = 0; i < P_COUNT; ++i) { g_cls[i].used = 0; g_cls[i].launches = 0; }
+  for (int i = 0; i < P_COUNT; ++i) { g_cls[i].used = 0; g_cls[i].launches = 0; g_cls[i].flops = 0; g_cls[i].bytes = 0; }
 }
 extern "C" int cqvad_profile_num_classes(void) { return P_COUNT; }
 extern "C" const char* cqvad_profile_class_name(int cls) { return (cls >= 0 && cls < P_COUNT) ? kNames[cls] : nullptr; }
@@ -59,5 +62,13 @@ extern "C" int cqvad_profile_read(int cls, double* total_ms, long* scopes, long*
   if (total_ms) *total_ms = tot;
   if (scopes) *scopes = (long)c.used;
   if (launches) *launches = c.launches;
+  return 0;
+}
+
+// algorithmic FLOPs and bytes (operands read once + result written once) of the kernels timed in a class since the enable call
+extern "C" int cqvad_profile_read_work(int cls, double* flops, double* bytes) {
+  if (cls < 0 || cls >= P_COUNT) return CQVAD_E_INVALID_ARG;
+  if (flops) *flops = g_cls[cls].flops;
+  if (bytes) *bytes = g_cls[cls].bytes;
   return 0;
 }

@@ -157,7 +157,7 @@ struct Trainer {
     static const bool off = [] { const char* e = getenv("CQVAD_TRAIN_WG_STREAM"); return e && atoi(e) == 0; }();
     static cudaEvent_t ev = [] { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); return e; }();
     static const long min_rows = [] { const char* e = getenv("CQVAD_TRAIN_WG_MIN_ROWS"); return e ? atol(e) : 1L; }();   // small-row wgrads too: 124 launches of ~8 us leave the loc chain
-    if (off || prof_enabled() || !two_streams || rows < min_rows || wg_stream() == nullptr || sizeof(T) != 2) return st;   // (the profiler times on st)
+    if (off || !two_streams || rows < min_rows || wg_stream() == nullptr || sizeof(T) != 2) return st;   // the profiler times each kernel on the stream it runs on
     if (cudaEventRecord(ev, st) != cudaSuccess || cudaStreamWaitEvent(wg_stream(), ev, 0) != cudaSuccess) return st;
     wg_used = true;
     return wg_stream();
@@ -189,6 +189,7 @@ struct Trainer {
   const T* Wm(int i) const { return (const T*)w[i]; }
   const float* Wf(int i) const { return (const float*)w[i]; }
   float* G(int i) const { return io.gw ? io.gw[i] : nullptr; }
+  static bool big(long rows) { return rows >= 8192; }   // profiler classes: large-M GEMMs vs the small-row (launch-bound) ones
   int loc(int l, int s) const { return l * LOC_COUNT + s; }
   int cls(int l, int s) const { return Lr * LOC_COUNT + l * CLS_COUNT + s; }
   int glob(int s) const { return Lr * (LOC_COUNT + CLS_COUNT) + s; }
@@ -259,7 +260,11 @@ struct Trainer {
       if (A2 && fuse_act) { e.c2 = A2->p; e.c2_act = c2_act; }
       if (dual) { e.dual_gelu = true; e.c2 = const_cast<T*>(A2->gref); }
       int r;
-      { ProfScope ps(P_T_FWD_GEMM, st); r = gemm<T>(X->p, Kd, Wm(widx), dual ? A2->p : Y->p, Nout, X->rows, Nout, Kd, e, nullptr, st); }
+      {
+        const double fl = 2.0 * X->rows * Nout * Kd, by = sizeof(T) * ((double)X->rows * (Kd + (dual ? 2.0 : 1.0) * Nout + (res ? Nout : 0)) + (double)Nout * Kd);
+        ProfScope ps(dual ? P_T_FWD_GEMM_GELU : big(X->rows) ? P_T_FWD_GEMM : P_T_FWD_GEMM_SMALL, st, fl, by);
+        r = gemm<T>(X->p, Kd, Wm(widx), dual ? A2->p : Y->p, Nout, X->rows, Nout, Kd, e, nullptr, st);
+      }
       if (r == 0 && A2 && !fuse_act && !dual) { ProfScope ps(P_T_FWD_OTHER, st); r = gelu_fwd<T>(Y->p, A2->p, A2->gact == 3 ? const_cast<T*>(A2->gref) : nullptr, Y->n(), st); }
       if (r == 0) r = dbg("lin", widx);
       if (r != 0 && rc && *rc == 0) *rc = r;
@@ -282,20 +287,21 @@ struct Trainer {
           if (res && res->hg) CQ_TRY(axpby<T>(res->g, Y->g, beta(res), Y->n(), st));
         }
         if (X->hg) {
-          ProfScope ps(P_T_DGRAD, st);
           CQ_TRY(build_wt(widx, Nout, Kd, false));
           Epilogue e;
           const float b = beta(X);
           if (b != 0.f) { e.res = X->g; e.ldr = Kd; }
-          if (X->gact && (fuse_act || fuse_act_bwd) && b == 0.f) {
-            if (b != 0.f) return set_error(CQVAD_E_INVALID_ARG, "backward: an activation output with two consumers is not supported");
-            e.mul_aux = X->gref; e.mul_mode = X->gact; X->gmasked = true;   // dX = (dY . W) * act'(.) in the epilogue
-          }
+          const bool actmul = X->gact && (fuse_act || fuse_act_bwd) && b == 0.f;
+          if (actmul) { e.mul_aux = X->gref; e.mul_mode = X->gact; X->gmasked = true; }   // dX = (dY . W) * act'(.) in the epilogue
+          const double fl = 2.0 * X->rows * Nout * Kd, by = sizeof(T) * ((double)X->rows * (Nout + Kd * (1.0 + (actmul ? 1 : 0) + (b != 0.f ? 1 : 0))) + (double)Nout * Kd);
+          ProfScope ps(!big(X->rows) ? P_T_DGRAD_SMALL : (actmul && X->gact == 3) ? P_T_DGRAD_ACT : P_T_DGRAD, st, fl, by);
           CQ_TRY(gemm<T>(Y->g, Nout, Wt, X->g, Kd, X->rows, Kd, Nout, e, nullptr, st));
         }
         if (G(widx) || G(widx + 1)) {
-          ProfScope ps(P_T_WGRAD, st);
-          CQ_TRY(wgrad<T>(Y->g, Nout, X->p, Kd, G(widx), Kd, G(widx + 1), X->rows, Nout, Kd, nullptr, wgrad_stream(X->rows)));
+          cudaStream_t ws = wgrad_stream(X->rows);
+          const double fl = 2.0 * X->rows * Nout * Kd, by = sizeof(T) * (double)X->rows * (Nout + Kd) + 4.0 * 2.0 * Nout * Kd;
+          ProfScope ps(big(X->rows) ? P_T_WGRAD : P_T_WGRAD_SMALL, ws, fl, by);
+          CQ_TRY(wgrad<T>(Y->g, Nout, X->p, Kd, G(widx), Kd, G(widx + 1), X->rows, Nout, Kd, nullptr, ws));
         }
         return 0;
       });
@@ -345,6 +351,9 @@ struct Trainer {
     }
     return A;
   }
+  // algorithmic work of one 3x3 conv over the N*S valid positions: 2*N*S*256*2304 FLOPs; X + Z + W bytes
+  double conv_flops() const { return 2.0 * (double)NS * kC * 9 * kC; }
+  double conv_bytes() const { return sizeof(T) * (2.0 * (double)Rp * kC + 9.0 * kC * kC); }
   // Z = conv3x3(X) + b on the y-padded layout
   Ten<T>* conv(Ten<T>* X, int widx, int* rc) {
     Ten<T>* Z = mk(X->rows, kC);
@@ -354,7 +363,7 @@ struct Trainer {
       Epilogue e;
       e.bias = Wf(widx + 1);
       int r;
-      { ProfScope ps(P_T_CONV_FWD, st); r = gemm<T>(X->p, kC, Wm(widx), Z->p, kC, X->rows, kC, 9 * kC, e, &cg, st); }
+      { ProfScope ps(P_T_CONV_FWD, st, conv_flops(), conv_bytes()); r = gemm<T>(X->p, kC, Wm(widx), Z->p, kC, X->rows, kC, 9 * kC, e, &cg, st); }
       if (r == 0) r = dbg("conv", widx);
       if (r != 0 && *rc == 0) *rc = r;
     }
@@ -363,15 +372,16 @@ struct Trainer {
         if (!Z->gi) return 0;
         if (X->hg) {
           CQ_TRY(build_wt(widx, 0, 0, true));
-          ProfScope ps(P_T_CONV_DGRAD, st);
+          ProfScope ps(P_T_CONV_DGRAD, st, conv_flops(), conv_bytes());
           Epilogue e;
           e.zero_period = Sp; e.zero_valid = S;
           const float b = beta(X);
           if (b != 0.f) { e.res = X->g; e.ldr = kC; }
           CQ_TRY(gemm<T>(Z->g, kC, Wd, X->g, kC, X->rows, kC, 9 * kC, e, &cg, st));
         }
-        ProfScope ps(P_T_CONV_WGRAD, st);
-        return wgrad<T>(Z->g, kC, X->p, kC, G(widx), 9 * kC, G(widx + 1), X->rows, kC, kC, &cg, wgrad_stream(X->rows));
+        cudaStream_t ws = wgrad_stream(X->rows);
+        ProfScope ps(P_T_CONV_WGRAD, ws, conv_flops(), conv_bytes());
+        return wgrad<T>(Z->g, kC, X->p, kC, G(widx), 9 * kC, G(widx + 1), X->rows, kC, kC, &cg, ws);
       });
     }
     return Z;

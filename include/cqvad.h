@@ -266,6 +266,9 @@ void cqvad_profile_enable(int on);
 int cqvad_profile_num_classes(void);
 const char* cqvad_profile_class_name(int cls);
 int cqvad_profile_read(int cls, double* total_ms_host, long* scopes_host, long* launches_host);
+/* Algorithmic work of the kernels timed in a class since the enable call: FLOPs (2 per multiply-add) and bytes (every operand
+ * read once, the result written once) -- the numerators of bench.py's per-class tensor-pipe / HBM roofline fractions. */
+int cqvad_profile_read_work(int cls, double* flops_host, double* bytes_host);
 /* Debug switch: route bf16 GEMMs through the CUDA-core kernel instead of tcgen05 (used by the parity tests to
  * cross-check the two implementations; not a fallback -- both are CUDA kernels of this library). */
 void cqvad_debug_force_simt(int on);
