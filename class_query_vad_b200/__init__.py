@@ -13,6 +13,7 @@ from .modules.position_encoding import PositionEmbeddingSine_3D, build_position_
 from .modules.encoder import (DeformableTransformerEncoderLayer, DeformableTransformerEncoder, encoder_layer_forward,
                               pack_encoder_layer_weights, encoder_to_decoder_memory)
 from .modules.transformer import Transformer, flatten_levels, input_proj_levels
+from .modules.criterion import HungarianMatcherAVA, SetCriterionAVA, PostProcessAVA, pack_targets
 from .modules.decoder import (MLP, ConvBlock, TransformerDecoderLayer, TransformerClassDecoderLayer, TransformerDecoder,
                               build_decoder)
 
@@ -20,4 +21,5 @@ __all__ = ["DecoderEngine", "DecoderFunction", "pack_decoder_weights", "MSDeform
            "MultiheadAttention", "PositionEmbeddingSine_3D", "build_position_encoding", "gen_sineembed_for_position",
            "MLP", "ConvBlock", "TransformerDecoderLayer", "TransformerClassDecoderLayer", "TransformerDecoder",
            "build_decoder", "DeformableTransformerEncoderLayer", "DeformableTransformerEncoder", "encoder_layer_forward",
-           "pack_encoder_layer_weights", "encoder_to_decoder_memory", "Transformer", "flatten_levels", "input_proj_levels"]
+           "pack_encoder_layer_weights", "encoder_to_decoder_memory", "Transformer", "flatten_levels", "input_proj_levels",
+           "HungarianMatcherAVA", "SetCriterionAVA", "PostProcessAVA", "pack_targets"]

@@ -17,6 +17,11 @@ class DecoderDesc(Structure):
                 ("layers", c_int), ("out_f32", c_int), ("flags", c_int)]
 
 
+class CriterionCfg(Structure):
+    _fields_ = [(n, c_float) for n in ("cost_class", "cost_bbox", "cost_giou", "w_ce", "w_bbox", "w_giou", "w_ce_b", "pos_weight",
+                                       "eos_coef", "focal_alpha", "focal_gamma", "label_smoothing")]
+
+
 class CqvadError(RuntimeError):
     pass
 
@@ -70,6 +75,9 @@ SYMBOLS = {
     "cqvad_wgrad_workspace_bytes": (c_size_t, []),
     "cqvad_linear_wgrad": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_int, c_void_p,
                                    c_size_t, c_void_p]),
+    "cqvad_criterion_ava_workspace_bytes": (c_size_t, [c_int]),
+    "cqvad_criterion_ava": (c_int, [POINTER(CriterionCfg)] + [c_void_p] * 6 + [c_int] * 4 + [c_void_p] * 6 + [c_size_t, c_void_p]),
+    "cqvad_postprocess_ava": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     "cqvad_last_launch_count": (c_long, []),
     "cqvad_profile_enable": (None, [c_int]),
     "cqvad_profile_num_classes": (c_int, []),

@@ -258,6 +258,44 @@ int cqvad_linear_wgrad(int dtype, const void* dY, const void* X, float* dW, floa
                        int conv_h, int conv_w, void* workspace, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Loss / matcher / post-process on the device.  Replaces, for the AVA configurations,
+ *   HungarianMatcherAVA.forward   (models/detr/matcher.py:39-78: cost = cost_bbox * L1 + cost_giou * (-GIoU) + cost_class *
+ *                                  (-softmax(pred_logits_b)[:, 1]); the reference copies the cost matrix to the host and calls
+ *                                  scipy.optimize.linear_sum_assignment per clip),
+ *   SetCriterionAVA.forward       (models/detr/criterion.py:50-138,184-224: loss_ce = sigmoid focal loss (alpha, gamma,
+ *                                  models/detr/segmentation.py:200-229) on label-smoothed multi-hot targets with weight
+ *                                  `pos_weight` on matched rows, / n_p; loss_ce_b = cross-entropy over {.., person, no-object}
+ *                                  with weight eos_coef on the last class; loss_bbox = L1 / num_boxes; loss_giou),
+ *   the weighted total of train.py:148 (sum over criterion.weight_dict: the LAST layer's four losses -- the reference computes
+ *   the auxiliary per-layer losses for logging only, their keys are not in weight_dict) and its gradient with respect to the
+ *   three prediction tensors, and PostProcessAVA.forward (criterion.py:740-773).
+ *   pred_logits [B,nq,K], pred_boxes [B,nq,4] (cx,cy,w,h), pred_logits_b [B,nq,3]  fp32 -- one decoder layer's head outputs;
+ *   tgt_boxes [B,maxT,4] (cx,cy,w,h: columns 1..4 of the reference's target["boxes"]), tgt_labels [B,maxT,K] multi-hot fp32,
+ *   n_tgt [B] int32 (targets of clip b; rows beyond it are ignored).  nq <= 64, maxT <= 64.
+ *   match [B,nq] int32 out: matched target index or -1 (the reference's `indices`);
+ *   losses [16] fp32 out: [0] loss_ce [1] loss_bbox [2] loss_giou [3] loss_ce_b [4] weighted total [5] class_error
+ *                         [6] matched pairs [7] num_boxes [8..10] normalisers (n_p, num_boxes, sum of CE weights);
+ *   grad_* (may be NULL): d total / d prediction, fully overwritten.  No host synchronisation: the assignment is solved by
+ *   the device (exact shortest-augmenting-path Hungarian in fp64 on the fp32 costs). */
+typedef struct cqvad_criterion_cfg {
+  float cost_class, cost_bbox, cost_giou;        /* MATCHER.COST_CLASS / COST_BBOX / COST_GIOU                         */
+  float w_ce, w_bbox, w_giou, w_ce_b;            /* weight_dict: LOSS_COFS.DICE_COF / BBOX_COF / GIOU_COF / PERSON_COF */
+  float pos_weight;                              /* LOSS_COFS.WEIGHT (criterion.py:84)                                 */
+  float eos_coef;                                /* LOSS_COFS.EOS_COF                                                  */
+  float focal_alpha, focal_gamma;                /* 0.25, 2 (criterion.py:46-47)                                       */
+  float label_smoothing;                         /* MODEL.LABEL_SMOOTHING_ALPHA (criterion.py:48: 0.1)                 */
+} cqvad_criterion_cfg;
+size_t cqvad_criterion_ava_workspace_bytes(int B);
+int cqvad_criterion_ava(const cqvad_criterion_cfg* cfg, const float* pred_logits, const float* pred_boxes,
+                        const float* pred_logits_b, const float* tgt_boxes, const float* tgt_labels, const int32_t* n_tgt,
+                        int B, int nq, int K, int maxT, int32_t* match, float* losses, float* grad_logits, float* grad_boxes,
+                        float* grad_logits_b, void* workspace, size_t ws_bytes, void* stream);
+/* detections [B, nq, K + 5] = [sigmoid(pred_logits) | box as (x0,y0,x1,y1) * (w,h,w,h) | softmax(pred_logits_b)[1]];
+ * target_sizes [B,2] fp32 (h, w) as in the reference. */
+int cqvad_postprocess_ava(const float* pred_logits, const float* pred_boxes, const float* pred_logits_b,
+                          const float* target_sizes, float* detections, int B, int nq, int K, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py).  cqvad_profile_enable(1) makes cqvad_decoder_forward bracket each kernel class with
  * CUDA events on the launch stream; cqvad_profile_read() synchronises and returns the accumulated milliseconds, the
  * number of timed scopes and of kernel launches inside them since the enable call.  Replaces the reference's host
