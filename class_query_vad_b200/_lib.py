@@ -51,6 +51,9 @@ SYMBOLS = {
     "cqvad_level_to_tokens": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_long, c_long, c_long, c_void_p]),
     "cqvad_encoder_to_decoder_memory": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_long, c_int, c_int, c_int,
                                                  c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "cqvad_level_to_tokens_backward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_long, c_long, c_long, c_void_p]),
+    "cqvad_encoder_to_decoder_memory_backward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_long, c_int, c_int, c_int,
+                                                          c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cqvad_deform_encoder_layer_num_weights": (c_int, []),
     "cqvad_deform_encoder_layer_workspace_bytes": (c_size_t, [c_int, c_int, c_long, c_int, c_int, c_int]),
     "cqvad_deform_encoder_layer_forward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

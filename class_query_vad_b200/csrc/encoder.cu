@@ -388,6 +388,94 @@ __global__ void __launch_bounds__(256) level_to_tokens_kernel(const T* __restric
   }
 }
 
+// Backward of interp_to_decoder_kernel: the same warp-per-memory-row geometry, each corner weight scatters the row's gradient into
+// the fp32 token gradient (red.global.add.v4.f32; with `eff` only 4 * H*W * B rows exist, against B*Len token rows to zero-fill).
+__device__ __forceinline__ void red_add_v4e(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__global__ void __launch_bounds__(256) interp_to_decoder_bwd_kernel(const float* __restrict__ gmem, const int64_t* __restrict__ shapes,
+                                                                    const int64_t* __restrict__ lsi, float* __restrict__ gtok, int L,
+                                                                    int B, long Len, int Tt, int H, int W, int nf, int eff) {
+  const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int Tp = eff ? 1 : nf;
+  const long BT = (long)B * Tp, S = (long)H * W;
+  if (wid >= (long)L * S * BT) return;
+  const long bt = wid % BT;
+  const long s = (wid / BT) % S;
+  const int l = (int)(wid / (BT * S));
+  const int b = (int)(bt / Tp), fr = eff ? nf / 2 : (int)(bt % Tp);
+  const int i = (int)(s / W), j = (int)(s % W);
+  const int Tl = (int)shapes[l * 3], Hl = (int)shapes[l * 3 + 1], Wl = (int)shapes[l * 3 + 2];
+  float* base = gtok + ((long)b * Len + lsi[l]) * kC + lane * 8;
+  float x, y, lt = 0.f;
+  int t0 = fr, nt = 1;
+  if (Tt == nf) {
+    x = unnorm(lin_m11(i, H), Wl); y = unnorm(lin_m11(j, W), Hl);
+  } else {
+    x = unnorm(lin_m11(j, W), Wl); y = unnorm(lin_m11(i, H), Hl);
+    const float t = unnorm(lin_m11(fr, nf), Tl);
+    t0 = (int)floorf(t); lt = t - (float)t0; nt = 2;
+  }
+  const int x0 = (int)floorf(x), y0 = (int)floorf(y);
+  const float lx = x - (float)x0, ly = y - (float)y0;
+  const float4 g0 = *reinterpret_cast<const float4*>(gmem + wid * kC + lane * 8);
+  const float4 g1 = *reinterpret_cast<const float4*>(gmem + wid * kC + lane * 8 + 4);
+  for (int kt = 0; kt < nt; ++kt) {
+    const int tz = t0 + kt;
+    const float wt = nt == 1 ? 1.f : (kt ? lt : 1.f - lt);
+    if (tz < 0 || tz >= Tl) continue;
+#pragma unroll
+    for (int ky = 0; ky < 2; ++ky) {
+      const int yz = y0 + ky;
+      if (yz < 0 || yz >= Hl) continue;
+#pragma unroll
+      for (int kx = 0; kx < 2; ++kx) {
+        const int xz = x0 + kx;
+        if (xz < 0 || xz >= Wl) continue;
+        const float wgt = wt * (ky ? ly : 1.f - ly) * (kx ? lx : 1.f - lx);
+        float* dst = base + ((long)(tz * Hl + yz) * Wl + xz) * kC;
+        red_add_v4e(dst, wgt * g0.x, wgt * g0.y, wgt * g0.z, wgt * g0.w);
+        red_add_v4e(dst + 4, wgt * g1.x, wgt * g1.y, wgt * g1.z, wgt * g1.w);
+      }
+    }
+  }
+}
+
+// Backward of level_to_tokens_kernel: token-major gradient rows -> channel-first gradient of the level (the same 32 x 33 tile the
+// other way round) and, for the position embedding, d level_embed[lvl][c] = sum over clips and positions (block partial sums,
+// one fp32 atomic per (block, channel)).
+template <typename T>
+__global__ void __launch_bounds__(256) level_to_tokens_bwd_kernel(const T* __restrict__ gtok, T* __restrict__ gx, float* __restrict__ gadd,
+                                                                  long N, long Len, long level_start, int C = kC) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const long n0 = (long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const T* gb = gtok + ((long)b * Len + level_start) * C;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {                          // rows = positions, columns = channels
+    const long n = n0 + r;
+    tile[r][tx] = n < N ? to_f(gb[n * C + c0 + tx]) : 0.f;
+  }
+  __syncthreads();
+  if (gx) {
+    T* xb = gx + (long)b * C * N;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {                        // rows = channels, columns = positions
+      const long n = n0 + tx;
+      if (n < N) xb[(long)(c0 + r) * N + n] = from_f<T>(tile[tx][r]);
+    }
+  }
+  if (gadd && ty == 0) {
+    float a = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) a += tile[r][tx];
+    atomicAdd(gadd + c0 + tx, a);
+  }
+}
+
 // ---- input projection of a backbone level (CSN configurations) ----------------------------------
 // models/model.py:64-71,162-164: input_proj[l] = Conv3d(C_in, 256, kernel_size = 1) -> GroupNorm(32, 256).  The 1x1x1 conv is a
 // GEMM over the level's positions; GroupNorm(32 groups of 8 channels) normalises over (8 channels x T*H*W) per clip: in the
@@ -616,6 +704,48 @@ extern "C" int cqvad_level_to_tokens(int dtype, const void* x, const float* add,
     level_to_tokens_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16*)x, add, (bf16*)tokens, N, Len, level_start);
   else
     return set_error(CQVAD_E_INVALID_ARG, "level_to_tokens: unknown dtype %d", dtype);
+  CQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cqvad_encoder_to_decoder_memory_backward(int dtype, const float* grad_memory, const int64_t* shapes,
+                                                        const int64_t* level_start, int L, int B, long Len, int Tt, int H, int W,
+                                                        int num_frames, int eff, void* grad_tokens, float* workspace, void* stream) {
+  CQ_CHECK_ARG(L >= 2 && B >= 0 && Len >= 0 && Tt >= 1 && H >= 1 && W >= 1 && num_frames >= 1,
+               "encoder_to_decoder_memory_backward: bad dimensions");
+  const long rows = (long)L * H * W * B * (eff ? 1 : num_frames);
+  const long n = (long)B * Len * kC;
+  if (n == 0) return 0;
+  CQ_CHECK_ARG(grad_memory && shapes && level_start && grad_tokens, "encoder_to_decoder_memory_backward: null pointer");
+  CQ_CHECK_ARG(dtype == CQVAD_F32 || dtype == CQVAD_BF16, "encoder_to_decoder_memory_backward: unknown dtype");
+  CQ_CHECK_ARG(dtype == CQVAD_F32 || workspace != nullptr, "encoder_to_decoder_memory_backward: bf16 needs the fp32 workspace [B*Len*256]");
+  cudaStream_t st = as_stream(stream);
+  float* acc = dtype == CQVAD_F32 ? (float*)grad_tokens : workspace;
+  CQ_CUDA(cudaMemsetAsync(acc, 0, (size_t)n * sizeof(float), st));
+  if (rows > 0) {
+    interp_to_decoder_bwd_kernel<<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(grad_memory, shapes, level_start, acc, L, B, Len, Tt, H,
+                                                                                 W, num_frames, eff ? 1 : 0);
+    CQ_LAUNCH_CHECK();
+  }
+  if (dtype == CQVAD_BF16) CQ_TRY(f32_to_t<bf16>(acc, (bf16*)grad_tokens, 0.f, n, st));
+  return 0;
+}
+
+extern "C" int cqvad_level_to_tokens_backward(int dtype, const void* grad_tokens, void* grad_x, float* grad_add, int B, long N, long Len,
+                                              long level_start, void* stream) {
+  CQ_CHECK_ARG(B >= 0 && N >= 0 && Len >= N && level_start >= 0 && level_start + N <= Len, "level_to_tokens_backward: bad dimensions");
+  if ((long)B * N == 0) return 0;
+  CQ_CHECK_ARG(grad_tokens && (grad_x || grad_add), "level_to_tokens_backward: null pointer");
+  CQ_CHECK_SHAPE(B <= 65535, "level_to_tokens_backward: batch %d > 65535", B);
+  const dim3 grid((unsigned)cdiv(N, 32), kC / 32, (unsigned)B);
+  if (dtype == CQVAD_F32)
+    level_to_tokens_bwd_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)grad_tokens, (float*)grad_x, grad_add, N, Len,
+                                                                           level_start);
+  else if (dtype == CQVAD_BF16)
+    level_to_tokens_bwd_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16*)grad_tokens, (bf16*)grad_x, grad_add, N, Len,
+                                                                          level_start);
+  else
+    return set_error(CQVAD_E_INVALID_ARG, "level_to_tokens_backward: unknown dtype %d", dtype);
   CQ_LAUNCH_CHECK();
   return 0;
 }

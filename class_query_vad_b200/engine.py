@@ -84,7 +84,15 @@ class DecoderEngine:
         self._ws = None
         self._tws = None
         self._train_ctx = None
+        self._train_gen = 0          # generation of the saved activations in _tws (one live training forward per engine)
         self.last_launches = 0
+
+    def repack(self, state):
+        """Refresh the packed weights IN PLACE after an optimizer step: pointer table, workspaces and the flat gradient buffer stay."""
+        keep, _ = pack_decoder_weights(state, self.layers, self.dtype, self.device)
+        for old, new in zip(self._keep, keep):
+            if old is not None:
+                old.copy_(new)
 
     def _workspace(self, desc):
         need = _lib.lib().cqvad_decoder_workspace_bytes(byref(desc))
@@ -182,12 +190,18 @@ class DecoderEngine:
         _lib.check(rc)
         self.last_launches = lib.cqvad_last_launch_count()
         self._train_ctx = (desc, m8, (nq, BT, S))
-        return dict(hs=hs, cls_hs=cls_hs, refs=refs)
+        self._train_gen += 1
+        return dict(hs=hs, cls_hs=cls_hs, refs=refs, generation=self._train_gen)
 
-    def backward(self, grad_hs=None, grad_cls_hs=None, grad_refs=None, zero=True, named=True):
-        """Backward of the last forward_train.  Returns dict(memory, tgt, refpoints_unsigmoid, params={reference name: grad})."""
+    def backward(self, grad_hs=None, grad_cls_hs=None, grad_refs=None, zero=True, named=True, generation=None):
+        """Backward of the last forward_train.  Returns dict(memory, tgt, refpoints_unsigmoid, params={reference name: grad}).
+        `generation` (the value forward_train returned): raises if another forward_train has overwritten the saved activations."""
         if self._train_ctx is None:
             raise RuntimeError("backward() without a preceding forward_train()")
+        if generation is not None and generation != self._train_gen:
+            raise RuntimeError("DecoderEngine.backward: the activations of this forward were overwritten by a later forward_train() on the "
+                               "same engine (one live training forward per engine: run backward before the next forward, or use a "
+                               "second TransformerDecoder / DecoderEngine)")
         lib = _lib.lib()
         desc, m8, (nq, BT, S) = self._train_ctx
         odt = torch.float32 if self.out_f32 else self.dtype

@@ -11,7 +11,7 @@ class DecoderFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, names, mask, pos, orig_res, tgt, memory, refpoints_unsigmoid, *params):
         out = engine.forward_train(tgt.detach(), memory.detach(), mask, pos.detach(), refpoints_unsigmoid.detach(), orig_res)
-        ctx.engine, ctx.names = engine, names
+        ctx.engine, ctx.names, ctx.generation = engine, names, out["generation"]
         ctx.need = (tgt.requires_grad, memory.requires_grad, refpoints_unsigmoid.requires_grad)
         ctx.in_dtypes = (tgt.dtype, memory.dtype, refpoints_unsigmoid.dtype)
         ctx.param_meta = [(p.shape, p.dtype) for p in params]
@@ -21,7 +21,7 @@ class DecoderFunction(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_hs, g_cls, g_refs):
-        g = ctx.engine.backward(g_hs, g_cls, g_refs, zero=True, named=True)
+        g = ctx.engine.backward(g_hs, g_cls, g_refs, zero=True, named=True, generation=ctx.generation)
         named = g["params"]
         pg = []
         for name, (shape, dtype) in zip(ctx.names, ctx.param_meta):

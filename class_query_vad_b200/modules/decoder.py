@@ -232,13 +232,17 @@ class TransformerDecoder(nn.Module):
         if self.bbox_embed is None:
             raise RuntimeError("decoder.bbox_embed must be attached (models/model.py:100-101) before forward")
         params = list(self.parameters())
-        key = (str(device), self.compute_dtype, self.out_dtype, tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+        key = (str(device), self.compute_dtype, self.out_dtype, tuple(p.data_ptr() for p in params))
+        ver = tuple(p._version for p in params)
         if self._engine is None or self._engine_key != key:
             sd = {k: v for k, v in self.state_dict().items()}
             F = self.layers[0].linear1.out_features
             self._engine = DecoderEngine(sd, nq=None, K=self.class_queries.num_embeddings, layers=self.num_layers, F=F,
                                          dtype=self.compute_dtype, device=device, out_f32=self.out_dtype == torch.float32)
-            self._engine_key = key
+            self._engine_key, self._engine_ver = key, ver
+        elif self._engine_ver != ver:        # optimizer step: refresh the packed copies in place, keep workspaces / gradient buffer
+            self._engine.repack({k: v for k, v in self.state_dict().items()})
+            self._engine_ver = ver
         return self._engine
 
     def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,

@@ -173,21 +173,56 @@ class DeformableTransformerEncoder(nn.Module):
         return output
 
 
-def encoder_to_decoder_memory(tokens, pos_tokens, shapes, level_start, num_frames, eff=True):
-    """The encoder -> decoder step of Transformer.forward (dab_transformer.py:349-393) through cqvad_encoder_to_decoder_memory:
-    tokens / pos_tokens [B, Len, 256] -> (memory [L, H*W, B*T', 256], pos0 [H*W, B*T', 256]) with (T, H, W) = shapes[-2]."""
+def _encoder_to_decoder_memory_raw(tokens, pos_tokens, shapes, level_start, num_frames, eff):
     _lib.require_cuda(tokens, shapes, level_start)
     dt = tokens.dtype
     B, Len, C = tokens.shape
     L = int(shapes.shape[0])
     Tt, H, W = (int(v) for v in shapes[L - 2].tolist())
     Tp = 1 if eff else int(num_frames)
-    tok = tokens.contiguous()
-    ptok = None if pos_tokens is None else pos_tokens.to(dt).contiguous()
+    tok = tokens.detach().contiguous()
+    ptok = None if pos_tokens is None else pos_tokens.detach().to(dt).contiguous()
     sh, ls = shapes.to(torch.int64).contiguous(), level_start.to(torch.int64).contiguous()
     memory = torch.empty((L, H * W, B * Tp, C), dtype=dt, device=tokens.device)
     pos0 = None if ptok is None else torch.empty((H * W, B * Tp, C), dtype=dt, device=tokens.device)
     p = _lib.ptr
     _lib.check(_lib.lib().cqvad_encoder_to_decoder_memory(_lib.dtype_id(dt), p(tok), p(ptok), p(sh), p(ls), L, B, Len, Tt, H, W,
                                                          int(num_frames), 1 if eff else 0, p(memory), p(pos0), _lib.stream_ptr()))
+    return memory, pos0, (sh, ls, L, B, Len, Tt, H, W)
+
+
+class EncoderToDecoderMemoryFunction(torch.autograd.Function):
+    """apply(tokens, pos_tokens, shapes, level_start, num_frames, eff) -> (memory, pos0).  backward: the trilinear scatter of
+    d(memory) into the token gradient (cqvad_encoder_to_decoder_memory_backward).  pos0 is marked non-differentiable: the decoder
+    consumes it only on the key side of softmax attentions."""
+
+    @staticmethod
+    def forward(ctx, tokens, pos_tokens, shapes, level_start, num_frames, eff):
+        memory, pos0, geo = _encoder_to_decoder_memory_raw(tokens, pos_tokens, shapes, level_start, num_frames, eff)
+        ctx.geo, ctx.nf, ctx.eff, ctx.dt = geo, int(num_frames), bool(eff), tokens.dtype
+        if pos0 is not None:
+            ctx.mark_non_differentiable(pos0)
+        return memory, pos0
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_mem, _g_pos0):
+        sh, ls, L, B, Len, Tt, H, W = ctx.geo
+        dt = ctx.dt
+        gm = g_mem.to(torch.float32).contiguous()
+        gtok = torch.empty((B, Len, 256), dtype=dt, device=gm.device)
+        ws = None if dt == torch.float32 else torch.empty((B, Len, 256), dtype=torch.float32, device=gm.device)
+        p = _lib.ptr
+        _lib.check(_lib.lib().cqvad_encoder_to_decoder_memory_backward(_lib.dtype_id(dt), p(gm), p(sh), p(ls), L, B, Len, Tt, H, W, ctx.nf,
+                                                                      1 if ctx.eff else 0, p(gtok), p(ws), _lib.stream_ptr()))
+        return gtok, None, None, None, None, None
+
+
+def encoder_to_decoder_memory(tokens, pos_tokens, shapes, level_start, num_frames, eff=True):
+    """The encoder -> decoder step of Transformer.forward (dab_transformer.py:349-393) through cqvad_encoder_to_decoder_memory:
+    tokens / pos_tokens [B, Len, 256] -> (memory [L, H*W, B*T', 256], pos0 [H*W, B*T', 256]) with (T, H, W) = shapes[-2].
+    Differentiable with respect to `tokens` (EncoderToDecoderMemoryFunction)."""
+    if torch.is_grad_enabled() and tokens.requires_grad:
+        return EncoderToDecoderMemoryFunction.apply(tokens, pos_tokens, shapes, level_start, num_frames, eff)
+    memory, pos0, _ = _encoder_to_decoder_memory_raw(tokens, pos_tokens, shapes, level_start, num_frames, eff)
     return memory, pos0

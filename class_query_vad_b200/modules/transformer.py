@@ -12,10 +12,7 @@ from .decoder import build_decoder
 from .encoder import DeformableTransformerEncoderLayer, DeformableTransformerEncoder, encoder_to_decoder_memory
 
 
-def flatten_levels(srcs, pos_embeds, level_embed):
-    """dab_transformer.py:310-327: per level [B, 256, T, H, W] -> (src_flatten, lvl_pos_embed_flatten) [B, Len, 256], shapes
-    [L, 3], level_start [L] through cqvad_level_to_tokens."""
-    _lib.require_cuda(*srcs)
+def _flatten_levels_raw(srcs, pos_embeds, level_embed):
     lib = _lib.lib()
     dt, dev = srcs[0].dtype, srcs[0].device
     B = srcs[0].shape[0]
@@ -30,10 +27,65 @@ def flatten_levels(srcs, pos_embeds, level_embed):
     for l, (s, pe) in enumerate(zip(srcs, pos_embeds)):
         if s.shape[1] != 256:
             raise ValueError("d_model must be 256")
-        sc, pc = s.contiguous(), pe.to(dt).contiguous()
+        sc, pc = s.detach().contiguous(), pe.detach().to(dt).contiguous()
         _lib.check(lib.cqvad_level_to_tokens(_lib.dtype_id(dt), p(sc), None, p(src_flat), B, ns[l], Len, start, _lib.stream_ptr()))
         _lib.check(lib.cqvad_level_to_tokens(_lib.dtype_id(dt), p(pc), p(le[l]), p(pos_flat), B, ns[l], Len, start, _lib.stream_ptr()))
         start += ns[l]
+    return src_flat, pos_flat, shapes, ns
+
+
+class LevelsToTokensFunction(torch.autograd.Function):
+    """apply(level_embed, *srcs, *pos_embeds) -> (src_flatten, lvl_pos_embed_flatten); the backward (cqvad_level_to_tokens_backward)
+    returns d level_embed [L, 256] (sum of the position-embedding gradient over clips and positions of each level) and the
+    channel-first gradients of the levels (and of the position embeddings when they require grad)."""
+
+    @staticmethod
+    def forward(ctx, level_embed, *levels):
+        L = len(levels) // 2
+        srcs, pos_embeds = levels[:L], levels[L:]
+        src_flat, pos_flat, shapes, ns = _flatten_levels_raw(srcs, pos_embeds, level_embed)
+        ctx.meta = (L, [tuple(s.shape) for s in srcs], ns, [s.dtype for s in srcs], [pe.dtype for pe in pos_embeds], level_embed.dtype)
+        ctx.need = [t.requires_grad for t in levels]
+        return src_flat, pos_flat
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_src, g_pos):
+        L, shp, ns, sdt, pdt, ledt = ctx.meta
+        lib = _lib.lib()
+        p = _lib.ptr
+        dt, dev = g_src.dtype, g_src.device
+        B, Len = g_src.shape[0], g_src.shape[1]
+        g_src, g_pos = g_src.contiguous(), g_pos.contiguous()
+        g_le = torch.zeros((L, 256), dtype=torch.float32, device=dev)
+        outs_s, outs_p = [], []
+        start = 0
+        for l in range(L):
+            gx = gp = None
+            if ctx.need[l]:
+                gx = torch.empty(shp[l], dtype=dt, device=dev)
+                _lib.check(lib.cqvad_level_to_tokens_backward(_lib.dtype_id(dt), p(g_src), p(gx), None, B, ns[l], Len, start,
+                                                              _lib.stream_ptr()))
+            if ctx.need[L + l]:
+                gp = torch.empty(shp[l], dtype=dt, device=dev)
+            _lib.check(lib.cqvad_level_to_tokens_backward(_lib.dtype_id(dt), p(g_pos), p(gp), p(g_le[l]), B, ns[l], Len, start,
+                                                          _lib.stream_ptr()))
+            outs_s.append(None if gx is None else gx.to(sdt[l]))
+            outs_p.append(None if gp is None else gp.to(pdt[l]))
+            start += ns[l]
+        return (g_le.to(ledt), *outs_s, *outs_p)
+
+
+def flatten_levels(srcs, pos_embeds, level_embed):
+    """dab_transformer.py:310-327: per level [B, 256, T, H, W] -> (src_flatten, lvl_pos_embed_flatten) [B, Len, 256], shapes
+    [L, 3], level_start [L] through cqvad_level_to_tokens (differentiable: LevelsToTokensFunction)."""
+    _lib.require_cuda(*srcs)
+    dev = srcs[0].device
+    shapes = [tuple(int(v) for v in s.shape[2:]) for s in srcs]
+    if torch.is_grad_enabled() and (level_embed.requires_grad or any(t.requires_grad for t in (*srcs, *pos_embeds))):
+        src_flat, pos_flat = LevelsToTokensFunction.apply(level_embed, *srcs, *pos_embeds)
+    else:
+        src_flat, pos_flat, _, _ = _flatten_levels_raw(srcs, pos_embeds, level_embed)
     sh = torch.tensor(shapes, dtype=torch.int64, device=dev)
     ls = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
     return src_flat, pos_flat, sh, ls

@@ -140,6 +140,11 @@ int cqvad_input_proj_3x3s2_gn(int dtype, const void* x, const void* weight_taps,
  * (fp32, for the position embedding; NULL for the features), tokens [B, Len, 256]. */
 int cqvad_level_to_tokens(int dtype, const void* x, const float* add, void* tokens, int B, long N, long Len, long level_start,
                           void* stream);
+/* Backward of cqvad_level_to_tokens (autograd of dab_transformer.py:316-321): grad_x [B, 256, N] channel-first (dtype; may be
+ * NULL) = the level's rows of grad_tokens [B, Len, 256] (dtype) transposed back; grad_add [256] fp32 (may be NULL) ACCUMULATES
+ * sum_{b,n} grad_tokens[b, level_start + n, :] = d level_embed[lvl] when called on the gradient of lvl_pos_embed_flatten. */
+int cqvad_level_to_tokens_backward(int dtype, const void* grad_tokens, void* grad_x, float* grad_add, int B, long N, long Len,
+                                   long level_start, void* stream);
 /* Encoder output -> decoder memory: the part of Transformer.forward between the two
  * (models/detr/dab_transformer.py:349-393): per-level un-flatten, make_interpolated_features (:239-294, grid_sample with
  * align_corners = False and zeros padding onto the (num_frames, H, W) grid of level -2, including the reference's (meshy, meshx)
@@ -150,6 +155,14 @@ int cqvad_level_to_tokens(int dtype, const void* x, const float* add, void* toke
 int cqvad_encoder_to_decoder_memory(int dtype, const void* tokens, const void* pos_tokens, const int64_t* shapes,
                                     const int64_t* level_start, int L, int B, long Len, int Tt, int H, int W, int num_frames,
                                     int eff, void* memory, void* pos0, void* stream);
+/* Backward of cqvad_encoder_to_decoder_memory (autograd of F.grid_sample + the slicing / rearrange around it): grad_memory fp32
+ * [L, H*W, B*T', 256] (what cqvad_decoder_backward writes) is scattered with the forward's trilinear weights into grad_tokens
+ * [B, Len, 256] (dtype), which is fully overwritten (tokens no consumed frame touches get zero).  workspace: fp32 [B*Len*256]
+ * accumulator, required for bf16 (NULL allowed for fp32).  pos0 is a copy of pos_tokens rows of level -2; the decoder uses it only
+ * on the key side of its softmax attentions, see INTEGRATION.md section 5 for why level_embed receives no gradient through it. */
+int cqvad_encoder_to_decoder_memory_backward(int dtype, const float* grad_memory, const int64_t* shapes, const int64_t* level_start,
+                                             int L, int B, long Len, int Tt, int H, int W, int num_frames, int eff, void* grad_tokens,
+                                             float* workspace, void* stream);
 /* Y[M,256] = LN?( res + W2 . act(W1 . X + b1) + b2 ): the FFN blocks of the decoder (dab_transformer.py:994-996,
  * 1043-1045, 1074-1076).  X [M,256], W1 [F,256], W2 [256,F] (dtype); ln_g/ln_b may be NULL (no LayerNorm); res may be
  * NULL.  hidden [M,F] (dtype) is scratch used only when the fused tensor-core kernel does not apply (fp32, or F % 128). */

@@ -205,3 +205,24 @@ def test_module_autograd_drop_in():
     idx = synth.grad_sample_index(w.size, seed)
     ref_s = g["gs.cls_layers.0.conv_blocks.0.conv1.weight"]
     assert np.abs(w.reshape(-1)[idx] - ref_s).max() / np.abs(ref_s).max() < TOL_FP32
+
+
+def test_backward_of_an_overwritten_forward_raises():
+    """One live training forward per engine: a backward whose saved activations were overwritten by a later forward_train must
+    fail loudly instead of returning gradients of the wrong graph."""
+    from class_query_vad_b200 import build_decoder
+    cfg = dict(synth.CONFIGS["tiny"])
+    dev = torch.device("cuda:0")
+    W = synth.make_decoder_weights(cfg["K"], cfg["layers"], cfg["F"], seed=0)
+    dec = build_decoder(num_queries=cfg["nq"], num_classes=cfg["K"], num_layers=cfg["layers"], dim_feedforward=cfg["F"])
+    dec.load_state_dict({k: torch.from_numpy(v) for k, v in W.items() if not k.startswith("heads.")}, strict=True)
+    dec = dec.to(dev).eval()
+    outs = []
+    for seed in (0, 1):
+        inp = synth.make_decoder_inputs(cfg, 2, seed=seed)
+        t = lambda a: torch.from_numpy(a).to(dev)
+        hs, cls_hs, refs = dec(t(inp["tgt"]), t(inp["memory"]).requires_grad_(True), memory_key_padding_mask=t(inp["mask"]), pos=t(inp["pos"]),
+                               refpoints_unsigmoid=t(inp["refpoints_unsigmoid"]), orig_res=inp["orig_res"])
+        outs.append(hs.sum())
+    with pytest.raises(RuntimeError, match="overwritten"):
+        (outs[0] + outs[1]).backward()
