@@ -14,6 +14,8 @@ from .modules.encoder import (DeformableTransformerEncoderLayer, DeformableTrans
                               pack_encoder_layer_weights, encoder_to_decoder_memory)
 from .modules.transformer import Transformer, flatten_levels, input_proj_levels
 from .modules.criterion import HungarianMatcherAVA, SetCriterionAVA, PostProcessAVA, pack_targets
+from .modules.heads import DETRHeads, HeadsFunction
+from .optim import FlatAdamW
 from .modules.decoder import (MLP, ConvBlock, TransformerDecoderLayer, TransformerClassDecoderLayer, TransformerDecoder,
                               build_decoder)
 
@@ -22,4 +24,4 @@ __all__ = ["DecoderEngine", "DecoderFunction", "pack_decoder_weights", "MSDeform
            "MLP", "ConvBlock", "TransformerDecoderLayer", "TransformerClassDecoderLayer", "TransformerDecoder",
            "build_decoder", "DeformableTransformerEncoderLayer", "DeformableTransformerEncoder", "encoder_layer_forward",
            "pack_encoder_layer_weights", "encoder_to_decoder_memory", "Transformer", "flatten_levels", "input_proj_levels",
-           "HungarianMatcherAVA", "SetCriterionAVA", "PostProcessAVA", "pack_targets"]
+           "DETRHeads", "HeadsFunction", "FlatAdamW", "HungarianMatcherAVA", "SetCriterionAVA", "PostProcessAVA", "pack_targets"]

@@ -2,7 +2,7 @@
 op fails loudly -- build it with `python -c "import __graft_entry__ as g; g.build()"` (or `make -C class_query_vad_b200/csrc`)."""
 import ctypes
 import os
-from ctypes import c_int, c_long, c_size_t, c_void_p, c_float, c_char_p, POINTER, Structure
+from ctypes import c_int, c_long, c_size_t, c_void_p, c_float, c_char_p, c_uint64, POINTER, Structure
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcqvad.so")
@@ -81,6 +81,12 @@ SYMBOLS = {
     "cqvad_criterion_ava_workspace_bytes": (c_size_t, [c_int]),
     "cqvad_criterion_ava": (c_int, [POINTER(CriterionCfg)] + [c_void_p] * 6 + [c_int] * 4 + [c_void_p] * 6 + [c_size_t, c_void_p]),
     "cqvad_postprocess_ava": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
+    "cqvad_heads_train_workspace_bytes": (c_size_t, [c_long]),
+    "cqvad_heads_train_forward": (c_int, [c_void_p] * 4 + [c_long, c_int, c_float, c_uint64] + [c_void_p] * 4 + [c_size_t, c_void_p]),
+    "cqvad_heads_train_backward": (c_int, [c_void_p] * 6 + [c_long, c_int, c_float, c_uint64] + [c_void_p] * 5 + [c_size_t, c_void_p]),
+    "cqvad_adamw_workspace_bytes": (c_size_t, []),
+    "cqvad_adamw_clip_step": (c_int, [c_void_p] * 5 + [c_long] + [c_float] * 5 + [c_long, c_float, c_float, c_int, c_void_p, c_void_p,
+                                                                                c_size_t, c_void_p]),
     "cqvad_last_launch_count": (c_long, []),
     "cqvad_profile_enable": (None, [c_int]),
     "cqvad_profile_num_classes": (c_int, []),

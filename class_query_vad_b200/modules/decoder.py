@@ -245,6 +245,10 @@ class TransformerDecoder(nn.Module):
             self._engine_ver = ver
         return self._engine
 
+    def weights_updated(self):
+        """Parameters were changed through raw pointers (FlatAdamW): refresh the packed copies at the next forward."""
+        self._engine_ver = None
+
     def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
                 memory_key_padding_mask=None, pos=None, refpoints_unsigmoid=None, orig_res=None):
         if tgt_mask is not None or memory_mask is not None or tgt_key_padding_mask is not None:

@@ -127,6 +127,9 @@ class DeformableTransformerEncoderLayer(nn.Module):
             self._packed = (ver, pack_encoder_layer_weights(self.state_dict(), dtype, device))
         return self._packed[1]
 
+    def weights_updated(self):
+        self._packed = None
+
     def forward(self, src, pos, reference_points, spatio_temporal_shapes, level_start_index, padding_mask=None):
         if self.training and (self.dropout1.p > 0 or self.dropout2.p > 0):
             import warnings

@@ -309,6 +309,38 @@ int cqvad_postprocess_ava(const float* pred_logits, const float* pred_boxes, con
                           const float* target_sizes, float* detections, int B, int nq, int K, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * DETR heads of the reference model in the TRAINING step (models/model.py:191-236), fp32 like the reference (autocast off):
+ *   pred_logits_b = class_embed_b(hs);  pred_boxes = sigmoid(bbox_embed(hs) + inverse_sigmoid(reference))  (utils/misc.py:530-534);
+ *   pred_logits = Dropout(p_drop)(cls_hs).mean(-1)  (models/model.py:103,219: p = 0.5 in training, 0 in eval).
+ * Rows R = Lr*BT*nq in the order of the decoder outputs: hs [R,256], refs [R,4], cls_hs [R,K,256] (all fp32).
+ * weights[8] = bbox_embed.layers.{0,1,2}.{weight,bias}, class_embed_b.{weight,bias} (fp32, PyTorch [out,in] layout).
+ * The dropout mask is a Philox4x32-10 stream keyed by `seed` (counter = element index): the backward regenerates it, nothing is
+ * stored.  The forward keeps the MLP hidden activations in `workspace`, which the backward of the SAME rows must receive.
+ * backward: grad_hs [R,256], grad_refs [R,4] (may be NULL), grad_cls_hs [R,K,256] (may be NULL) are overwritten;
+ * grad_weights[8] (may be NULL) are ACCUMULATED (bbox_embed is shared with the decoder's box refinement, models/model.py:100-101). */
+size_t cqvad_heads_train_workspace_bytes(long R);
+int cqvad_heads_train_forward(const float* const* weights, const float* hs, const float* cls_hs, const float* refs, long R, int K,
+                              float p_drop, uint64_t seed, float* pred_logits, float* pred_boxes, float* pred_logits_b,
+                              void* workspace, size_t ws_bytes, void* stream);
+int cqvad_heads_train_backward(const float* const* weights, const float* hs, const float* refs, const float* grad_logits,
+                               const float* grad_boxes, const float* grad_logits_b, long R, int K, float p_drop, uint64_t seed,
+                               float* grad_hs, float* grad_cls_hs, float* grad_refs, float* const* grad_weights, void* workspace,
+                               size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Optimizer step of the reference training loop (train.py:83,158-167) over ONE flat fp32 buffer of n parameters:
+ *   torch.nn.utils.clip_grad_norm_(parameters, max_norm) -- global L2 norm of all gradients, coef = min(1, max_norm/(norm+1e-6)),
+ *   torch.optim.AdamW(lr, (beta1, beta2), eps, weight_decay).step() -- decoupled decay, bias-corrected moments.
+ * grads are first multiplied by grad_scale (1 / world size after a SUM all-reduce; 1 otherwise): the norm is that of the scaled
+ * gradient.  step = 1-based count of this update.  max_norm <= 0 disables clipping.  params_bf16 (may be NULL): a bf16 copy of
+ * the updated parameters written in the same pass (tensor-core operand).  zero_grad != 0 zero-fills grads afterwards
+ * (optimizer.zero_grad()).  grad_norm_out (may be NULL): the pre-clip norm, device scalar.  Two launches, no host sync. */
+size_t cqvad_adamw_workspace_bytes(void);
+int cqvad_adamw_clip_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16, long n, float lr,
+                          float beta1, float beta2, float eps, float weight_decay, long step, float max_norm, float grad_scale,
+                          int zero_grad, float* grad_norm_out, void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py).  cqvad_profile_enable(1) makes cqvad_decoder_forward bracket each kernel class with
  * CUDA events on the launch stream; cqvad_profile_read() synchronises and returns the accumulated milliseconds, the
  * number of timed scopes and of kernel launches inside them since the enable call.  Replaces the reference's host
