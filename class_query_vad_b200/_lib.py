@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libcqvad.so")
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 DEC_SKIP_CLS_HS = 1
+DEC_FP32_CLS_STREAM = 2
 
 
 class DecoderDesc(Structure):

@@ -91,7 +91,11 @@ def flat(grads):
     return {k: v.double().cpu() for k, v in d.items()}
 
 
-for name in sys.argv[1:] or ["grad_ava_vitb_b1_l2"]:
+RECORD = {}          # DUMP_JSON=path: per case {ours, weight_quantisation_alone, reference_autocast_bf16}: {median, p90, max}
+stats = lambda l2: {"median": float(np.median(list(l2.values()))), "p90": float(np.percentile(list(l2.values()), 90)),
+                    "max": float(max(l2.values())), "tensors": len(l2)}
+
+for name in [a for a in sys.argv[1:] if not a.startswith("-")] or ["grad_ava_vitb_b1_l2"]:
     g = load_golden(name)
     cfg, B, W, inp = case_from_golden(g)
     seed = int(g["meta"][8])
@@ -100,12 +104,14 @@ for name in sys.argv[1:] or ["grad_ava_vitb_b1_l2"]:
     _, gA, engA = run_train(cfg, B, W, inp, seed, torch.bfloat16)
     _, l2A = grad_errors(gA, g, seed, tgt_zero=tz, want_l2=True)
     summary("A bf16 path vs reference (fp32, unrounded weights)", l2A)
+    RECORD[name] = {"ours_bf16": stats(l2A)}
     fA = flat(gA)
     del engA
     Wr = round_matrices(W, cfg["layers"])
     _, gB, engB = run_train(cfg, B, Wr, inp, seed, torch.float32)
     _, l2B = grad_errors(gB, g, seed, tgt_zero=tz, want_l2=True)
     summary("B fp32 path, bf16-rounded matrices vs reference (weight quantisation alone)", l2B)
+    RECORD[name]["weight_quantisation_alone"] = stats(l2B)
     fB = flat(gB)
     Gmed = float(np.median([float(v.abs().max()) for v in fB.values()]))
     l2C = {}
@@ -132,5 +138,14 @@ for name in sys.argv[1:] or ["grad_ava_vitb_b1_l2"]:
     try:
         for tag, l2D in reference_bf16_errors(g, cfg, B, W, inp, seed, tz).items():
             summary(f"D {tag} vs reference fp32 fixture", l2D)
+            if tag.startswith("autocast"):
+                RECORD[name]["reference_autocast_bf16"] = stats(l2D)
     except Exception as e:
         print("  [D] reference bf16 evaluation failed:", str(e)[:200])
+
+if os.environ.get("DUMP_JSON"):
+    import json
+    RECORD["_about"] = ("per-tensor relative-L2 gradient error against the fp32 reference-autograd fixtures, measured on B200 by tools/diag_bf16_budget.py: "
+                        "ours_bf16 = the tcgen05 bf16 path; weight_quantisation_alone = the fp32 path with the matrices rounded to bf16; "
+                        "reference_autocast_bf16 = the UNMODIFIED reference decoder (baseline/_ref) under torch.autocast(bf16) on the same GPU")
+    json.dump(RECORD, open(os.environ["DUMP_JSON"], "w"), indent=1)
