@@ -482,6 +482,10 @@ def main():
             line["encoder_layer"] = encoder_layer_numbers(dev)
         except Exception as e:                      # the headline never depends on the extra measurement
             line["encoder_layer"] = {"error": str(e)[:200]}
+        try:
+            line["vit_neck"] = vit_neck_numbers(dev)
+        except Exception as e:
+            line["vit_neck"] = {"error": str(e)[:200]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -614,6 +618,32 @@ def other_config_inference(dev, world, timed_fn, steps=3):
         del eng, sets
         torch.cuda.empty_cache()
     return out
+
+
+def vit_neck_numbers(dev, B=4, iters=5):
+    """the ViT simple-feature-pyramid neck (4 levels) on BASELINE configs[0]'s features
+    (8x14x14x768 per clip) -> the encoder's 33 320-token sequence, bf16, inputs resident, CUDA events, median."""
+    import torch
+    from class_query_vad_b200 import SimpleFeaturePyramid
+    torch.manual_seed(3)
+    neck = SimpleFeaturePyramid(768).to(dev)
+    x = [torch.randn((B, 768, 8, 14, 14), device=dev).bfloat16() for _ in range(4)]
+    ts = []
+    for _ in range(iters + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        neck.forward_tokens(x)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts[2:]))
+    # algorithmic FLOPs per clip: ConvT GEMMs + 1x1x1 + 3x3x3 convs (2 * rows * K * N)
+    r = 8 * 14 * 14
+    fl = 2.0 * (r * 768 * 1536 + 4 * r * 384 * 768 + 16 * r * 192 * 256 + r * 768 * 1536 + 4 * r * 384 * 256 + r * 768 * 256 + (r // 4) * 768 * 256
+                + (16 + 4 + 1) * r * 6912 * 256 + (8 * 7 * 7) * 6912 * 256)
+    return {"workload": f"ViT-B simple feature pyramid (lateral_convs x4) on 8x14x14x768 features -> 33 320 tokens, bf16, {B} clips",
+            "ms": round(ms, 3), "clips_per_s": round(B / ms * 1e3, 1), "gflop_per_clip": round(fl / 1e9, 1),
+            "tflops": round(B * fl / ms / 1e9, 1)}
 
 
 def reference_gpu_eager(dev, mode, B, iters=5):

@@ -52,6 +52,8 @@ SYMBOLS = {
     "cqvad_level_to_tokens": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_long, c_long, c_long, c_void_p]),
     "cqvad_encoder_to_decoder_memory": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_long, c_int, c_int, c_int,
                                                  c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "cqvad_vit_neck_workspace_bytes": (c_size_t, [c_int] * 7),
+    "cqvad_vit_neck_level": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_long, c_long, c_void_p, c_size_t] + [c_int] * 5 + [c_void_p]),
     "cqvad_level_to_tokens_backward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_long, c_long, c_long, c_void_p]),
     "cqvad_encoder_to_decoder_memory_backward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_long, c_int, c_int, c_int,
                                                           c_int, c_int, c_void_p, c_void_p, c_void_p]),

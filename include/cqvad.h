@@ -135,6 +135,18 @@ size_t cqvad_input_proj_3x3s2_workspace_bytes(int dtype, int B, int Cin, int T, 
 int cqvad_input_proj_3x3s2_gn(int dtype, const void* x, const void* weight_taps, const float* bias, const float* gn_weight,
                               const float* gn_bias, float eps, void* tokens, void* workspace, size_t workspace_bytes, int B, int Cin,
                               int T, int H, int W, long Len, long level_start, void* stream);
+/* ViT simple-feature-pyramid neck: one `lateral_convs[kind]` of the reference Backbone
+ * (models/backbone_3d_builder.py:133-182; space_forward :190-200) applied to a ViT feature map x [B, C_in, T, H, W] (dtype,
+ * channel-first) and written into the encoder's token sequence tokens [B, Len, 256] at level_start (conv + norm + flatten).
+ * kind 0 = scale 4 (ConvTranspose3d x2 with channel LayerNorm + GELU between; output T x 4H x 4W), 1 = scale 2 (one ConvTranspose3d;
+ * T x 2H x 2W), 2 = scale 1, 3 = scale 0.5 (MaxPool3d (1,2,2); T x H/2 x W/2); each followed by Conv3d 1x1x1 (no bias) -> channel
+ * LayerNorm(256, eps 1e-6) -> Conv3d 3x3x3 (padding 1, no bias).  weights: the host-packed table documented in csrc/neck.cu
+ * (class_query_vad_b200/modules/neck.py::pack_neck_weights): ConvTranspose weights as [(dy,dx,c_out), c_in] (dtype) with the bias
+ * tiled 4x (fp32), 1x1x1 weight [256, C] (dtype), LayerNorm affine fp32, 3x3x3 weight as [kt][256][(ky,kx), 256] (dtype).
+ * C_in % 256 == 0, 4*W <= 128. */
+size_t cqvad_vit_neck_workspace_bytes(int dtype, int kind, int B, int Cin, int T, int H, int W);
+int cqvad_vit_neck_level(int dtype, int kind, const void* x, const void* const* weights, void* tokens, long Len, long level_start,
+                         void* workspace, size_t ws_bytes, int B, int Cin, int T, int H, int W, void* stream);
 /* One pyramid level into the encoder's token sequence (Transformer.forward, models/detr/dab_transformer.py:310-327):
  * tokens[b, level_start + n, c] = x[b, c, n] (+ add[c]) for x [B, 256, N = T*H*W] channel-first (dtype), add = level_embed[lvl]
  * (fp32, for the position embedding; NULL for the features), tokens [B, Len, 256]. */
