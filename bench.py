@@ -7,7 +7,8 @@ A step (default --mode train = BASELINE.json configs[1] "full decoder fwd+bwd bf
 TransformerDecoder.forward (cqvad_decoder_train_forward) + its backward (cqvad_decoder_backward: gradients of every decoder
 parameter, memory, tgt and refpoints_unsigmoid) over one batch of synthetic clips (AVA22_ViT-B shapes: nq 15, S 14x14, K 80,
 6 layers, F 2048), bf16 tensor-core path, loss = sum(w_hs*hs) + sum(w_cls*cls_hs) + sum(w_refs*refs) (SURVEY.md section 8d
-Config 2; dropout = identity).  --mode infer times the inference forward + DETR heads (cqvad_decoder_forward); the default
+Config 2), nn.Dropout(0.1) ON at the nine residual-branch / FFN-hidden sites of every layer pair (Philox masks regenerated in the
+backward; the reference arms run the reference modules in eval mode: dropout is extra work only on this arm).  --mode infer times the inference forward + DETR heads (cqvad_decoder_forward); the default
 run reports it under "inference_forward"; at N=1 the line also carries "encoder_layer" (one
 deformable encoder layer, forward and forward + backward, on the ViT-B/224 pyramid).
   value : whole-job clips/s with inputs already resident in HBM (CUDA events, max over ranks)
@@ -39,6 +40,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+DROPOUT_P = 0.1                        # --dropout
 CFG = "ava_vitb"                       # --config: BASELINE.json configs[1] by default; configs[2..3] shapes selectable
 # decoder forward GFLOP per clip (reference flop count); fwd + bwd = 3x
 FWD_GFLOP = {"ava_vitb": 148.18, "ava_csn152": 187.98, "ucf_vitb": 2147.7, "jhmdb_vitb": 1162.8}
@@ -153,7 +155,8 @@ class _Work(dict):
         c = synth.CONFIGS[CFG]
         shape = f"({c['layers']} layers, nq {c['nq']}, T' {c['tprime']}, S {c['h'] * c['w']}, K {c['K']}, F {c['F']}"
         if mode == "train":
-            return f"{CFG_NAME[CFG]} class-query decoder fwd + bwd {shape}; gradients of all parameters, memory, tgt, refpoints)"
+            return (f"{CFG_NAME[CFG]} class-query decoder fwd + bwd {shape}; gradients of all parameters, memory, tgt, refpoints; "
+                    f"nn.Dropout(p={DROPOUT_P}) on at the residual-branch / FFN-hidden sites)")
         return f"{CFG_NAME[CFG]} class-query decoder forward + heads {shape})"
 
 
@@ -206,12 +209,14 @@ def main():
     ap.add_argument("--config", default="ava_vitb", choices=sorted(FWD_GFLOP))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--dropout", type=float, default=0.1, help="decoder nn.Dropout p in the training step (configuration/*.yaml DROPOUT 0.1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs / full training step extra keys")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    global CFG
+    global CFG, DROPOUT_P
     CFG = args.config
+    DROPOUT_P = args.dropout
     if args.batch <= 0:
         args.batch = DEFAULT_BATCH[CFG]
 
@@ -273,8 +278,12 @@ def main():
         launches["n"] = eng.last_launches + 1 + (1 if world > 1 else 0)
         return out
 
+    step_no = {"n": 0}
+
     def train_step(inp):
-        out = eng.forward_train(inp["tgt"], inp["memory"], inp["mask"], inp["pos"], inp["refpoints_unsigmoid"], orig_res)
+        step_no["n"] += 1          # nn.Dropout(0.1) ON, as in the reference training loop: a fresh Philox stream per step
+        out = eng.forward_train(inp["tgt"], inp["memory"], inp["mask"], inp["pos"], inp["refpoints_unsigmoid"], orig_res,
+                                dropout_p=args.dropout, seed=1000 + step_no["n"])
         eng.backward(g_hs, g_cls, g_refs, zero=True, named=False)
         if world > 1:
             allreduce_gradients(eng)

@@ -2,7 +2,7 @@
 op fails loudly -- build it with `python -c "import __graft_entry__ as g; g.build()"` (or `make -C class_query_vad_b200/csrc`)."""
 import ctypes
 import os
-from ctypes import c_int, c_long, c_size_t, c_void_p, c_float, c_char_p, c_uint64, POINTER, Structure
+from ctypes import c_int, c_long, c_size_t, c_void_p, c_float, c_char_p, c_uint64, c_uint32, c_uint, POINTER, Structure
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcqvad.so")
@@ -15,7 +15,7 @@ DEC_FP32_CLS_STREAM = 2
 
 class DecoderDesc(Structure):
     _fields_ = [("dtype", c_int), ("BT", c_int), ("nq", c_int), ("h", c_int), ("w", c_int), ("K", c_int), ("F", c_int),
-                ("layers", c_int), ("out_f32", c_int), ("flags", c_int)]
+                ("layers", c_int), ("out_f32", c_int), ("flags", c_int), ("dropout_p", c_float), ("seed_lo", c_uint), ("seed_hi", c_uint)]
 
 
 class CriterionCfg(Structure):
@@ -39,9 +39,11 @@ SYMBOLS = {
     "cqvad_linear_dgrad_act": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_long, c_int, c_int, c_void_p]),
     "cqvad_deform_encoder_layer_train_workspace_bytes": (c_size_t, [c_int, c_int, c_long, c_int, c_int, c_int]),
     "cqvad_deform_encoder_layer_train_forward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                                          c_void_p, c_void_p, c_size_t, c_int, c_long, c_int, c_int, c_int, c_void_p]),
+                                                          c_void_p, c_void_p, c_size_t, c_int, c_long, c_int, c_int, c_int, c_float, c_uint64,
+                                                          c_void_p]),
     "cqvad_deform_encoder_layer_backward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                                     c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_long, c_int, c_int, c_int, c_void_p]),
+                                                     c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_long, c_int, c_int, c_int, c_float, c_uint64,
+                                                     c_void_p]),
     "cqvad_input_proj_3x3s2_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "cqvad_input_proj_3x3s2_gn": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t,
                                            c_int, c_int, c_int, c_int, c_int, c_long, c_long, c_void_p]),
@@ -84,6 +86,7 @@ SYMBOLS = {
     "cqvad_criterion_ava_workspace_bytes": (c_size_t, [c_int]),
     "cqvad_criterion_ava": (c_int, [POINTER(CriterionCfg)] + [c_void_p] * 6 + [c_int] * 4 + [c_void_p] * 6 + [c_size_t, c_void_p]),
     "cqvad_postprocess_ava": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
+    "cqvad_dropout": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_long, c_float, c_uint64, c_uint32, c_void_p]),
     "cqvad_heads_train_workspace_bytes": (c_size_t, [c_long]),
     "cqvad_heads_train_forward": (c_int, [c_void_p] * 4 + [c_long, c_int, c_float, c_uint64] + [c_void_p] * 4 + [c_size_t, c_void_p]),
     "cqvad_heads_train_backward": (c_int, [c_void_p] * 6 + [c_long, c_int, c_float, c_uint64] + [c_void_p] * 5 + [c_size_t, c_void_p]),

@@ -11,6 +11,7 @@
 // Dropout is the identity (eval / the native path's documented divergence).  Heads = 8, d_model = 256 (all shipped configs).
 #include "common.cuh"
 #include "bwd.cuh"
+#include "dropout.cuh"
 
 #include <stdlib.h>
 
@@ -214,7 +215,8 @@ struct EncTrainWs {
 
 template <typename T>
 int enc_train_fwd_t(const void* const* W, const T* src, const T* pos, const float* refp, const int64_t* shapes, const int64_t* lsi,
-                    const uint8_t* mask, T* out, void* ws, size_t ws_bytes, int B, long Len, int L, int P, int F, cudaStream_t st) {
+                    const uint8_t* mask, T* out, void* ws, size_t ws_bytes, int B, long Len, int L, int P, int F, float pdrop,
+                    uint64_t seed, cudaStream_t st) {
   const long rows = (long)B * Len;
   if (rows == 0) return 0;
   const int LP3 = kM * L * P * 3, LP1 = kM * L * P;
@@ -222,6 +224,7 @@ int enc_train_fwd_t(const void* const* W, const T* src, const T* pos, const floa
   if (ws_bytes < w.bytes) return set_error(CQVAD_E_WORKSPACE, "deform_encoder_layer (training): workspace too small");
   auto Wm = [&](int i) { return (const T*)W[i]; };
   auto Wf = [&](int i) { return (const float*)W[i]; };
+  const bool drop = pdrop > 0.f;   // dropout1 / dropout2 / dropout3 of dab_transformer.py:499-519 = sites 1 / 2 / 3
   const long n8 = rows * kC / 8;
   add_rows_kernel<T><<<(unsigned)cdiv(n8, 256), 256, 0, st>>>(src, pos, w.q, n8);
   CQ_LAUNCH_CHECK();
@@ -232,17 +235,22 @@ int enc_train_fwd_t(const void* const* W, const T* src, const T* pos, const floa
   msda_prepare_kernel<<<(unsigned)cdiv(rows * kM * 32, 256), 256, 0, st>>>(w.off32, w.lg32, refp, shapes, w.loc, w.attn, rows, L, P);
   CQ_LAUNCH_CHECK();
   CQ_TRY(cqvad_msda3d_forward(DT<T>::id, w.value, shapes, lsi, w.loc, w.attn, w.samp, B, (int)Len, kM, kC / kM, L, (int)Len, P, (void*)st));
-  { Epilogue e; e.bias = Wf(E_OUT_B); e.res = src; e.ldr = kC; CQ_TRY(gemm<T>(w.samp, kC, Wm(E_OUT_W), w.z1, kC, rows, kC, kC, e, nullptr, st)); }
+  { Epilogue e; e.bias = Wf(E_OUT_B); if (!drop) { e.res = src; e.ldr = kC; }
+    CQ_TRY(gemm<T>(w.samp, kC, Wm(E_OUT_W), w.z1, kC, rows, kC, kC, e, nullptr, st)); }
+  if (drop) CQ_TRY(dropout_apply<T>(w.z1, src, w.z1, rows * kC, pdrop, seed, 1, st));            // src + dropout1(src2)
   CQ_TRY(layernorm_rows<T>(w.z1, nullptr, Wf(E_N1_W), Wf(E_N1_B), 1e-5f, w.x1, false, rows, st));
   { Epilogue e; e.bias = Wf(E_L1_B); e.act = CQVAD_ACT_RELU; CQ_TRY(gemm<T>(w.x1, kC, Wm(E_L1_W), w.h, F, rows, F, kC, e, nullptr, st)); }
-  { Epilogue e; e.bias = Wf(E_L2_B); e.res = w.x1; e.ldr = kC; CQ_TRY(gemm<T>(w.h, F, Wm(E_L2_W), w.z2, kC, rows, kC, F, e, nullptr, st)); }
+  if (drop) CQ_TRY(dropout_apply<T>(w.h, nullptr, w.h, rows * F, pdrop, seed, 2, st));            // dropout2(activation(linear1))
+  { Epilogue e; e.bias = Wf(E_L2_B); if (!drop) { e.res = w.x1; e.ldr = kC; }
+    CQ_TRY(gemm<T>(w.h, F, Wm(E_L2_W), w.z2, kC, rows, kC, F, e, nullptr, st)); }
+  if (drop) CQ_TRY(dropout_apply<T>(w.z2, w.x1, w.z2, rows * kC, pdrop, seed, 3, st));           // src + dropout3(src2)
   return layernorm_rows<T>(w.z2, nullptr, Wf(E_N2_W), Wf(E_N2_B), 1e-5f, out, false, rows, st);
 }
 
 template <typename T>
 int enc_train_bwd_t(const void* const* W, const T* src, const int64_t* shapes, const int64_t* lsi, const uint8_t* mask,
                     const T* gout, T* gsrc, T* gpos, float* const* G, void* ws, size_t ws_bytes, int B, long Len, int L, int P, int F,
-                    cudaStream_t st) {
+                    float pdrop, uint64_t seed, cudaStream_t st) {
   const long rows = (long)B * Len;
   if (rows == 0) return 0;
   const int LP3 = kM * L * P * 3, LP1 = kM * L * P;
@@ -261,15 +269,21 @@ int enc_train_bwd_t(const void* const* W, const T* src, const int64_t* shapes, c
   CQ_TRY(transpose_w<T>(Wm(E_L2_W), wt_l2, kC, F, st));
   // out = LN2(z2)
   CQ_TRY(ln_bwd<T>(w.z2, nullptr, Wf(E_N2_W), 1e-5f, gout, false, 0, 0, 0, w.dz2, 0.f, nullptr, 0.f, G[E_N2_W], G[E_N2_B], rows, st));
-  // z2 = x1 + linear2(h), h = relu(linear1(x1))
-  CQ_TRY(wgrad<T>(w.dz2, kC, w.h, F, G[E_L2_W], F, G[E_L2_B], rows, kC, F, nullptr, st));
-  { Epilogue e; e.mul_aux = w.h; e.mul_mode = 1; CQ_TRY(gemm<T>(w.dz2, kC, wt_l2, w.dh, F, rows, F, kC, e, nullptr, st)); }
+  // z2 = x1 + dropout3(linear2(h)), h = dropout2(relu(linear1(x1)))
+  const bool drop = pdrop > 0.f;
+  const T* dbr2 = w.dz2;                                 // gradient entering the linear2 branch (masked copy under dropout3)
+  if (drop) { CQ_TRY(dropout_apply<T>(w.dz2, nullptr, w.dz1, rows * kC, pdrop, seed, 3, st)); dbr2 = w.dz1; }
+  CQ_TRY(wgrad<T>(dbr2, kC, w.h, F, G[E_L2_W], F, G[E_L2_B], rows, kC, F, nullptr, st));
+  { Epilogue e; e.mul_aux = w.h; e.mul_mode = 1; CQ_TRY(gemm<T>(dbr2, kC, wt_l2, w.dh, F, rows, F, kC, e, nullptr, st)); }
+  if (drop) CQ_TRY(dropout_apply<T>(w.dh, nullptr, w.dh, rows * F, pdrop, seed, 2, st));   // (h > 0 already excludes the dropped units)
   CQ_TRY(wgrad<T>(w.dh, F, w.x1, kC, G[E_L1_W], kC, G[E_L1_B], rows, F, kC, nullptr, st));
   { Epilogue e; e.res = w.dz2; e.ldr = kC; CQ_TRY(gemm<T>(w.dh, F, wt_l1, w.dx1, kC, rows, kC, F, e, nullptr, st)); }
-  // x1 = LN1(z1), z1 = src + output_proj(samp)
+  // x1 = LN1(z1), z1 = src + dropout1(output_proj(samp))
   CQ_TRY(ln_bwd<T>(w.z1, nullptr, Wf(E_N1_W), 1e-5f, w.dx1, false, 0, 0, 0, w.dz1, 0.f, nullptr, 0.f, G[E_N1_W], G[E_N1_B], rows, st));
-  CQ_TRY(wgrad<T>(w.dz1, kC, w.samp, kC, G[E_OUT_W], kC, G[E_OUT_B], rows, kC, kC, nullptr, st));
-  { Epilogue e; CQ_TRY(gemm<T>(w.dz1, kC, wt_out, w.dsamp, kC, rows, kC, kC, e, nullptr, st)); }
+  const T* dbr1 = w.dz1;                                 // dx1 is free again: masked copy of dz1 for the output_proj branch
+  if (drop) { CQ_TRY(dropout_apply<T>(w.dz1, nullptr, w.dx1, rows * kC, pdrop, seed, 1, st)); dbr1 = w.dx1; }
+  CQ_TRY(wgrad<T>(dbr1, kC, w.samp, kC, G[E_OUT_W], kC, G[E_OUT_B], rows, kC, kC, nullptr, st));
+  { Epilogue e; CQ_TRY(gemm<T>(dbr1, kC, wt_out, w.dsamp, kC, rows, kC, kC, e, nullptr, st)); }
   // sampling
   CQ_CUDA(cudaMemsetAsync(w.dval32, 0, (size_t)rows * kC * 4, st));
   CQ_TRY(cqvad_msda3d_backward(DT<T>::id, w.value, shapes, lsi, w.loc, w.attn, w.dsamp, w.dval32, w.dloc, w.dattn, B, (int)Len, kM,
@@ -631,8 +645,8 @@ extern "C" int cqvad_deform_encoder_layer_train_forward(int dtype, const void* c
                                                         const float* reference_points, const int64_t* shapes,
                                                         const int64_t* level_start, const uint8_t* padding_mask, void* out,
                                                         void* workspace, size_t workspace_bytes, int B, long Len, int L, int P,
-                                                        int F, void* stream) {
-  CQ_CHECK_ARG(B >= 0 && Len >= 0 && L >= 1 && P >= 1 && F >= 1, "deform_encoder_layer: bad dimensions");
+                                                        int F, float dropout_p, uint64_t seed, void* stream) {
+  CQ_CHECK_ARG(B >= 0 && Len >= 0 && L >= 1 && P >= 1 && F >= 1 && dropout_p >= 0.f && dropout_p < 1.f, "deform_encoder_layer: bad dimensions");
   if ((long)B * Len == 0) return 0;
   CQ_CHECK_ARG(weights && src && pos && reference_points && shapes && level_start && out && workspace,
                "deform_encoder_layer: null pointer");
@@ -640,17 +654,18 @@ extern "C" int cqvad_deform_encoder_layer_train_forward(int dtype, const void* c
   CQ_CHECK_SHAPE(F % 8 == 0 && (kM * L * P) % 8 == 0, "deform_encoder_layer: F and heads*levels*points must be multiples of 8");
   if (dtype == CQVAD_F32)
     return enc_train_fwd_t<float>(weights, (const float*)src, (const float*)pos, reference_points, shapes, level_start, padding_mask,
-                                  (float*)out, workspace, workspace_bytes, B, Len, L, P, F, as_stream(stream));
+                                  (float*)out, workspace, workspace_bytes, B, Len, L, P, F, dropout_p, seed, as_stream(stream));
   if (dtype == CQVAD_BF16)
     return enc_train_fwd_t<bf16>(weights, (const bf16*)src, (const bf16*)pos, reference_points, shapes, level_start, padding_mask,
-                                 (bf16*)out, workspace, workspace_bytes, B, Len, L, P, F, as_stream(stream));
+                                 (bf16*)out, workspace, workspace_bytes, B, Len, L, P, F, dropout_p, seed, as_stream(stream));
   return set_error(CQVAD_E_INVALID_ARG, "deform_encoder_layer: unknown dtype %d", dtype);
 }
 
 extern "C" int cqvad_deform_encoder_layer_backward(int dtype, const void* const* weights, const void* src, const int64_t* shapes,
                                                    const int64_t* level_start, const uint8_t* padding_mask, const void* grad_out,
                                                    void* grad_src, void* grad_pos, float* const* grad_weights, void* workspace,
-                                                   size_t workspace_bytes, int B, long Len, int L, int P, int F, void* stream) {
+                                                   size_t workspace_bytes, int B, long Len, int L, int P, int F, float dropout_p,
+                                                   uint64_t seed, void* stream) {
   CQ_CHECK_ARG(B >= 0 && Len >= 0 && L >= 1 && P >= 1 && F >= 1, "deform_encoder_layer: bad dimensions");
   if ((long)B * Len == 0) return 0;
   CQ_CHECK_ARG(weights && src && shapes && level_start && grad_out && grad_src && grad_pos && grad_weights && workspace,
@@ -660,11 +675,11 @@ extern "C" int cqvad_deform_encoder_layer_backward(int dtype, const void* const*
   if (dtype == CQVAD_F32)
     return enc_train_bwd_t<float>(weights, (const float*)src, shapes, level_start, padding_mask, (const float*)grad_out,
                                   (float*)grad_src, (float*)grad_pos, grad_weights, workspace, workspace_bytes, B, Len, L, P, F,
-                                  as_stream(stream));
+                                  dropout_p, seed, as_stream(stream));
   if (dtype == CQVAD_BF16)
     return enc_train_bwd_t<bf16>(weights, (const bf16*)src, shapes, level_start, padding_mask, (const bf16*)grad_out,
                                  (bf16*)grad_src, (bf16*)grad_pos, grad_weights, workspace, workspace_bytes, B, Len, L, P, F,
-                                 as_stream(stream));
+                                 dropout_p, seed, as_stream(stream));
   return set_error(CQVAD_E_INVALID_ARG, "deform_encoder_layer_backward: unknown dtype %d", dtype);
 }
 

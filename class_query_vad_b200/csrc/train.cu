@@ -9,7 +9,9 @@
 //
 // Autograd semantics reproduced (dab_transformer.py:810,823): reference points are detached between layers (only layer 0
 // back-propagates into refpoints_unsigmoid), the actor feature is detached on entry to the class branch, while q_memory,
-// query_sine_embed and the class-query chain are not.  Dropout is the identity (parity / eval semantics).
+// query_sine_embed and the class-query chain are not.  Dropout: desc.dropout_p > 0 applies nn.Dropout at the nine residual-branch /
+// FFN-hidden sites of a layer pair (Philox masks, dropout.cu); the dropout on attention probabilities (attention.py:402) is not
+// applied; dropout_p = 0 is the parity / eval semantics.
 #include <stdlib.h>
 #include <deque>
 #include <functional>
@@ -18,6 +20,7 @@
 #include "kernels_mem.cuh"
 #include "attention.cuh"
 #include "bwd.cuh"
+#include "dropout.cuh"
 #include "prof.cuh"
 #include "wtable.cuh"
 
@@ -308,6 +311,27 @@ struct Trainer {
     }
     return Y;
   }
+  // nn.Dropout(p) on X, in place (activation in the forward, its gradient in the backward; the Philox mask is regenerated from
+  // (seed, site), dropout.cu).  A ReLU output keeps working as its own derivative mask: dropped units are zero.
+  Ten<T>* drop(Ten<T>* X, int l, int k, int* rc) {
+    const float p = d.dropout_p;
+    if (!(p > 0.f)) return X;
+    const uint64_t seed = ((uint64_t)d.seed_hi << 32) | d.seed_lo;
+    const uint32_t site = 0x1000u + 16u * (uint32_t)l + (uint32_t)k;
+    if (fwd()) {
+      ProfScope ps(P_T_FWD_OTHER, st);
+      int r = dropout_apply<T>(X->p, nullptr, X->p, X->n(), p, seed, site, st);
+      if (r != 0 && rc && *rc == 0) *rc = r;
+    }
+    if (rec()) {
+      tape.push_back([=]() -> int {
+        if (!X->gi) return 0;
+        ProfScope ps(P_T_ACT_BWD, st);
+        return dropout_apply<T>(X->g, nullptr, X->g, X->n(), p, seed, site, st);
+      });
+    }
+    return X;
+  }
   // Y = LN(X (+ res))
   Ten<T>* ln(Ten<T>* X, Ten<T>* res, int lnidx, float eps, int* rc) {
     Ten<T>* Y = mk(X->rows, kC);
@@ -496,7 +520,7 @@ int Trainer<T>::run() {
     s1.q_ls = s1.k_ls = s1.v_ls = s1.o_ls = (long)BT * kC;
     s1.q_bs = s1.k_bs = s1.v_bs = s1.o_bs = kC;
     Ten<T>* sao = mha(saq, nullptr, sak, nullptr, sav, N, nq, nq, BT, 32, 32, s1, &rc);
-    Ten<T>* out1 = ln(lin(sao, loc(l, SA_O), kC, 0, nullptr, 0, 0, &rc), out, loc(l, NORM1), 1e-5f, &rc);
+    Ten<T>* out1 = ln(drop(lin(sao, loc(l, SA_O), kC, 0, nullptr, 0, 0, &rc), l, 0, &rc), out, loc(l, NORM1), 1e-5f, &rc);   // dropout1 :937
     // ---- level-weighted query-specific memory :943-946 ----
     float* lvlw = takef(N * 4);
     float* dlvlw = takef(N * 4);
@@ -541,8 +565,8 @@ int Trainer<T>::run() {
         return 0;
       });
     }
-    Ten<T>* actor = ln(lin(cao, loc(l, CA_O), kC, 0, nullptr, 0, 0, &rc), out1, loc(l, NORM2), 1e-5f, &rc);   // tgt_temp :992-993
-    Ten<T>* ffn = lin(lin(actor, loc(l, LIN1), F, CQVAD_ACT_RELU, nullptr, 0, 0, &rc), loc(l, LIN2), kC, 0, nullptr, 0, 0, &rc);
+    Ten<T>* actor = ln(drop(lin(cao, loc(l, CA_O), kC, 0, nullptr, 0, 0, &rc), l, 1, &rc), out1, loc(l, NORM2), 1e-5f, &rc);   // tgt_temp :991-993 (dropout2)
+    Ten<T>* ffn = drop(lin(drop(lin(actor, loc(l, LIN1), F, CQVAD_ACT_RELU, nullptr, 0, 0, &rc), l, 2, &rc), loc(l, LIN2), kC, 0, nullptr, 0, 0, &rc), l, 3, &rc);   // dropout, dropout3 :995-996
     Ten<T>* out2 = ln(ffn, actor, loc(l, NORM3), 1e-5f, &rc);
 
     if (rc != 0) return rc;
@@ -550,7 +574,7 @@ int Trainer<T>::run() {
     // ---- class-query layer :1040-1079 (actor feature detached, :810) ----
     CQ_TRY(set_branch(1));
     Ten<T>* actor_d = detach(actor);
-    Ten<T>* cffn = lin(lin(actor_d, cls(l, C_L1), F, CQVAD_ACT_RELU, nullptr, 0, 0, &rc), cls(l, C_L2), kC, 0, nullptr, 0, 0, &rc);
+    Ten<T>* cffn = drop(lin(drop(lin(actor_d, cls(l, C_L1), F, CQVAD_ACT_RELU, nullptr, 0, 0, &rc), l, 4, &rc), cls(l, C_L2), kC, 0, nullptr, 0, 0, &rc), l, 5, &rc);   // dropout1, dropout2 :1043-1044
     Ten<T>* acls = ln(cffn, actor_d, cls(l, C_NORM), 1e-5f, &rc);
     Ten<T>* X = mk(Rp, kC);
     if (fwd()) {
@@ -580,7 +604,7 @@ int Trainer<T>::run() {
     s2.q_ls = s2.k_ls = s2.v_ls = s2.o_ls = kC;
     if (first) {   // identical for every actor instance: computed once on K rows, then broadcast
       Ten<T>* cq1 = mha(cq, nullptr, cq, nullptr, cq, K, K, K, 1, 32, 32, s2, &rc);
-      Ten<T>* cq2 = ln(lin(cq1, cls(l, C_SA_O), kC, 0, nullptr, 0, 0, &rc), cq, cls(l, C_NORM1), 1e-5f, &rc);
+      Ten<T>* cq2 = ln(drop(lin(cq1, cls(l, C_SA_O), kC, 0, nullptr, 0, 0, &rc), l, 6, &rc), cq, cls(l, C_NORM1), 1e-5f, &rc);   // dropout3 :1062 (one mask for all instances: the rows are shared)
       Qin = mk(NK, kC);
       if (fwd()) CQ_TRY(broadcast_rows<T>(cq2->p, Qin->p, NK, K, st));
       if (rec()) {
@@ -614,7 +638,7 @@ int Trainer<T>::run() {
       } else {
         saoc = mha(Qprev, nullptr, Qprev, nullptr, Qprev, NK, K, K, (int)N, 32, 32, s2, &rc);
       }
-      Qin = ln(lin(saoc, cls(l, C_SA_O), kC, 0, nullptr, 0, 0, &rc), Qprev, cls(l, C_NORM1), 1e-5f, &rc);
+      Qin = ln(drop(lin(saoc, cls(l, C_SA_O), kC, 0, nullptr, 0, 0, &rc), l, 6, &rc), Qprev, cls(l, C_NORM1), 1e-5f, &rc);   // dropout3 :1062
     }
     // class cross-attention :1067-1071
     Ten<T>* kx = lin(X3, cls(l, C_KPROJ), kC, 0, nullptr, 0, 0, &rc);     // on the padded layout
@@ -663,7 +687,7 @@ int Trainer<T>::run() {
       caoc = O;
     }
     Ten<T>* cls0 = lin(caoc, cls(l, C_CA_O), kC, 0, nullptr, 0, 0, &rc);
-    Ten<T>* cf = lin(lin(cls0, cls(l, C_L1_), F, CQVAD_ACT_RELU, nullptr, 0, 0, &rc), cls(l, C_L2_), kC, 0, nullptr, 0, 0, &rc);
+    Ten<T>* cf = drop(lin(drop(lin(cls0, cls(l, C_L1_), F, CQVAD_ACT_RELU, nullptr, 0, 0, &rc), l, 7, &rc), cls(l, C_L2_), kC, 0, nullptr, 0, 0, &rc), l, 8, &rc);   // dropout1_, dropout2_ :1076-1077
     Ten<T>* cls_out = ln(cf, cls0, cls(l, C_NORM_), 1e-5f, &rc);
     Qprev = cls_out;
 
@@ -782,6 +806,7 @@ extern "C" int cqvad_decoder_train_forward(const cqvad_decoder_desc* d, const vo
                                            void* workspace, size_t ws_bytes, void* stream) {
   CQ_TRY(check_train_desc(d));
   CQ_CHECK_ARG(weights && tgt && memory && pos && refpoints_unsigmoid && hs && cls_hs && refs && workspace, "decoder: null pointer");
+  CQ_CHECK_ARG(d->dropout_p >= 0.f && d->dropout_p < 1.f, "decoder: dropout_p must be in [0, 1)");
   TrainIO io{};
   io.tgt = tgt; io.memory = memory; io.pos = pos; io.mask = mask; io.ref_u = refpoints_unsigmoid;
   io.hs = hs; io.cls_hs = cls_hs; io.refs = refs;

@@ -158,9 +158,10 @@ class DecoderEngine:
                 self._gtab[i] = None if self._meta[i][1] is None else self._gflat.data_ptr() + 4 * int(offs[i])
         return self._gflat, self._gtab
 
-    def forward_train(self, tgt, memory, mask, pos, refpoints_unsigmoid, orig_res):
+    def forward_train(self, tgt, memory, mask, pos, refpoints_unsigmoid, orig_res, dropout_p=0.0, seed=0):
         """TransformerDecoder.forward keeping what the backward needs.  Returns dict(hs, cls_hs, refs); follow with
-        `backward(grad_hs, grad_cls_hs, grad_refs)`."""
+        `backward(grad_hs, grad_cls_hs, grad_refs)`.  dropout_p > 0: nn.Dropout at the residual-branch / FFN-hidden sites of every
+        layer (dab_transformer.py:937,991,995,1043,1062,1076) with Philox masks keyed by `seed`; the backward regenerates them."""
         lib = _lib.lib()
         h, w = orig_res
         nq, BT = tgt.shape[0], tgt.shape[1]
@@ -175,7 +176,7 @@ class DecoderEngine:
             m8 = mask.to(self.device).contiguous()
             m8 = m8.view(torch.uint8) if m8.dtype == torch.bool else m8.to(torch.uint8)
         desc = _lib.DecoderDesc(_lib.dtype_id(self.dtype), BT, nq, h, w, self.K, self.F, self.layers,
-                                1 if self.out_f32 else 0, 0)
+                                1 if self.out_f32 else 0, 0, float(dropout_p), int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF)
         need = lib.cqvad_decoder_train_workspace_bytes(byref(desc))
         if need == 0:
             _lib.check(-1)

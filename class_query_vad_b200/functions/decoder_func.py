@@ -10,7 +10,9 @@ import torch
 class DecoderFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, names, mask, pos, orig_res, tgt, memory, refpoints_unsigmoid, *params):
-        out = engine.forward_train(tgt.detach(), memory.detach(), mask, pos.detach(), refpoints_unsigmoid.detach(), orig_res)
+        p_drop, seed = getattr(engine, "train_dropout", (0.0, 0))
+        out = engine.forward_train(tgt.detach(), memory.detach(), mask, pos.detach(), refpoints_unsigmoid.detach(), orig_res,
+                                   dropout_p=p_drop, seed=seed)
         ctx.engine, ctx.names, ctx.generation = engine, names, out["generation"]
         ctx.need = (tgt.requires_grad, memory.requires_grad, refpoints_unsigmoid.requires_grad)
         ctx.in_dtypes = (tgt.dtype, memory.dtype, refpoints_unsigmoid.dtype)

@@ -260,11 +260,11 @@ class TransformerDecoder(nn.Module):
                                                   memory.requires_grad or refpoints_unsigmoid.requires_grad)
         if needs_grad:
             # training step: native forward that keeps the backward's intermediates + native backward behind autograd.
-            # Dropout is the identity on this path (the reference trains with p = 0.1 / 0.5: DESIGN.md "divergences").
-            if self.training and not getattr(self, "_warned_dropout", False):
-                import warnings
-                warnings.warn("class_query_vad_b200: dropout is the identity in the native training path")
-                self._warned_dropout = True
+            # In train() mode nn.Dropout(p) is applied at the residual-branch / FFN-hidden sites (Philox masks, a fresh seed per
+            # call); the dropout on attention probabilities (attention.py:402) is not.
+            p_drop = float(self.layers[0].dropout1.p) if self.training else 0.0
+            self._train_calls = getattr(self, "_train_calls", 0) + 1
+            eng.train_dropout = (p_drop, (getattr(self, "dropout_seed", 0x1234) << 24) + self._train_calls)
             from ..functions.decoder_func import DecoderFunction
             hs, cls_hs, refs = DecoderFunction.apply(eng, [n for n, _ in named], memory_key_padding_mask, pos, orig_res, tgt,
                                                      memory, refpoints_unsigmoid, *[p for _, p in named])

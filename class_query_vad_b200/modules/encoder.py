@@ -1,8 +1,8 @@
 """Drop-ins for the reference `DeformableTransformerEncoderLayer` / `DeformableTransformerEncoder`
 (models/detr/dab_transformer.py:425-523): same constructors, forward signatures and parameter names (a reference state_dict
 loads with strict=True); one layer = ONE C-ABI call, cqvad_deform_encoder_layer_forward (csrc/encoder.cu); with gradients
-enabled the layer goes through EncoderLayerFunction (cqvad_deform_encoder_layer_train_forward / _backward).  Dropout =
-identity; no torch arithmetic on the activation path -- `get_reference_points` (a [B, Len, L, 3] meshgrid of the
+enabled the layer goes through EncoderLayerFunction (cqvad_deform_encoder_layer_train_forward / _backward).  In train() mode
+dropout1/2/3 are applied there (Philox masks); no torch arithmetic on the activation path -- `get_reference_points` (a [B, Len, L, 3] meshgrid of the
 level shapes and valid ratios, computed once per forward) is host-side glue written with torch like the reference's."""
 import ctypes
 import copy
@@ -66,7 +66,7 @@ class EncoderLayerFunction(torch.autograd.Function):
     apply(src, pos, reference_points, shapes, level_start, padding_mask, n_points, d_ffn, *16 parameters in state_dict order)."""
 
     @staticmethod
-    def forward(ctx, src, pos, reference_points, shapes, level_start, padding_mask, n_points, d_ffn, *params):
+    def forward(ctx, src, pos, reference_points, shapes, level_start, padding_mask, n_points, d_ffn, p_drop, seed, *params):
         _lib.require_cuda(src, pos, reference_points, shapes, level_start)
         lib = _lib.lib()
         dt = src.dtype
@@ -86,13 +86,14 @@ class EncoderLayerFunction(torch.autograd.Function):
         out = torch.empty_like(src_c)
         p = _lib.ptr
         _lib.check(lib.cqvad_deform_encoder_layer_train_forward(_lib.dtype_id(dt), tab, p(src_c), p(pos_c), p(refp), p(sh), p(ls), p(m8),
-                                                                p(out), p(ws), need, B, Len, L, n_points, d_ffn, _lib.stream_ptr()))
-        ctx.saved = (keep, tab, src_c, sh, ls, m8, ws, need, (B, Len, L, n_points, d_ffn), [q.dtype for q in params])
+                                                                p(out), p(ws), need, B, Len, L, n_points, d_ffn, float(p_drop), int(seed),
+                                                                _lib.stream_ptr()))
+        ctx.saved = (keep, tab, src_c, sh, ls, m8, ws, need, (B, Len, L, n_points, d_ffn, float(p_drop), int(seed)), [q.dtype for q in params])
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        keep, tab, src_c, sh, ls, m8, ws, need, (B, Len, L, n_points, d_ffn), pdt = ctx.saved
+        keep, tab, src_c, sh, ls, m8, ws, need, (B, Len, L, n_points, d_ffn, p_drop, seed), pdt = ctx.saved
         lib = _lib.lib()
         dt = src_c.dtype
         go = grad_out.to(dt).contiguous()
@@ -101,8 +102,8 @@ class EncoderLayerFunction(torch.autograd.Function):
         gtab = (ctypes.c_void_p * len(gw))(*[g.data_ptr() for g in gw])
         p = _lib.ptr
         _lib.check(lib.cqvad_deform_encoder_layer_backward(_lib.dtype_id(dt), tab, p(src_c), p(sh), p(ls), p(m8), p(go), p(gsrc), p(gpos),
-                                                           gtab, p(ws), need, B, Len, L, n_points, d_ffn, _lib.stream_ptr()))
-        return (gsrc, gpos, None, None, None, None, None, None) + tuple(g.to(d) for g, d in zip(gw, pdt))
+                                                           gtab, p(ws), need, B, Len, L, n_points, d_ffn, p_drop, seed, _lib.stream_ptr()))
+        return (gsrc, gpos, None, None, None, None, None, None, None, None) + tuple(g.to(d) for g, d in zip(gw, pdt))
 
 
 class DeformableTransformerEncoderLayer(nn.Module):
@@ -120,6 +121,7 @@ class DeformableTransformerEncoderLayer(nn.Module):
         self.norm2 = nn.LayerNorm(d_model)
         self.n_points, self.d_ffn = n_points, d_ffn
         self._packed = None
+        self.dropout_seed = 0x4321            # Philox key of this layer's dropout masks (+ a per-call counter)
 
     def _pack(self, dtype, device):
         ver = tuple(p._version for p in self.parameters()) + (dtype, str(device))
@@ -131,16 +133,16 @@ class DeformableTransformerEncoderLayer(nn.Module):
         self._packed = None
 
     def forward(self, src, pos, reference_points, spatio_temporal_shapes, level_start_index, padding_mask=None):
-        if self.training and (self.dropout1.p > 0 or self.dropout2.p > 0):
-            import warnings
-            warnings.warn("libcqvad encoder layer applies no dropout (inference semantics)", stacklevel=2)
         if pos is None:
             pos = torch.zeros_like(src)
         if torch.is_grad_enabled() and (src.requires_grad or any(p.requires_grad for p in self.parameters())):
             sd = dict(self.named_parameters())
             params = [sd[f"{b}.{l}"] for b in ENC_WEIGHT_ORDER for l in ("weight", "bias")]
+            p_drop = float(self.dropout1.p) if self.training else 0.0          # dropout1 / 2 / 3 (dab_transformer.py:499-519)
+            self._train_calls = getattr(self, "_train_calls", 0) + 1
+            seed = (int(getattr(self, "dropout_seed", 0x4321)) << 24) + self._train_calls
             return EncoderLayerFunction.apply(src, pos, reference_points, spatio_temporal_shapes, level_start_index, padding_mask,
-                                              self.n_points, self.d_ffn, *params)
+                                              self.n_points, self.d_ffn, p_drop, seed, *params)
         return encoder_layer_forward(self._pack(src.dtype, src.device), src, pos, reference_points, spatio_temporal_shapes,
                                      level_start_index, padding_mask, self.n_points, self.d_ffn)
 
@@ -149,6 +151,8 @@ class DeformableTransformerEncoder(nn.Module):
     def __init__(self, encoder_layer, num_layers, gradient_checkpointing=False):
         super().__init__()
         self.layers = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])
+        for i, layer in enumerate(self.layers):
+            layer.dropout_seed = 0x4321 + i          # distinct Philox keys per layer (a fresh stream per call on top)
         self.num_layers = num_layers
         self.gradient_checkpointing = gradient_checkpointing
 

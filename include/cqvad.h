@@ -106,17 +106,20 @@ int cqvad_deform_encoder_layer_forward(int dtype, const void* const* weights, co
  * cqvad_deform_encoder_layer_forward with unfused LayerNorms / FFN, keeping q, value, locations, attention weights, the
  * sampled values, both pre-norm sums and the FFN hidden in `workspace`; backward consumes that workspace (same pointer, same
  * size, untouched in between), writes grad_src / grad_pos [B, Len, 256] (dtype) and ACCUMULATES the 16 parameter gradients
- * (fp32, state_dict order, caller zero-fills).  Dropout = identity.  reference_points get no gradient (derived from shapes). */
+ * (fp32, state_dict order, caller zero-fills).  dropout_p > 0: dropout1 / dropout2 / dropout3 of dab_transformer.py:499-519 with
+ * Philox masks keyed by `seed` (the backward must receive the forward's p and seed; 0 = eval semantics).  reference_points get no
+ * gradient (derived from shapes). */
 size_t cqvad_deform_encoder_layer_train_workspace_bytes(int dtype, int B, long Len, int L, int P, int F);
 int cqvad_deform_encoder_layer_train_forward(int dtype, const void* const* weights, const void* src, const void* pos,
                                              const float* reference_points, const int64_t* shapes,
                                              const int64_t* level_start, const uint8_t* padding_mask, void* out,
                                              void* workspace, size_t workspace_bytes, int B, long Len, int L, int P, int F,
-                                             void* stream);
+                                             float dropout_p, uint64_t seed, void* stream);
 int cqvad_deform_encoder_layer_backward(int dtype, const void* const* weights, const void* src, const int64_t* shapes,
                                         const int64_t* level_start, const uint8_t* padding_mask, const void* grad_out,
                                         void* grad_src, void* grad_pos, float* const* grad_weights, void* workspace,
-                                        size_t workspace_bytes, int B, long Len, int L, int P, int F, void* stream);
+                                        size_t workspace_bytes, int B, long Len, int L, int P, int F, float dropout_p, uint64_t seed,
+                                        void* stream);
 /* Input projection of one backbone level (CSN configurations, models/model.py:64-71,162-164):
  * tokens[b, level_start + n, :] = GroupNorm(32, 256)( Conv3d(C_in, 256, kernel_size = 1)(x) )[b, :, n] for x [B, C_in, N = T*H*W]
  * channel-first (dtype): transpose to token-major, tcgen05 GEMM with W [256, C_in] (dtype) + bias, per-clip group statistics
@@ -216,6 +219,8 @@ typedef struct cqvad_decoder_desc {
   int layers;       /* DEC_LAYERS                                                                      */
   int out_f32;      /* 1: hs/cls_hs written as fp32 (reference dtype); 0: written in `dtype`           */
   int flags;        /* CQVAD_DEC_* below                                                               */
+  float dropout_p;  /* TRAINING calls only: p of the decoder's nn.Dropout modules (0 = identity, eval semantics)        */
+  unsigned seed_lo, seed_hi;   /* Philox key of this step's masks; cqvad_decoder_backward must receive the forward's   */
 } cqvad_decoder_desc;
 enum { CQVAD_DEC_SKIP_CLS_HS = 1 /* do not materialise cls_hs (only pred_logits) */,
        CQVAD_DEC_FP32_CLS_STREAM = 2 /* bf16 path: keep fp32 side copies of the class-token residual/output stream */ };
@@ -319,6 +324,11 @@ int cqvad_criterion_ava(const cqvad_criterion_cfg* cfg, const float* pred_logits
  * target_sizes [B,2] fp32 (h, w) as in the reference. */
 int cqvad_postprocess_ava(const float* pred_logits, const float* pred_boxes, const float* pred_logits_b,
                           const float* target_sizes, float* detections, int B, int nq, int K, void* stream);
+
+/* Dropout pass of the native training path: out = (res ? res : 0) + keep * x / (1 - p), keep ~ Bernoulli(1 - p) from a
+ * Philox4x32-10 counter keyed by (seed, site, element index / 8) -- nothing is stored; calling it on a gradient with the same
+ * (seed, site) applies the forward's mask (nn.Dropout backward).  n % 8 == 0; in place when out == x; p is quantised to 1/65536. */
+int cqvad_dropout(int dtype, const void* x, const void* res, void* out, long n, float p, uint64_t seed, uint32_t site, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * DETR heads of the reference model in the TRAINING step (models/model.py:191-236), fp32 like the reference (autocast off):

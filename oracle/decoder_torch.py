@@ -69,14 +69,15 @@ def mha_query_specific(q, k, v, H, w_o, b_o, kpm=None):      # attention.py mode
     return F.linear(out, w_o, b_o)
 
 
-def decoder_layer(W, p, tgt, memory, mask, pos, query_pos, qse, is_first, H=8):     # dab_transformer.py:907-997
+def decoder_layer(W, p, tgt, memory, mask, pos, query_pos, qse, is_first, H=8, drop=None):     # dab_transformer.py:907-997
+    drop = drop or (lambda x, k: x)          # dropout hook: (tensor, site 0..3) -> tensor  (:937,991,995)
     g = lambda n: W[p + n]
     lin = lambda x, n: F.linear(x, g(n + ".weight"), g(n + ".bias"))
     nq, BT, C = tgt.shape
     q = lin(tgt, "sa_qcontent_proj") + lin(query_pos, "sa_qpos_proj")
     k = lin(tgt, "sa_kcontent_proj") + lin(query_pos, "sa_kpos_proj")
     v = lin(tgt, "sa_v_proj")
-    tgt = F.layer_norm(tgt + mha_standard(q, k, v, H, g("self_attn.out_proj.weight"), g("self_attn.out_proj.bias")), (C,),
+    tgt = F.layer_norm(tgt + drop(mha_standard(q, k, v, H, g("self_attn.out_proj.weight"), g("self_attn.out_proj.bias")), 0), (C,),
                        g("norm1.weight"), g("norm1.bias"))
     lvl_w = lin(tgt, "lvl_w_embed").softmax(-1)
     q_memory = F.layer_norm(torch.einsum("ntl,lhtc->nhtc", lvl_w, memory), (C,), g("norm_.weight"), g("norm_.bias"))
@@ -94,9 +95,9 @@ def decoder_layer(W, p, tgt, memory, mask, pos, query_pos, qse, is_first, H=8): 
     q = torch.cat([q.view(nq, BT, H, hd), lin(qse, "ca_qpos_sine_proj").view(nq, BT, H, hd)], dim=3).view(nq, BT, 2 * C)
     k = torch.cat([k.view(nq, S, BT, H, hd), k_pos.reshape(nq, S, BT, H, hd)], dim=4).view(nq, S, BT, 2 * C)
     tgt2 = mha_query_specific(q, k, v, H, g("cross_attn.out_proj.weight"), g("cross_attn.out_proj.bias"), kpm=mask)
-    tgt = F.layer_norm(tgt + tgt2, (C,), g("norm2.weight"), g("norm2.bias"))
+    tgt = F.layer_norm(tgt + drop(tgt2, 1), (C,), g("norm2.weight"), g("norm2.bias"))
     tgt_temp = tgt
-    tgt = F.layer_norm(tgt + lin(F.relu(lin(tgt, "linear1")), "linear2"), (C,), g("norm3.weight"), g("norm3.bias"))
+    tgt = F.layer_norm(tgt + drop(lin(drop(F.relu(lin(tgt, "linear1")), 2), "linear2"), 3), (C,), g("norm3.weight"), g("norm3.bias"))
     return tgt, tgt_temp, q_memory
 
 
@@ -108,13 +109,14 @@ def conv_block(W, p, x):                                     # dab_transformer.p
     return x + y.permute(0, 3, 1, 2)
 
 
-def class_decoder_layer(W, p, actor_feature, q_memory, pos0, qse, class_queries, orig_res, is_first, H=8):   # :1040-1079
+def class_decoder_layer(W, p, actor_feature, q_memory, pos0, qse, class_queries, orig_res, is_first, H=8, drop=None):   # :1040-1079
+    drop = drop or (lambda x, k: x)          # dropout hook, sites 4..8 (:1043-1044,1062,1076-1077)
     g = lambda n: W[p + n]
     lin = lambda x, n: F.linear(x, g(n + ".weight"), g(n + ".bias"))
     nq, BT, C = actor_feature.shape
     h, w = orig_res
     S, N = h * w, nq * BT
-    actor = F.layer_norm(actor_feature + lin(F.relu(lin(actor_feature, "cls_linear1")), "cls_linear2"), (C,),
+    actor = F.layer_norm(actor_feature + drop(lin(drop(F.relu(lin(actor_feature, "cls_linear1")), 4), "cls_linear2"), 5), (C,),
                          g("cls_norm.weight"), g("cls_norm.bias"))
     enc = q_memory.permute(0, 2, 3, 1).reshape(N, C, h, w)                                        # (N BT) D H W
     feat = actor.reshape(N, C, 1, 1) + enc
@@ -123,8 +125,8 @@ def class_decoder_layer(W, p, actor_feature, q_memory, pos0, qse, class_queries,
         feat = conv_block(W, p + "conv_blocks.0.", feat)
     query = class_queries[:, None].expand(-1, N, -1) if is_first else class_queries
     K = query.shape[0]
-    query = F.layer_norm(query + mha_standard(query, query, query, H, g("self_attn.out_proj.weight"),
-                                              g("self_attn.out_proj.bias")), (C,), g("norm1.weight"), g("norm1.bias"))
+    query = F.layer_norm(query + drop(mha_standard(query, query, query, H, g("self_attn.out_proj.weight"),
+                                                   g("self_attn.out_proj.bias")), 6), (C,), g("norm1.weight"), g("norm1.bias"))
     kx = F.conv2d(feat, g("k_proj.weight"), g("k_proj.bias")).flatten(2).permute(2, 0, 1)
     key = torch.cat([kx, pos0[:, None].expand(-1, nq, -1, -1).flatten(1, 2)], dim=-1)
     cqp = lin(qse, "cls_qpos_sine_proj").flatten(0, 1)[None].expand(K, -1, -1)
@@ -132,12 +134,12 @@ def class_decoder_layer(W, p, actor_feature, q_memory, pos0, qse, class_queries,
     out = mha_standard(torch.cat([query, cqp], dim=-1), key, value, H, g("cross_attn.out_proj.weight"),
                        g("cross_attn.out_proj.bias"))
     cls_output = out.reshape(K, nq, BT, C).permute(1, 2, 0, 3)
-    cls_output = F.layer_norm(cls_output + lin(F.relu(lin(cls_output, "cls_linear1_")), "cls_linear2_"), (C,),
+    cls_output = F.layer_norm(cls_output + drop(lin(drop(F.relu(lin(cls_output, "cls_linear1_")), 7), "cls_linear2_"), 8), (C,),
                               g("cls_norm_.weight"), g("cls_norm_.bias"))
     return cls_output, cls_output.permute(2, 0, 1, 3).flatten(1, 2)
 
 
-def decoder_forward(W, tgt, memory, mask, pos, refpoints_unsigmoid, orig_res, layers):
+def decoder_forward(W, tgt, memory, mask, pos, refpoints_unsigmoid, orig_res, layers, drop=None):
     """TransformerDecoder.forward (dab_transformer.py:722-852) on torch CPU tensors (W: name -> tensor, possibly with
     requires_grad).  Returns hs [Lr,BT,nq,C], cls_hs [Lr,BT,nq,K,C], references [Lr,BT,nq,4]."""
     C = tgt.shape[-1]
@@ -155,9 +157,10 @@ def decoder_forward(W, tgt, memory, mask, pos, refpoints_unsigmoid, orig_res, la
         refHW = _mlp(output, W, "ref_anchor_head", 2).sigmoid()
         qse = torch.cat([qse[..., :C // 2] * (refHW[..., 1] / obj_center[..., 3]).unsqueeze(-1),
                          qse[..., C // 2:] * (refHW[..., 0] / obj_center[..., 2]).unsqueeze(-1)], dim=-1)   # :762-763
-        output, actor, q_memory = decoder_layer(W, f"layers.{lid}.", output, memory, mask, pos, query_pos, qse, lid == 0)
+        dl = None if drop is None else (lambda x, k, _l=lid: drop(x, _l, k))          # training-mode nn.Dropout sites of this layer pair
+        output, actor, q_memory = decoder_layer(W, f"layers.{lid}.", output, memory, mask, pos, query_pos, qse, lid == 0, drop=dl)
         cls_output, class_queries = class_decoder_layer(W, f"cls_layers.{lid}.", actor.clone().detach(), q_memory, pos[0], qse,
-                                                        class_queries, orig_res, lid == 0)          # :810
+                                                        class_queries, orig_res, lid == 0, drop=dl)          # :810
         tmp = _mlp(output, W, "bbox_embed", 3)
         new_ref = (tmp[..., :4] + _inverse_sigmoid(reference_points)).sigmoid()
         if lid != layers - 1:
@@ -168,7 +171,7 @@ def decoder_forward(W, tgt, memory, mask, pos, refpoints_unsigmoid, orig_res, la
     return (torch.stack(inter).transpose(1, 2), torch.stack(cls_inter).transpose(1, 2), torch.stack(ref_points).transpose(1, 2))
 
 
-def train_step(Wnp, inp, lw, layers, threads=None):
+def train_step(Wnp, inp, lw, layers, threads=None, drop=None):
     """One decoder fwd + bwd on the host: loss = sum(w_hs*hs) + sum(w_cls*cls_hs) + sum(w_refs*refs).  Returns
     (loss, {name: grad ndarray}, grad_memory, grad_tgt, grad_refpoints)."""
     if threads:
@@ -177,7 +180,7 @@ def train_step(Wnp, inp, lw, layers, threads=None):
     W = {k: t(v).requires_grad_(True) for k, v in Wnp.items() if not k.startswith("heads.") and ".conv_blocks.1." not in k
          and ".conv_blocks.2." not in k}
     tgt, memory, ref = (t(inp[k]).requires_grad_(True) for k in ("tgt", "memory", "refpoints_unsigmoid"))
-    hs, cls_hs, refs = decoder_forward(W, tgt, memory, t(inp["mask"]), t(inp["pos"]), ref, inp["orig_res"], layers)
+    hs, cls_hs, refs = decoder_forward(W, tgt, memory, t(inp["mask"]), t(inp["pos"]), ref, inp["orig_res"], layers, drop=drop)
     loss = (t(lw["w_hs"]) * hs).sum() + (t(lw["w_cls"]) * cls_hs).sum() + (t(lw["w_refs"]) * refs).sum()
     loss.backward()
     grads = {k: (torch.zeros_like(v) if v.grad is None else v.grad).numpy() for k, v in W.items()}
