@@ -50,6 +50,15 @@ struct Decoder {
       *qs, *cao, *XA, *XB, *Xn, *Hc, *Qc[2], *cq1, *cq2, *saoc, *kx, *vx, *vt, *qt, *cqp, *caoc, *cls0, *Hf, *hsn, *bb1, *bb2;
   long ldvt, ldqt; int K8;
   float *r_cur, *r_next, *lvlw, *cls0_32, *clsout_32;   // *_32: fp32 side copies of the class-token stream (bf16 path)
+  // Two-stream schedule of the inference forward: the localisation chain of layer l+1 (small-row latency-bound kernels, the
+  // k/v projection of q_memory, the level mix) depends only on the localisation chain of layer l, so it runs ahead on the
+  // caller's stream while the class branch of layer l (ConvBlocks, class attention, class FFN: the large kernels) runs on a side
+  // stream.  What the class branch reads from the localisation chain is kept per layer (actor, query sine embedding) or
+  // double-buffered with back-pressure (q_memory, 48 MB at B = 32).  CQVAD_INFER_STREAMS=1 restores the single-stream order.
+  static constexpr int kMaxLayers = 16;
+  T *actor_l[kMaxLayers], *qse_l[kMaxLayers], *qm_l[2], *tmpC;
+  cudaStream_t st0 = nullptr, st1 = nullptr;
+  bool two_streams = false;
 
   Decoder(const cqvad_decoder_desc& dd, const void* const* ww, cudaStream_t s) : d(dd), w(ww), st(s) {
     BT = d.BT; nq = d.nq; h = d.h; wd = d.w; S = h * wd; Sp = (h + 1) * wd; K = d.K; F = d.F; Lr = d.layers;
@@ -70,6 +79,9 @@ struct Decoder {
     K8 = (K + 7) & ~7; ldqt = N * K8 + 64; qt = t(kC * ldqt); cqp = t(N * kC); caoc = t(NK * kC); cls0 = t(NK * kC); Hf = t(NK * F);
     hsn = t(N * kC); bb1 = t(N * kC); bb2 = t(N * kC);
     r_cur = f(N * 4); r_next = f(N * 4); lvlw = f(N * 4);
+    actor_l[0] = actor; qse_l[0] = qse; qm_l[0] = qm;
+    for (int l = 1; l < Lr && l < kMaxLayers; ++l) { actor_l[l] = t(N * kC); qse_l[l] = t(N * kC); }
+    qm_l[1] = t(NSq * kC); tmpC = t(N * Fm);
     cls0_32 = clsout_32 = nullptr;
     // fp32 side copies of the class-token stream: measured on B200 to leave the bf16 error unchanged (it is dominated by
     // GEMM operand rounding, tools/diag_bf16.py) while costing 0.33 ms/step -> off unless CQVAD_DEC_FP32_CLS_STREAM
@@ -202,6 +214,20 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
                     void* hs, void* cls_hs, float* refs, float* pred_logits, float* pred_boxes, float* pred_logits_b) {
   const bool of32 = d.out_f32 != 0;
   const size_t osz = of32 ? sizeof(float) : sizeof(T);
+  // ---- streams / events of the two-stream schedule (process-wide, created once) ----
+  static cudaStream_t side = [] { cudaStream_t x = nullptr; cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking); return x; }();
+  static cudaEvent_t ev_loc[kMaxLayers], ev_cls[kMaxLayers];
+  static const bool ev_ok = [] {
+    bool ok = true;
+    for (int i = 0; i < kMaxLayers; ++i)
+      ok = ok && cudaEventCreateWithFlags(&ev_loc[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&ev_cls[i], cudaEventDisableTiming) == cudaSuccess;
+    return ok;
+  }();
+  static const bool one_stream = [] { const char* e = getenv("CQVAD_INFER_STREAMS"); return e && atoi(e) == 1; }();
+  st0 = st;
+  two_streams = !one_stream && side != nullptr && ev_ok && Lr <= kMaxLayers;
+  st1 = two_streams ? side : st0;
   // inputs -> compute dtype.  Only pos[0] is ever used (dab_transformer.py:958, :810).
   ProfScope* ps = new ProfScope(P_INPUT, st);
   CQ_TRY(convert_f32<T>(memory, memc, 4L * S * BT * kC, st));
@@ -219,8 +245,14 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
   ps = nullptr;
   const double eb = sizeof(T), NSd = (double)N * S;   // algorithmic work: valid rows only, operands once, result once
 
+  if (Sq != S && two_streams) CQ_CUDA(cudaMemsetAsync(qm_l[1], 0, (size_t)NSq * kC * sizeof(T), st));
   for (int l = 0; l < Lr; ++l) {
     const bool first = (l == 0);
+    st = st0;                       // ---- localisation chain: caller's stream ----
+    if (two_streams) {
+      actor = actor_l[l]; qse = qse_l[l]; qm = qm_l[l & 1];
+      if (l >= 2) CQ_CUDA(cudaStreamWaitEvent(st0, ev_cls[l - 2], 0));   // q_memory buffer l & 1 is free again
+    }
     // ---- prologue :742-763 ----
     PROF(P_SMALL);
     CQ_TRY(sine_embed<T>(r_cur, e512, N, st));
@@ -271,10 +303,36 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
     CQ_TRY(dec_qsk_attn<T>(qc, qs, kv, kv + kC, 2 * kC, kp, mask, cao, N, S, Sq, BT, first, st));
     PROF(P_SMALL);
     CQ_TRY(lin(cao, N, kC, loc(l, CA_O), actor, kC, CQVAD_ACT_NONE, out, loc(l, NORM2)));   // tgt_temp :992-993
+    if (two_streams) { delete ps; ps = nullptr; CQ_CUDA(cudaEventRecord(ev_loc[l], st0)); }   // actor, q_memory, qse of layer l are final
+    PROF(P_SMALL);
     CQ_TRY(mlp(actor, N, F, loc(l, LIN1), loc(l, LIN2), CQVAD_ACT_RELU, actor, loc(l, NORM3), 1e-5f, out, tmpN));
 
+    // ---- outputs of this layer :826-827 and heads (models/model.py:192-221) ----
+    PROF(P_OUT_LN);
+    CQ_TRY(layernorm_rows<T>(out, nullptr, Wf(glob(G_NORM)), Wf(glob(G_NORM) + 1), 1e-5f, hsn, false, N, st));
+    CQ_TRY(layernorm_permute<T>(out, Wf(glob(G_NORM)), Wf(glob(G_NORM) + 1), 1e-5f, (char*)hs + (size_t)l * N * kC * osz,
+                                of32, N, nq, BT, 1, nullptr, st));
+    if (pred_logits_b)
+      CQ_TRY(logits_b<T>(hsn, Wf(glob(G_CEB)), Wf(glob(G_CEB) + 1), pred_logits_b + (size_t)l * N * 3, N, nq, BT, st));
+    if (pred_boxes) {
+      CQ_TRY(lin(hsn, N, kC, glob(G_BB0), bb1, kC, CQVAD_ACT_RELU));
+      CQ_TRY(lin(bb1, N, kC, glob(G_BB1), bb2, kC, CQVAD_ACT_RELU));
+      CQ_TRY(box_refine<T>(bb2, Wf(glob(G_BB2)), Wf(glob(G_BB2) + 1), r_cur, nullptr, pred_boxes + (size_t)l * N * 4, N, nq,
+                           BT, false, st));
+    }
+    // ---- iterative box refinement :813-823 ----
+    PROF(P_SMALL);
+    CQ_TRY(lin(out, N, kC, glob(G_BB0), bb1, kC, CQVAD_ACT_RELU));
+    CQ_TRY(lin(bb1, N, kC, glob(G_BB1), bb2, kC, CQVAD_ACT_RELU));
+    CQ_TRY(box_refine<T>(bb2, Wf(glob(G_BB2)), Wf(glob(G_BB2) + 1), r_cur, r_next,
+                         (l != Lr - 1) ? refs + (size_t)(l + 1) * N * 4 : nullptr, N, nq, BT, false, st));
+    float* t = r_cur; r_cur = r_next; r_next = t;
+    delete ps; ps = nullptr;
+
+    st = st1;                       // ---- class branch: side stream, one layer behind the localisation chain at most two ----
+    if (two_streams) CQ_CUDA(cudaStreamWaitEvent(st1, ev_loc[l], 0));
     // ---- class-query layer :1040-1079 ----
-    CQ_TRY(mlp(actor, N, F, cls(l, C_L1), cls(l, C_L2), CQVAD_ACT_RELU, actor, cls(l, C_NORM), 1e-5f, acls, tmpN));
+    CQ_TRY(mlp(actor, N, F, cls(l, C_L1), cls(l, C_L2), CQVAD_ACT_RELU, actor, cls(l, C_NORM), 1e-5f, acls, tmpC));
     PROF(P_ADDLN);
     CQ_TRY(add_ln_pad<T>(acls, qm, Wf(cls(l, C_CONVNORM)), Wf(cls(l, C_CONVNORM) + 1), XA, N, S, Sq, Sp, st));
     T* xin = XA; T* xout = XB;
@@ -319,11 +377,7 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
     CQ_TRY(mlp(cls0, NK, F, cls(l, C_L1_), cls(l, C_L2_), CQVAD_ACT_RELU, cls0, cls(l, C_NORM_), 1e-5f, cls_out, Hf, 0, 0,
                /*emit_qt=*/l + 1 < Lr, cls0_32, clsout_32));
 
-    // ---- outputs of this layer :826-827 and heads (models/model.py:192-221) ----
     PROF(P_OUT_LN);
-    CQ_TRY(layernorm_rows<T>(out, nullptr, Wf(glob(G_NORM)), Wf(glob(G_NORM) + 1), 1e-5f, hsn, false, N, st));
-    CQ_TRY(layernorm_permute<T>(out, Wf(glob(G_NORM)), Wf(glob(G_NORM) + 1), 1e-5f, (char*)hs + (size_t)l * N * kC * osz,
-                                of32, N, nq, BT, 1, nullptr, st));
     {
       void* dst = cls_hs ? (void*)((char*)cls_hs + (size_t)l * NK * kC * osz) : nullptr;
       float* lg = pred_logits ? pred_logits + (size_t)l * NK : nullptr;
@@ -334,22 +388,11 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
         CQ_TRY(layernorm_permute<T>(cls_out, Wf(glob(G_CLSNORM2)), Wf(glob(G_CLSNORM2) + 1), 1e-5f, dst, of32, NK, nq, BT,
                                     K, lg, st));
     }
-    if (pred_logits_b)
-      CQ_TRY(logits_b<T>(hsn, Wf(glob(G_CEB)), Wf(glob(G_CEB) + 1), pred_logits_b + (size_t)l * N * 3, N, nq, BT, st));
-    if (pred_boxes) {
-      CQ_TRY(lin(hsn, N, kC, glob(G_BB0), bb1, kC, CQVAD_ACT_RELU));
-      CQ_TRY(lin(bb1, N, kC, glob(G_BB1), bb2, kC, CQVAD_ACT_RELU));
-      CQ_TRY(box_refine<T>(bb2, Wf(glob(G_BB2)), Wf(glob(G_BB2) + 1), r_cur, nullptr, pred_boxes + (size_t)l * N * 4, N, nq,
-                           BT, false, st));
-    }
-    // ---- iterative box refinement :813-823 ----
-    PROF(P_SMALL);
-    CQ_TRY(lin(out, N, kC, glob(G_BB0), bb1, kC, CQVAD_ACT_RELU));
-    CQ_TRY(lin(bb1, N, kC, glob(G_BB1), bb2, kC, CQVAD_ACT_RELU));
-    CQ_TRY(box_refine<T>(bb2, Wf(glob(G_BB2)), Wf(glob(G_BB2) + 1), r_cur, r_next,
-                         (l != Lr - 1) ? refs + (size_t)(l + 1) * N * 4 : nullptr, N, nq, BT, false, st));
-    float* t = r_cur; r_cur = r_next; r_next = t;
+    delete ps; ps = nullptr;
+    if (two_streams) CQ_CUDA(cudaEventRecord(ev_cls[l], st1));
   }
+  st = st0;
+  if (two_streams) CQ_CUDA(cudaStreamWaitEvent(st0, ev_cls[Lr - 1], 0));   // join: the caller's stream owns every output again
   delete ps;
 #undef PROF
 #undef WORK
