@@ -261,6 +261,9 @@ def main():
     det_all = torch.empty((world * BT, nq, K + 4 + 3), dtype=torch.float32, device=dev) if world > 1 else det_local
     det_host = torch.empty((BT, nq, K + 4 + 3), dtype=torch.float32).pin_memory()
     from class_query_vad_b200.dist import allreduce_gradients
+    if world > 1 and args.mode == "train":
+        eng._grad_table()
+        eng.enable_layer_events()
     lw = synth.make_loss_weights(cfg, B, seed=1)
     g_hs = torch.from_numpy(lw["w_hs"]).to(dev).bfloat16()
     g_cls = torch.from_numpy(lw["w_cls"]).to(dev).bfloat16()
@@ -285,8 +288,8 @@ def main():
         out = eng.forward_train(inp["tgt"], inp["memory"], inp["mask"], inp["pos"], inp["refpoints_unsigmoid"], orig_res,
                                 dropout_p=args.dropout, seed=1000 + step_no["n"])
         eng.backward(g_hs, g_cls, g_refs, zero=True, named=False)
-        if world > 1:
-            allreduce_gradients(eng)
+        if world > 1:       # per-layer buckets on a communication stream, each released by its layer's gradient-complete event
+            allreduce_gradients(eng, overlap=True)
         launches["n"] = eng.last_launches + eng.last_launches_bwd + (1 if world > 1 else 0)
         return out
 

@@ -90,6 +90,7 @@ SYMBOLS = {
     "cqvad_heads_train_workspace_bytes": (c_size_t, [c_long]),
     "cqvad_heads_train_forward": (c_int, [c_void_p] * 4 + [c_long, c_int, c_float, c_uint64] + [c_void_p] * 4 + [c_size_t, c_void_p]),
     "cqvad_heads_train_backward": (c_int, [c_void_p] * 6 + [c_long, c_int, c_float, c_uint64] + [c_void_p] * 5 + [c_size_t, c_void_p]),
+    "cqvad_decoder_backward_layer_events": (c_int, [c_void_p, c_int]),
     "cqvad_adamw_workspace_bytes": (c_size_t, []),
     "cqvad_adamw_clip_step": (c_int, [c_void_p] * 5 + [c_long] + [c_float] * 5 + [c_long, c_float, c_float, c_int, c_void_p, c_void_p,
                                                                                 c_size_t, c_void_p]),

@@ -26,6 +26,11 @@
 
 namespace cqvad {
 
+static thread_local void* const* g_layer_events = nullptr;
+static thread_local int g_layer_events_n = 0;
+static void* const* layer_events() { return g_layer_events; }
+static int layer_events_count() { return g_layer_events_n; }
+
 int cls_xattn_tc(const bf16* Qin, const bf16* cqp, const bf16* kx, const bf16* pos0, const bf16* vt, long ldvt,
                  const float* bv, bf16* out, long N, int K, int S, int Sq, int Sp_rows, int BT, cudaStream_t st);
 int cls_sattn_tc(const bf16* x, const bf16* xt, long ldxt, bf16* out, long N, int K, int K8, cudaStream_t st);
@@ -101,11 +106,12 @@ struct Trainer {
   int BT, nq, h, wd, S, Sp, Sq, K, F, Lr;
   long N, NS, NSq, Rp, NK;
   std::deque<Ten<T>> tens;
-  struct TapeEntry { std::function<int()> fn; int branch; };
+  struct TapeEntry { std::function<int()> fn; int branch; int layer; };
   struct Tape {
-    std::vector<TapeEntry> v; int* cur;
-    void push_back(std::function<int()> f) { v.push_back(TapeEntry{std::move(f), *cur}); }
+    std::vector<TapeEntry> v; int* cur; int* layer;
+    void push_back(std::function<int()> f) { v.push_back(TapeEntry{std::move(f), *cur, *layer}); }
   } tape;
+  int cur_layer = -1;   // layer whose ops are being recorded (-1: prologue / global ops)
   std::vector<T*> wt;   // transposed / flipped weight copies for the data-gradient GEMMs, by weight index
   std::vector<char> wt_alloc, wt_built;
 
@@ -114,7 +120,7 @@ struct Trainer {
     BT = d.BT; nq = d.nq; h = d.h; wd = d.w; S = h * wd; Sp = (h + 1) * wd; K = d.K; F = d.F; Lr = d.layers;
     Sq = (S + 7) & ~7;
     N = (long)nq * BT; NS = N * S; NSq = N * Sq; Rp = N * Sp; NK = N * K;
-    tape.cur = &cur_branch;
+    tape.cur = &cur_branch; tape.layer = &cur_layer;
     static const bool one = [] { const char* e = getenv("CQVAD_TRAIN_STREAMS"); return e && atoi(e) == 1; }();
     two_streams = !one && mode != PLAN && side_stream() != nullptr;
     streams[0] = st; streams[1] = two_streams ? side_stream() : st;
@@ -171,6 +177,25 @@ struct Trainer {
     CQ_CUDA(cudaEventRecord(ev, wg_stream()));
     CQ_CUDA(cudaStreamWaitEvent(streams[0], ev, 0));
     wg_used = false;
+    return 0;
+  }
+  // Gradient-bucket signalling (cqvad_decoder_backward_layer_events): once every backward op of layer l is enqueued, the caller's
+  // event l is recorded behind all three streams, so a communication stream can all-reduce that layer's parameter gradients
+  // while the backward of the layers below still runs.
+  int signal_layer(int l) {
+    void* const* evs = layer_events();
+    if (!evs || l >= layer_events_count() || !evs[l]) return 0;
+    static cudaStream_t sig = [] { cudaStream_t x = nullptr; cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking); return x; }();
+    static cudaEvent_t tmp[3] = {nullptr, nullptr, nullptr};
+    for (int i = 0; i < 3; ++i)
+      if (!tmp[i]) CQ_CUDA(cudaEventCreateWithFlags(&tmp[i], cudaEventDisableTiming));
+    cudaStream_t srcs[3] = {streams[0], streams[1], wg_used ? wg_stream() : streams[0]};
+    for (int i = 0; i < 3; ++i) {
+      if (i > 0 && srcs[i] == srcs[0]) continue;
+      CQ_CUDA(cudaEventRecord(tmp[i], srcs[i]));
+      CQ_CUDA(cudaStreamWaitEvent(sig, tmp[i], 0));
+    }
+    CQ_CUDA(cudaEventRecord((cudaEvent_t)evs[l], sig));
     return 0;
   }
   int link(int from, int to) {   // stream `to` waits for everything enqueued on stream `from` so far
@@ -485,6 +510,7 @@ int Trainer<T>::run() {
   Ten<T>* Qprev = nullptr;
   for (int l = 0; l < Lr; ++l) {
     const bool first = (l == 0);
+    cur_layer = l;
     float* r_cur = rl[l];
     float* dr_cur = first ? drl[0] : nullptr;   // reference points are detached between layers (:823)
     // ---- prologue :742-763 ----
@@ -741,8 +767,10 @@ int Trainer<T>::run() {
     st = streams[0];
     CQ_CUDA(cudaMemsetAsync(drl[0], 0, (size_t)N * 4 * sizeof(float), st));
     CQ_TRY(link(0, 1));            // fork: the class-branch stream starts after everything already on the caller's stream
-    int ti = (int)tape.v.size(), prev = 0;
+    int ti = (int)tape.v.size(), prev = 0, done_layer = Lr;
     for (auto it = tape.v.rbegin(); it != tape.v.rend(); ++it) {
+      // every backward op of the layers above it->layer has been enqueued: signal their parameter gradients as final
+      while (done_layer - 1 > it->layer && done_layer - 1 >= 0) { --done_layer; CQ_TRY(signal_layer(done_layer)); }
       const int b = it->branch;
       if (b == 0 && prev == 1) CQ_TRY(link(1, 0));   // the loc layer consumes the class branch's gradients (q_memory, qse)
       prev = b;
@@ -751,6 +779,7 @@ int Trainer<T>::run() {
       CQ_TRY(it->fn());
       CQ_TRY(dbg("tape", --ti));
     }
+    while (done_layer > 0) { --done_layer; CQ_TRY(signal_layer(done_layer)); }
     CQ_TRY(link(1, 0));            // join
     CQ_TRY(wgrad_join());
     st = streams[0];
@@ -790,6 +819,13 @@ int check_train_desc(const cqvad_decoder_desc* d) {
 }  // namespace cqvad
 
 using namespace cqvad;
+
+extern "C" int cqvad_decoder_backward_layer_events(void* const* events, int n) {
+  CQ_CHECK_ARG(n >= 0 && (n == 0 || events != nullptr), "decoder_backward_layer_events: bad arguments");
+  g_layer_events = n > 0 ? events : nullptr;
+  g_layer_events_n = n;
+  return 0;
+}
 
 extern "C" size_t cqvad_decoder_train_workspace_bytes(const cqvad_decoder_desc* d) {
   if (check_train_desc(d) != 0) return 0;

@@ -51,13 +51,53 @@ def gather_detections(det_local, n_clips_total=None, group=None):
     return torch.cat([out[r * bmax: r * bmax + counts[r]] for r in range(world)], dim=0)
 
 
-def allreduce_gradients(engine, group=None, average=True):
-    """Training: ONE all-reduce over the engine's flat fp32 gradient buffer (all decoder parameters, ~133 MB for the 6-layer
-    AVA decoder) per optimizer step -- what DDP does per bucket in the reference (utils/model_utils.py:113-121).  Parameters
-    the reference never uses (q_proj, cls_norm) are not in the buffer, which is what static_graph=True DDP skips."""
+def allreduce_gradients(engine, group=None, average=True, overlap=False, comm_stream=None):
+    """Training: all-reduce of the engine's flat fp32 gradient buffer (all decoder parameters, ~133 MB for the 6-layer AVA decoder)
+    once per optimizer step -- what DDP does per bucket in the reference (utils/model_utils.py:113-121).  Parameters the reference
+    never uses (q_proj, cls_norm) are not in the buffer, which is what static_graph=True DDP skips.
+
+    overlap=False: ONE collective after the backward.  overlap=True (call it right after `engine.backward(...)` returned, i.e.
+    while the GPU is still executing that backward; needs `engine.enable_layer_events()`): one collective per decoder layer on
+    `comm_stream`, each waiting only for its layer's gradient-complete event, layers-1 first, then the shared-module bucket after
+    the whole backward; the caller's stream waits for the communication stream at the end.  The average is folded into the
+    buckets as they complete."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return engine._gflat
-    dist.all_reduce(engine._gflat, op=dist.ReduceOp.SUM, group=group)
-    if average:
-        engine._gflat.div_(dist.get_world_size(group))
+    world = dist.get_world_size(group)
+    if not overlap or getattr(engine, "layer_events", None) is None:
+        dist.all_reduce(engine._gflat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            engine._gflat.div_(world)
+        return engine._gflat
+    cur = torch.cuda.current_stream()
+    comm = comm_stream or _comm_stream(engine._gflat.device)
+    buckets = engine.grad_buckets
+    with torch.cuda.stream(comm):
+        for l in reversed(range(len(buckets) - 1)):
+            lo, hi = buckets[l]
+            if hi <= lo:
+                continue
+            comm.wait_event(engine.layer_events[l])
+            _reduce_bucket(engine._gflat[lo:hi], world, average, group)
+        comm.wait_stream(cur)                               # shared modules: final when the backward's own stream is
+        lo, hi = buckets[-1]
+        if hi > lo:
+            _reduce_bucket(engine._gflat[lo:hi], world, average, group)
+    cur.wait_stream(comm)
     return engine._gflat
+
+
+_COMM_STREAMS = {}
+
+
+def _comm_stream(device):
+    key = str(device)
+    if key not in _COMM_STREAMS:
+        _COMM_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COMM_STREAMS[key]
+
+
+def _reduce_bucket(t, world, average, group):
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        t.div_(world)

@@ -67,6 +67,27 @@ def pack_decoder_weights(state, layers, dtype, device, meta=None):
     return keep, arr
 
 
+def grad_bucket_layout(names, sizes, layers):
+    """Offsets of every weight gradient in the flat fp32 buffer and the bucket boundaries: one contiguous bucket per decoder layer
+    (layers.l.* then cls_layers.l.*), then the shared modules.  Returns (offs [n+1], [(lo, hi)] * (layers + 1))."""
+    n = len(sizes)
+    layer_of = []
+    for name in names:
+        parts = name.split(".")
+        layer_of.append(int(parts[1]) if parts[0] in ("layers", "cls_layers") and parts[1].isdigit() else layers)
+    order = sorted(range(n), key=lambda i: (layer_of[i], i))
+    offs = np.zeros(n + 1, dtype=np.int64)
+    pos, bounds = 0, [0] * (layers + 2)
+    for i in order:
+        offs[i] = pos
+        pos += (sizes[i] + 63) // 64 * 64
+        bounds[layer_of[i] + 1] = pos
+    for b in range(1, len(bounds)):
+        bounds[b] = max(bounds[b], bounds[b - 1])
+    offs[n] = pos
+    return offs, [(bounds[b], bounds[b + 1]) for b in range(layers + 1)]
+
+
 class DecoderEngine:
     """TransformerDecoder.forward (+ DETR heads) on one GPU.
 
@@ -147,16 +168,33 @@ class DecoderEngine:
 
     # ---- training step (BASELINE.json configs[1]: decoder fwd + bwd) ----------------------------------------------
     def _grad_table(self):
-        """One flat fp32 buffer holding every weight gradient + the pointer table cqvad_decoder_backward takes."""
+        """One flat fp32 buffer holding every weight gradient + the pointer table cqvad_decoder_backward takes.  Layout = one
+        contiguous bucket per decoder layer (layers.l.* followed by cls_layers.l.*), then the shared modules: the buckets are
+        what `dist.allreduce_gradients(overlap=True)` reduces while the backward of the lower layers still runs."""
         if getattr(self, "_gflat", None) is None:
             sizes = [0 if shp is None else int(np.prod(shp)) for (_, shp, _) in self._meta]
-            offs = np.concatenate([[0], np.cumsum([(n + 63) // 64 * 64 for n in sizes])]).astype(np.int64)
-            self._gflat = torch.zeros(int(offs[-1]), dtype=torch.float32, device=self.device)
+            offs, self.grad_buckets = grad_bucket_layout([m[0] for m in self._meta], sizes, self.layers)   # [layer 0 .. L-1, shared]
+            pos = offs[-1]
+            self._gflat = torch.zeros(int(pos), dtype=torch.float32, device=self.device)
             self._goffs, self._gsizes = offs, sizes
             self._gtab = (c_void_p * len(sizes))()
-            for i, n in enumerate(sizes):
+            for i, sz in enumerate(sizes):
                 self._gtab[i] = None if self._meta[i][1] is None else self._gflat.data_ptr() + 4 * int(offs[i])
         return self._gflat, self._gtab
+
+    def enable_layer_events(self, on=True):
+        """Have every later backward record one CUDA event per decoder layer as soon as that layer's parameter gradients are final
+        (cqvad_decoder_backward_layer_events); `self.layer_events[l]` are torch events a communication stream can wait on."""
+        lib = _lib.lib()
+        if not on:
+            _lib.check(lib.cqvad_decoder_backward_layer_events(None, 0))
+            self.layer_events = None
+            return
+        self.layer_events = [torch.cuda.Event() for _ in range(self.layers)]
+        for e in self.layer_events:
+            e.record()                                   # creates the underlying cudaEvent_t
+        self._evtab = (c_void_p * self.layers)(*[e.cuda_event for e in self.layer_events])
+        _lib.check(lib.cqvad_decoder_backward_layer_events(self._evtab, self.layers))
 
     def forward_train(self, tgt, memory, mask, pos, refpoints_unsigmoid, orig_res, dropout_p=0.0, seed=0):
         """TransformerDecoder.forward keeping what the backward needs.  Returns dict(hs, cls_hs, refs); follow with

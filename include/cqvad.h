@@ -268,6 +268,13 @@ long cqvad_last_launch_count(void);
  *       Autograd semantics of the reference: reference points detached between layers (:823), actor feature detached on
  *       entry to the class branch (:810); `pos` gets no gradient (it is not a decoder parameter; level_embed lives in
  *       Transformer). */
+/* Gradient-bucket signalling for data-parallel training (the reference wraps the model in DDP, utils/model_utils.py:113-121, whose
+ * buckets all-reduce while the backward still runs): events[l] (cudaEvent_t, l = 0..n-1 = decoder layer; NULL entries skipped) is
+ * recorded by every later cqvad_decoder_backward ON THIS THREAD as soon as all parameter gradients of layers.l.* / cls_layers.l.*
+ * are final (behind the three streams of the backward), layers-1 first.  The gradients of the shared modules (ref_point_head,
+ * query_scale, ref_anchor_head, bbox_embed, norm, cls_norm2, class_queries) are final when the call's stream is.  n = 0 disables.
+ * The array must stay valid until it is replaced. */
+int cqvad_decoder_backward_layer_events(void* const* events, int n);
 size_t cqvad_decoder_train_workspace_bytes(const cqvad_decoder_desc* d);
 int cqvad_decoder_train_forward(const cqvad_decoder_desc* d, const void* const* weights,
                                 const float* tgt, const float* memory, const float* pos, const uint8_t* mask,

@@ -94,3 +94,26 @@ def test_gradient_allreduce_world2():
         p.join(timeout=60)
     expect = [1.5 * i for i in range(10)]      # mean of (1x, 2x)
     assert res[0] == expect and res[1] == expect
+
+
+def test_gradient_bucket_layout_is_one_contiguous_bucket_per_layer():
+    """Host logic of the overlapped gradient all-reduce: the flat gradient buffer holds layers.l.* + cls_layers.l.* contiguously per
+    layer (bucket l), the shared modules last; buckets tile the buffer without gaps or overlap."""
+    from class_query_vad_b200 import _lib
+    from class_query_vad_b200.engine import grad_bucket_layout
+    lib = _lib.lib()
+    layers = 6
+    n = lib.cqvad_decoder_num_weights(layers)
+    names = [lib.cqvad_decoder_weight_name(i, layers).decode() for i in range(n)]
+    sizes = [(i * 37) % 1000 + 1 for i in range(n)]
+    offs, buckets = grad_bucket_layout(names, sizes, layers)
+    assert len(buckets) == layers + 1 and buckets[0][0] == 0 and buckets[-1][1] == offs[-1]
+    for (lo, hi), (lo2, _) in zip(buckets, buckets[1:]):
+        assert hi == lo2 and hi > lo
+    for i, name in enumerate(names):
+        parts = name.split(".")
+        b = int(parts[1]) if parts[0] in ("layers", "cls_layers") else layers
+        lo, hi = buckets[b]
+        assert lo <= offs[i] and offs[i] + sizes[i] <= hi, name
+    spans = sorted((int(offs[i]), int(offs[i]) + sizes[i]) for i in range(n))
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))          # no two gradients overlap

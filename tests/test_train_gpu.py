@@ -187,7 +187,8 @@ def test_module_autograd_drop_in():
     seed = int(g["meta"][8])
     dec = build_decoder(cfg["nq"], cfg["K"], cfg["layers"], cfg["F"])
     dec.load_state_dict({k: torch.from_numpy(v) for k, v in W.items() if not k.startswith("heads.")}, strict=True)
-    dec = dec.cuda().train()
+    dec = dec.cuda().eval()          # the fixture is the reference in eval mode (dropout = identity); train() mode applies nn.Dropout,
+                                     # whose parity is tests/test_dropout_gpu.py
     dec.compute_dtype = torch.float32
     t = lambda a: torch.from_numpy(a).cuda()
     memory = t(inp["memory"]).requires_grad_(True)
