@@ -256,7 +256,8 @@ long cqvad_last_launch_count(void);
  * the MSDA op, ops/functions/ms_deform_attn_func.py:36-45).
  *   cqvad_decoder_train_forward : same inputs/outputs as cqvad_decoder_forward without the heads (hs, cls_hs, refs are
  *       what TransformerDecoder.forward returns) and keeps every intermediate the backward needs in `workspace`
- *       (cqvad_decoder_train_workspace_bytes; ~13 GB at 32 AVA clips in bf16).  Dropout is the identity.
+ *       (cqvad_decoder_train_workspace_bytes; 25.9 GiB at 32 AVA clips in bf16).  desc.dropout_p > 0 applies nn.Dropout at the
+ *       nine residual-branch / FFN-hidden sites of every layer pair (Philox masks keyed by desc.seed_*; 0 = eval semantics).
  *   cqvad_decoder_backward : given dL/d(hs), dL/d(cls_hs) (element type of the forward outputs: fp32 when out_f32, else
  *       `dtype`) and dL/d(refs) (fp32); any may be NULL = zero.  MUST be called with the same descriptor, weights and
  *       workspace as the preceding train_forward, before anything else touches the workspace.
@@ -266,8 +267,8 @@ long cqvad_last_launch_count(void);
  *         grad_memory      [4,S,BT,256] fp32      grad_tgt [nq,BT,256] fp32 (may be NULL)
  *         grad_refpoints_unsigmoid [nq,BT,4] fp32 (may be NULL)
  *       Autograd semantics of the reference: reference points detached between layers (:823), actor feature detached on
- *       entry to the class branch (:810); `pos` gets no gradient (it is not a decoder parameter; level_embed lives in
- *       Transformer). */
+ *       entry to the class branch (:810); `pos` gets no gradient: it enters only on the key side of softmax attentions, so the
+ *       per-level constant level_embed (Transformer) has an identically zero gradient through the decoder. */
 /* Gradient-bucket signalling for data-parallel training (the reference wraps the model in DDP, utils/model_utils.py:113-121, whose
  * buckets all-reduce while the backward still runs): events[l] (cudaEvent_t, l = 0..n-1 = decoder layer; NULL entries skipped) is
  * recorded by every later cqvad_decoder_backward ON THIS THREAD as soon as all parameter gradients of layers.l.* / cls_layers.l.*
