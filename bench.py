@@ -495,6 +495,10 @@ def main():
         except Exception as e:                      # the headline never depends on the extra measurement
             line["encoder_layer"] = {"error": str(e)[:200]}
         try:
+            line["latency_batch1"] = batch1_latency(dev)
+        except Exception as e:
+            line["latency_batch1"] = {"error": str(e)[:200]}
+        try:
             line["vit_neck"] = vit_neck_numbers(dev)
         except Exception as e:
             line["vit_neck"] = {"error": str(e)[:200]}
@@ -656,6 +660,48 @@ def vit_neck_numbers(dev, B=4, iters=5):
     return {"workload": f"ViT-B simple feature pyramid (lateral_convs x4) on 8x14x14x768 features -> 33 320 tokens, bf16, {B} clips",
             "ms": round(ms, 3), "clips_per_s": round(B / ms * 1e3, 1), "gflop_per_clip": round(fl / 1e9, 1),
             "tflops": round(B * fl / ms / 1e9, 1)}
+
+
+def batch1_latency(dev, iters=50):
+    """BASELINE configs[0]'s shape on the GPU: AVA22_ViT-B decoder forward + heads for ONE clip (the case the reference runs on the
+    CPU).  Launch-bound (317 kernels): timed eagerly and as a CUDA-graph replay (DecoderEngine.capture_forward), inputs resident,
+    and end to end (pinned-host inputs -> static buffers -> replay -> detections back on the host)."""
+    import torch
+    from class_query_vad_b200 import DecoderEngine
+    from oracle import synth
+    cfg = synth.CONFIGS["ava_vitb"]
+    W = synth.make_decoder_weights(cfg["K"], cfg["layers"], cfg["F"], seed=0)
+    eng = DecoderEngine(W, nq=cfg["nq"], K=cfg["K"], layers=cfg["layers"], F=cfg["F"], dtype=torch.bfloat16, device=dev, out_f32=False)
+    inp = synth.make_decoder_inputs("ava_vitb", 1, seed=3)
+    host = {k: torch.from_numpy(np.ascontiguousarray(inp[k])).pin_memory() for k in ("tgt", "memory", "pos", "mask", "refpoints_unsigmoid")}
+    d = {k: v.to(dev) for k, v in host.items()}
+    res = (cfg["h"], cfg["w"])
+    eager = lambda: eng.forward(d["tgt"], d["memory"], d["mask"], d["pos"], d["refpoints_unsigmoid"], res, heads=True)
+    g = eng.capture_forward(d["tgt"], d["memory"], d["mask"], d["pos"], d["refpoints_unsigmoid"], res, heads=True)
+    ref = eager()
+    out = g()
+    torch.cuda.synchronize()
+    same = all(torch.equal(ref[k], out[k]) for k in ("hs", "refs", "pred_logits", "pred_boxes"))
+    det_host = torch.empty((1, cfg["nq"], cfg["K"] + 7), dtype=torch.float32).pin_memory()
+
+    def e2e():
+        o = g(**host)
+        det_host.copy_(torch.cat([o["pred_logits"][-1], o["pred_boxes"][-1], o["pred_logits_b"][-1]], dim=-1), non_blocking=True)
+
+    def t(fn):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    return {"workload": "AVA22_ViT-B class-query decoder forward + heads, ONE clip (BASELINE configs[0] shape), bf16",
+            "eager_ms": round(t(eager), 4), "cuda_graph_ms": round(t(lambda: g()), 4), "cuda_graph_e2e_ms": round(t(e2e), 4),
+            "graph_replay_bit_identical_to_eager": bool(same), "launches": int(eng.last_launches)}
 
 
 def reference_gpu_eager(dev, mode, B, iters=5):

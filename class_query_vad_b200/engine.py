@@ -88,6 +88,19 @@ def grad_bucket_layout(names, sizes, layers):
     return offs, [(bounds[b], bounds[b + 1]) for b in range(layers + 1)]
 
 
+class GraphedForward:
+    """A captured DecoderEngine.forward (DecoderEngine.capture_forward)."""
+
+    def __init__(self, graph, inputs, outputs):
+        self.graph, self.inputs, self.outputs = graph, inputs, outputs
+
+    def __call__(self, **new_inputs):
+        for k, v in new_inputs.items():
+            self.inputs[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.outputs
+
+
 class DecoderEngine:
     """TransformerDecoder.forward (+ DETR heads) on one GPU.
 
@@ -165,6 +178,29 @@ class DecoderEngine:
         if heads:
             out.update(pred_logits=pl, pred_boxes=pb, pred_logits_b=plb)
         return out
+
+    def capture_forward(self, tgt, memory, mask, pos, refpoints_unsigmoid, orig_res, heads=True, skip_cls_hs=False):
+        """CUDA-graph capture of one inference forward at fixed shapes (launch-bound at small batch: 317 kernels on two streams).
+        Returns a GraphedForward: `g.inputs` are the static input tensors (copy new data into them), `g()` replays the graph on
+        the current stream and returns the static output dict.  The library's side stream joins the capture through its
+        fork / join events; tensor maps are kernel parameters, so nothing is re-encoded on replay."""
+        cur = torch.cuda.current_stream()
+        f32 = lambda t: t.to(device=self.device, dtype=torch.float32).contiguous().clone()
+        static = dict(tgt=f32(tgt), memory=f32(memory), pos=f32(pos), refpoints_unsigmoid=f32(refpoints_unsigmoid),
+                      mask=None if mask is None else mask.to(self.device).contiguous().clone())
+        run = lambda: self.forward(static["tgt"], static["memory"], static["mask"], static["pos"], static["refpoints_unsigmoid"], orig_res,
+                                   heads=heads, skip_cls_hs=skip_cls_hs)
+        warm = torch.cuda.Stream(device=self.device)
+        warm.wait_stream(cur)
+        with torch.cuda.stream(warm):                 # workspace allocation, kernel attributes, lazy inits: outside the capture
+            for _ in range(2):
+                run()
+        cur.wait_stream(warm)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = run()
+        return GraphedForward(graph, static, out)
 
     # ---- training step (BASELINE.json configs[1]: decoder fwd + bwd) ----------------------------------------------
     def _grad_table(self):

@@ -6,6 +6,7 @@ import pytest
 import torch
 
 from helpers import load_golden, case_from_meta, rel_err, TOL_FP32, TOL_BF16
+from oracle import synth
 
 pytestmark = pytest.mark.gpu
 
@@ -149,3 +150,25 @@ def test_decoder_module_drop_in_fp32():
     assert rel_err(hs.cpu().numpy(), g["hs"]) < TOL_FP32
     assert rel_err(cls_hs.cpu().numpy(), g["cls_hs"]) < TOL_FP32
     assert rel_err(refs.cpu().numpy(), g["refs"]) < TOL_FP32
+
+
+def test_cuda_graph_replay_is_bit_identical_to_the_eager_forward():
+    """DecoderEngine.capture_forward: the two-stream forward captured in a CUDA graph replays bit-identically, also after new
+    inputs are copied into its static buffers."""
+    from class_query_vad_b200 import DecoderEngine
+    cfg = dict(synth.CONFIGS["small"])
+    dev = torch.device("cuda:0")
+    W = synth.make_decoder_weights(cfg["K"], cfg["layers"], cfg["F"], seed=1)
+    eng = DecoderEngine(W, nq=cfg["nq"], K=cfg["K"], layers=cfg["layers"], F=cfg["F"], dtype=torch.bfloat16, device=dev)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    a = synth.make_decoder_inputs(cfg, 2, seed=1, masked=True)
+    b = synth.make_decoder_inputs(cfg, 2, seed=2, masked=True)
+    args = lambda i: (t(i["tgt"]), t(i["memory"]), t(i["mask"]), t(i["pos"]), t(i["refpoints_unsigmoid"]), i["orig_res"])
+    g = eng.capture_forward(*args(a))
+    for inp in (a, b, a):
+        ref = {k: v.clone() for k, v in eng.forward(*args(inp)).items()}
+        out = g(tgt=t(inp["tgt"]), memory=t(inp["memory"]), mask=t(inp["mask"]), pos=t(inp["pos"]),
+                refpoints_unsigmoid=t(inp["refpoints_unsigmoid"]))
+        torch.cuda.synchronize()
+        for k in ref:
+            assert torch.equal(ref[k], out[k]), k
