@@ -583,8 +583,10 @@ def full_training_step(dev, world, B=2, steps=4, warmup=2):
     first_loss = float(loss_host[4])
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    h0 = time.perf_counter()
     for i in range(steps):
         step(i)
+    host_ms = (time.perf_counter() - h0) * 1e3 / steps          # host time to ENQUEUE a step (no synchronisation inside)
     e1.record()
     sync()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -598,7 +600,7 @@ def full_training_step(dev, world, B=2, steps=4, warmup=2):
            "value": world * B / ms * 1e3, "unit": "clips/s", "ms_per_step": round(ms, 3), "steps": steps, "warmup": warmup,
            "n_gpus": world, "batch_per_gpu": B, "parameters": int(n_params), "allreduce_bytes_per_step": int(4 * n_params) if world > 1 else 0,
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 64, "loss_first": round(first_loss, 4), "loss_last": round(float(loss_host[4]), 4),
-           "peak_memory_gib": round(peak_gb, 2), "timing": "CUDA events, max over ranks, host copies inside the timed region (e2e)"}
+           "peak_memory_gib": round(peak_gb, 2), "host_enqueue_ms_per_step": round(host_ms, 2), "timing": "CUDA events, max over ranks, host copies inside the timed region (e2e)"}
     del model, opt, host
     torch.cuda.empty_cache()
     return res

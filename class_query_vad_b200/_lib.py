@@ -149,3 +149,31 @@ def require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise RuntimeError("Not implemented on the CPU")  # same message as ops/src/cpu/ms_deform_attn_cpu.cpp:26
+
+
+# ---- level-shape tensors: built once per (shapes, device), with their host copies kept beside them so that the forward path
+# never reads a shape back from the device (a .tolist() / .item() there is a full stream synchronisation per call)
+_SHAPE_CACHE = {}
+_SHAPE_HOST = {}
+
+
+def shape_tensors(shapes, device):
+    """shapes: sequence of (T, H, W).  Returns (shapes [L,3] int64, level_start [L] int64) on `device` (cached)."""
+    import torch
+    key = (tuple(tuple(int(v) for v in s) for s in shapes), str(device))
+    hit = _SHAPE_CACHE.get(key)
+    if hit is None:
+        sh = torch.tensor(key[0], dtype=torch.int64, device=device)
+        ls = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+        hit = (sh, ls)
+        _SHAPE_CACHE[key] = hit
+        _SHAPE_HOST[(sh.data_ptr(), str(device))] = [list(s) for s in key[0]]
+    return hit
+
+
+def host_shapes(sh):
+    """[[T, H, W], ...] of a level-shape tensor: from the cache when it came from shape_tensors(), else one device read."""
+    if not hasattr(sh, "data_ptr"):
+        return [list(s) for s in sh]
+    hit = _SHAPE_HOST.get((sh.data_ptr(), str(sh.device)))
+    return hit if hit is not None else sh.tolist()

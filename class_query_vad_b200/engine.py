@@ -123,10 +123,25 @@ class DecoderEngine:
 
     def repack(self, state):
         """Refresh the packed weights IN PLACE after an optimizer step: pointer table, workspaces and the flat gradient buffer stay."""
-        keep, _ = pack_decoder_weights(state, self.layers, self.dtype, self.device)
-        for old, new in zip(self._keep, keep):
-            if old is not None:
-                old.copy_(new)
+        plain_dst, plain_src = [], []
+        for (name, shp, orig), old in zip(self._meta, self._keep):
+            if old is None:
+                continue
+            if ".__ca_kv." in name:
+                pre, leaf = name.split(".__ca_kv.")
+                half = old.shape[0] // 2
+                plain_dst += [old[:half], old[half:]]
+                plain_src += [_as_tensor(state[f"{pre}.ca_kcontent_proj.{leaf}"]), _as_tensor(state[f"{pre}.ca_v_proj.{leaf}"])]
+            elif name not in state:
+                continue                                   # synthesised zeros (absent heads): nothing to refresh
+            elif name.endswith("conv1.weight"):
+                src = _as_tensor(state[name])
+                old.view(src.shape[0], 3, 3, src.shape[1]).copy_(src.permute(0, 2, 3, 1))
+            else:
+                plain_dst.append(old)
+                plain_src.append(_as_tensor(state[name]).reshape(old.shape))
+        if plain_dst:
+            torch._foreach_copy_(plain_dst, plain_src)      # one multi-tensor cast / copy launch group instead of ~4 kernels per weight
 
     def _workspace(self, desc):
         need = _lib.lib().cqvad_decoder_workspace_bytes(byref(desc))
@@ -302,6 +317,68 @@ class DecoderEngine:
         if named:
             out["params"] = self.named_grads()
         return out
+
+    def backward_into(self, param_grads, grad_hs=None, grad_cls_hs=None, grad_refs=None, generation=None):
+        """Backward of the last forward_train that ACCUMULATES the weight gradients straight into caller-owned fp32 tensors
+        (`param_grads`: reference parameter name -> contiguous fp32 tensor of the parameter's shape, e.g. the `.grad` views of a
+        FlatAdamW buffer): cqvad_decoder_backward adds into them in place, which is autograd's accumulate semantics, so no
+        per-parameter clone / add pass exists.  Only the two re-laid-out kinds (3x3 conv taps, stacked [k ; v] projection) go
+        through a staging slot of the engine's own buffer.  Returns dict(memory, tgt, refpoints_unsigmoid)."""
+        if self._train_ctx is None:
+            raise RuntimeError("backward() without a preceding forward_train()")
+        if generation is not None and generation != self._train_gen:
+            raise RuntimeError("DecoderEngine.backward: the activations of this forward were overwritten by a later forward_train() on the "
+                               "same engine (one live training forward per engine)")
+        lib = _lib.lib()
+        desc, m8, (nq, BT, S) = self._train_ctx
+        gflat, gtab0 = self._grad_table()
+        key = tuple(t.data_ptr() for t in param_grads.values())
+        plan = getattr(self, "_direct_plan", None)
+        if plan is None or plan[0] != key:
+            tab = (c_void_p * len(self._meta))()
+            staged = []                                   # (slot view, [(target tensor, view of the slot in the target's layout)])
+            for i, (name, shp, orig) in enumerate(self._meta):
+                tab[i] = gtab0[i]
+                if shp is None or name.startswith("heads."):
+                    continue
+                slot = gflat[int(self._goffs[i]):int(self._goffs[i]) + self._gsizes[i]].view(shp)
+                if ".__ca_kv." in name:
+                    pre, leaf = name.split(".__ca_kv.")
+                    half = shp[0] // 2
+                    staged.append((slot, [(param_grads[f"{pre}.ca_kcontent_proj.{leaf}"], slot[:half]),
+                                          (param_grads[f"{pre}.ca_v_proj.{leaf}"], slot[half:])]))
+                elif name.endswith("conv1.weight"):
+                    staged.append((slot, [(param_grads[name], slot.view(orig[0], 3, 3, orig[1]).permute(0, 3, 1, 2))]))
+                else:
+                    tgt = param_grads.get(name)
+                    if tgt is None:
+                        raise KeyError(f"backward_into: no gradient tensor for '{name}'")
+                    if tgt.dtype != torch.float32 or not tgt.is_contiguous() or tgt.numel() != self._gsizes[i]:
+                        raise ValueError(f"backward_into: gradient of '{name}' must be a contiguous fp32 tensor of {self._gsizes[i]} elements")
+                    tab[i] = tgt.data_ptr()
+            plan = (key, tab, staged)
+            self._direct_plan = plan
+        _, tab, staged = plan
+        odt = torch.float32 if self.out_f32 else self.dtype
+        prep = lambda g, dt: None if g is None else g.to(device=self.device, dtype=dt).contiguous()
+        grad_hs, grad_cls_hs, grad_refs = prep(grad_hs, odt), prep(grad_cls_hs, odt), prep(grad_refs, torch.float32)
+        for slot, _ in staged:
+            slot.zero_()
+        if getattr(self, "_gin", None) is None or self._gin[0].shape[2] != BT:
+            self._gin = (torch.empty((4, S, BT, 256), dtype=torch.float32, device=self.device),
+                         torch.empty((nq, BT, 256), dtype=torch.float32, device=self.device),
+                         torch.empty((nq, BT, 4), dtype=torch.float32, device=self.device))
+        gmem, gtgt, gref = self._gin
+        for t in self._gin:
+            t.zero_()
+        p = _lib.ptr
+        _lib.check(lib.cqvad_decoder_backward(byref(desc), self._wtab, p(m8), p(grad_hs), p(grad_cls_hs), p(grad_refs), tab, p(gmem),
+                                              p(gtgt), p(gref), p(self._tws), self._tws.numel(), _lib.stream_ptr()))
+        self.last_launches_bwd = lib.cqvad_last_launch_count()
+        for _, targets in staged:
+            for tgt, view in targets:
+                tgt.add_(view)
+        return dict(memory=gmem, tgt=gtgt, refpoints_unsigmoid=gref)
 
     def named_grads(self):
         """Weight gradients under the reference state_dict names and shapes."""

@@ -17,12 +17,23 @@ class DecoderFunction(torch.autograd.Function):
         ctx.need = (tgt.requires_grad, memory.requires_grad, refpoints_unsigmoid.requires_grad)
         ctx.in_dtypes = (tgt.dtype, memory.dtype, refpoints_unsigmoid.dtype)
         ctx.param_meta = [(p.shape, p.dtype) for p in params]
+        ctx.params = params
         ctx.mark_non_differentiable()
         return out["hs"], out["cls_hs"], out["refs"]
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_hs, g_cls, g_refs):
+        # fast path: every parameter already owns a contiguous fp32 .grad (e.g. the persistent views of FlatAdamW): the native
+        # backward accumulates into them in place and autograd receives no per-parameter tensors at all
+        grads = {n: p.grad for n, p in zip(ctx.names, ctx.params)}
+        used = [n for n in ctx.names if not ("q_proj." in n or n.startswith("cls_norm."))]
+        if all(grads[n] is not None and grads[n].dtype == torch.float32 and grads[n].is_contiguous() and grads[n].is_cuda for n in used):
+            g = ctx.engine.backward_into({n: grads[n] for n in used}, g_hs, g_cls, g_refs, generation=ctx.generation)
+            gt = g["tgt"].to(ctx.in_dtypes[0]).clone() if ctx.need[0] else None
+            gm = g["memory"].to(ctx.in_dtypes[1]).clone() if ctx.need[1] else None
+            gr = g["refpoints_unsigmoid"].to(ctx.in_dtypes[2]).clone() if ctx.need[2] else None
+            return (None, None, None, None, None, gt, gm, gr, *([None] * len(ctx.params)))
         g = ctx.engine.backward(g_hs, g_cls, g_refs, zero=True, named=True, generation=ctx.generation)
         named = g["params"]
         pg = []

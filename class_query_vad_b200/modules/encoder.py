@@ -61,6 +61,25 @@ def encoder_layer_forward(packed, src, pos, reference_points, shapes, level_star
     return (out, attn_out) if want_attn else out
 
 
+# Training workspaces (several GB per layer at the 33 320-token pyramid) are recycled through a small free list instead of going
+# back to the caching allocator after every backward: a forward takes one, the matching backward returns it.
+_TRAIN_WS_FREE = {}
+
+
+def _take_train_ws(need, device):
+    free = _TRAIN_WS_FREE.setdefault(str(device), [])
+    for i, t in enumerate(free):
+        if t.numel() >= need:
+            return free.pop(i)
+    return torch.empty(need, dtype=torch.uint8, device=device)
+
+
+def _give_train_ws(ws):
+    free = _TRAIN_WS_FREE.setdefault(str(ws.device), [])
+    if len(free) < 16:
+        free.append(ws)
+
+
 class EncoderLayerFunction(torch.autograd.Function):
     """loss.backward() through one encoder layer: cqvad_deform_encoder_layer_train_forward / _backward.
     apply(src, pos, reference_points, shapes, level_start, padding_mask, n_points, d_ffn, *16 parameters in state_dict order)."""
@@ -82,7 +101,7 @@ class EncoderLayerFunction(torch.autograd.Function):
             m8 = padding_mask.to(src.device).contiguous()
             m8 = m8.view(torch.uint8) if m8.dtype == torch.bool else m8.to(torch.uint8)
         need = lib.cqvad_deform_encoder_layer_train_workspace_bytes(_lib.dtype_id(dt), B, Len, L, n_points, d_ffn)
-        ws = torch.empty(need, dtype=torch.uint8, device=src.device)
+        ws = _take_train_ws(need, src.device)
         out = torch.empty_like(src_c)
         p = _lib.ptr
         _lib.check(lib.cqvad_deform_encoder_layer_train_forward(_lib.dtype_id(dt), tab, p(src_c), p(pos_c), p(refp), p(sh), p(ls), p(m8),
@@ -103,6 +122,8 @@ class EncoderLayerFunction(torch.autograd.Function):
         p = _lib.ptr
         _lib.check(lib.cqvad_deform_encoder_layer_backward(_lib.dtype_id(dt), tab, p(src_c), p(sh), p(ls), p(m8), p(go), p(gsrc), p(gpos),
                                                            gtab, p(ws), need, B, Len, L, n_points, d_ffn, p_drop, seed, _lib.stream_ptr()))
+        _give_train_ws(ws)
+        ctx.saved = None
         return (gsrc, gpos, None, None, None, None, None, None, None, None) + tuple(g.to(d) for g, d in zip(gw, pdt))
 
 
@@ -160,8 +181,7 @@ class DeformableTransformerEncoder(nn.Module):
     def get_reference_points(spatio_temporal_shapes, valid_ratios, device):
         # dab_transformer.py:433-452
         reference_points_list = []
-        for lvl, (T_, H_, W_) in enumerate(spatio_temporal_shapes.tolist() if torch.is_tensor(spatio_temporal_shapes)
-                                           else spatio_temporal_shapes):
+        for lvl, (T_, H_, W_) in enumerate(_lib.host_shapes(spatio_temporal_shapes)):
             ref_t, ref_y, ref_x = torch.meshgrid(torch.linspace(0.5, T_ - 0.5, T_, dtype=torch.float32, device=device),
                                                  torch.linspace(0.5, H_ - 0.5, H_, dtype=torch.float32, device=device),
                                                  torch.linspace(0.5, W_ - 0.5, W_, dtype=torch.float32, device=device), indexing="ij")
@@ -185,7 +205,7 @@ def _encoder_to_decoder_memory_raw(tokens, pos_tokens, shapes, level_start, num_
     dt = tokens.dtype
     B, Len, C = tokens.shape
     L = int(shapes.shape[0])
-    Tt, H, W = (int(v) for v in shapes[L - 2].tolist())
+    Tt, H, W = (int(v) for v in _lib.host_shapes(shapes)[L - 2])
     Tp = 1 if eff else int(num_frames)
     tok = tokens.detach().contiguous()
     ptok = None if pos_tokens is None else pos_tokens.detach().to(dt).contiguous()

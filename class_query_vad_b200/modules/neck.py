@@ -114,8 +114,7 @@ class SimpleFeaturePyramid(nn.Module):
             _lib.check(lib.cqvad_vit_neck_level(_lib.dtype_id(dt), kind, p(fc), tab, p(tokens), Len, start, p(ws), need, B, C, T, H, W,
                                                 _lib.stream_ptr()))
             start += ns[kind]
-        sh = torch.tensor(shapes, dtype=torch.int64, device=dev)
-        ls = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+        sh, ls = _lib.shape_tensors(shapes, dev)
         return tokens, sh, ls
 
     @torch.no_grad()
@@ -123,7 +122,8 @@ class SimpleFeaturePyramid(nn.Module):
         """`space_forward` format: {"0": [B,256,T,4H,4W], "1": ..., "2": ..., "3": ...} (a re-layout of forward_tokens' result)."""
         tokens, sh, ls = self.forward_tokens(features)
         out = {}
-        for l, (t, h, w) in enumerate(sh.tolist()):
-            s = int(ls[l])
+        start = 0
+        for l, (t, h, w) in enumerate(_lib.host_shapes(sh)):
+            s, start = start, start + t * h * w
             out[str(l)] = tokens[:, s:s + t * h * w].reshape(tokens.shape[0], t, h, w, 256).permute(0, 4, 1, 2, 3).contiguous()
         return out

@@ -86,8 +86,7 @@ def flatten_levels(srcs, pos_embeds, level_embed):
         src_flat, pos_flat = LevelsToTokensFunction.apply(level_embed, *srcs, *pos_embeds)
     else:
         src_flat, pos_flat, _, _ = _flatten_levels_raw(srcs, pos_embeds, level_embed)
-    sh = torch.tensor(shapes, dtype=torch.int64, device=dev)
-    ls = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+    sh, ls = _lib.shape_tensors(shapes, dev)
     return src_flat, pos_flat, sh, ls
 
 
@@ -122,9 +121,11 @@ class Transformer(nn.Module):
         src_flat, pos_flat, sh, ls = flatten_levels(srcs, pos_embeds, self.level_embed)
         mask_flat = torch.cat([m.flatten(1) for m in masks], 1)
         valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
-        memory = self.encoder(src_flat, sh, ls, valid_ratios, pos=pos_flat, padding_mask=mask_flat if bool(mask_flat.any()) else None)
+        # the padding mask is always handed over (an all-False mask is a no-op in the kernels): testing it with .any() would
+        # synchronise the stream once per forward
+        memory = self.encoder(src_flat, sh, ls, valid_ratios, pos=pos_flat, padding_mask=mask_flat)
         L = self.num_feature_levels
-        Tt, H, W = (int(v) for v in sh[L - 2].tolist())
+        Tt, H, W = (int(v) for v in srcs[L - 2].shape[2:])
         mem_l, pos0 = encoder_to_decoder_memory(memory, pos_flat, sh, ls, num_frames=self.temp_len, eff=self.eff)
         # mask of level -2 repeated in time (:250-252), key-frame slice, "(B T) (H W)" (:393)
         m = masks[L - 2].repeat(1, self.temp_len // masks[L - 2].size(1), 1, 1)
@@ -186,6 +187,5 @@ def input_proj_levels(feats, convs, norms):
             _lib.check(lib.cqvad_input_proj_3x3s2_gn(_lib.dtype_id(dt), p(f), p(w), p(b), p(g), p(be), float(gn.eps), p(tokens), p(ws), need,
                                                      B, Cin, T, H, W, Len, start, _lib.stream_ptr()))
         start += ns[l]
-    sh = torch.tensor(shapes, dtype=torch.int64, device=dev)
-    ls = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+    sh, ls = _lib.shape_tensors(shapes, dev)
     return tokens, sh, ls

@@ -178,10 +178,13 @@ def test_backward_is_linear_in_the_output_gradients():
         assert float((gc[k] - ref).abs().max()) / scale < 1e-3, k
 
 
-def test_module_autograd_drop_in():
+@pytest.mark.parametrize("flat_optimizer", [False, True])
+def test_module_autograd_drop_in(flat_optimizer):
     """nn.Module boundary in training: loss.backward() through build_decoder()'s TransformerDecoder fills .grad of the
-    reference-named parameters (fp32 path, against the reference-autograd fixture)."""
-    from class_query_vad_b200 import build_decoder
+    reference-named parameters (fp32 path, against the reference-autograd fixture).  flat_optimizer: the parameters' .grad are the
+    persistent fp32 views of a FlatAdamW buffer, so the native backward accumulates into them in place (DecoderEngine.backward_into)
+    -- run twice to check the accumulate semantics (gradients double)."""
+    from class_query_vad_b200 import build_decoder, FlatAdamW
     g = load_golden("grad_tiny_masked")
     cfg, B, W, inp = case_from_golden(g)
     seed = int(g["meta"][8])
@@ -191,19 +194,24 @@ def test_module_autograd_drop_in():
                                      # whose parity is tests/test_dropout_gpu.py
     dec.compute_dtype = torch.float32
     t = lambda a: torch.from_numpy(a).cuda()
-    memory = t(inp["memory"]).requires_grad_(True)
-    import warnings
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
+    opt = FlatAdamW(dec.named_parameters(), module=dec) if flat_optimizer else None
+    lw = synth.make_loss_weights(cfg, B, seed=seed)
+    reps = 2 if flat_optimizer else 1
+    for _ in range(reps):
+        memory = t(inp["memory"]).requires_grad_(True)
         hs, cls_hs, refs = dec(t(inp["tgt"]), memory, memory_key_padding_mask=t(inp["mask"]), pos=t(inp["pos"]),
                                refpoints_unsigmoid=t(inp["refpoints_unsigmoid"]), orig_res=inp["orig_res"])
-    lw = synth.make_loss_weights(cfg, B, seed=seed)
-    loss = (t(lw["w_hs"]) * hs).sum() + (t(lw["w_cls"]) * cls_hs).sum() + (t(lw["w_refs"]) * refs).sum()
-    loss.backward()
+        loss = (t(lw["w_hs"]) * hs).sum() + (t(lw["w_cls"]) * cls_hs).sum() + (t(lw["w_refs"]) * refs).sum()
+        loss.backward()
     assert abs(float(loss) - float(g["loss"])) < 1e-3 * max(1.0, abs(float(g["loss"])))
     assert rel_err(memory.grad.cpu().numpy(), g["gin.memory"]) < TOL_FP32
     P = dict(dec.named_parameters())
     assert P["cls_layers.0.q_proj.weight"].grad is None and P["cls_norm.weight"].grad is None     # unused in the reference too
+    if flat_optimizer:
+        assert all(P[n].grad.data_ptr() == opt.grad[o:o + 1].data_ptr() for n, o in zip(opt.names, opt.offsets))   # still the flat views
+        for q in P.values():
+            if q.grad is not None:
+                q.grad.mul_(0.5)          # two accumulated backward passes
     for nm in ("norm.weight", "cls_norm2.bias", "layers.1.norm3.weight", "cls_layers.1.conv_blocks.0.norm.bias",
                "ref_anchor_head.layers.1.weight", "bbox_embed.layers.2.weight", "layers.0.lvl_w_embed.weight"):
         assert rel_err(P[nm].grad.cpu().numpy(), g["g." + nm]) < TOL_FP32, nm
