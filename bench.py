@@ -495,6 +495,10 @@ def main():
         except Exception as e:                      # the headline never depends on the extra measurement
             line["encoder_layer"] = {"error": str(e)[:200]}
         try:
+            line["transformer_forward"] = transformer_forward_numbers(dev)
+        except Exception as e:
+            line["transformer_forward"] = {"error": str(e)[:200]}
+        try:
             line["latency_batch1"] = batch1_latency(dev)
         except Exception as e:
             line["latency_batch1"] = {"error": str(e)[:200]}
@@ -704,6 +708,60 @@ def batch1_latency(dev, iters=50):
     return {"workload": "AVA22_ViT-B class-query decoder forward + heads, ONE clip (BASELINE configs[0] shape), bf16",
             "eager_ms": round(t(eager), 4), "cuda_graph_ms": round(t(lambda: g()), 4), "cuda_graph_e2e_ms": round(t(e2e), 4),
             "graph_replay_bit_identical_to_eager": bool(same), "launches": int(eng.last_launches)}
+
+
+def transformer_forward_numbers(dev, B=8, iters=5):
+    """The whole inference path this library covers, end to end on one GPU: ViT features [B,768,8,14,14] x4 -> simple-feature-pyramid
+    neck -> level flatten + level_embed -> 6 deformable encoder layers (MSDA-3D, 33 320 tokens/clip) -> resample -> 6-layer class-query
+    decoder (bf16) through the drop-in modules under torch.no_grad(); inputs resident; CUDA events, median."""
+    import torch
+    from class_query_vad_b200 import Transformer, SimpleFeaturePyramid, PositionEmbeddingSine_3D
+    from oracle import synth
+    torch.manual_seed(5)
+    shapes = [(8, 56, 56), (8, 28, 28), (8, 14, 14), (8, 7, 7)]
+    tr = Transformer(num_queries=15, num_encoder_layers=6, num_decoder_layers=6, dim_feedforward=2048, enc_n_points=8, num_classes=80, temp_len=16)
+    We = synth.make_encoder_layer_weights(2048, 4, 8, seed=5)
+    Wd = synth.make_decoder_weights(80, 6, 2048, seed=0)
+    sd = {"level_embed": torch.randn(4, 256)}
+    for l in range(6):
+        sd.update({f"encoder.layers.{l}." + k: torch.from_numpy(v) for k, v in We.items()})
+    sd.update({"decoder." + k: torch.from_numpy(v) for k, v in Wd.items() if not k.startswith("heads.")})
+    tr.load_state_dict(sd, strict=True)
+    tr = tr.to(dev).eval()
+    tr.decoder.out_dtype = torch.bfloat16
+    neck = SimpleFeaturePyramid(768).to(dev).eval()
+    feats = [torch.randn((B, 768, 8, 14, 14), device=dev).bfloat16() for _ in range(4)]
+    masks = [torch.zeros((B,) + s_, dtype=torch.bool, device=dev) for s_ in shapes]
+    pe = PositionEmbeddingSine_3D(256, normalize=True)
+
+    class _NT:
+        def __init__(self, m):
+            self.tensors, self.mask = m, m
+    poss = [pe(_NT(m)).to(torch.bfloat16) for m in masks]
+    refpoint = torch.randn(15, 1, 4, device=dev)
+
+    def run():
+        with torch.no_grad():
+            lv = neck(feats)                                   # space_forward's channel-first maps, as models/model.py consumes them
+            return tr([lv[str(i)] for i in range(4)], masks, poss, refpoint)
+    ts = {"all": [], "neck": []}
+    for _ in range(iters + 2):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        with torch.no_grad():
+            lv = neck(feats)
+        e1.record()
+        with torch.no_grad():
+            tr([lv[str(i)] for i in range(4)], masks, poss, refpoint)
+        e2.record()
+        torch.cuda.synchronize()
+        ts["neck"].append(e0.elapsed_time(e1)); ts["all"].append(e0.elapsed_time(e2))
+    ms, ms_neck = float(np.median(ts["all"][2:])), float(np.median(ts["neck"][2:]))
+    del tr, neck, feats
+    torch.cuda.empty_cache()
+    return {"workload": f"ViT-B/224 AVA inference path after the backbone: neck + Transformer (6 encoder layers with MSDA-3D, resample, 6 decoder "
+                        f"layers), bf16, {B} clips", "ms": round(ms, 3), "clips_per_s": round(B / ms * 1e3, 1), "neck_ms": round(ms_neck, 3),
+            "encoder_plus_decoder_ms": round(ms - ms_neck, 3)}
 
 
 def reference_gpu_eager(dev, mode, B, iters=5):
