@@ -4,8 +4,10 @@ TransformerDecoderLayer (:854-997), TransformerClassDecoderLayer (:999-1079), Tr
 Constructors, attribute/parameter names and forward signatures are the reference's, so `load_state_dict` of a
 reference checkpoint works and `models/model.py:100-101,191` (which injects `decoder.bbox_embed` and calls the
 transformer) is unchanged.  `TransformerDecoder.forward` runs the whole layer stack natively (one call of
-cqvad_decoder_forward); the per-layer `forward`s compose the same kernels through the building-block entry points.
-Eval semantics only: dropout layers exist for checkpoint/attribute parity and are identity.
+cqvad_decoder_forward; with gradients enabled cqvad_decoder_train_forward / _backward behind DecoderFunction, where the
+nn.Dropout modules' p is applied in train() mode).  The per-layer `forward`s are stand-alone inference conveniences: they
+compose the building-block entry points (linear, LayerNorm, attention core, ConvBlock) and keep small tensor glue in torch
+(the 4-way level softmax + einsum mix, per-head concatenations); they are not on the measured path and apply no dropout.
 """
 import copy
 

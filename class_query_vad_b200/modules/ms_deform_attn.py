@@ -1,6 +1,10 @@
 """Drop-in for the reference `ops.modules.MSDeformAttn3D` (ops/modules/ms_deform_attn.py:117-203): same constructor,
-forward signature, parameter names and initialisation; the four linears run through cqvad_linear and the sampling
-through MSDeformAttnFunction (libcqvad.so)."""
+forward signature, parameter names and initialisation; the four linears run through cqvad_linear, the softmax + sampling
+locations through cqvad_msda3d_prepare and the sampling through MSDeformAttnFunction (libcqvad.so).  Stand-alone inference
+convenience (the encoder layer's hot path is ONE call, cqvad_deform_encoder_layer_forward): the dtype casts of the offsets /
+logits to fp32 and the padding-mask fill are torch tensor glue here.  The constructor and `_reset_parameters` reproduce the
+Deformable-DETR initialisation recipe (Apache-2.0, SenseTime; reference NOTICE) because parameter names and initial values are
+part of the drop-in contract."""
 import math
 import warnings
 

@@ -1,5 +1,6 @@
-"""Thin torch-facing wrappers of the libcqvad building blocks (no autograd; inference path).  Every function launches
-kernels of libcqvad.so -- there is no torch arithmetic fallback."""
+"""Thin torch-facing wrappers of the libcqvad building blocks (no autograd; inference path).  Every function here launches
+kernels of libcqvad.so for its arithmetic -- there is no torch fallback; dtype casts / .contiguous() of the arguments are torch
+tensor plumbing.  (The stand-alone per-layer module forwards that call these keep some small glue in torch: see their docstrings.)"""
 import torch
 
 from .. import _lib
