@@ -168,7 +168,7 @@ HOST_KIND = {"train": "fp32 torch-CPU restatement of the reference decoder (orac
 def bench_config(mode, B, world):
     """The `config` object of the JSON line -- identical for both arms (the reference arm measures a bounded sample of it)."""
     return {"workload": WORK[mode] + f", {B} clips/GPU", "mode": mode, "config": CFG, "batch_per_gpu": B,
-            "parallelism": f"clip-sharded x{world}" + (", bucketed gradient all-reduce overlapped with the backward" if mode == "train" and world > 1 else ""),
+            "parallelism": f"clip-sharded x{world}" + (", one NCCL all-reduce of the flat fp32 gradient per step" if mode == "train" and world > 1 else ""),
             "l2": "4 input sets cycled (128 MB) + GBs of intermediates per step >> 126 MB L2"}
 
 
@@ -261,7 +261,8 @@ def main():
     det_all = torch.empty((world * BT, nq, K + 4 + 3), dtype=torch.float32, device=dev) if world > 1 else det_local
     det_host = torch.empty((BT, nq, K + 4 + 3), dtype=torch.float32).pin_memory()
     from class_query_vad_b200.dist import allreduce_gradients
-    if world > 1 and args.mode == "train":
+    OVERLAP = os.environ.get("CQVAD_BENCH_OVERLAP") is not None
+    if world > 1 and args.mode == "train" and OVERLAP:
         eng._grad_table()
         eng.enable_layer_events()
     lw = synth.make_loss_weights(cfg, B, seed=1)
@@ -288,8 +289,10 @@ def main():
         out = eng.forward_train(inp["tgt"], inp["memory"], inp["mask"], inp["pos"], inp["refpoints_unsigmoid"], orig_res,
                                 dropout_p=args.dropout, seed=1000 + step_no["n"])
         eng.backward(g_hs, g_cls, g_refs, zero=True, named=False)
-        if world > 1:       # per-layer buckets on a communication stream, each released by its layer's gradient-complete event
-            allreduce_gradients(eng, overlap=True)
+        if world > 1:       # one NCCL all-reduce of the flat gradient after the backward.  CQVAD_BENCH_OVERLAP=1: per-layer buckets on a
+            # communication stream released by the layers' gradient-complete events -- measured no faster at 2 and 8 GPUs (the
+            # NCCL CTAs contend with the persistent one-CTA-per-SM kernels of the backward): DESIGN.md section 8
+            allreduce_gradients(eng, overlap=OVERLAP)
         launches["n"] = eng.last_launches + eng.last_launches_bwd + (1 if world > 1 else 0)
         return out
 

@@ -111,6 +111,10 @@ constexpr int kH = 8;    // heads
 constexpr int kL = 4;    // feature levels
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+// Auxiliary (non-blocking) streams and timing-free events of the multi-stream schedules, created lazily PER DEVICE (a process may
+// drive several GPUs): slot = purpose.  One host thread per device is assumed (the events are reused from call to call).
+cudaStream_t aux_stream(int slot);   // slot in [0, 8)
+cudaEvent_t aux_event(int slot);     // slot in [0, 96)
 inline long cdiv(long a, long b) { return (a + b - 1) / b; }
 
 // ---- internal entry points shared between translation units -----------------------------------------------------

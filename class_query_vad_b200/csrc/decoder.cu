@@ -10,6 +10,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <mutex>
 #include "common.cuh"
 #include <stdlib.h>
 #include "kernels_mem.cuh"
@@ -32,6 +33,28 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+namespace {
+constexpr int kAuxDev = 32, kAuxStreams = 8, kAuxEvents = 96;
+cudaStream_t g_aux_streams[kAuxDev][kAuxStreams];
+cudaEvent_t g_aux_events[kAuxDev][kAuxEvents];
+std::mutex g_aux_mu;
+}  // namespace
+cudaStream_t aux_stream(int slot) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kAuxDev || slot < 0 || slot >= kAuxStreams) return nullptr;
+  std::lock_guard<std::mutex> lk(g_aux_mu);
+  if (!g_aux_streams[dev][slot] && cudaStreamCreateWithFlags(&g_aux_streams[dev][slot], cudaStreamNonBlocking) != cudaSuccess)
+    g_aux_streams[dev][slot] = nullptr;
+  return g_aux_streams[dev][slot];
+}
+cudaEvent_t aux_event(int slot) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kAuxDev || slot < 0 || slot >= kAuxEvents) return nullptr;
+  std::lock_guard<std::mutex> lk(g_aux_mu);
+  if (!g_aux_events[dev][slot] && cudaEventCreateWithFlags(&g_aux_events[dev][slot], cudaEventDisableTiming) != cudaSuccess)
+    g_aux_events[dev][slot] = nullptr;
+  return g_aux_events[dev][slot];
 }
 void count_launch(int n) { g_launches += n; }
 void reset_launch_count() { g_launches = 0; }
@@ -215,15 +238,13 @@ int Decoder<T>::run(const float* tgt, const float* memory, const float* pos, con
   const bool of32 = d.out_f32 != 0;
   const size_t osz = of32 ? sizeof(float) : sizeof(T);
   // ---- streams / events of the two-stream schedule (process-wide, created once) ----
-  static cudaStream_t side = [] { cudaStream_t x = nullptr; cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking); return x; }();
-  static cudaEvent_t ev_loc[kMaxLayers], ev_cls[kMaxLayers];
-  static const bool ev_ok = [] {
-    bool ok = true;
-    for (int i = 0; i < kMaxLayers; ++i)
-      ok = ok && cudaEventCreateWithFlags(&ev_loc[i], cudaEventDisableTiming) == cudaSuccess &&
-           cudaEventCreateWithFlags(&ev_cls[i], cudaEventDisableTiming) == cudaSuccess;
-    return ok;
-  }();
+  cudaStream_t side = aux_stream(0);
+  cudaEvent_t ev_loc[kMaxLayers], ev_cls[kMaxLayers];
+  bool ev_ok = true;
+  for (int i = 0; i < kMaxLayers; ++i) {
+    ev_loc[i] = aux_event(i); ev_cls[i] = aux_event(kMaxLayers + i);
+    ev_ok = ev_ok && ev_loc[i] && ev_cls[i];
+  }
   static const bool one_stream = [] { const char* e = getenv("CQVAD_INFER_STREAMS"); return e && atoi(e) == 1; }();
   st0 = st;
   two_streams = !one_stream && side != nullptr && ev_ok && Lr <= kMaxLayers;

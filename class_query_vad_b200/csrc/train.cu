@@ -145,35 +145,26 @@ struct Trainer {
   int cur_branch = 0;
   bool two_streams = false;
   float* wg_scr[2] = {nullptr, nullptr};
-  static cudaStream_t side_stream() {
-    static cudaStream_t s = [] { cudaStream_t x = nullptr; cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking); return x; }();
-    return s;
-  }
-  static cudaEvent_t sync_event(int i) {
-    static cudaEvent_t ev[2] = {nullptr, nullptr};
-    if (!ev[i]) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
-    return ev[i];
-  }
+  static cudaStream_t side_stream() { return aux_stream(1); }          // per device (common.cuh)
+  static cudaEvent_t sync_event(int i) { return aux_event(40 + i); }
   // Third stream: the large weight-gradient GEMMs only feed the (atomically accumulated) parameter gradients, so they leave
   // the dgrad chain's stream as soon as their dY is final and fill the SMs that chain's kernel tails leave idle; joined at
   // the end of the backward.  CQVAD_TRAIN_WG_STREAM=0 disables.
-  static cudaStream_t wg_stream() {
-    static cudaStream_t s = [] { cudaStream_t x = nullptr; cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking); return x; }();
-    return s;
-  }
+  static cudaStream_t wg_stream() { return aux_stream(2); }
   bool wg_used = false;
   cudaStream_t wgrad_stream(long rows) {
     static const bool off = [] { const char* e = getenv("CQVAD_TRAIN_WG_STREAM"); return e && atoi(e) == 0; }();
-    static cudaEvent_t ev = [] { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); return e; }();
+    cudaEvent_t ev = aux_event(42);
     static const long min_rows = [] { const char* e = getenv("CQVAD_TRAIN_WG_MIN_ROWS"); return e ? atol(e) : 1L; }();   // small-row wgrads too: 124 launches of ~8 us leave the loc chain
-    if (off || !two_streams || rows < min_rows || wg_stream() == nullptr || sizeof(T) != 2) return st;   // the profiler times each kernel on the stream it runs on
+    if (off || !two_streams || rows < min_rows || wg_stream() == nullptr || ev == nullptr || sizeof(T) != 2) return st;   // the profiler times each kernel on the stream it runs on
     if (cudaEventRecord(ev, st) != cudaSuccess || cudaStreamWaitEvent(wg_stream(), ev, 0) != cudaSuccess) return st;
     wg_used = true;
     return wg_stream();
   }
   int wgrad_join() {
     if (!wg_used) return 0;
-    static cudaEvent_t ev = [] { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); return e; }();
+    cudaEvent_t ev = aux_event(43);
+    CQ_CHECK_ARG(ev != nullptr, "training: could not create the weight-gradient join event");
     CQ_CUDA(cudaEventRecord(ev, wg_stream()));
     CQ_CUDA(cudaStreamWaitEvent(streams[0], ev, 0));
     wg_used = false;
@@ -185,10 +176,9 @@ struct Trainer {
   int signal_layer(int l) {
     void* const* evs = layer_events();
     if (!evs || l >= layer_events_count() || !evs[l]) return 0;
-    static cudaStream_t sig = [] { cudaStream_t x = nullptr; cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking); return x; }();
-    static cudaEvent_t tmp[3] = {nullptr, nullptr, nullptr};
-    for (int i = 0; i < 3; ++i)
-      if (!tmp[i]) CQ_CUDA(cudaEventCreateWithFlags(&tmp[i], cudaEventDisableTiming));
+    cudaStream_t sig = aux_stream(3);
+    cudaEvent_t tmp[3] = {aux_event(44), aux_event(45), aux_event(46)};
+    CQ_CHECK_ARG(sig && tmp[0] && tmp[1] && tmp[2], "training: could not create the gradient-bucket signalling stream / events");
     cudaStream_t srcs[3] = {streams[0], streams[1], wg_used ? wg_stream() : streams[0]};
     for (int i = 0; i < 3; ++i) {
       if (i > 0 && srcs[i] == srcs[0]) continue;
