@@ -9,6 +9,10 @@ namespace cqvad {
 
 // Wt[in][out] = W[out][in]
 template <typename T> int transpose_w(const T* W, T* Wt, int out, int in, cudaStream_t st);
+// the same for up to kMaxTransposeJobs matrices in ONE launch (the job table travels as a kernel parameter)
+constexpr int kMaxTransposeJobs = 96;
+struct TransposeJob { const void* W; void* Wt; int out, in; };
+template <typename T> int transpose_w_batch(const TransposeJob* jobs, int n, cudaStream_t st);
 // conv dgrad weights: Wd[ci][8-tap][co] = W[co][tap][ci]  (both [256][9][256])
 template <typename T> int conv_w_flip(const T* W, T* Wd, cudaStream_t st);
 

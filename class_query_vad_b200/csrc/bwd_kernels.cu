@@ -6,6 +6,7 @@
 //
 // Gradient spec = autograd of the reference forward (models/detr/dab_transformer.py:722-852, 907-997, 1040-1079); parity is
 // checked against torch autograd of the unmodified reference (tests/golden/grad_*.npz, oracle/make_golden_grads.py).
+#include <algorithm>
 #include "common.cuh"
 #include "bwd.cuh"
 #include "kernels_mem.cuh"
@@ -693,6 +694,52 @@ int transpose_w(const T* W, T* Wt, int out, int in, cudaStream_t st) {
 }
 template int transpose_w<float>(const float*, float*, int, int, cudaStream_t);
 template int transpose_w<bf16>(const bf16*, bf16*, int, int, cudaStream_t);
+
+// All transposed weight copies of a backward in one launch: block -> (job, 32 x 32 tile) through the tile prefix table.
+struct TransposeBatch {
+  TransposeJob job[kMaxTransposeJobs];
+  int tile_start[kMaxTransposeJobs + 1];
+  int n;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_batch_kernel(const __grid_constant__ TransposeBatch b) {
+  __shared__ T tile[32][33];
+  int lo = 0, hi = b.n;                       // last job whose first tile is <= blockIdx.x
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (b.tile_start[mid] <= (int)blockIdx.x) lo = mid; else hi = mid; }
+  const TransposeJob& j = b.job[lo];
+  const int t = blockIdx.x - b.tile_start[lo];
+  const int tx_n = (j.in + 31) >> 5;
+  const int bx = t % tx_n, by = t / tx_n;
+  const T* W = (const T*)j.W; T* Wt = (T*)j.Wt;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x = bx * 32 + tx, y0 = by * 32;
+  for (int r = ty; r < 32; r += 8)
+    if (x < j.in && y0 + r < j.out) tile[r][tx] = W[(long)(y0 + r) * j.in + x];
+  __syncthreads();
+  const int ox = by * 32 + tx, oy0 = bx * 32;
+  for (int r = ty; r < 32; r += 8)
+    if (ox < j.out && oy0 + r < j.in) Wt[(long)(oy0 + r) * j.out + ox] = tile[tx][r];
+}
+template <typename T>
+int transpose_w_batch(const TransposeJob* jobs, int n, cudaStream_t st) {
+  for (int base = 0; base < n; base += kMaxTransposeJobs) {
+    TransposeBatch b;
+    b.n = std::min(kMaxTransposeJobs, n - base);
+    int tiles = 0;
+    for (int i = 0; i < b.n; ++i) {
+      b.job[i] = jobs[base + i];
+      b.tile_start[i] = tiles;
+      tiles += ((b.job[i].in + 31) / 32) * ((b.job[i].out + 31) / 32);
+    }
+    b.tile_start[b.n] = tiles;
+    if (tiles == 0) continue;
+    transpose_batch_kernel<T><<<(unsigned)tiles, 256, 0, st>>>(b);
+    CQ_LAUNCH_CHECK();
+  }
+  return 0;
+}
+template int transpose_w_batch<float>(const TransposeJob*, int, cudaStream_t);
+template int transpose_w_batch<bf16>(const TransposeJob*, int, cudaStream_t);
 
 template <typename T>
 int conv_w_flip(const T* W, T* Wd, cudaStream_t st) {

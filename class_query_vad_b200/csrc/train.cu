@@ -232,9 +232,25 @@ struct Trainer {
   static float beta(Ten<T>* t) { const float b = t->gi ? 1.f : 0.f; t->gi = true; return b; }
 
   // transposed weight for dX = dY . W  (built at backward time: the weights may have changed since the forward)
-  const T* WT(int widx, long elems) {
-    if (!wt_alloc[widx]) { wt[widx] = take(elems); wt_alloc[widx] = 1; }
+  struct WtJob { int widx, out, in; bool conv; };
+  std::vector<WtJob> wt_jobs;     // every transposed / flipped copy this backward needs, built in one launch before the tape runs
+  const T* WT(int widx, long elems, int out = 0, int in = 0, bool conv = false) {
+    if (!wt_alloc[widx]) {
+      wt[widx] = take(elems); wt_alloc[widx] = 1;
+      if (rec()) wt_jobs.push_back(WtJob{widx, out, in, conv});
+    }
     return wt[widx];
+  }
+  int build_all_wt() {            // REPLAY mode, before the tape: the weights may have changed since the forward
+    std::vector<TransposeJob> jobs;
+    for (const WtJob& j : wt_jobs) {
+      if (!w[j.widx] || wt_built[j.widx]) continue;
+      wt_built[j.widx] = 1;
+      if (j.conv) CQ_TRY(conv_w_flip<T>(Wm(j.widx), wt[j.widx], st));
+      else jobs.push_back(TransposeJob{w[j.widx], wt[j.widx], j.out, j.in});
+    }
+    ProfScope ps(P_T_ACT_BWD, st);
+    return transpose_w_batch<T>(jobs.data(), (int)jobs.size(), st);
   }
   int build_wt(int widx, int out, int in, bool conv) {
     if (wt_built[widx]) return 0;   // shared weights (the ConvBlock, the global MLP heads) are transposed once per backward
@@ -270,7 +286,7 @@ struct Trainer {
       if (c2_act == CQVAD_ACT_GELU && !fuse_act && fuse_act_bwd) { A2->gact = 3; A2->gref = take(Y->n()); }   // gelu'(Y) stored by gelu_fwd
       last_c2 = A2;
     }
-    const T* Wt = X->hg ? WT(widx, (long)Nout * Kd) : nullptr;
+    const T* Wt = X->hg ? WT(widx, (long)Nout * Kd, Nout, Kd, false) : nullptr;
     const bool dual = A2 && A2->gact == 3 && dual_gelu && !res && zp == 0 && act == CQVAD_ACT_NONE;
     if (fwd()) {
       Epilogue e;
@@ -396,7 +412,7 @@ struct Trainer {
   // Z = conv3x3(X) + b on the y-padded layout
   Ten<T>* conv(Ten<T>* X, int widx, int* rc) {
     Ten<T>* Z = mk(X->rows, kC);
-    const T* Wd = WT(widx, 256L * 9 * 256);
+    const T* Wd = WT(widx, 256L * 9 * 256, 0, 0, true);
     ConvGeom cg; cg.h = h; cg.w = wd;
     if (fwd()) {
       Epilogue e;
@@ -756,6 +772,7 @@ int Trainer<T>::run() {
     // ---- backward: zero what is accumulated, then run the tape in reverse ----
     st = streams[0];
     CQ_CUDA(cudaMemsetAsync(drl[0], 0, (size_t)N * 4 * sizeof(float), st));
+    CQ_TRY(build_all_wt());       // one launch for every transposed weight copy (280 launches of ~3 us on the chains before)
     CQ_TRY(link(0, 1));            // fork: the class-branch stream starts after everything already on the caller's stream
     int ti = (int)tape.v.size(), prev = 0, done_layer = Lr;
     for (auto it = tape.v.rbegin(); it != tape.v.rend(); ++it) {
