@@ -96,6 +96,7 @@ SYMBOLS = {
                                                                                 c_size_t, c_void_p]),
     "cqvad_last_launch_count": (c_long, []),
     "cqvad_profile_enable": (None, [c_int]),
+    "cqvad_profile_timeline": (c_long, [c_void_p, c_void_p, c_void_p, c_void_p, c_long]),
     "cqvad_profile_num_classes": (c_int, []),
     "cqvad_profile_class_name": (c_char_p, [c_int]),
     "cqvad_profile_read": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(c_long), POINTER(c_long)]),

@@ -382,6 +382,9 @@ int cqvad_profile_read(int cls, double* total_ms_host, long* scopes_host, long* 
 /* Algorithmic work of the kernels timed in a class since the enable call: FLOPs (2 per multiply-add) and bytes (every operand
  * read once, the result written once) -- the numerators of bench.py's per-class tensor-pipe / HBM roofline fractions. */
 int cqvad_profile_read_work(int cls, double* flops_host, double* bytes_host);
+/* Timeline of the timed scopes since cqvad_profile_enable(1), in host issue order: class, stream id (0, 1, 2 ... by first
+ * appearance), start / end in ms relative to the earliest start.  Returns the number of scopes; at most `max` are written. */
+long cqvad_profile_timeline(int* cls, int* stream_id, double* start_ms, double* end_ms, long max);
 /* Debug switch: route bf16 GEMMs through the CUDA-core kernel instead of tcgen05 (used by the parity tests to
  * cross-check the two implementations; not a fallback -- both are CUDA kernels of this library). */
 void cqvad_debug_force_simt(int on);
