@@ -13,7 +13,8 @@ from .modules.position_encoding import PositionEmbeddingSine_3D, build_position_
 from .modules.encoder import (DeformableTransformerEncoderLayer, DeformableTransformerEncoder, encoder_layer_forward,
                               pack_encoder_layer_weights, encoder_to_decoder_memory)
 from .modules.transformer import Transformer, flatten_levels, input_proj_levels
-from .modules.criterion import HungarianMatcherAVA, SetCriterionAVA, PostProcessAVA, pack_targets
+from .modules.criterion import (HungarianMatcherAVA, SetCriterionAVA, PostProcessAVA, PostProcessUCF, PostProcessJHMDB,
+                                pack_targets)
 from .modules.heads import DETRHeads, HeadsFunction
 from .optim import FlatAdamW
 from .modules.neck import SimpleFeaturePyramid
@@ -25,4 +26,4 @@ __all__ = ["DecoderEngine", "DecoderFunction", "pack_decoder_weights", "MSDeform
            "MLP", "ConvBlock", "TransformerDecoderLayer", "TransformerClassDecoderLayer", "TransformerDecoder",
            "build_decoder", "DeformableTransformerEncoderLayer", "DeformableTransformerEncoder", "encoder_layer_forward",
            "pack_encoder_layer_weights", "encoder_to_decoder_memory", "Transformer", "flatten_levels", "input_proj_levels",
-           "SimpleFeaturePyramid", "DETRHeads", "HeadsFunction", "FlatAdamW", "HungarianMatcherAVA", "SetCriterionAVA", "PostProcessAVA", "pack_targets"]
+           "SimpleFeaturePyramid", "DETRHeads", "HeadsFunction", "FlatAdamW", "HungarianMatcherAVA", "SetCriterionAVA", "PostProcessAVA", "PostProcessUCF", "PostProcessJHMDB", "pack_targets"]

@@ -86,6 +86,7 @@ SYMBOLS = {
     "cqvad_criterion_ava_workspace_bytes": (c_size_t, [c_int]),
     "cqvad_criterion_ava": (c_int, [POINTER(CriterionCfg)] + [c_void_p] * 6 + [c_int] * 4 + [c_void_p] * 6 + [c_size_t, c_void_p]),
     "cqvad_postprocess_ava": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
+    "cqvad_postprocess_ucf": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     "cqvad_dropout": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_long, c_float, c_uint64, c_uint32, c_void_p]),
     "cqvad_heads_train_workspace_bytes": (c_size_t, [c_long]),
     "cqvad_heads_train_forward": (c_int, [c_void_p] * 4 + [c_long, c_int, c_float, c_uint64] + [c_void_p] * 4 + [c_size_t, c_void_p]),

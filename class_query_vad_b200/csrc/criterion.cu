@@ -267,13 +267,30 @@ __global__ void crit_reduce_kernel(CritCfg c, const float* __restrict__ part, co
 }
 
 // PostProcessAVA.forward (criterion.py:740-773): det[b, q, :] = [sigmoid(logits) (K) | box xyxy * (w, h, w, h) (4) | softmax(logits_b)[1]]
+// ucf != 0: PostProcessUCF / PostProcessJHMDB (criterion.py:775-846): scores = sigmoid(inverse_sigmoid(sigmoid(logits) * person_prob))
 __global__ void postprocess_ava_kernel(const float* __restrict__ logits, const float* __restrict__ boxes, const float* __restrict__ logits_b,
-                                       const float* __restrict__ sizes /* [B,2] (h, w) */, float* __restrict__ det, long rows, int nq, int K) {
+                                       const float* __restrict__ sizes /* [B,2] (h, w) */, float* __restrict__ det, long rows, int nq, int K,
+                                       int ucf) {
   const long r = blockIdx.x;
   if (r >= rows) return;
   const int b = (int)(r / nq);
   float* o = det + r * (K + 5);
-  for (int k = threadIdx.x; k < K; k += blockDim.x) o[k] = 1.f / (1.f + expf(-logits[r * K + k]));
+  float pb = 1.f;
+  if (ucf) {
+    const float* z = logits_b + r * 3;
+    const float mx = fmaxf(z[0], fmaxf(z[1], z[2]));
+    const float e0 = expf(z[0] - mx), e1 = expf(z[1] - mx), e2 = expf(z[2] - mx);
+    pb = e1 / (e0 + e1 + e2);
+  }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float p = 1.f / (1.f + expf(-logits[r * K + k]));
+    if (ucf) {   // inverse_sigmoid (utils/misc.py:530-534, eps 1e-5) followed by sigmoid
+      const float x = fminf(fmaxf(p * pb, 0.f), 1.f);
+      const float y = logf(fmaxf(x, 1e-5f) / fmaxf(1.f - x, 1e-5f));
+      p = 1.f / (1.f + expf(-y));
+    }
+    o[k] = p;
+  }
   if (threadIdx.x == 0) {
     const float ih = sizes[b * 2], iw = sizes[b * 2 + 1];
     float x0, y0, x1, y1;
@@ -327,7 +344,18 @@ extern "C" int cqvad_postprocess_ava(const float* pred_logits, const float* pred
                "postprocess_ava: bad argument");
   if (B == 0) return 0;
   postprocess_ava_kernel<<<(unsigned)((long)B * nq), 128, 0, as_stream(stream)>>>(pred_logits, pred_boxes, pred_logits_b, target_sizes,
-                                                                                  detections, (long)B * nq, nq, K);
+                                                                                  detections, (long)B * nq, nq, K, 0);
+  CQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cqvad_postprocess_ucf(const float* pred_logits, const float* pred_boxes, const float* pred_logits_b,
+                                     const float* target_sizes, float* detections, int B, int nq, int K, void* stream) {
+  CQ_CHECK_ARG(pred_logits && pred_boxes && pred_logits_b && target_sizes && detections && B >= 0 && nq >= 1 && K >= 1,
+               "postprocess_ucf: bad argument");
+  if (B == 0) return 0;
+  postprocess_ava_kernel<<<(unsigned)((long)B * nq), 128, 0, as_stream(stream)>>>(pred_logits, pred_boxes, pred_logits_b, target_sizes,
+                                                                                  detections, (long)B * nq, nq, K, 1);
   CQ_LAUNCH_CHECK();
   return 0;
 }

@@ -170,6 +170,8 @@ class SetCriterionAVA(nn.Module):
 
 
 class PostProcessAVA(nn.Module):
+    _entry = "cqvad_postprocess_ava"
+
     @torch.no_grad()
     def detections(self, outputs, target_sizes):
         """[B, nq, K+5] device tensor = [sigmoid scores | xyxy boxes in pixels | person probability] (what dist.gather_detections ships)."""
@@ -182,7 +184,7 @@ class PostProcessAVA(nn.Module):
         B, nq, K = pl.shape
         det = torch.empty((B, nq, K + 5), dtype=torch.float32, device=pl.device)
         p = _lib.ptr
-        _lib.check(_lib.lib().cqvad_postprocess_ava(p(pl), p(pb), p(plb), p(ts), p(det), B, nq, K, _lib.stream_ptr()))
+        _lib.check(getattr(_lib.lib(), self._entry)(p(pl), p(pb), p(plb), p(ts), p(det), B, nq, K, _lib.stream_ptr()))
         return det
 
     @torch.no_grad()
@@ -190,3 +192,12 @@ class PostProcessAVA(nn.Module):
         det = self.detections(outputs, target_sizes).cpu().numpy()
         K = outputs["pred_logits"].shape[-1]
         return det[..., :K], det[..., K:K + 4], det[..., K + 4:K + 5]
+
+
+class PostProcessUCF(PostProcessAVA):
+    """models/detr/criterion.py:775-809: class scores gated by the person probability (outputs flattened to frames: [B*T', nq, .])."""
+    _entry = "cqvad_postprocess_ucf"
+
+
+class PostProcessJHMDB(PostProcessUCF):
+    """models/detr/criterion.py:811-846 (identical arithmetic to PostProcessUCF)."""

@@ -332,6 +332,10 @@ int cqvad_criterion_ava(const cqvad_criterion_cfg* cfg, const float* pred_logits
  * target_sizes [B,2] fp32 (h, w) as in the reference. */
 int cqvad_postprocess_ava(const float* pred_logits, const float* pred_boxes, const float* pred_logits_b,
                           const float* target_sizes, float* detections, int B, int nq, int K, void* stream);
+/* PostProcessUCF / PostProcessJHMDB (criterion.py:775-846; BASELINE configs[3]): same layout, scores = sigmoid(inverse_sigmoid(
+ * sigmoid(pred_logits) * softmax(pred_logits_b)[1])) (utils/misc.py:530-534).  B = number of frames (clips x T'). */
+int cqvad_postprocess_ucf(const float* pred_logits, const float* pred_boxes, const float* pred_logits_b,
+                          const float* target_sizes, float* detections, int B, int nq, int K, void* stream);
 
 /* Dropout pass of the native training path: out = (res ? res : 0) + keep * x / (1 - p), keep ~ Bernoulli(1 - p) from a
  * Philox4x32-10 counter keyed by (seed, site, element index / 8) -- nothing is stored; calling it on a gradient with the same

@@ -128,3 +128,14 @@ def postprocess_ava(pred_logits, pred_boxes, pred_logits_b, target_sizes):
     ts = np.asarray(target_sizes, dtype=np.float64)
     scale = np.stack([ts[:, 1], ts[:, 0], ts[:, 1], ts[:, 0]], 1)[:, None, :]
     return np.concatenate([1.0 / (1.0 + np.exp(-pl)), cxcywh_to_xyxy(pb) * scale, softmax(plb)[..., 1:2]], -1)
+
+
+def postprocess_ucf(pred_logits, pred_boxes, pred_logits_b, target_sizes):
+    """PostProcessUCF / PostProcessJHMDB (criterion.py:775-846): scores gated by the person probability through inverse_sigmoid
+    (utils/misc.py:530-534, eps 1e-5) and sigmoid."""
+    det = postprocess_ava(pred_logits, pred_boxes, pred_logits_b, target_sizes)
+    K = np.asarray(pred_logits).shape[-1]
+    x = np.clip(det[..., :K] * det[..., K + 4:K + 5], 0.0, 1.0)
+    y = np.log(np.maximum(x, 1e-5) / np.maximum(1 - x, 1e-5))
+    det[..., :K] = 1.0 / (1.0 + np.exp(-y))
+    return det

@@ -69,13 +69,17 @@ def main():
         total = sum(loss_dict[k] * w for k, w in crit.weight_dict.items())           # train.py:148
         total.backward()
         scores, boxes, person = crit_mod.PostProcessAVA()({k: v.detach() for k, v in outputs.items()}, torch.from_numpy(sizes))
+        s_u, b_u, p_u = crit_mod.PostProcessUCF()({k: v.detach() for k, v in outputs.items()}, torch.from_numpy(sizes))
+        s_j, b_j, p_j = crit_mod.PostProcessJHMDB()({k: v.detach() for k, v in outputs.items()}, torch.from_numpy(sizes))
+        assert np.array_equal(s_u, s_j) and np.array_equal(b_u, b_j)
         ce = loss_dict["class_error"]
         np.savez_compressed(
             os.path.join(GOLD, name + ".npz"), pred_logits=pl, pred_boxes=pb, pred_logits_b=plb, tgt_boxes=tb, tgt_labels=tlab,
             n_tgt=nt, sizes=sizes, smooth=np.float32(smooth), match=match,
             losses=np.array([float(loss_dict[k]) for k in ("loss_ce", "loss_bbox", "loss_giou", "loss_ce_b")] + [float(total), float(ce)]),
             g_logits=t[0].grad.numpy(), g_boxes=t[1].grad.numpy(), g_logits_b=t[2].grad.numpy(),
-            det=np.concatenate([scores, boxes, person], -1).astype(np.float32))
+            det=np.concatenate([scores, boxes, person], -1).astype(np.float32),
+            det_ucf=np.concatenate([s_u, b_u, p_u], -1).astype(np.float32))
         print(name, {k: float(v) for k, v in loss_dict.items()}, "total", float(total), "pairs", int((match >= 0).sum()))
 
 

@@ -20,6 +20,8 @@ def test_oracle_matches_reference_criterion(name):
         assert abs(out[k] - ref) <= 2e-6 * max(1.0, abs(ref)), (k, out[k], ref)
     det = criterion_np.postprocess_ava(g["pred_logits"], g["pred_boxes"], g["pred_logits_b"], g["sizes"])
     assert rel_err(det, g["det"]) < 1e-6
+    det_u = criterion_np.postprocess_ucf(g["pred_logits"], g["pred_boxes"], g["pred_logits_b"], g["sizes"])
+    assert rel_err(det_u, g["det_ucf"]) < 1e-6
 
 
 def _gpu_inputs(g):
@@ -83,6 +85,12 @@ def test_device_criterion_matches_reference(name):
     scores, boxes, person = post(outputs, t["sizes"])
     det = np.concatenate([scores, boxes, person], -1)
     assert rel_err(det, g["det"]) < 1e-5
+    from class_query_vad_b200 import PostProcessUCF, PostProcessJHMDB
+    for cls in (PostProcessUCF, PostProcessJHMDB):
+        s_u, b_u, p_u = cls()(outputs, t["sizes"])
+        K = g["pred_logits"].shape[-1]
+        assert np.abs(s_u - g["det_ucf"][..., :K]).max() < 1e-6            # probabilities: absolute
+        assert rel_err(np.concatenate([b_u, p_u], -1), g["det_ucf"][..., K:]) < 1e-5
 
 
 @pytest.mark.gpu
