@@ -843,7 +843,18 @@ def encoder_layer_numbers(dev, B=4, iters=5):
         torch.cuda.synchronize()
         tt.append(e0.elapsed_time(e1))
     mf, mt = float(np.median(tf[1:])), float(np.median(tt[1:]))
-    return {"workload": f"one DeformableTransformerEncoderLayer, ViT-B/224 pyramid (33 320 tokens/clip), F 2048, 8 points, bf16, {B} clips",
+    # the same layer in the fp32 parity mode (CUDA-core FFMA GEMMs, fp32 sampling): what the 1e-3 tests run, not a performance path
+    f32 = []
+    s32, p32 = src.float(), pos.float()
+    for _ in range(3):
+        e0, e1 = ev(), ev()
+        e0.record()
+        with torch.no_grad():
+            layer(s32, p32, refp, sh, ls, None)
+        e1.record()
+        torch.cuda.synchronize()
+        f32.append(e0.elapsed_time(e1))
+    return {"forward_ms_fp32_parity_mode": round(float(np.median(f32[1:])), 3), "workload": f"one DeformableTransformerEncoderLayer, ViT-B/224 pyramid (33 320 tokens/clip), F 2048, 8 points, bf16, {B} clips",
             "forward_ms": round(mf, 3), "forward_clips_per_s": round(B / mf * 1e3, 1),
             "train_step_ms": round(mt, 3), "train_step_clips_per_s": round(B / mt * 1e3, 1), "gemm_gflop_per_clip_forward": 96.1}
 

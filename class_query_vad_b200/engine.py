@@ -301,12 +301,15 @@ class DecoderEngine:
         prep = lambda g, dt: None if g is None else g.to(device=self.device, dtype=dt).contiguous()
         grad_hs, grad_cls_hs, grad_refs = prep(grad_hs, odt), prep(grad_cls_hs, odt), prep(grad_refs, torch.float32)
         gflat, gtab = self._grad_table()
-        if zero or getattr(self, "_gin", None) is None or self._gin[0].shape[2] != BT:
-            if zero:
-                gflat.zero_()
+        if getattr(self, "_gin", None) is None or self._gin[0].shape[2] != BT or self._gin[0].shape[1] != S:
             self._gin = (torch.zeros((4, S, BT, 256), dtype=torch.float32, device=self.device),
                          torch.zeros((nq, BT, 256), dtype=torch.float32, device=self.device),
                          torch.zeros((nq, BT, 4), dtype=torch.float32, device=self.device))
+        elif zero:                       # persistent buffers, zero-filled in place (no allocator traffic in the step)
+            for t in self._gin:
+                t.zero_()
+        if zero:
+            gflat.zero_()
         gmem, gtgt, gref = self._gin
         p = _lib.ptr
         rc = lib.cqvad_decoder_backward(byref(desc), self._wtab, p(m8), p(grad_hs), p(grad_cls_hs), p(grad_refs), gtab, p(gmem),
