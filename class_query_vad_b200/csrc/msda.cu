@@ -485,6 +485,21 @@ __global__ void __launch_bounds__(kWarps * 32) msda_bwd_kernel(const T* __restri
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// 4 consecutive elements at p and 4 at p + second -> v[0..3], v[4..7]
+__device__ __forceinline__ void load4x2(const float* p, int second, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + second);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load4x2(const bf16* p, int second, float (&v)[8]) {
+  const uint2 a = *reinterpret_cast<const uint2*>(p), b = *reinterpret_cast<const uint2*>(p + second);
+  const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  float2 f;
+  f = __bfloat1622float2(ha[0]); v[0] = f.x; v[1] = f.y;
+  f = __bfloat1622float2(ha[1]); v[2] = f.x; v[3] = f.y;
+  f = __bfloat1622float2(hb[0]); v[4] = f.x; v[5] = f.y;
+  f = __bfloat1622float2(hb[1]); v[6] = f.x; v[7] = f.y;
+}
 template <typename T>
 __global__ void __launch_bounds__(kWarps * 32) msda_bwd_vec_kernel(const T* __restrict__ value,
                                                                    const int64_t* __restrict__ shapes,
@@ -506,13 +521,18 @@ __global__ void __launch_bounds__(kWarps * 32) msda_bwd_vec_kernel(const T* __re
   const long row_stride = (long)M * D;
   const int lpp = D >> 3, G = 32 / lpp;
   const int g = lane / lpp, ch = lane % lpp;
-  const long voff = (long)b * Len * row_stride + (long)m * D + ch * 8;
+  // Channel ownership is INTERLEAVED: lane `ch` of a point's lpp lanes owns channels [4 ch, 4 ch + 4) and [D/2 + 4 ch, D/2 + 4 ch + 4),
+  // so that one red.global.add.v4.f32 of the lpp lanes covers D/2 * 4 CONTIGUOUS bytes (full 32-byte sectors) of the voxel's gradient row.
+  // With 8 consecutive channels per lane every instruction left half of each sector it touched unwritten: 1.45 G sector operations for
+  // 35 GB of payload (ncu, profiles/r02_ncu_kernels.txt), and the kernel is bound by exactly that rate (l1tex 81 %, lts 65 %).
+  const int hD = D >> 1;
+  const long voff = (long)b * Len * row_stride + (long)m * D + ch * 4;
   const T* vbase = value + voff;
   float* gvbase = grad_value + voff;
   const float* locp = loc + wid * LP * 3;
   const float* attp = attn + wid * LP;
   float go[8];
-  load8(grad_out + wid * D + ch * 8, go);
+  load4x2(grad_out + wid * D + ch * 4, hD, go);
   for (int p0 = 0; p0 < LP; p0 += G) {
     const int pt = p0 + g;
     float g_w = 0.f, g_h = 0.f, g_t = 0.f, g_a = 0.f;
@@ -534,13 +554,13 @@ __global__ void __launch_bounds__(kWarps * 32) msda_bwd_vec_kernel(const T* __re
           const long row = (long)(base + kt * ts + kh * hs + kw) * row_stride;
           const float wgt = ft[kt] * fh[kh] * fw[kw];
           float v[8];
-          load8(vbase + row, v);
+          load4x2(vbase + row, hD, v);
           float dot = 0.f;
 #pragma unroll
           for (int e = 0; e < 8; ++e) dot = fmaf(v[e], go[e], dot);
           const float s = a * wgt;
           red_add_v4(gvbase + row, s * go[0], s * go[1], s * go[2], s * go[3]);
-          red_add_v4(gvbase + row + 4, s * go[4], s * go[5], s * go[6], s * go[7]);
+          red_add_v4(gvbase + row + hD, s * go[4], s * go[5], s * go[6], s * go[7]);
           g_a = fmaf(wgt, dot, g_a);
           g_w = fmaf((kw ? 1.f : -1.f) * ft[kt] * fh[kh], dot, g_w);
           g_h = fmaf((kh ? 1.f : -1.f) * ft[kt] * fw[kw], dot, g_h);
