@@ -179,3 +179,21 @@ def host_shapes(sh):
         return [list(s) for s in sh]
     hit = _SHAPE_HOST.get((sh.data_ptr(), str(sh.device)))
     return hit if hit is not None else sh.tolist()
+
+
+_WARNED_NO_GRAD = set()
+
+
+def warn_if_grad(what, *tensors):
+    """The building-block wrappers (modules/ops.py, MSDeformAttn3D.forward, the stand-alone per-layer forwards) launch kernels through
+    raw pointers and record NO autograd graph.  Called with gradients enabled on tensors that require them they would silently cut
+    the graph, so they say so once per entry point; training goes through TransformerDecoder / Transformer / the encoder layer
+    modules, whose forwards are autograd Functions."""
+    import torch
+    if what in _WARNED_NO_GRAD or not torch.is_grad_enabled():
+        return
+    if any(t is not None and getattr(t, "requires_grad", False) for t in tensors):
+        import warnings
+        _WARNED_NO_GRAD.add(what)
+        warnings.warn(f"class_query_vad_b200.{what} is an inference building block: no autograd graph is recorded, gradients will not "
+                      "flow through it (use torch.no_grad(), or the module-level training paths)", stacklevel=3)

@@ -13,6 +13,7 @@ def _w(t, dtype):
 def linear(x, weight, bias=None, act=_lib.ACT_NONE, res=None):
     """act(x @ weight.T + bias) (+ res) through cqvad_linear.  x [..., K]; weight [N, K] (or 1x1 conv [N,K,1,1])."""
     _lib.require_cuda(x)
+    _lib.warn_if_grad("ops.linear", x, weight, bias, res)
     dt = x.dtype
     K = x.shape[-1]
     x2 = x.reshape(-1, K).contiguous()
@@ -30,6 +31,7 @@ def linear(x, weight, bias=None, act=_lib.ACT_NONE, res=None):
 def layer_norm(x, weight, bias, eps=1e-5, res=None):
     """LayerNorm(x (+ res)) over the last dim (256) through cqvad_layernorm."""
     _lib.require_cuda(x)
+    _lib.warn_if_grad("ops.layer_norm", x, weight, bias, res)
     dt = x.dtype
     C = x.shape[-1]
     x2 = x.reshape(-1, C).contiguous()
@@ -45,6 +47,7 @@ def layer_norm(x, weight, bias, eps=1e-5, res=None):
 def ffn(x, w1, b1, w2, b2, act=_lib.ACT_RELU, res=None, ln_weight=None, ln_bias=None, eps=1e-5):
     """LN?( res + w2 . act(w1 . x + b1) + b2 ) through cqvad_mlp (fused tcgen05 kernel in bf16 when F % 128 == 0)."""
     _lib.require_cuda(x)
+    _lib.warn_if_grad("ops.ffn", x, w1, w2, res)
     dt = x.dtype
     C = x.shape[-1]
     x2 = x.reshape(-1, C).contiguous()
@@ -65,6 +68,7 @@ def ffn(x, w1, b1, w2, b2, act=_lib.ACT_RELU, res=None, ln_weight=None, ln_bias=
 def mha_core(q, k, v, num_heads, key_padding_mask=None, query_specific_key=False):
     """Attention core (attention.py:336-414) through cqvad_mha_core.  Returns [L, Nb, Ev] before out_proj."""
     _lib.require_cuda(q, k, v)
+    _lib.warn_if_grad("ops.mha_core", q, k, v)
     dt = q.dtype
     L, Nb, E = q.shape
     S = k.shape[1] if query_specific_key else k.shape[0]
