@@ -106,10 +106,10 @@ struct Trainer {
   int BT, nq, h, wd, S, Sp, Sq, K, F, Lr;
   long N, NS, NSq, Rp, NK;
   std::deque<Ten<T>> tens;
-  struct TapeEntry { std::function<int()> fn; int branch; int layer; };
+  struct TapeEntry { std::function<int()> fn; int branch; int layer; bool class_sync = false; };
   struct Tape {
     std::vector<TapeEntry> v; int* cur; int* layer;
-    void push_back(std::function<int()> f) { v.push_back(TapeEntry{std::move(f), *cur, *layer}); }
+    void push_back(std::function<int()> f) { v.push_back(TapeEntry{std::move(f), *cur, *layer, false}); }
   } tape;
   int cur_layer = -1;   // layer whose ops are being recorded (-1: prologue / global ops)
   std::vector<T*> wt;   // transposed / flipped weight copies for the data-gradient GEMMs, by weight index
@@ -578,6 +578,10 @@ int Trainer<T>::run() {
     Ten<T>* qc = lin(out1, loc(l, CA_QC), kC, 0, nullptr, 0, 0, &rc);
     if (first) qc = lin(qpos, loc(l, CA_QP), kC, 0, qc, 0, 0, &rc);
     Ten<T>* qs = lin(qse, loc(l, CA_QS), kC, 0, nullptr, 0, 0, &rc);
+    // Backward schedule: everything recorded AFTER this op in the loc layer (cross-attention core, its output projection, the FFN,
+    // the two LayerNorms) consumes only gradients produced on the loc stream, so it may run while the class branch of this layer is
+    // still in flight; this op's backward is the first to touch a buffer the class branch writes (qse->g, then qm->g).
+    if (rec() && !tape.v.empty()) tape.v.back().class_sync = true;
     Ten<T>* cao = mk(N, kC);
     if (fwd()) {
       ProfScope ps(P_T_FWD_OTHER, st);
@@ -775,11 +779,16 @@ int Trainer<T>::run() {
     CQ_TRY(build_all_wt());       // one launch for every transposed weight copy (280 launches of ~3 us on the chains before)
     CQ_TRY(link(0, 1));            // fork: the class-branch stream starts after everything already on the caller's stream
     int ti = (int)tape.v.size(), prev = 0, done_layer = Lr;
+    static const bool eager_link = getenv("CQVAD_TRAIN_EAGER_LINK") != nullptr;   // A/B switch: join at the first loc op (round-1 schedule)
+    bool pending_link = false;
     for (auto it = tape.v.rbegin(); it != tape.v.rend(); ++it) {
       // every backward op of the layers above it->layer has been enqueued: signal their parameter gradients as final
       while (done_layer - 1 > it->layer && done_layer - 1 >= 0) { --done_layer; CQ_TRY(signal_layer(done_layer)); }
       const int b = it->branch;
-      if (b == 0 && prev == 1) CQ_TRY(link(1, 0));   // the loc layer consumes the class branch's gradients (q_memory, qse)
+      // the loc layer consumes the class branch's gradients (q_memory, qse) -- but only from its `class_sync` op downwards: the
+      // join is deferred to that op, so the head of the loc layer's backward overlaps the class branch
+      if (b == 0 && prev == 1) pending_link = true;
+      if (pending_link && (b == 1 || it->class_sync || eager_link)) { CQ_TRY(link(1, 0)); pending_link = false; }
       prev = b;
       st = streams[two_streams ? b : 0];
       set_wgrad_scratch(wg_scr[b], wgrad_scratch_bytes());
