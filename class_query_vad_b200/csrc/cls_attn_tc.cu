@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(128) cls_xattn_pos_kernel(const bf16* __restri
     }
   }
   float mx = -INFINITY;
-  for (int s = lane; s < S; s += 32) {
+#pragma unroll 2
+  for (int s = lane; s < S; s += 32) {      // two keys (16 x 16-byte loads) in flight per lane
     const bf16* kp = pos0 + ((long)s * BT + bb) * kC + hh * 64;
     float a = 0.f;
 #pragma unroll
@@ -257,14 +258,27 @@ __global__ void __launch_bounds__(128) cls_xattn_pos_kernel(const bf16* __restri
   const float inv = 1.0f / sum;
   const int c0 = 128 + hh * 32;
   float my_o = 0.f;   // lane d keeps o[d]
-  for (int d = 0; d < 32; ++d) {
-    const bf16* vr = vt + (long)(c0 + d) * ldvt + i * Sq;
-    float a = 0.f;
-    for (int s = lane; s < S; s += 32) a = fmaf(pr[s], __bfloat162float(vr[s]), a);
-    a = warp_sum(a);
-    if (lane == d) my_o = a * inv + bv[c0 + d];
+  // eight value channels per step: their (independent) key loops and shuffle reductions overlap instead of paying one full
+  // load latency + reduction chain per channel
+#pragma unroll 1
+  for (int d0 = 0; d0 < 32; d0 += 8) {
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = lane; s < S; s += 32) {
+      const float pv = pr[s];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = fmaf(pv, __bfloat162float(vt[(long)(c0 + d0 + j) * ldvt + i * Sq + s]), a[j]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (lane == d0 + j) my_o = a[j] * inv + bv[c0 + d0 + j];
   }
   const bf16 ob = __float2bfloat16_rn(my_o);
+#pragma unroll 8
   for (int k = 0; k < K; ++k) out[(i * K + k) * kC + c0 + lane] = ob;
 }
 
