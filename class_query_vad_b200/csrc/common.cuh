@@ -140,6 +140,9 @@ struct Epilogue {
   int c2_act = CQVAD_ACT_NONE;
   const void* mul_aux = nullptr;
   int mul_mode = 0;
+  // mul_mode 1 only: kept elements are additionally scaled (the 1 / (1 - p) of a dropout that followed the ReLU: the dropped
+  // activation doubles as the mask, so the backward needs no dropout pass of its own)
+  float mul_scale = 1.f;
   // training forward of a GELU layer in ONE epilogue: C = gelu(v), c2 = gelu'(v) with v = acc + bias (act / c2_act ignored);
   // the pre-activation itself is never written (the backward needs only gelu' -- mul_mode 3 -- and the activation)
   bool dual_gelu = false;

@@ -38,7 +38,7 @@ int dropout_apply(const T* x, const T* res, T* out, long n, float p, uint64_t se
   CQ_CHECK_ARG(n % 8 == 0, "dropout: element count must be a multiple of 8");
   CQ_CHECK_ARG(p >= 0.f && p < 1.f, "dropout: p must be in [0, 1)");
   const unsigned thr16 = (unsigned)std::min(65535.0, (double)p * 65536.0 + 0.5);   // keep iff u16 >= thr16: P(keep) = 1 - thr16 / 65536
-  const float scale = 1.f / (1.f - (float)thr16 / 65536.f);
+  const float scale = dropout_keep_scale(p);
   const long n8 = n / 8;
   const unsigned grid = (unsigned)std::min<long>(cdiv(n8, 256), 148L * 16);
   dropout_kernel<T><<<grid, 256, 0, st>>>(x, res, out, n8, scale, thr16, seed, site);

@@ -274,8 +274,10 @@ int enc_train_bwd_t(const void* const* W, const T* src, const int64_t* shapes, c
   const T* dbr2 = w.dz2;                                 // gradient entering the linear2 branch (masked copy under dropout3)
   if (drop) { CQ_TRY(dropout_apply<T>(w.dz2, nullptr, w.dz1, rows * kC, pdrop, seed, 3, st)); dbr2 = w.dz1; }
   CQ_TRY(wgrad<T>(dbr2, kC, w.h, F, G[E_L2_W], F, G[E_L2_B], rows, kC, F, nullptr, st));
-  { Epilogue e; e.mul_aux = w.h; e.mul_mode = 1; CQ_TRY(gemm<T>(dbr2, kC, wt_l2, w.dh, F, rows, F, kC, e, nullptr, st)); }
-  if (drop) CQ_TRY(dropout_apply<T>(w.dh, nullptr, w.dh, rows * F, pdrop, seed, 2, st));   // (h > 0 already excludes the dropped units)
+  // dropout2: h holds the DROPPED activation, so (h > 0) is ReLU mask and keep mask at once; only the 1 / (1 - p) is left, folded
+  // into the same epilogue (no dropout pass over the [rows x F] gradient)
+  { Epilogue e; e.mul_aux = w.h; e.mul_mode = 1; if (drop) e.mul_scale = dropout_keep_scale(pdrop);
+    CQ_TRY(gemm<T>(dbr2, kC, wt_l2, w.dh, F, rows, F, kC, e, nullptr, st)); }
   CQ_TRY(wgrad<T>(w.dh, F, w.x1, kC, G[E_L1_W], kC, G[E_L1_B], rows, F, kC, nullptr, st));
   { Epilogue e; e.res = w.dz2; e.ldr = kC; CQ_TRY(gemm<T>(w.dh, F, wt_l1, w.dx1, kC, rows, kC, F, e, nullptr, st)); }
   // x1 = LN1(z1), z1 = src + dropout1(output_proj(samp))

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
       else if (epi.act == CQVAD_ACT_GELU) v = gelu_erf(v);
       if (epi.mul_mode) {
         const float a = to_f(reinterpret_cast<const T*>(epi.mul_aux)[r * ldc + c]);
-        v *= epi.mul_mode == 1 ? (a > 0.f ? 1.f : 0.f) : (epi.mul_mode == 3 ? a : gelu_grad(a));
+        v *= epi.mul_mode == 1 ? (a > 0.f ? epi.mul_scale : 0.f) : (epi.mul_mode == 3 ? a : gelu_grad(a));
       }
       if (epi.res32) v += epi.res32[r * epi.ldr + c];
       else if (res) v += to_f(res[r * epi.ldr + c]);

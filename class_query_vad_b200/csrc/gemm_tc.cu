@@ -54,7 +54,7 @@ struct TcParams {
   const float* bias; int act; const bf16* res; long ldr; const float* res32; float* c32;
   const float* ln_g; const float* ln_b; float ln_eps;
   int zero_period, zero_valid;
-  bf16* c2; int c2_act; const bf16* mul_aux; int mul_mode;
+  bf16* c2; int c2_act; const bf16* mul_aux; int mul_mode; float mul_scale;
   // conv
   int conv; int cw; int rt;  // image width, image rows per tile
   int m_tiles, n_tiles;
@@ -91,7 +91,7 @@ __device__ __forceinline__ float gelu_grad(float x) {
 // stage that paces the K = 256 GEMMs (MMA 1.1 us, loads hidden).
 // SIDE: 0 none, 1 += side (residual), 2 ReLU mask (side > 0), 3 *= side (stored activation derivative)
 template <int SIDE>
-__device__ __forceinline__ void ts_lean_half(uint32_t t_addr, const float* bias, uint32_t row_base, int sw, float lo, bool gelu) {
+__device__ __forceinline__ void ts_lean_half(uint32_t t_addr, const float* bias, uint32_t row_base, int sw, float lo, bool gelu, float msc = 1.f) {
 #pragma unroll
   for (int cc = 0; cc < 64; cc += 32) {
     uint32_t r[32];
@@ -123,7 +123,7 @@ __device__ __forceinline__ void ts_lean_half(uint32_t t_addr, const float* bias,
         if constexpr (SIDE != 0) {
           const float sa = __uint_as_float(sw32[j] << 16), sb = __uint_as_float(sw32[j] & 0xffff0000u);   // bf16 pair -> fp32
           if constexpr (SIDE == 1) { a += sa; b += sb; }
-          else if constexpr (SIDE == 2) { a = sa > 0.f ? a : 0.f; b = sb > 0.f ? b : 0.f; }
+          else if constexpr (SIDE == 2) { a = sa > 0.f ? a * msc : 0.f; b = sb > 0.f ? b * msc : 0.f; }
           else { a *= sa; b *= sb; }
         }
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(ow[j]) : "f"(b), "f"(a));
@@ -399,7 +399,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
               const bool ge = p.act == CQVAD_ACT_GELU;
               if (p.side == 0) ts_lean_half<0>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge);
               else if (p.side == 1) ts_lean_half<1>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge);
-              else if (p.mul_mode == 1) ts_lean_half<2>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge);
+              else if (p.mul_mode == 1) ts_lean_half<2>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge, p.mul_scale);
               else ts_lean_half<3>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge);
             } else {
 #pragma unroll 1
@@ -439,7 +439,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
                     } else if constexpr (EXTRA) {
                       if (p.mul_mode == 1) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = sx[j] > 0.f ? v[j] : 0.f;
+                        for (int j = 0; j < 8; ++j) v[j] = sx[j] > 0.f ? v[j] * p.mul_scale : 0.f;
                       } else if (p.mul_mode == 3) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] *= sx[j];
@@ -602,7 +602,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
                 unpack8(anext[g8], ax);
                 if (p.mul_mode == 1) {
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j] = ax[j] > 0.f ? v[j] : 0.f;
+                  for (int j = 0; j < 8; ++j) v[j] = ax[j] > 0.f ? v[j] * p.mul_scale : 0.f;
                 } else if (p.mul_mode == 3) {
 #pragma unroll
                   for (int j = 0; j < 8; ++j) v[j] *= ax[j];
@@ -755,7 +755,7 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
   p.bias = epi.bias; p.act = epi.act; p.res = (const bf16*)epi.res; p.ldr = epi.ldr; p.res32 = epi.res32; p.c32 = epi.c32;
   p.ln_g = epi.ln_g; p.ln_b = epi.ln_b; p.ln_eps = epi.ln_eps;
   p.zero_period = epi.zero_period; p.zero_valid = epi.zero_valid;
-  p.c2 = (bf16*)epi.c2; p.c2_act = epi.c2_act; p.mul_aux = (const bf16*)epi.mul_aux; p.mul_mode = epi.mul_mode;
+  p.c2 = (bf16*)epi.c2; p.c2_act = epi.c2_act; p.mul_aux = (const bf16*)epi.mul_aux; p.mul_mode = epi.mul_mode; p.mul_scale = epi.mul_scale;
   p.n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
   if (const char* tr = getenv("CQVAD_GEMM_TRACE")) p.trace = (long long*)strtoull(tr, nullptr, 0);
   CUtensorMap tmA, tmB;

@@ -83,6 +83,10 @@ struct Ten {
   int gact = 0;             // 0 none, 1 ReLU (gref = this tensor), 2 GELU (gref = pre-activation), 3 stored derivative (gref = act')
   const T* gref = nullptr;
   bool gmasked = false;
+  // a dropout followed this ReLU output in place: its backward is the ReLU mask (dropped units are zero) times gscale, folded into
+  // the consumer's data-gradient epilogue (gfolded set there); otherwise the dropout's own backward pass runs
+  float gscale = 1.f;
+  bool gfolded = false;
   long n() const { return rows * cols; }
 };
 
@@ -326,7 +330,10 @@ struct Trainer {
           const float b = beta(X);
           if (b != 0.f) { e.res = X->g; e.ldr = Kd; }
           const bool actmul = X->gact && (fuse_act || fuse_act_bwd) && b == 0.f;
-          if (actmul) { e.mul_aux = X->gref; e.mul_mode = X->gact; X->gmasked = true; }   // dX = (dY . W) * act'(.) in the epilogue
+          if (actmul) {   // dX = (dY . W) * act'(.) in the epilogue
+            e.mul_aux = X->gref; e.mul_mode = X->gact; X->gmasked = true;
+            if (X->gact == 1 && X->gscale != 1.f) { e.mul_scale = X->gscale; X->gfolded = true; }
+          }
           const double fl = 2.0 * X->rows * Nout * Kd, by = sizeof(T) * ((double)X->rows * (Nout + Kd * (1.0 + (actmul ? 1 : 0) + (b != 0.f ? 1 : 0))) + (double)Nout * Kd);
           ProfScope ps(!big(X->rows) ? P_T_DGRAD_SMALL : (actmul && X->gact == 3) ? P_T_DGRAD_ACT : P_T_DGRAD, st, fl, by);
           CQ_TRY(gemm<T>(Y->g, Nout, Wt, X->g, Kd, X->rows, Kd, Nout, e, nullptr, st));
@@ -355,8 +362,9 @@ struct Trainer {
       if (r != 0 && rc && *rc == 0) *rc = r;
     }
     if (rec()) {
+      if (X->gact == 1 && X->gref == X->p) X->gscale = dropout_keep_scale(p);
       tape.push_back([=]() -> int {
-        if (!X->gi) return 0;
+        if (!X->gi || X->gfolded) return 0;     // folded: the consumer's ReLU-mask epilogue already applied mask and scale
         ProfScope ps(P_T_ACT_BWD, st);
         return dropout_apply<T>(X->g, nullptr, X->g, X->n(), p, seed, site, st);
       });
