@@ -519,8 +519,8 @@ def full_training_step(dev, world, B=2, steps=4, warmup=2):
     ONE optimizer step through the public modules -- pinned-host pyramid -> H2D -> drop-in `Transformer` (level flatten + level_embed,
     6 deformable encoder layers with the MSDA-3D ops path, inter-stage resample, 6-layer class-query decoder) -> DETR heads (Philox
     Dropout(0.5) ON) -> device Hungarian matcher + SetCriterionAVA -> backward of the whole chain -> NCCL all-reduce of the flat
-    gradient -> fused clip_grad_norm_ + AdamW (train.py:126-167).  Encoder / decoder dropout p = 0.1 is the identity (stated in
-    DESIGN.md).  CUDA events, max over ranks; the D2H read of the loss is inside the timed region."""
+    gradient -> fused clip_grad_norm_ + AdamW (train.py:126-167).  The modules run in train() mode: encoder / decoder nn.Dropout(0.1) at
+    the residual-branch / FFN-hidden sites and Dropout(0.5) on the class tokens are applied (not the attention-probability dropout).  CUDA events, max over ranks; the D2H read of the loss is inside the timed region."""
     import torch
     import torch.distributed as dist
     from class_query_vad_b200 import Transformer, DETRHeads, SetCriterionAVA, HungarianMatcherAVA, FlatAdamW, PositionEmbeddingSine_3D
