@@ -103,3 +103,16 @@ def test_flat_adamw_grad_scale_is_the_all_reduce_average():
     a.grad.copy_(g * 8.0); b.grad.copy_(g)
     oa.step(grad_scale=1.0 / 8.0); ob.step()
     assert float((a.detach() - b.detach()).abs().max()) < 1e-7
+
+
+def test_flat_adamw_zero_gradient_step_only_decays():
+    """Property: with zero gradients AdamW moves a parameter by the decoupled weight decay alone, p <- p (1 - lr wd) (moments stay 0),
+    and by nothing at all with weight_decay = 0."""
+    from class_query_vad_b200 import FlatAdamW
+    dev = torch.device("cuda:0")
+    a = torch.nn.Parameter(torch.linspace(-2, 2, 1003, device=dev)); b = torch.nn.Parameter(a.detach().clone())
+    ref = a.detach().clone()
+    FlatAdamW([("a", a)], lr=1e-2, weight_decay=0.1).step()
+    FlatAdamW([("b", b)], lr=1e-2, weight_decay=0.0).step()
+    assert float((a.detach() - ref * (1 - 1e-2 * 0.1)).abs().max()) < 1e-6
+    assert torch.equal(b.detach(), ref)

@@ -32,3 +32,18 @@ def test_vit_neck_matches_reference_lateral_convs(tag, dtype, tol):
         assert rel_err(got, ref) < tol, (l, rel_err(got, ref))
     tokens, sh, ls = neck.forward_tokens(xs)
     assert tokens.shape[1] == int(sh.prod(1).sum()) and int(ls[1]) == kw["T"] * 16 * kw["H"] * kw["W"]
+
+
+def test_vit_neck_batch_independence_at_full_size():
+    """Size-independent property at BASELINE configs[0]'s feature size (8 x 14 x 14 x 768 per clip -> 33 320 tokens): clips are
+    independent, so the neck of a 2-clip batch equals the two single-clip results bit for bit (tcgen05 path, bf16)."""
+    from class_query_vad_b200 import SimpleFeaturePyramid
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    neck = SimpleFeaturePyramid(768).to(dev)
+    x = [torch.randn((2, 768, 8, 14, 14), device=dev).bfloat16() for _ in range(4)]
+    both, sh, ls = neck.forward_tokens(x)
+    assert both.shape == (2, 33320, 256) and torch.isfinite(both.float()).all()
+    for b in range(2):
+        one, _, _ = neck.forward_tokens([t[b:b + 1].contiguous() for t in x])
+        assert torch.equal(one[0], both[b]), b
