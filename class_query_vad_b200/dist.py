@@ -65,9 +65,7 @@ def allreduce_gradients(engine, group=None, average=True, overlap=False, comm_st
         return engine._gflat
     world = dist.get_world_size(group)
     if not overlap or getattr(engine, "layer_events", None) is None:
-        dist.all_reduce(engine._gflat, op=dist.ReduceOp.SUM, group=group)
-        if average:
-            engine._gflat.div_(world)
+        _reduce_bucket(engine._gflat, world, average, group)
         return engine._gflat
     cur = torch.cuda.current_stream()
     comm = comm_stream or _comm_stream(engine._gflat.device)
@@ -98,6 +96,9 @@ def _comm_stream(device):
 
 
 def _reduce_bucket(t, world, average, group):
+    if average and t.is_cuda and dist.get_backend(group) == "nccl":
+        dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)       # NCCL averages inside the collective: no division pass
+        return
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     if average:
         t.div_(world)
