@@ -78,6 +78,29 @@ __global__ void __launch_bounds__(256) msda_prepare_kernel(const float* __restri
   }
 }
 
+// per-column tables of the offsets projection (column n = ((m*L + l)*P + p)*3 + i) for Epilogue::rowop 2: the offset normaliser
+// (T_l, W_l, H_l)[i] and the index l*3 + i into the row's reference points
+__global__ void msda_colmap_kernel(const int64_t* __restrict__ shapes, int L, int P, float* __restrict__ norm, int* __restrict__ idx, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int i = c % 3, l = (c / (3 * P)) % L;
+  norm[c] = (float)shapes[l * 3 + (i == 0 ? 0 : i == 1 ? 2 : 1)];
+  idx[c] = l * 3 + i;
+}
+
+// loc / attn [rows, M, L, P, (3)] from q in two GEMMs with the prepare arithmetic in their epilogues; false = shape not taken by the
+// tcgen05 path (the caller runs the unfused sequence)
+static bool msda_projections_prepared(const bf16* q, const bf16* w_off, const float* b_off, const bf16* w_att, const float* b_att,
+                                      const float* refp, const int64_t* shapes, float* loc, float* attn, float* col_norm, int* col_idx,
+                                      long rows, int L, int P, cudaStream_t st) {
+  const int LP3 = kM * L * P * 3, LP1 = kM * L * P;
+  msda_colmap_kernel<<<(unsigned)cdiv(LP3, 256), 256, 0, st>>>(shapes, L, P, col_norm, col_idx, LP3);
+  Epilogue e; e.bias = b_off; e.c32 = loc; e.rowop = 2; e.ro_ref = refp; e.ro_ref_ld = (long)L * 3; e.ro_norm = col_norm; e.ro_idx = col_idx;
+  if (gemm_tc(q, kC, w_off, nullptr, LP3, rows, LP3, kC, e, nullptr, st) != 0) return false;
+  Epilogue a; a.bias = b_att; a.c32 = attn; a.rowop = 1;
+  return gemm_tc(q, kC, w_att, nullptr, LP1, rows, LP1, kC, a, nullptr, st) == 0;
+}
+
 struct EncWs {
   char* base; size_t off = 0, cap;
   EncWs(void* p, size_t c) : base((char*)p), cap(c) {}
@@ -102,6 +125,7 @@ size_t enc_ws_bytes(long rows, int L, int P, int F) {
   w.take((size_t)rows * kC * sizeof(T));                        // sampled
   w.take((size_t)rows * kC * sizeof(T));                        // x1
   w.take((size_t)rows * F * sizeof(T));                         // FFN hidden (only used off the fused-MLP path)
+  w.take((size_t)LP3 * 8);                                      // column tables of the fused location epilogue
   return w.off + 256;
 }
 
@@ -125,6 +149,8 @@ int enc_layer_t(const void* const* W, const T* src, const T* pos, const float* r
   T* samp = (T*)w.take((size_t)rows * kC * sizeof(T));
   T* x1 = (T*)w.take((size_t)rows * kC * sizeof(T));
   T* hid = (T*)w.take((size_t)rows * F * sizeof(T));
+  float* col_norm = (float*)w.take((size_t)LP3 * 8);
+  int* col_idx = (int*)(col_norm + LP3);
   auto Wm = [&](int i) { return (const T*)W[i]; };
   auto Wf = [&](int i) { return (const float*)W[i]; };
 
@@ -136,22 +162,23 @@ int enc_layer_t(const void* const* W, const T* src, const T* pos, const float* r
     mask_rows_kernel<T><<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(value, mask, rows);
     CQ_LAUNCH_CHECK();
   }
-  // offsets / logits: fp32 straight from the accumulators (bf16: fp32 side output of the epilogue), so that the sampling
-  // locations carry no bf16 rounding of their own
-  { Epilogue e; e.bias = Wf(E_OFF_B); if (sizeof(T) == 2) e.c32 = off32; CQ_TRY(gemm<T>(q, kC, Wm(E_OFF_W), offT, LP3, rows, LP3, kC, e, nullptr, st)); }
-  { Epilogue e; e.bias = Wf(E_ATT_B); if (sizeof(T) == 2) e.c32 = lg32; CQ_TRY(gemm<T>(q, kC, Wm(E_ATT_W), lgT, LP1, rows, LP1, kC, e, nullptr, st)); }
-  // Two kernels by default: msda_prepare (softmax + locations, fully parallel) then the sampling kernel.  Folding the softmax
-  // and the location arithmetic into the sampling kernel's phase 1 (msda_fwd_fused: nothing of size [rows, 8, L, P, 3] is
-  // materialised) measured 3.5 % SLOWER on B200 (3.96 vs 3.83 ms per layer at B = 4): the sampling warps are latency bound
-  // and the two extra warp reductions + expf / division sit on their critical path.  Kept behind CQVAD_ENC_FUSED=1.
-  static const bool no_fused = getenv("CQVAD_ENC_FUSED") == nullptr;
-  int fr = no_fused ? 1 : msda_fwd_fused(DT<T>::id, value, shapes, lsi, off32, lg32, refp, samp, B, (int)Len, kM, kC / kM, L, (int)Len, P, st);
-  if (fr < 0) return fr;
-  if (fr == 1) {
+  // bf16 path: softmax and sampling-location arithmetic (msda_prepare) run in the epilogues of the two query projections, straight
+  // from the fp32 accumulators -- the raw offsets / logits are never written (1.4 GB of traffic per layer at 4 clips)
+  static const bool no_rowop = getenv("CQVAD_ENC_NO_ROWOP") != nullptr;
+  bool prepared = false;
+  if (sizeof(T) == 2 && !no_rowop && L * P == 32) {
+    prepared = msda_projections_prepared((const bf16*)q, (const bf16*)Wm(E_OFF_W), Wf(E_OFF_B), (const bf16*)Wm(E_ATT_W), Wf(E_ATT_B), refp,
+                                         shapes, loc, attn, col_norm, col_idx, rows, L, P, st);
+  }
+  if (!prepared) {
+    // offsets / logits: fp32 straight from the accumulators (bf16: fp32 side output of the epilogue), so that the sampling
+    // locations carry no bf16 rounding of their own
+    { Epilogue e; e.bias = Wf(E_OFF_B); if (sizeof(T) == 2) e.c32 = off32; CQ_TRY(gemm<T>(q, kC, Wm(E_OFF_W), offT, LP3, rows, LP3, kC, e, nullptr, st)); }
+    { Epilogue e; e.bias = Wf(E_ATT_B); if (sizeof(T) == 2) e.c32 = lg32; CQ_TRY(gemm<T>(q, kC, Wm(E_ATT_W), lgT, LP1, rows, LP1, kC, e, nullptr, st)); }
     msda_prepare_kernel<<<(unsigned)cdiv(rows * kM * 32, 256), 256, 0, st>>>(off32, lg32, refp, shapes, loc, attn, rows, L, P);
     CQ_LAUNCH_CHECK();
-    CQ_TRY(cqvad_msda3d_forward(DT<T>::id, value, shapes, lsi, loc, attn, samp, B, (int)Len, kM, kC / kM, L, (int)Len, P, (void*)st));
   }
+  CQ_TRY(cqvad_msda3d_forward(DT<T>::id, value, shapes, lsi, loc, attn, samp, B, (int)Len, kM, kC / kM, L, (int)Len, P, (void*)st));
   if (attn_out) {   // the module's own output (tests): output_proj(samp)
     Epilogue e; e.bias = Wf(E_OUT_B);
     CQ_TRY(gemm<T>(samp, kC, Wm(E_OUT_W), attn_out, kC, rows, kC, kC, e, nullptr, st));
@@ -193,7 +220,8 @@ struct EncTrainWs {
   T *q, *value, *offT, *lgT, *samp, *z1, *x1, *h, *z2;
   float *off32, *lg32, *loc, *attn;
   T *dz2, *dh, *dx1, *dz1, *dsamp, *doffT, *dlgT, *dq, *dvalT, *wt;
-  float *dval32, *dloc, *dattn;
+  float *dval32, *dloc, *dattn, *col_norm;
+  int* col_idx;
   size_t bytes;
   EncTrainWs(void* base, size_t cap, long rows, int L, int P, int F) {
     EncWs w(base, cap);
@@ -209,6 +237,7 @@ struct EncTrainWs {
     doffT = tk(R * LP3); dlgT = tk(R * LP1); dq = tk(R * C); dvalT = tk(R * C);
     dval32 = tf(R * C); dloc = tf(R * LP3); dattn = tf(R * LP1);
     wt = tk(2 * C * C + LP3 * C + LP1 * C + 2 * (size_t)F * C);      // transposed weights for the data gradients
+    col_norm = tf(2 * LP3); col_idx = (int*)(col_norm + LP3);        // column tables of the fused location epilogue
     bytes = w.off + 256;
   }
 };
@@ -230,10 +259,17 @@ int enc_train_fwd_t(const void* const* W, const T* src, const T* pos, const floa
   CQ_LAUNCH_CHECK();
   { Epilogue e; e.bias = Wf(E_VAL_B); CQ_TRY(gemm<T>(src, kC, Wm(E_VAL_W), w.value, kC, rows, kC, kC, e, nullptr, st)); }
   if (mask) { mask_rows_kernel<T><<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(w.value, mask, rows); CQ_LAUNCH_CHECK(); }
-  { Epilogue e; e.bias = Wf(E_OFF_B); if (sizeof(T) == 2) e.c32 = w.off32; CQ_TRY(gemm<T>(w.q, kC, Wm(E_OFF_W), w.offT, LP3, rows, LP3, kC, e, nullptr, st)); }
-  { Epilogue e; e.bias = Wf(E_ATT_B); if (sizeof(T) == 2) e.c32 = w.lg32; CQ_TRY(gemm<T>(w.q, kC, Wm(E_ATT_W), w.lgT, LP1, rows, LP1, kC, e, nullptr, st)); }
-  msda_prepare_kernel<<<(unsigned)cdiv(rows * kM * 32, 256), 256, 0, st>>>(w.off32, w.lg32, refp, shapes, w.loc, w.attn, rows, L, P);
-  CQ_LAUNCH_CHECK();
+  static const bool no_rowop = getenv("CQVAD_ENC_NO_ROWOP") != nullptr;
+  bool prepared = false;
+  if (sizeof(T) == 2 && !no_rowop && L * P == 32)     // softmax / location arithmetic in the projections' epilogues (see enc_layer_t)
+    prepared = msda_projections_prepared((const bf16*)w.q, (const bf16*)Wm(E_OFF_W), Wf(E_OFF_B), (const bf16*)Wm(E_ATT_W), Wf(E_ATT_B), refp,
+                                         shapes, w.loc, w.attn, w.col_norm, w.col_idx, rows, L, P, st);
+  if (!prepared) {
+    { Epilogue e; e.bias = Wf(E_OFF_B); if (sizeof(T) == 2) e.c32 = w.off32; CQ_TRY(gemm<T>(w.q, kC, Wm(E_OFF_W), w.offT, LP3, rows, LP3, kC, e, nullptr, st)); }
+    { Epilogue e; e.bias = Wf(E_ATT_B); if (sizeof(T) == 2) e.c32 = w.lg32; CQ_TRY(gemm<T>(w.q, kC, Wm(E_ATT_W), w.lgT, LP1, rows, LP1, kC, e, nullptr, st)); }
+    msda_prepare_kernel<<<(unsigned)cdiv(rows * kM * 32, 256), 256, 0, st>>>(w.off32, w.lg32, refp, shapes, w.loc, w.attn, rows, L, P);
+    CQ_LAUNCH_CHECK();
+  }
   CQ_TRY(cqvad_msda3d_forward(DT<T>::id, w.value, shapes, lsi, w.loc, w.attn, w.samp, B, (int)Len, kM, kC / kM, L, (int)Len, P, (void*)st));
   { Epilogue e; e.bias = Wf(E_OUT_B); if (!drop) { e.res = src; e.ldr = kC; }
     CQ_TRY(gemm<T>(w.samp, kC, Wm(E_OUT_W), w.z1, kC, rows, kC, kC, e, nullptr, st)); }

@@ -52,6 +52,7 @@ constexpr int TMEM_COLS = 512;
 struct TcParams {
   bf16* C; long ldc; long M; int N; int K;
   const float* bias; int act; const bf16* res; long ldr; const float* res32; float* c32;
+  int rowop; const float* ro_ref; long ro_ref_ld; const float* ro_norm; const int* ro_idx;   // Epilogue::rowop
   const float* ln_g; const float* ln_b; float ln_eps;
   int zero_period, zero_valid;
   bf16* c2; int c2_act; const bf16* mul_aux; int mul_mode; float mul_scale;
@@ -552,6 +553,55 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
 #pragma unroll 1
       for (int c = 0; c < 128; c += 32) {
         if (n0 + c0 + c >= p.N) break;  // warp-uniform
+        if (p.rowop != 0) {
+          // MSDA "prepare" folded into the two query projections (Epilogue::rowop): each thread owns one row's 32 consecutive
+          // columns = one head's L*P logits (softmax in registers) or 32 offset components (location arithmetic); fp32 out only
+          uint32_t r[32];
+          tmem_ld32(t_addr + c, r);
+          tmem_ld_wait();
+          float x[32];
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            float bs[8];
+            load8(bcur + c0 + c + g8 * 8, bs);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[g8 * 8 + j] = __uint_as_float(r[g8 * 8 + j]) + bs[j];
+          }
+          if (p.rowop == 1) {
+            float mx = x[0];
+#pragma unroll
+            for (int j = 1; j < 32; ++j) mx = fmaxf(mx, x[j]);
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { x[j] = expf(x[j] - mx); s4[j & 3] += x[j]; }
+            const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = x[j] / sum;
+          } else if (row_ok) {
+            const float* rr = p.ro_ref + grow * p.ro_ref_ld;
+            const int cbase = n0 + c0 + c;
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              float nm[8];
+              load8(p.ro_norm + cbase + g8 * 8, nm);
+              const int4 i0 = *reinterpret_cast<const int4*>(p.ro_idx + cbase + g8 * 8);
+              const int4 i1 = *reinterpret_cast<const int4*>(p.ro_idx + cbase + g8 * 8 + 4);
+              const int ix[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[g8 * 8 + j] = rr[ix[j]] + __fdiv_rn(x[g8 * 8 + j], nm[j]);
+            }
+          }
+          if (row_ok) {
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = x[g8 * 8 + j];
+              store8(crow32 + c + g8 * 8, v);
+            }
+          }
+          continue;
+        }
         uint4 rcur[4];
         if (!do_ln) {
 #pragma unroll
@@ -744,6 +794,9 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
   if (epi.res && ((((uintptr_t)epi.res) & 15) || epi.ldr % 8 != 0)) return 1;
   if ((epi.res32 && ((((uintptr_t)epi.res32) & 15) || epi.ldr % 8 != 0)) || (epi.c32 && (((uintptr_t)epi.c32) & 15))) return 1;
   if (epi.ln_g && N != BLOCK_N) return 1;
+  if (epi.rowop && (N % 32 != 0 || !epi.c32 || epi.res || epi.res32 || epi.ln_g || epi.c2 || epi.mul_mode || epi.act != CQVAD_ACT_NONE ||
+                    epi.zero_period || conv || (epi.rowop == 2 && (!epi.ro_ref || !epi.ro_norm || !epi.ro_idx))))
+    return 1;
   if ((epi.c2 || epi.mul_mode) && (epi.ln_g || N % 8 != 0)) return 1;
   if ((epi.c2 && (((uintptr_t)epi.c2) & 15)) || (epi.mul_aux && (((uintptr_t)epi.mul_aux) & 15))) return 1;
   if (conv && (conv->w > 128 || lda != kC || K != 9 * kC)) return 1;
@@ -753,6 +806,7 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
   TcParams p{};
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
   p.bias = epi.bias; p.act = epi.act; p.res = (const bf16*)epi.res; p.ldr = epi.ldr; p.res32 = epi.res32; p.c32 = epi.c32;
+  p.rowop = epi.rowop; p.ro_ref = epi.ro_ref; p.ro_ref_ld = epi.ro_ref_ld; p.ro_norm = epi.ro_norm; p.ro_idx = epi.ro_idx;
   p.ln_g = epi.ln_g; p.ln_b = epi.ln_b; p.ln_eps = epi.ln_eps;
   p.zero_period = epi.zero_period; p.zero_valid = epi.zero_valid;
   p.c2 = (bf16*)epi.c2; p.c2_act = epi.c2_act; p.mul_aux = (const bf16*)epi.mul_aux; p.mul_mode = epi.mul_mode; p.mul_scale = epi.mul_scale;

@@ -327,13 +327,18 @@ __device__ __forceinline__ void tile_step(const char* __restrict__ ubase, unsign
 }
 
 // NW: 32-bit words per lane and corner.  bf16: NW = 8 (16 channels, D % 16 == 0) or 4 (8 channels); fp32: NW = 8 (8 channels).
-template <typename T, int NW>
+// FUSED: `loc` holds the raw sampling OFFSETS and `attn` the raw attention LOGITS of the two query projections; the softmax over the
+// head's L*P logits and loc = ref + off / (T_l, W_l, H_l) (ops/modules/ms_deform_attn.py:186-192, the reference's normaliser order;
+// same arithmetic as msda_prepare_kernel: IEEE division, expf) happen in the geometry phase, so neither sampling_locations nor the
+// attention weights (136 MB per clip in fp32) are ever written or re-read.
+template <typename T, int NW, bool FUSED = false>
 __global__ void __launch_bounds__(kWarps * 32) msda_fwd_tile_kernel(const T* __restrict__ value,
                                                                     const int64_t* __restrict__ shapes,
                                                                     const int64_t* __restrict__ lsi,
                                                                     const float* __restrict__ loc,
                                                                     const float* __restrict__ attn, T* __restrict__ out,
-                                                                    int n_tiles, int Len, int M, int D, int L, int Lq, int P) {
+                                                                    int n_tiles, int Len, int M, int D, int L, int Lq, int P,
+                                                                    const float* __restrict__ ref = nullptr) {
   constexpr int NC = NW * (4 / sizeof(T));   // channels per lane
   __shared__ int s_T[kMaxLevels], s_H[kMaxLevels], s_W[kMaxLevels], s_ls[kMaxLevels];
   if (threadIdx.x < L) {
@@ -353,38 +358,64 @@ __global__ void __launch_bounds__(kWarps * 32) msda_fwd_tile_kernel(const T* __r
   const char* ubase = reinterpret_cast<const char*>(value + (long)b * Len * ((long)M * D) + (long)m * D);
   const unsigned choff = (unsigned)ch * (unsigned)(NC * sizeof(T));
   const int q_end = min(Lq, (tile + 1) * kTileQ);
-  for (int q = tile * kTileQ + warp; q < q_end; q += kWarps) {
+  // geometry of up to 32 sampling points of query q (one per lane): corner base offset, strides, validity mask, lerp weights and
+  // the attention weight
+  auto geometry = [&](int q, int p0, unsigned& g_b0, unsigned& g_dh, unsigned& g_dt, unsigned& g_mask, float& g_lt, float& g_lh,
+                      float& g_lw, float& g_a) {
     const long wid = ((long)b * Lq + q) * M + m;
     const float* locp = loc + wid * LP * 3;
     const float* attp = attn + wid * LP;
-    float acc[NC];
-#pragma unroll
-    for (int e = 0; e < NC; ++e) acc[e] = 0.f;
-    for (int p0 = 0; p0 < LP; p0 += 32) {
-      const int pt = p0 + lane;
-      unsigned g_b0 = 0, g_dh = 0, g_dt = 0, g_mask = 0; float g_lt = 0, g_lh = 0, g_lw = 0, g_a = 0;
-      if (pt < LP) {
-        const int l = pt / P;
-        const int Tt = s_T[l], H = s_H[l], W = s_W[l];
-        int tl, hl, wl;
-        point_geometry(locp[pt * 3], locp[pt * 3 + 1], locp[pt * 3 + 2], Tt, H, W, tl, hl, wl, g_mask, g_lt, g_lh, g_lw);
-        g_dh = (unsigned)W * rsb; g_dt = (unsigned)(H * W) * rsb;
-        g_b0 = (unsigned)(s_ls[l] + (tl * H + hl) * W + wl) * rsb;   // wraps for invalid low corners; those are never read
-        g_a = attp[pt];
-      }
-      const int np = min(32, LP - p0);
-      for (int j0 = 0; j0 < np; j0 += G) {
-        const int src = min(j0 + g, 31);
-        unsigned mk = __shfl_sync(0xffffffffu, g_mask, src);
-        const unsigned b0 = __shfl_sync(0xffffffffu, g_b0, src) + choff;
-        const unsigned dh = __shfl_sync(0xffffffffu, g_dh, src), dt = __shfl_sync(0xffffffffu, g_dt, src);
-        const float lt = __shfl_sync(0xffffffffu, g_lt, src), lh = __shfl_sync(0xffffffffu, g_lh, src);
-        const float lw = __shfl_sync(0xffffffffu, g_lw, src), a = __shfl_sync(0xffffffffu, g_a, src);
-        if (j0 + g >= np) mk = 0;
-        if (__all_sync(0xffffffffu, mk == 0xffu)) tile_step<T, NW, true>(ubase, b0, rsb, dh, dt, mk, lt, lh, lw, a, acc);
-        else if (__any_sync(0xffffffffu, mk != 0u)) tile_step<T, NW, false>(ubase, b0, rsb, dh, dt, mk, lt, lh, lw, a, acc);
+    const int pt = p0 + lane;
+    g_b0 = g_dh = g_dt = g_mask = 0; g_lt = g_lh = g_lw = g_a = 0.f;
+    float sm_max = 0.f, sm_sum = 1.f, lg = 0.f;
+    if constexpr (FUSED) {
+      if (LP <= 32) {                       // one logit per lane: a single load feeds the max, the sum and the weight
+        lg = pt < LP ? attp[pt] : -INFINITY;
+        sm_max = warp_max(lg);
+        sm_sum = warp_sum(pt < LP ? expf(lg - sm_max) : 0.f);
+      } else {
+        sm_max = -INFINITY;
+        for (int j = lane; j < LP; j += 32) sm_max = fmaxf(sm_max, attp[j]);
+        sm_max = warp_max(sm_max);
+        sm_sum = 0.f;
+        for (int j = lane; j < LP; j += 32) sm_sum += expf(attp[j] - sm_max);
+        sm_sum = warp_sum(sm_sum);
+        if (pt < LP) lg = attp[pt];
       }
     }
+    if (pt < LP) {
+      const int l = pt / P;
+      const int Tt = s_T[l], H = s_H[l], W = s_W[l];
+      int tl, hl, wl;
+      float lx = locp[pt * 3], ly = locp[pt * 3 + 1], lz = locp[pt * 3 + 2];
+      if constexpr (FUSED) {
+        const float* r = ref + (((long)b * Lq + q) * L + l) * 3;
+        lx = r[0] + __fdiv_rn(lx, (float)Tt); ly = r[1] + __fdiv_rn(ly, (float)W); lz = r[2] + __fdiv_rn(lz, (float)H);
+        g_a = expf(lg - sm_max) / sm_sum;   // exactly msda_prepare_kernel's arithmetic
+      } else {
+        g_a = attp[pt];
+      }
+      point_geometry(lx, ly, lz, Tt, H, W, tl, hl, wl, g_mask, g_lt, g_lh, g_lw);
+      g_dh = (unsigned)W * rsb; g_dt = (unsigned)(H * W) * rsb;
+      g_b0 = (unsigned)(s_ls[l] + (tl * H + hl) * W + wl) * rsb;   // wraps for invalid low corners; those are never read
+    }
+  };
+  auto gather = [&](int np, unsigned g_b0, unsigned g_dh, unsigned g_dt, unsigned g_mask, float g_lt, float g_lh, float g_lw, float g_a,
+                    float (&acc)[NC]) {
+    for (int j0 = 0; j0 < np; j0 += G) {
+      const int src = min(j0 + g, 31);
+      unsigned mk = __shfl_sync(0xffffffffu, g_mask, src);
+      const unsigned b0 = __shfl_sync(0xffffffffu, g_b0, src) + choff;
+      const unsigned dh = __shfl_sync(0xffffffffu, g_dh, src), dt = __shfl_sync(0xffffffffu, g_dt, src);
+      const float lt = __shfl_sync(0xffffffffu, g_lt, src), lh = __shfl_sync(0xffffffffu, g_lh, src);
+      const float lw = __shfl_sync(0xffffffffu, g_lw, src), a = __shfl_sync(0xffffffffu, g_a, src);
+      if (j0 + g >= np) mk = 0;
+      if (__all_sync(0xffffffffu, mk == 0xffu)) tile_step<T, NW, true>(ubase, b0, rsb, dh, dt, mk, lt, lh, lw, a, acc);
+      else if (__any_sync(0xffffffffu, mk != 0u)) tile_step<T, NW, false>(ubase, b0, rsb, dh, dt, mk, lt, lh, lw, a, acc);
+    }
+  };
+  auto finish = [&](int q, float (&acc)[NC]) {
+    const long wid = ((long)b * Lq + q) * M + m;
     for (int o = lpp; o < 32; o <<= 1) {
 #pragma unroll
       for (int e = 0; e < NC; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
@@ -398,6 +429,36 @@ __global__ void __launch_bounds__(kWarps * 32) msda_fwd_tile_kernel(const T* __r
         store8(out + wid * D + ch * NC + e0, o8);
       }
     }
+  };
+  int q = tile * kTileQ + warp;
+  if (q >= q_end) return;
+  if (LP <= 32) {
+    // software pipeline over the warp's queries: the next query's geometry (its loc / logit loads, the softmax reductions) is
+    // issued before the current query's gathers, so its latency hides under them
+    unsigned c_b0, c_dh, c_dt, c_mask; float c_lt, c_lh, c_lw, c_a;
+    geometry(q, 0, c_b0, c_dh, c_dt, c_mask, c_lt, c_lh, c_lw, c_a);
+    for (; q < q_end; q += kWarps) {
+      unsigned n_b0 = 0, n_dh = 0, n_dt = 0, n_mask = 0; float n_lt = 0, n_lh = 0, n_lw = 0, n_a = 0;
+      if (q + kWarps < q_end) geometry(q + kWarps, 0, n_b0, n_dh, n_dt, n_mask, n_lt, n_lh, n_lw, n_a);
+      float acc[NC];
+#pragma unroll
+      for (int e = 0; e < NC; ++e) acc[e] = 0.f;
+      gather(LP, c_b0, c_dh, c_dt, c_mask, c_lt, c_lh, c_lw, c_a, acc);
+      finish(q, acc);
+      c_b0 = n_b0; c_dh = n_dh; c_dt = n_dt; c_mask = n_mask; c_lt = n_lt; c_lh = n_lh; c_lw = n_lw; c_a = n_a;
+    }
+    return;
+  }
+  for (; q < q_end; q += kWarps) {
+    float acc[NC];
+#pragma unroll
+    for (int e = 0; e < NC; ++e) acc[e] = 0.f;
+    for (int p0 = 0; p0 < LP; p0 += 32) {
+      unsigned g_b0, g_dh, g_dt, g_mask; float g_lt, g_lh, g_lw, g_a;
+      geometry(q, p0, g_b0, g_dh, g_dt, g_mask, g_lt, g_lh, g_lw, g_a);
+      gather(min(32, LP - p0), g_b0, g_dh, g_dt, g_mask, g_lt, g_lh, g_lw, g_a, acc);
+    }
+    finish(q, acc);
   }
 }
 
@@ -656,6 +717,20 @@ int msda_fwd_fused_t(const void* value, const int64_t* shapes, const int64_t* ls
   if (nw == 0) return 0;
   const int lpp = D >> 3;
   if (D % 8 != 0 || lpp < 1 || lpp > 32 || (lpp & (lpp - 1)) != 0 || (((uintptr_t)value) & 15) || (((uintptr_t)out) & 15)) return 1;
+  if (L <= kMaxLevels && (long)Len * M * D * (long)sizeof(T) < (1L << 32)) {       // query-tile kernel (the default sampling kernel)
+    const int n_tiles = (int)cdiv(Lq, kTileQ);
+    const long n_cta = (long)n_tiles * N * M;
+    if (n_cta < (1L << 31)) {
+      if (sizeof(T) == 4)
+        msda_fwd_tile_kernel<T, 8, true><<<(unsigned)n_cta, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, off, logit, (T*)out, n_tiles,
+                                                                                  Len, M, D, L, Lq, P, ref);
+      else if constexpr (sizeof(T) == 2)
+        msda_fwd_tile_kernel<T, 4, true><<<(unsigned)n_cta, kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, off, logit, (T*)out, n_tiles,
+                                                                                  Len, M, D, L, Lq, P, ref);
+      CQ_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   msda_fwd_vec_kernel<T, true><<<(unsigned)cdiv(nw, kWarps), kWarps * 32, 0, st>>>((const T*)value, shapes, lsi, off, logit, ref,
                                                                                   (T*)out, nw, Len, M, D, L, Lq, P);
   CQ_LAUNCH_CHECK();
