@@ -17,6 +17,7 @@ from .modules.criterion import (HungarianMatcherAVA, SetCriterionAVA, PostProces
                                 pack_targets)
 from .modules.heads import DETRHeads, HeadsFunction
 from .optim import FlatAdamW
+from . import detections
 from .modules.neck import SimpleFeaturePyramid
 from .modules.decoder import (MLP, ConvBlock, TransformerDecoderLayer, TransformerClassDecoderLayer, TransformerDecoder,
                               build_decoder)
