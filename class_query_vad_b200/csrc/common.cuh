@@ -146,13 +146,14 @@ struct Epilogue {
   // training forward of a GELU layer in ONE epilogue: C = gelu(v), c2 = gelu'(v) with v = acc + bias (act / c2_act ignored);
   // the pre-activation itself is never written (the backward needs only gelu' -- mul_mode 3 -- and the activation)
   bool dual_gelu = false;
-  // MSDA "prepare" folded into the two query projections (tcgen05 path only, fp32 output c32 ONLY -- C is not written; N % 32 == 0):
+  // MSDA "prepare" folded into the two query projections (tcgen05 path only; fp32 output c32 ONLY through TMA stores -- C is not
+  // written; N % 32 == 0, ldc counts c32 elements):
   //   rowop 1: softmax over every aligned group of 32 columns (one head's L*P = 32 attention logits)
-  //   rowop 2: sampling locations  c32[r, n] = ro_ref[r * ro_ref_ld + ro_idx[n]] + (acc + bias) / ro_norm[n]  (IEEE division)
+  //   rowop 2: sampling locations for L = 4 levels x P = 8 points, column n = ((m*4 + l)*8 + p)*3 + i:
+  //            c32[r, n] = ro_ref[r*12 + l*3 + i] + (acc + bias) / ro_norm[l*3 + i]   (IEEE division)
   int rowop = 0;
-  const float* ro_ref = nullptr; long ro_ref_ld = 0;
-  const float* ro_norm = nullptr;   // [N]
-  const int* ro_idx = nullptr;      // [N]
+  const float* ro_ref = nullptr;    // [M, 12]
+  const float* ro_norm = nullptr;   // [12]
 };
 struct ConvGeom {  // implicit-GEMM 3x3 conv on the y-padded NHWC layout [n_img, h+1, w, 256]
   int h = 0, w = 0;

@@ -78,24 +78,22 @@ __global__ void __launch_bounds__(256) msda_prepare_kernel(const float* __restri
   }
 }
 
-// per-column tables of the offsets projection (column n = ((m*L + l)*P + p)*3 + i) for Epilogue::rowop 2: the offset normaliser
-// (T_l, W_l, H_l)[i] and the index l*3 + i into the row's reference points
-__global__ void msda_colmap_kernel(const int64_t* __restrict__ shapes, int L, int P, float* __restrict__ norm, int* __restrict__ idx, int n) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
-  const int i = c % 3, l = (c / (3 * P)) % L;
+// the 12 offset normalisers (T_l, W_l, H_l) of Epilogue::rowop 2, index l*3 + i
+__global__ void msda_norm12_kernel(const int64_t* __restrict__ shapes, float* __restrict__ norm) {
+  const int c = threadIdx.x;
+  if (c >= 12) return;
+  const int i = c % 3, l = c / 3;
   norm[c] = (float)shapes[l * 3 + (i == 0 ? 0 : i == 1 ? 2 : 1)];
-  idx[c] = l * 3 + i;
 }
 
 // loc / attn [rows, M, L, P, (3)] from q in two GEMMs with the prepare arithmetic in their epilogues; false = shape not taken by the
 // tcgen05 path (the caller runs the unfused sequence)
 static bool msda_projections_prepared(const bf16* q, const bf16* w_off, const float* b_off, const bf16* w_att, const float* b_att,
-                                      const float* refp, const int64_t* shapes, float* loc, float* attn, float* col_norm, int* col_idx,
-                                      long rows, int L, int P, cudaStream_t st) {
-  const int LP3 = kM * L * P * 3, LP1 = kM * L * P;
-  msda_colmap_kernel<<<(unsigned)cdiv(LP3, 256), 256, 0, st>>>(shapes, L, P, col_norm, col_idx, LP3);
-  Epilogue e; e.bias = b_off; e.c32 = loc; e.rowop = 2; e.ro_ref = refp; e.ro_ref_ld = (long)L * 3; e.ro_norm = col_norm; e.ro_idx = col_idx;
+                                      const float* refp, const int64_t* shapes, float* loc, float* attn, float* norm12, long rows,
+                                      cudaStream_t st) {
+  const int LP3 = kM * 4 * 8 * 3, LP1 = kM * 4 * 8;
+  msda_norm12_kernel<<<1, 32, 0, st>>>(shapes, norm12);
+  Epilogue e; e.bias = b_off; e.c32 = loc; e.rowop = 2; e.ro_ref = refp; e.ro_norm = norm12;
   if (gemm_tc(q, kC, w_off, nullptr, LP3, rows, LP3, kC, e, nullptr, st) != 0) return false;
   Epilogue a; a.bias = b_att; a.c32 = attn; a.rowop = 1;
   return gemm_tc(q, kC, w_att, nullptr, LP1, rows, LP1, kC, a, nullptr, st) == 0;
@@ -125,7 +123,7 @@ size_t enc_ws_bytes(long rows, int L, int P, int F) {
   w.take((size_t)rows * kC * sizeof(T));                        // sampled
   w.take((size_t)rows * kC * sizeof(T));                        // x1
   w.take((size_t)rows * F * sizeof(T));                         // FFN hidden (only used off the fused-MLP path)
-  w.take((size_t)LP3 * 8);                                      // column tables of the fused location epilogue
+  w.take((size_t)LP3 * 8);                                      // offset normalisers of the fused location epilogue (12 used)
   return w.off + 256;
 }
 
@@ -149,8 +147,7 @@ int enc_layer_t(const void* const* W, const T* src, const T* pos, const float* r
   T* samp = (T*)w.take((size_t)rows * kC * sizeof(T));
   T* x1 = (T*)w.take((size_t)rows * kC * sizeof(T));
   T* hid = (T*)w.take((size_t)rows * F * sizeof(T));
-  float* col_norm = (float*)w.take((size_t)LP3 * 8);
-  int* col_idx = (int*)(col_norm + LP3);
+  float* col_norm = (float*)w.take((size_t)LP3 * 8);   // 12 floats used
   auto Wm = [&](int i) { return (const T*)W[i]; };
   auto Wf = [&](int i) { return (const float*)W[i]; };
 
@@ -166,9 +163,9 @@ int enc_layer_t(const void* const* W, const T* src, const T* pos, const float* r
   // from the fp32 accumulators -- the raw offsets / logits are never written (1.4 GB of traffic per layer at 4 clips)
   static const bool no_rowop = getenv("CQVAD_ENC_NO_ROWOP") != nullptr;
   bool prepared = false;
-  if (sizeof(T) == 2 && !no_rowop && L * P == 32) {
+  if (sizeof(T) == 2 && !no_rowop && L == 4 && P == 8) {
     prepared = msda_projections_prepared((const bf16*)q, (const bf16*)Wm(E_OFF_W), Wf(E_OFF_B), (const bf16*)Wm(E_ATT_W), Wf(E_ATT_B), refp,
-                                         shapes, loc, attn, col_norm, col_idx, rows, L, P, st);
+                                         shapes, loc, attn, col_norm, rows, st);
   }
   if (!prepared) {
     // offsets / logits: fp32 straight from the accumulators (bf16: fp32 side output of the epilogue), so that the sampling
@@ -221,7 +218,6 @@ struct EncTrainWs {
   float *off32, *lg32, *loc, *attn;
   T *dz2, *dh, *dx1, *dz1, *dsamp, *doffT, *dlgT, *dq, *dvalT, *wt;
   float *dval32, *dloc, *dattn, *col_norm;
-  int* col_idx;
   size_t bytes;
   EncTrainWs(void* base, size_t cap, long rows, int L, int P, int F) {
     EncWs w(base, cap);
@@ -237,7 +233,7 @@ struct EncTrainWs {
     doffT = tk(R * LP3); dlgT = tk(R * LP1); dq = tk(R * C); dvalT = tk(R * C);
     dval32 = tf(R * C); dloc = tf(R * LP3); dattn = tf(R * LP1);
     wt = tk(2 * C * C + LP3 * C + LP1 * C + 2 * (size_t)F * C);      // transposed weights for the data gradients
-    col_norm = tf(2 * LP3); col_idx = (int*)(col_norm + LP3);        // column tables of the fused location epilogue
+    col_norm = tf(2 * LP3);                                          // offset normalisers of the fused location epilogue (12 used)
     bytes = w.off + 256;
   }
 };
@@ -261,9 +257,9 @@ int enc_train_fwd_t(const void* const* W, const T* src, const T* pos, const floa
   if (mask) { mask_rows_kernel<T><<<(unsigned)cdiv(rows * 32, 256), 256, 0, st>>>(w.value, mask, rows); CQ_LAUNCH_CHECK(); }
   static const bool no_rowop = getenv("CQVAD_ENC_NO_ROWOP") != nullptr;
   bool prepared = false;
-  if (sizeof(T) == 2 && !no_rowop && L * P == 32)     // softmax / location arithmetic in the projections' epilogues (see enc_layer_t)
+  if (sizeof(T) == 2 && !no_rowop && L == 4 && P == 8)     // softmax / location arithmetic in the projections' epilogues (see enc_layer_t)
     prepared = msda_projections_prepared((const bf16*)w.q, (const bf16*)Wm(E_OFF_W), Wf(E_OFF_B), (const bf16*)Wm(E_ATT_W), Wf(E_ATT_B), refp,
-                                         shapes, w.loc, w.attn, w.col_norm, w.col_idx, rows, L, P, st);
+                                         shapes, w.loc, w.attn, w.col_norm, rows, st);
   if (!prepared) {
     { Epilogue e; e.bias = Wf(E_OFF_B); if (sizeof(T) == 2) e.c32 = w.off32; CQ_TRY(gemm<T>(w.q, kC, Wm(E_OFF_W), w.offT, LP3, rows, LP3, kC, e, nullptr, st)); }
     { Epilogue e; e.bias = Wf(E_ATT_B); if (sizeof(T) == 2) e.c32 = w.lg32; CQ_TRY(gemm<T>(w.q, kC, Wm(E_ATT_W), w.lgT, LP1, rows, LP1, kC, e, nullptr, st)); }

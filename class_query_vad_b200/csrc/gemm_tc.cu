@@ -52,7 +52,7 @@ constexpr int TMEM_COLS = 512;
 struct TcParams {
   bf16* C; long ldc; long M; int N; int K;
   const float* bias; int act; const bf16* res; long ldr; const float* res32; float* c32;
-  int rowop; const float* ro_ref; long ro_ref_ld; const float* ro_norm; const int* ro_idx;   // Epilogue::rowop
+  int rowop; const float* ro_ref; const float* ro_norm;   // Epilogue::rowop
   const float* ln_g; const float* ln_b; float ln_eps;
   int zero_period, zero_valid;
   bf16* c2; int c2_act; const bf16* mul_aux; int mul_mode; float mul_scale;
@@ -167,6 +167,30 @@ __device__ __forceinline__ void ts_dual_gelu_half(uint32_t t_addr, const float* 
 // 128 x 256 output tiles with ONE M = 256 UMMA stream issued by the leader; each CTA loads its own A tile and only HALF of
 // the weight tile, so the weight traffic L2 -> SM halves (the conv / large-K GEMMs were bound by the ~6300 B/clk L2 slice
 // throughput, not by the tensor pipe: B re-reads were 2/3 of the conv's L2 traffic) and the ring holds 6 (TS: 4) k-blocks.
+// Correctly rounded x / n from r = RN(1 / n) without the division instruction sequence: q0 = RN(x r), then two residual
+// corrections q <- RN(q + RN(x - n q) r) (the residual is exact in an FMA).  The first makes q faithful, the second rounds it
+// correctly (Markstein's theorem; quotients in the normal range -- offsets / grid sizes are).  5 FMA-pipe instructions against
+// ~11 for div.rn.f32; checked against exact rational arithmetic in tests/test_exact_division_cpu.py.
+__device__ __forceinline__ float div_rn_by(float x, float n, float r) {
+  float q = x * r;
+  float e = fmaf(-q, n, x);
+  q = fmaf(e, r, q);
+  e = fmaf(-q, n, x);
+  return fmaf(e, r, q);
+}
+
+// Epilogue::rowop 2, one 32-column step whose first column is PH (mod 96): column n = ((m*4 + l)*8 + p)*3 + i of the offsets
+// projection -> sampling location  ref[l*3 + i] + x / norm[l*3 + i]  (the IEEE quotient, as msda_prepare_kernel); l and i are
+// compile-time per unrolled column, so the row's 12 reference values, the 12 normalisers and their reciprocals stay in registers
+template <int PH>
+__device__ __forceinline__ void rowop_loc_step(float (&x)[32], const float (&ref)[12], const float (&nrm)[12], const float (&rcp)[12]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int n = PH + j, l = (n / 24) % 4, i = n % 3;
+    x[j] = ref[l * 3 + i] + div_rn_by(x[j], nrm[l * 3 + i], rcp[l * 3 + i]);
+  }
+}
+
 template <bool EXTRA, bool TS, bool CTA2>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                              const CUtensorMap& tmR, const TcParams& p) {
@@ -342,6 +366,67 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
         const long grow = (long)row0 + lane;
         const bool zero_row = p.zero_period > 0 && (int)(grow % p.zero_period) >= p.zero_valid;
+        if (p.rowop != 0) {
+          // MSDA "prepare" folded into the two query projections (Epilogue::rowop): each thread owns one row's 32 consecutive
+          // columns per step = one head's 32 attention logits (softmax in registers) or 32 offset components (location
+          // arithmetic).  fp32 output through the staging boxes: a [32 rows x 32 fp32] box has the 128-byte rows of the bf16
+          // boxes, so the same swizzle and TMA store apply (tmC is an fp32 map here); 4 steps alternate the warp's two boxes.
+          float ref12[12], nrm12[12], rcp12[12];
+          if (p.rowop == 2) {
+            const float4* rr = reinterpret_cast<const float4*>(p.ro_ref + (grow < p.M ? grow : 0) * 12);
+            const float4 a0 = rr[0], a1 = rr[1], a2 = rr[2];
+            ref12[0] = a0.x; ref12[1] = a0.y; ref12[2] = a0.z; ref12[3] = a0.w; ref12[4] = a1.x; ref12[5] = a1.y;
+            ref12[6] = a1.z; ref12[7] = a1.w; ref12[8] = a2.x; ref12[9] = a2.y; ref12[10] = a2.z; ref12[11] = a2.w;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) { nrm12[j] = p.ro_norm[j]; rcp12[j] = __frcp_rn(nrm12[j]); }
+          }
+#pragma unroll 1
+          for (int s4 = 0; s4 < 4; ++s4) {
+            const int c = s4 * 32;
+            if (colw + c < p.N) {   // warp-uniform
+              if (s4 >= 2) { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }   // the store two steps back has read this box
+              uint32_t r[32];
+              tmem_ld32(t_addr + c, r);
+              tmem_ld_wait();
+              float x[32];
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8) {
+                float bs[8];
+                load8(bcur + c0 + c + g8 * 8, bs);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[g8 * 8 + j] = __uint_as_float(r[g8 * 8 + j]) + bs[j];
+              }
+              if (p.rowop == 1) {
+                float mx = x[0];
+#pragma unroll
+                for (int j = 1; j < 32; ++j) mx = fmaxf(mx, x[j]);
+                float sp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { x[j] = __expf(x[j] - mx); sp[j & 3] += x[j]; }
+                const float inv = __frcp_rn((sp[0] + sp[1]) + (sp[2] + sp[3]));   // weights to ~2 ulp: they feed bf16 arithmetic
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] *= inv;
+              } else {
+                const int ph = (colw + c) % 96;      // warp-uniform
+                if (ph == 0) rowop_loc_step<0>(x, ref12, nrm12, rcp12);
+                else if (ph == 32) rowop_loc_step<32>(x, ref12, nrm12, rcp12);
+                else rowop_loc_step<64>(x, ref12, nrm12, rcp12);
+              }
+              const uint32_t buf = my_row + (uint32_t)((s4 & 1) * STG_BOX_BYTES);
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                uint4 o;
+                o.x = __float_as_uint(x[j4 * 4]); o.y = __float_as_uint(x[j4 * 4 + 1]);
+                o.z = __float_as_uint(x[j4 * 4 + 2]); o.w = __float_as_uint(x[j4 * 4 + 3]);
+                sts128(buf + (uint32_t)((j4 ^ sw) << 4), o);
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) tma_store_2d(&tmC, stg + (uint32_t)((s4 & 1) * STG_BOX_BYTES), colw + c, row0);
+            }
+            if (lane == 0) bulk_commit();
+          }
+        } else {
         float mean = 0.f, rstd = 1.f;
         if (do_ln) {
           // pass 1 (N == 256): v = act(acc + bias) (+res); stash v in TMEM; partial row statistics over this warp's 128 columns
@@ -478,6 +563,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
           }
           if (lane == 0) bulk_commit();     // always two groups per tile (an empty group for a half outside the matrix)
         }
+        }   // !rowop
         if (p.side) {
           if (act0) rph0 ^= 1;
           if (act1) rph1 ^= 1;
@@ -553,55 +639,6 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
 #pragma unroll 1
       for (int c = 0; c < 128; c += 32) {
         if (n0 + c0 + c >= p.N) break;  // warp-uniform
-        if (p.rowop != 0) {
-          // MSDA "prepare" folded into the two query projections (Epilogue::rowop): each thread owns one row's 32 consecutive
-          // columns = one head's L*P logits (softmax in registers) or 32 offset components (location arithmetic); fp32 out only
-          uint32_t r[32];
-          tmem_ld32(t_addr + c, r);
-          tmem_ld_wait();
-          float x[32];
-#pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            float bs[8];
-            load8(bcur + c0 + c + g8 * 8, bs);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[g8 * 8 + j] = __uint_as_float(r[g8 * 8 + j]) + bs[j];
-          }
-          if (p.rowop == 1) {
-            float mx = x[0];
-#pragma unroll
-            for (int j = 1; j < 32; ++j) mx = fmaxf(mx, x[j]);
-            float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { x[j] = expf(x[j] - mx); s4[j & 3] += x[j]; }
-            const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = x[j] / sum;
-          } else if (row_ok) {
-            const float* rr = p.ro_ref + grow * p.ro_ref_ld;
-            const int cbase = n0 + c0 + c;
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              float nm[8];
-              load8(p.ro_norm + cbase + g8 * 8, nm);
-              const int4 i0 = *reinterpret_cast<const int4*>(p.ro_idx + cbase + g8 * 8);
-              const int4 i1 = *reinterpret_cast<const int4*>(p.ro_idx + cbase + g8 * 8 + 4);
-              const int ix[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) x[g8 * 8 + j] = rr[ix[j]] + __fdiv_rn(x[g8 * 8 + j], nm[j]);
-            }
-          }
-          if (row_ok) {
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = x[g8 * 8 + j];
-              store8(crow32 + c + g8 * 8, v);
-            }
-          }
-          continue;
-        }
         uint4 rcur[4];
         if (!do_ln) {
 #pragma unroll
@@ -794,8 +831,9 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
   if (epi.res && ((((uintptr_t)epi.res) & 15) || epi.ldr % 8 != 0)) return 1;
   if ((epi.res32 && ((((uintptr_t)epi.res32) & 15) || epi.ldr % 8 != 0)) || (epi.c32 && (((uintptr_t)epi.c32) & 15))) return 1;
   if (epi.ln_g && N != BLOCK_N) return 1;
-  if (epi.rowop && (N % 32 != 0 || !epi.c32 || epi.res || epi.res32 || epi.ln_g || epi.c2 || epi.mul_mode || epi.act != CQVAD_ACT_NONE ||
-                    epi.zero_period || conv || (epi.rowop == 2 && (!epi.ro_ref || !epi.ro_norm || !epi.ro_idx))))
+  if (epi.rowop && (N % 32 != 0 || !epi.c32 || ldc % 4 != 0 || epi.res || epi.res32 || epi.ln_g || epi.c2 || epi.mul_mode ||
+                    epi.act != CQVAD_ACT_NONE || epi.zero_period || conv || epi.dual_gelu ||
+                    (epi.rowop == 2 && (!epi.ro_ref || !epi.ro_norm || N % 96 != 0 || (((uintptr_t)epi.ro_ref) & 15)))))
     return 1;
   if ((epi.c2 || epi.mul_mode) && (epi.ln_g || N % 8 != 0)) return 1;
   if ((epi.c2 && (((uintptr_t)epi.c2) & 15)) || (epi.mul_aux && (((uintptr_t)epi.mul_aux) & 15))) return 1;
@@ -806,7 +844,7 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
   TcParams p{};
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
   p.bias = epi.bias; p.act = epi.act; p.res = (const bf16*)epi.res; p.ldr = epi.ldr; p.res32 = epi.res32; p.c32 = epi.c32;
-  p.rowop = epi.rowop; p.ro_ref = epi.ro_ref; p.ro_ref_ld = epi.ro_ref_ld; p.ro_norm = epi.ro_norm; p.ro_idx = epi.ro_idx;
+  p.rowop = epi.rowop; p.ro_ref = epi.ro_ref; p.ro_norm = epi.ro_norm;
   p.ln_g = epi.ln_g; p.ln_b = epi.ln_b; p.ln_eps = epi.ln_eps;
   p.zero_period = epi.zero_period; p.zero_valid = epi.zero_valid;
   p.c2 = (bf16*)epi.c2; p.c2_act = epi.c2_act; p.mul_aux = (const bf16*)epi.mul_aux; p.mul_mode = epi.mul_mode; p.mul_scale = epi.mul_scale;
@@ -848,11 +886,17 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
   static const bool no_ts = getenv("CQVAD_GEMM_NO_TS") != nullptr;
   const bool dual = epi.dual_gelu;
   if (dual && (!epi.c2 || epi.res || epi.mul_mode || epi.ln_g || epi.zero_period || conv)) return 1;
-  const bool ts = !no_ts && !conv && !epi.c32 && !epi.res32 && (!epi.c2 || dual) && N % 8 == 0 && !(epi.res && epi.mul_mode);
+  const bool ts = epi.rowop || (!no_ts && !conv && !epi.c32 && !epi.res32 && (!epi.c2 || dual) && N % 8 == 0 && !(epi.res && epi.mul_mode));
   if (dual && !ts) return 1;
   const bool extra = p.c2 || p.mul_mode;
   CUtensorMap tmC = tmA, tmR = tmA;
-  if (ts) {
+  if (epi.rowop) {     // fp32 output only: [32 rows x 32 fp32] boxes of the same 128-byte rows
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint64_t sc[1] = {(cuuint64_t)ldc * 4};
+    CQ_TRY(make_tmap_f32(&tmC, epi.c32, 2, dims, sc, box));
+    tmR = tmC;
+  } else if (ts) {
     const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
     const cuuint32_t box[2] = {64, 32};
     const cuuint64_t sc[1] = {(cuuint64_t)ldc * 2};
@@ -871,8 +915,8 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
     }
   }
   static const bool no_lean = getenv("CQVAD_GEMM_NO_LEAN") != nullptr, no_stg1 = getenv("CQVAD_GEMM_NO_STG1") != nullptr;
-  p.lean = ts && !epi.ln_g && epi.zero_period == 0 && epi.mul_mode != 2 && !no_lean;
-  p.stg_single = ts && pair && !p.side && !dual && K >= 8 * BLOCK_K && !no_stg1;   // load-bound shapes only: measured +7..10% at K >= 512, -12% at K = 256 (epilogue-bound)
+  p.lean = ts && !epi.rowop && !epi.ln_g && epi.zero_period == 0 && epi.mul_mode != 2 && !no_lean;
+  p.stg_single = ts && !epi.rowop && pair && !p.side && !dual && K >= 8 * BLOCK_K && !no_stg1;   // load-bound shapes only: measured +7..10% at K >= 512, -12% at K = 256 (epilogue-bound)
   const size_t smem = ts ? SMEM_BYTES_TS : SMEM_BYTES;
 #define CQ_LAUNCH_TC(KERN)                                                                            \
   do {                                                                                                \
