@@ -442,7 +442,15 @@ def main():
     if os.path.exists(tp):
         traffic_tab = json.load(open(tp))
     if classes:
-        dom = max(classes, key=lambda k: classes[k]["ms_per_step"])
+        # candidates: classes that carry at least 2 % of the step's algorithmic bytes or FLOPs.  The small-row classes (localisation
+        # chain, [480 x C] operands, 0.2 % of the work) run on their own stream UNDER the large class-branch kernels: their in-situ
+        # time is mostly queueing behind persistent 148-CTA kernels, not work on the critical path, so they never bound the step.
+        tot_b = sum(c_["mbytes"] for c_ in classes.values()) or 1.0
+        tot_f = sum(c_["gflop"] for c_ in classes.values()) or 1.0
+        for c_ in classes.values():
+            c_["share_of_step_work"] = round(max(c_["mbytes"] / tot_b, c_["gflop"] / tot_f), 4)
+        cand = [k for k in classes if classes[k]["share_of_step_work"] >= 0.02] or list(classes)
+        dom = max(cand, key=lambda k: classes[k]["ms_per_step"])
         c = classes[dom]
         per_launch_ms = c["ms_per_step"] / max(c["launches"], 1)
         if c["bound"] == "tensor":
@@ -453,7 +461,7 @@ def main():
                     "peak_source": peaks["src"] + " HBM copy"}
         roof.update({"traffic": (traffic_tab.get(dom) or {}).get("dram_bytes_per_launch"), "launch_ms": round(per_launch_ms, 5),
                      "launches_per_step": c["launches"], "ms_per_step": c["ms_per_step"],
-                     "selection": "largest ms/step among the kernel classes of this step (see kernel_classes)",
+                     "selection": "largest ms/step among the kernel classes carrying >= 2 % of the step's algorithmic bytes or FLOPs (see kernel_classes)",
                      "timing": "in situ: CUDA events on each kernel's own stream, concurrent streams enabled"})
     else:
         roof = None

@@ -163,10 +163,6 @@ __device__ __forceinline__ void ts_dual_gelu_half(uint32_t t_addr, const float* 
   }
 }
 
-// CTA2 = true: CTA pair (cluster of 2 on one TPC, tcgen05 cta_group::2).  The pair computes two vertically adjacent
-// 128 x 256 output tiles with ONE M = 256 UMMA stream issued by the leader; each CTA loads its own A tile and only HALF of
-// the weight tile, so the weight traffic L2 -> SM halves (the conv / large-K GEMMs were bound by the ~6300 B/clk L2 slice
-// throughput, not by the tensor pipe: B re-reads were 2/3 of the conv's L2 traffic) and the ring holds 6 (TS: 4) k-blocks.
 // Correctly rounded x / n from r = RN(1 / n) without the division instruction sequence: q0 = RN(x r), then two residual
 // corrections q <- RN(q + RN(x - n q) r) (the residual is exact in an FMA).  The first makes q faithful, the second rounds it
 // correctly (Markstein's theorem; quotients in the normal range -- offsets / grid sizes are).  5 FMA-pipe instructions against
@@ -191,6 +187,10 @@ __device__ __forceinline__ void rowop_loc_step(float (&x)[32], const float (&ref
   }
 }
 
+// CTA2 = true: CTA pair (cluster of 2 on one TPC, tcgen05 cta_group::2).  The pair computes two vertically adjacent
+// 128 x 256 output tiles with ONE M = 256 UMMA stream issued by the leader; each CTA loads its own A tile and only HALF of
+// the weight tile, so the weight traffic L2 -> SM halves (the conv / large-K GEMMs were bound by the ~6300 B/clk L2 slice
+// throughput, not by the tensor pipe: B re-reads were 2/3 of the conv's L2 traffic) and the ring holds 6 (TS: 4) k-blocks.
 template <bool EXTRA, bool TS, bool CTA2>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                              const CUtensorMap& tmR, const TcParams& p) {

@@ -165,6 +165,16 @@ struct Trainer {
     wg_used = true;
     return wg_stream();
   }
+  // error path: whatever was already enqueued on the side / weight-gradient streams is ordered before anything the caller
+  // enqueues next on its own stream (e.g. the release of the workspace); errors here are ignored, the first one is reported
+  void join_after_error() {
+    if (mode == PLAN) return;
+    if (two_streams && sync_event(1) && cudaEventRecord(sync_event(1), streams[1]) == cudaSuccess)
+      cudaStreamWaitEvent(st, sync_event(1), 0);
+    if (wg_used && aux_event(43) && cudaEventRecord(aux_event(43), wg_stream()) == cudaSuccess)
+      cudaStreamWaitEvent(st, aux_event(43), 0);
+    wg_used = false;
+  }
   int wgrad_join() {
     if (!wg_used) return 0;
     cudaEvent_t ev = aux_event(43);
@@ -826,6 +836,7 @@ int run_train(const cqvad_decoder_desc* d, const void* const* weights, const Tra
   }
   Trainer<T> t(*d, weights, io, st, a, mode);
   int r = t.run();
+  if (r != 0) t.join_after_error();
   if (need) *need = a.off + 1024;
   return r;
 }
