@@ -42,6 +42,7 @@ struct MlpParams {
   const float* ln_g; const float* ln_b; float ln_eps;
   int zero_period, zero_valid;
   int m_tiles;
+  long long* trace;   // dev tool (CQVAD_MLP_TRACE = device pointer to int64[4096]): pipeline timestamps of CTA 0, tools/trace_mlp.py
   bf16* YT; long ldyt; int yt_rows, yt_pitch;   // optional transposed copy: YT[c][(row/yt_rows)*yt_pitch + row%yt_rows]
 };
 
@@ -54,6 +55,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+
+__device__ __forceinline__ long long mlp_gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define MLP_TRACE(slot, idx, lim) do { if (p.trace && blockIdx.x == 0 && (idx) < (lim)) p.trace[(slot) + (idx)] = mlp_gtimer(); } while (0)
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
@@ -101,8 +109,10 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     if (lane == 0) {
       // ===== TMA producer: loads in exactly the order the MMA warp consumes them =====
       int slot = 0; uint32_t wphase = 0; uint32_t xphase = 0;
+      int tev = 0;
       auto load_w1 = [&](int j) {   // W1 rows [j*64, j*64+64): four k-block boxes [64 k x 64 rows] of 8 KB
         mbar_wait(w_empty + 8 * slot, wphase ^ 1);
+        MLP_TRACE(0, tev, 256); ++tev;
         const uint32_t fb = w_full + 8 * slot;
         mbar_arrive_expect_tx(fb, SLOT_BYTES);
         for (int kb = 0; kb < 4; ++kb) tma_load_2d(sW + slot * SLOT_BYTES + kb * 8192, &tmW1, fb, kb * BK, j * CH);
@@ -135,6 +145,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       int slot = 0; uint32_t wphase = 0, xphase = 0, yphase = 0;
       uint32_t hacc_ph = 0, hs_ph = 0;    // one phase bit per buffer
       bool y_started = false;
+      int e1 = 0, e2 = 0;
       auto gemm2 = [&](int c) {
         const int b = c & (NB - 1);
         if (!y_started) {   // first GEMM2 of the tile: the previous tile's Y epilogue must have drained TMEM
@@ -142,8 +153,10 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           tc_fence_after();
         }
         mbar_wait(hs_full + 8 * b, (hs_ph >> b) & 1u);
+        MLP_TRACE(1024, e2, 256);
         hs_ph ^= 1u << b;
         mbar_wait(w_full + 8 * slot, wphase);
+        MLP_TRACE(1280, e2, 256); ++e2;
         tc_fence_after();
         const uint64_t a_desc = make_smem_desc_sw128(sH + b * HS_BYTES);
         const uint64_t b_desc = make_smem_desc_sw128(sW + slot * SLOT_BYTES);
@@ -162,9 +175,12 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         y_started = false;
         for (int j = 0; j < nch; ++j) {
           const int b = j & (NB - 1);
+          MLP_TRACE(256, e1, 256);
           mbar_wait(hacc_empty + 8 * b, ((hacc_ph >> b) & 1u) ^ 1u);   // epilogue of chunk j-4 has drained TMEM buffer b
+          MLP_TRACE(512, e1, 256);
           hacc_ph ^= 1u << b;
           mbar_wait(w_full + 8 * slot, wphase);
+          MLP_TRACE(768, e1, 256); ++e1;
           tc_fence_after();
           const uint32_t t_h = t_h0 + b * CH;
 #pragma unroll
@@ -201,6 +217,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     // ncu source page of the first version, profiles/)
     float nb = tg < CH ? p.b1[((g + rot) % nch) * CH + tg] : 0.f;
     uint32_t bpar = 0;
+    int ee = 0;
+    const bool trw = lane == 0 && (warp == 2 || warp == 6);
+    const int tbase = 1536 + g * 1024;          // group 0: [1536, 2560), group 1: [2560, 3584)
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
       for (int j = g; j < nch; j += 2) {
         const int b = j & (NB - 1);
@@ -209,7 +228,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         bpar ^= 1;
         asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
         if (tg < CH) nb = p.b1[((((j + 2 < nch) ? (j + 2) : g) + rot) % nch) * CH + tg];
+        if (trw) MLP_TRACE(tbase, ee, 256);
         mbar_wait(hacc_full + 8 * b, (hacc_ph >> b) & 1u);
+        if (trw) MLP_TRACE(tbase + 256, ee, 256);
         hacc_ph ^= 1u << b;
         tc_fence_after();
         mbar_wait(hs_empty + 8 * b, ((hs_ph >> b) & 1u) ^ 1u);   // GEMM2 of chunk j-4 has finished reading Hs[b]
@@ -252,7 +273,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         fence_proxy_async_smem();   // make the st.shared above visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) { mbar_arrive(hacc_empty + 8 * b); mbar_arrive(hs_full + 8 * b); }
+        if (trw) { MLP_TRACE(tbase + 512, ee, 256); ++ee; }
       }
+      if (trw) { MLP_TRACE(tbase + 768, tile / (int)gridDim.x * 2, 256); }
       // ---- final epilogue of the tile: group g owns output columns [g*128, g*128+128) ----
       const long grow = (long)tile * BM + row_in_tile;
       const bool row_ok = grow < p.M;
@@ -360,6 +383,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(y_empty);
+      if (trw) { MLP_TRACE(tbase + 768, tile / (int)gridDim.x * 2 + 1, 256); }
       if (do_ln) asm volatile("bar.sync 1, 256;" ::: "memory");   // stats buffer reuse across tiles
     }
   }
@@ -414,6 +438,7 @@ int mlp_tc(const bf16* X, const bf16* W1, const float* b1, const bf16* W2, const
   p.Y = Y; p.M = M; p.F = F; p.b1 = b1; p.b2 = b2; p.act = act; p.res = res;
   p.ln_g = ln_g; p.ln_b = ln_b; p.ln_eps = ln_eps; p.zero_period = zero_period; p.zero_valid = zero_valid;
   p.m_tiles = (int)((M + BM - 1) / BM);
+  if (const char* tr = getenv("CQVAD_MLP_TRACE")) p.trace = (long long*)strtoull(tr, nullptr, 0);
   p.res32 = res32; p.Y32 = Y32;
   p.YT = YT; p.ldyt = ldyt; p.yt_rows = yt_rows > 0 ? yt_rows : 1; p.yt_pitch = yt_pitch;
   const int grid = p.m_tiles < sms ? p.m_tiles : sms;
