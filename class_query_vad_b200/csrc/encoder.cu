@@ -162,8 +162,10 @@ int enc_layer_t(const void* const* W, const T* src, const T* pos, const float* r
   // bf16 path: softmax and sampling-location arithmetic (msda_prepare) run in the epilogues of the two query projections, straight
   // from the fp32 accumulators -- the raw offsets / logits are never written (1.4 GB of traffic per layer at 4 clips)
   static const bool no_rowop = getenv("CQVAD_ENC_NO_ROWOP") != nullptr;
-  bool prepared = false;
-  if (sizeof(T) == 2 && !no_rowop && L == 4 && P == 8) {
+  // CQVAD_ENC_FUSED=1 (opt-in, measured slower): softmax + location arithmetic inside the SAMPLING kernel instead (msda_fwd_fused)
+  static const bool fused_sampling = getenv("CQVAD_ENC_FUSED") != nullptr;
+  bool prepared = false, sampled = false;
+  if (sizeof(T) == 2 && !no_rowop && !fused_sampling && L == 4 && P == 8) {
     prepared = msda_projections_prepared((const bf16*)q, (const bf16*)Wm(E_OFF_W), Wf(E_OFF_B), (const bf16*)Wm(E_ATT_W), Wf(E_ATT_B), refp,
                                          shapes, loc, attn, col_norm, rows, st);
   }
@@ -172,10 +174,17 @@ int enc_layer_t(const void* const* W, const T* src, const T* pos, const float* r
     // locations carry no bf16 rounding of their own
     { Epilogue e; e.bias = Wf(E_OFF_B); if (sizeof(T) == 2) e.c32 = off32; CQ_TRY(gemm<T>(q, kC, Wm(E_OFF_W), offT, LP3, rows, LP3, kC, e, nullptr, st)); }
     { Epilogue e; e.bias = Wf(E_ATT_B); if (sizeof(T) == 2) e.c32 = lg32; CQ_TRY(gemm<T>(q, kC, Wm(E_ATT_W), lgT, LP1, rows, LP1, kC, e, nullptr, st)); }
-    msda_prepare_kernel<<<(unsigned)cdiv(rows * kM * 32, 256), 256, 0, st>>>(off32, lg32, refp, shapes, loc, attn, rows, L, P);
-    CQ_LAUNCH_CHECK();
+    if (fused_sampling) {
+      const int fr = msda_fwd_fused(DT<T>::id, value, shapes, lsi, off32, lg32, refp, samp, B, (int)Len, kM, kC / kM, L, (int)Len, P, st);
+      if (fr < 0) return fr;
+      sampled = fr == 0;
+    }
+    if (!sampled) {
+      msda_prepare_kernel<<<(unsigned)cdiv(rows * kM * 32, 256), 256, 0, st>>>(off32, lg32, refp, shapes, loc, attn, rows, L, P);
+      CQ_LAUNCH_CHECK();
+    }
   }
-  CQ_TRY(cqvad_msda3d_forward(DT<T>::id, value, shapes, lsi, loc, attn, samp, B, (int)Len, kM, kC / kM, L, (int)Len, P, (void*)st));
+  if (!sampled) CQ_TRY(cqvad_msda3d_forward(DT<T>::id, value, shapes, lsi, loc, attn, samp, B, (int)Len, kM, kC / kM, L, (int)Len, P, (void*)st));
   if (attn_out) {   // the module's own output (tests): output_proj(samp)
     Epilogue e; e.bias = Wf(E_OUT_B);
     CQ_TRY(gemm<T>(samp, kC, Wm(E_OUT_W), attn_out, kC, rows, kC, kC, e, nullptr, st));

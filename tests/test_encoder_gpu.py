@@ -103,6 +103,45 @@ def test_encoder_layer_fused_sampling_variant_matches_reference():
     assert r.returncode == 0 and "fused ok" in r.stdout, r.stderr[-2000:]
 
 
+def test_encoder_projection_epilogues_match_unfused_path_at_full_size(tmp_path):
+    """bf16 layer forward on the full 33 320-token pyramid: the default path (softmax / sampling locations computed in the epilogues
+    of the two query projections, Epilogue::rowop) against the unfused sequence (fp32 side outputs -> msda_prepare with IEEE
+    division and expf -> sampling), selected by CQVAD_ENC_NO_ROWOP=1 (read once per process, hence a subprocess).  The locations
+    are bit-identical by construction (exact quotient); the attention weights differ by ~2 ulp (__expf, reciprocal), which can flip
+    a bf16 rounding of the sampled values here and there."""
+    import os, subprocess, sys
+    code = ("import sys, numpy as np, torch; sys.path.insert(0, 'tests'); "
+            "from test_encoder_gpu import _full_pyramid_forward; "
+            "out = _full_pyramid_forward(); np.save(sys.argv[1], out.float().cpu().numpy()); print('saved')")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = str(tmp_path / "unfused.npy")
+    r = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=dict(os.environ, CQVAD_ENC_NO_ROWOP="1"), capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "saved" in r.stdout, r.stderr[-2000:]
+    ref = np.load(path)
+    out = _full_pyramid_forward().float().cpu().numpy()
+    assert out.shape == ref.shape and out.shape[1] == 33320
+    assert rel_err(out, ref) < 5e-3
+    assert (out == ref).mean() > 0.98          # all but a few bf16 roundings are identical
+
+
+def _full_pyramid_forward():
+    from class_query_vad_b200 import pack_encoder_layer_weights, encoder_layer_forward
+    from oracle import encoder_np
+    shapes = [(8, 56, 56), (8, 28, 28), (8, 14, 14), (8, 7, 7)]
+    Wn = synth.make_encoder_layer_weights(2048, 4, 8, seed=5)
+    inp = synth.make_encoder_inputs(1, shapes, seed=5)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    packed = pack_encoder_layer_weights({k: torch.from_numpy(v) for k, v in Wn.items()}, torch.bfloat16, dev)
+    refp = t(encoder_np.reference_points(shapes, inp["valid_ratios"]))
+    sh = torch.tensor(shapes, dtype=torch.int64, device=dev)
+    ls = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+    out = encoder_layer_forward(packed, t(inp["src"]).bfloat16(), t(inp["pos"]).bfloat16(), refp, sh, ls, None, 8, 2048)
+    torch.cuda.synchronize()
+    return out
+
+
 ENC_GRAD_CASES = ["enc_grad_tiny", "enc_grad_small_masked"]
 
 
