@@ -31,7 +31,8 @@ constexpr int HS_BYTES = BM * CH * 2;          // 16 KB: one k-block [128 x 64]
 constexpr int SLOT_BYTES = 32 * 1024;          // W1 chunk: 4 k-blocks of [64 x 64]; W2 chunk: one k-block of [256 x 64]
 constexpr int SLOTS = 3;
 constexpr int SMEM_DATA = X_BYTES + NB * HS_BYTES + SLOTS * SLOT_BYTES;   // 229 376
-constexpr int SMEM_AUX = 256 /*barriers*/ + 1024 /*b1 chunk, double buffered: [2 groups][2][64] f32*/;
+constexpr int SMEM_AUX = 256 /*barriers*/ + 2048 /*b1 chunk, double buffered: [2 groups][2][64] f32; the LN statistics [2][128][2] f32 of the
+                                                      Y epilogue alias it (the chunk epilogues are over by then)*/ + 64 /*residual barriers*/;
 constexpr int SMEM_BYTES = SMEM_DATA + SMEM_AUX;   // <= 227 KB; the dynamic buffer is declared 1024-aligned (no slack)
 constexpr int NUM_THREADS = 320;
 
@@ -42,6 +43,8 @@ struct MlpParams {
   const float* ln_g; const float* ln_b; float ln_eps;
   int zero_period, zero_valid;
   int m_tiles;
+  int ts_res;         // with ts_out: the bf16 residual arrives as TMA boxes in the same staging (in-place epilogue)
+  int ts_out;         // Y leaves through shared-memory staging + TMA stores (plain bf16 output: no Y32 / YT copies)
   long long* trace;   // dev tool (CQVAD_MLP_TRACE = device pointer to int64[4096]): pipeline timestamps of CTA 0, tools/trace_mlp.py
   bf16* YT; long ldyt; int yt_rows, yt_pitch;   // optional transposed copy: YT[c][(row/yt_rows)*yt_pitch + row%yt_rows]
 };
@@ -65,7 +68,8 @@ __device__ __forceinline__ long long mlp_gtimer() {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-              const __grid_constant__ CUtensorMap tmW2, const MlpParams p) {
+              const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY,
+              const __grid_constant__ CUtensorMap tmR, const MlpParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);   // 1024-byte aligned (128-B swizzle atoms)
   const uint32_t sX = base, sH = base + X_BYTES, sW = sH + NB * HS_BYTES;
@@ -78,8 +82,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   const uint32_t y_full = bars + 192, y_empty = bars + 200;
   const uint32_t tmem_slot = bars + 208;
   const uint32_t b1s = bars + 256;                                     // float[2 groups][2][64]: b1 of the chunk in flight
-  // LN partial sums float[2][128][2] alias the first 2 KB of Hs[0]: all GEMM2 reads of Hs are complete once y_full fires
-  const uint32_t stats = sH;
+  // LN partial sums float[2][128][2] alias the b1 staging buffers (+1 KB): no chunk epilogue runs during the Y epilogue
+  const uint32_t stats = b1s;
+  const uint32_t rbar_base = bars + 256 + 2048;                        // one per epilogue warp: the residual boxes have landed
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = p.F / CH;
   // (a per-CTA rotation of the chunk order was tried against L2 hot-spotting: no gain on B200, and it makes the fp32
@@ -95,6 +100,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       mbar_init(hs_full + 8 * b, 4); mbar_init(hs_empty + 8 * b, 1);
     }
     mbar_init(y_full, 1); mbar_init(y_empty, 8);
+    for (int i = 0; i < 8; ++i) mbar_init(rbar_base + 8 * i, 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -216,7 +222,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     // read back as broadcast LDS.128 (a global load per 8 columns left the epilogue exposed to the full L2 latency:
     // ncu source page of the first version, profiles/)
     float nb = tg < CH ? p.b1[((g + rot) % nch) * CH + tg] : 0.f;
-    uint32_t bpar = 0;
+    uint32_t bpar = 0, rphase = 0;
     int ee = 0;
     const bool trw = lane == 0 && (warp == 2 || warp == 6);
     const int tbase = 1536 + g * 1024;          // group 0: [1536, 2560), group 1: [2560, 3584)
@@ -275,14 +281,15 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         if (lane == 0) { mbar_arrive(hacc_empty + 8 * b); mbar_arrive(hs_full + 8 * b); }
         if (trw) { MLP_TRACE(tbase + 512, ee, 256); ++ee; }
       }
-      if (trw) { MLP_TRACE(tbase + 768, tile / (int)gridDim.x * 2, 256); }
+      const int tix = tile / (int)gridDim.x * 8;
+      if (trw) { MLP_TRACE(tbase + 768, tix, 256); }
       // ---- final epilogue of the tile: group g owns output columns [g*128, g*128+128) ----
       const long grow = (long)tile * BM + row_in_tile;
       const bool row_ok = grow < p.M;
       // The bf16 residual is fetched one 32-column step ahead (4 x 16 bytes in flight per thread): one exposed L2 round
       // trip per step instead of one per 8 columns (ncu: 18% of all stall samples sat on these loads while Y blocked the
       // next tile).  Hoisting all 16 loads above the y_full wait was tried and lost to register spills.
-      const bool res_bf16 = p.res != nullptr && p.res32 == nullptr && row_ok;
+      const bool res_bf16 = p.res != nullptr && p.res32 == nullptr && row_ok && !p.ts_res;
       const uint4* rp = reinterpret_cast<const uint4*>(p.res + (res_bf16 ? grow * C + g * 128 : 0));
       uint4 rnext[4];
 #pragma unroll
@@ -290,11 +297,33 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       mbar_wait(y_full, yphase);
       yphase ^= 1;
       tc_fence_after();
+      if (trw) { MLP_TRACE(tbase + 768, tix + 1, 256); }
+      // TMA-store epilogue: this warp's rows [q*32, +32) x its group's 128 columns = two [32 x 64] bf16 boxes (128-byte rows, 128-byte
+      // swizzle) staged in the H tiles, which are idle from y_full until the next tile's first chunk epilogue; the bf16 residual is
+      // fetched into the same boxes (one exposed TMA round trip per tile) and the result overwrites it in place.  One row per
+      // thread straight from / to global memory cost 32 L1 wavefronts per 16-byte instruction and one L2 round trip per 32-column
+      // step (measured: 8.9 us of a 31 us tile).
+      const uint32_t ystg = sH + (uint32_t)((warp - 2) * 8192);
+      const uint32_t ymy = ystg + (uint32_t)(lane * 128);
+      const int ysw = lane & 7;
+      if (p.ts_res) {
+        const uint32_t rb = rbar_base + (uint32_t)((warp - 2) * 8);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(rb, 8192);
+          tma_load_2d(ystg, &tmR, rb, g * 128, tile * BM + q * 32);
+          tma_load_2d(ystg + 4096, &tmR, rb, g * 128 + 64, tile * BM + q * 32);
+        }
+        mbar_wait(rb, rphase);
+        rphase ^= 1;
+        if (trw) { MLP_TRACE(tbase + 768, tix + 5, 256); }
+      }
       const bool zero_row = p.zero_period > 0 && (int)(grow % p.zero_period) >= p.zero_valid;
       const uint32_t t_yrow = t_y + lane_off + g * 128;
       const int col0 = g * 128;
       const bool do_ln = p.ln_g != nullptr;
       float mean = 0.f, rstd = 1.f;
+      // address of the 16-byte chunk holding columns [c + 8 g8, +8) of this thread's row inside the warp's two staging boxes
+      auto ychunk = [&](int c, int g8) { return ymy + (uint32_t)((c >> 6) * 4096) + (uint32_t)(((((c & 63) >> 3) + g8) ^ ysw) << 4); };
       if (do_ln) {
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
@@ -313,7 +342,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           for (int g8 = 0; g8 < 4; ++g8) {
             float bs[8], rs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             load8(p.b2 + col0 + c + g8 * 8, bs);
-            if (p.res32) { if (row_ok) load8(p.res32 + grow * C + col0 + c + g8 * 8, rs); }
+            if (p.ts_res) unpack8(lds128(ychunk(c, g8)), rs);
+            else if (p.res32) { if (row_ok) load8(p.res32 + grow * C + col0 + c + g8 * 8, rs); }
             else unpack8(rcur[g8], rs);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -325,6 +355,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           tmem_st32(t_yrow + c, r);
         }
         tmem_st_wait();
+        if (trw) { MLP_TRACE(tbase + 768, tix + 2, 256); }
         stats_f[(g * 128 + row_in_tile) * 2] = s1;
         stats_f[(g * 128 + row_in_tile) * 2 + 1] = s2;
         asm volatile("bar.sync 1, 256;" ::: "memory");   // the two epilogue groups (8 warps)
@@ -332,7 +363,45 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         mean = (s1 + o1) * (1.0f / C);
         const float var = fmaxf((s2 + o2) * (1.0f / C) - mean * mean, 0.f);
         rstd = rsqrtf(var + p.ln_eps);
+        if (trw) { MLP_TRACE(tbase + 768, tix + 3, 256); }
       }
+      if (p.ts_out) {
+        // lean store pass (plain bf16 output): no per-output branches or 64-bit address arithmetic in the inner loop
+        const float zm = zero_row ? 0.f : 1.f;
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_yrow + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const int cb = col0 + c + g8 * 8;
+            const uint32_t addr = ychunk(c, g8);
+            float v[8];
+            if (do_ln) {
+              float gm[8], bt[8];
+              load8(p.ln_g + cb, gm);
+              load8(p.ln_b + cb, bt);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = ((__uint_as_float(r[g8 * 8 + e]) - mean) * rstd * gm[e] + bt[e]) * zm;
+            } else {
+              float bs[8], rs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+              load8(p.b2 + cb, bs);
+              if (p.ts_res) unpack8(lds128(addr), rs);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = (__uint_as_float(r[g8 * 8 + e]) + bs[e] + rs[e]) * zm;
+            }
+            uint4 o;
+            o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+            sts128(addr, o);
+          }
+          if (c & 32) {     // a 64-column box is complete
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&tmY, ystg + (uint32_t)((c >> 6) * 4096), col0 + (c >> 6) * 64, tile * BM + q * 32); bulk_commit(); }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < 128; c += 32) {
         uint4 rcur[4];
@@ -380,11 +449,17 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           }
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(y_empty);
-      if (trw) { MLP_TRACE(tbase + 768, tile / (int)gridDim.x * 2 + 1, 256); }
-      if (do_ln) asm volatile("bar.sync 1, 256;" ::: "memory");   // stats buffer reuse across tiles
+      if (trw) { MLP_TRACE(tbase + 768, tix + 4, 256); }
+      if (p.ts_out) {   // the stores have read the staging boxes before any warp's next chunk epilogue writes the H tiles
+        if (lane == 0) bulk_wait_read<0>();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      } else if (do_ln) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // stats buffer reuse across tiles
+      }
     }
   }
 
@@ -415,7 +490,17 @@ int mlp_tc(const bf16* X, const bf16* W1, const float* b1, const bf16* W2, const
     CQ_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     g_attr_set = true;
   }
-  CUtensorMap tmX, tmW1, tmW2;
+  CUtensorMap tmX, tmW1, tmW2, tmY, tmR;
+  static const bool no_ts_out = getenv("CQVAD_MLP_NO_TS") != nullptr;
+  const bool ts_out = !no_ts_out && !YT && !Y32;
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    const cuuint32_t box[2] = {64, 32};
+    CQ_TRY(make_tmap_bf16(&tmY, Y, 2, dims, strides, box));
+    tmR = tmY;
+    if (ts_out && res && !res32) CQ_TRY(make_tmap_bf16(&tmR, res, 2, dims, strides, box));
+  }
   {
     const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)M};
     const cuuint64_t strides[1] = {(cuuint64_t)C * 2};
@@ -439,10 +524,10 @@ int mlp_tc(const bf16* X, const bf16* W1, const float* b1, const bf16* W2, const
   p.ln_g = ln_g; p.ln_b = ln_b; p.ln_eps = ln_eps; p.zero_period = zero_period; p.zero_valid = zero_valid;
   p.m_tiles = (int)((M + BM - 1) / BM);
   if (const char* tr = getenv("CQVAD_MLP_TRACE")) p.trace = (long long*)strtoull(tr, nullptr, 0);
-  p.res32 = res32; p.Y32 = Y32;
+  p.res32 = res32; p.Y32 = Y32; p.ts_out = ts_out ? 1 : 0; p.ts_res = (ts_out && res && !res32) ? 1 : 0;
   p.YT = YT; p.ldyt = ldyt; p.yt_rows = yt_rows > 0 ? yt_rows : 1; p.yt_pitch = yt_pitch;
   const int grid = p.m_tiles < sms ? p.m_tiles : sms;
-  mlp_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmX, tmW1, tmW2, p);
+  mlp_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmX, tmW1, tmW2, tmY, tmR, p);
   CQ_LAUNCH_CHECK();
   return 0;
 }

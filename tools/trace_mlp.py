@@ -37,4 +37,5 @@ for gi, base in ((0, 1536), (1, 2560)):
     print(f"epi group {gi} chunk wait begins :", seg(base, n // 2))
     print(f"epi group {gi} hacc_full passed  :", seg(base + 256, n // 2))
     print(f"epi group {gi} chunk done        :", seg(base + 512, n // 2))
-    print(f"epi group {gi} [Y epilogue begin, end] per tile:", seg(base + 768, 8))
+    for tl in range(3):
+        print(f"epi group {gi} tile {tl} Y epilogue [chunks done, y_full passed, LN pass 1 done, stats exchanged, stores issued, residual landed]:", seg(base + 768 + 8 * tl, 6))
