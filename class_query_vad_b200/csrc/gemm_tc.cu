@@ -191,7 +191,9 @@ __device__ __forceinline__ void rowop_loc_step(float (&x)[32], const float (&ref
 // 128 x 256 output tiles with ONE M = 256 UMMA stream issued by the leader; each CTA loads its own A tile and only HALF of
 // the weight tile, so the weight traffic L2 -> SM halves (the conv / large-K GEMMs were bound by the ~6300 B/clk L2 slice
 // throughput, not by the tensor pipe: B re-reads were 2/3 of the conv's L2 traffic) and the ring holds 6 (TS: 4) k-blocks.
-template <bool EXTRA, bool TS, bool CTA2>
+// ROWOP = true: the Epilogue::rowop instantiation (softmax / sampling-location epilogues of the encoder's query projections), kept
+// out of the other kernels so that their epilogues carry none of its registers (154 instead of 126 with it compiled in).
+template <bool EXTRA, bool TS, bool CTA2, bool ROWOP = false>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                              const CUtensorMap& tmR, const TcParams& p) {
   // ring depth: pair 6 (TS: 4, or 5 with single-buffered output staging when there is no side input), single CTA 4 (TS: 3)
@@ -366,7 +368,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
         const long grow = (long)row0 + lane;
         const bool zero_row = p.zero_period > 0 && (int)(grow % p.zero_period) >= p.zero_valid;
-        if (p.rowop != 0) {
+        if constexpr (ROWOP) {
           // MSDA "prepare" folded into the two query projections (Epilogue::rowop): each thread owns one row's 32 consecutive
           // columns per step = one head's 32 attention logits (softmax in registers) or 32 offset components (location
           // arithmetic).  fp32 output through the staging boxes: a [32 rows x 32 fp32] box has the 128-byte rows of the bf16
@@ -427,6 +429,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
             if (lane == 0) bulk_commit();
           }
         } else {
+          (void)zero_row;
         float mean = 0.f, rstd = 1.f;
         if (do_ln) {
           // pass 1 (N == 256): v = act(acc + bias) (+res); stash v in TMEM; partial row statistics over this warp's 128 columns
@@ -764,6 +767,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
   gemm_tc_body<EXTRA, TS, true>(tmA, tmB, tmC, tmR, p);
 }
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_rowop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
+  gemm_tc_body<false, true, false, true>(tmA, tmB, tmC, tmR, p);
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tc2_rowop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
+  gemm_tc_body<false, true, true, true>(tmA, tmB, tmC, tmR, p);
+}
 
 // ---- host side ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -791,6 +804,8 @@ void init_once() {
   if (cudaFuncSetAttribute(gemm_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) g_init_err = 2;
   if (cudaFuncSetAttribute(gemm_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
   if (cudaFuncSetAttribute(gemm_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc_rowop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc2_rowop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
 }
 
 }  // namespace
@@ -925,7 +940,10 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
     else if (ts) KERN<false, true><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);            \
     else KERN<false, false><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);                   \
   } while (0)
-  if (pair) CQ_LAUNCH_TC(gemm_tc2_kernel);
+  if (epi.rowop) {
+    if (pair) gemm_tc2_rowop_kernel<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);
+    else gemm_tc_rowop_kernel<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);
+  } else if (pair) CQ_LAUNCH_TC(gemm_tc2_kernel);
   else CQ_LAUNCH_TC(gemm_tc_kernel);
 #undef CQ_LAUNCH_TC
   CQ_LAUNCH_CHECK();
