@@ -117,3 +117,49 @@ def test_gradient_bucket_layout_is_one_contiguous_bucket_per_layer():
         assert lo <= offs[i] and offs[i] + sizes[i] <= hi, name
     spans = sorted((int(offs[i]), int(offs[i]) + sizes[i]) for i in range(n))
     assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))          # no two gradients overlap
+
+
+def _wire_worker(rank, world, port, n_clips, out_dir, q):
+    """Evaluation loop of the N>1 path end to end on the host side: shard -> per-rank detections -> all-gather -> rank 0 writes the
+    reference's text file and the binary dump (class_query_vad_b200/detections.py)."""
+    import numpy as np
+    from class_query_vad_b200.detections import save_detections, write_reference_text
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        K, nq = 6, 3
+        g = torch.Generator().manual_seed(99)
+        full = torch.rand(n_clips, nq, K + 5, generator=g)          # [scores | boxes | person] of every clip
+        lo, hi = shard_range(n_clips, world, rank)
+        det = gather_detections(full[lo:hi].contiguous(), n_clips_total=n_clips)
+        if rank == 0:
+            ids = [f"v{b},{b:04d}" for b in range(n_clips)]
+            write_reference_text(os.path.join(out_dir, "0.txt"), ids, det, K)
+            save_detections(os.path.join(out_dir, "det.npz"), ids, det, K)
+            q.put(bool(torch.equal(det, full)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_detection_wire_format_world2_gloo(tmp_path):
+    import numpy as np
+    from class_query_vad_b200.detections import load_detections, read_reference_text
+    n_clips, K, nq = 5, 6, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_wire_worker, args=(r, 2, port, n_clips, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get() is True
+    full = torch.rand(n_clips, nq, K + 5, generator=torch.Generator().manual_seed(99)).numpy()
+    ids, det = load_detections(tmp_path / "det.npz")
+    assert ids == [f"v{b},{b:04d}" for b in range(n_clips)] and np.array_equal(det, full)
+    lid, boxes, scores, person = read_reference_text(tmp_path / "0.txt", K)
+    flat = full.reshape(-1, K + 5).astype(np.float64)
+    assert lid == [i for i in ids for _ in range(nq)]
+    assert np.array_equal(boxes, flat[:, K:K + 4]) and np.array_equal(scores, flat[:, :K]) and np.array_equal(person, flat[:, K + 4])
