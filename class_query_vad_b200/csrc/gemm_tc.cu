@@ -193,7 +193,10 @@ __device__ __forceinline__ void rowop_loc_step(float (&x)[32], const float (&ref
 // throughput, not by the tensor pipe: B re-reads were 2/3 of the conv's L2 traffic) and the ring holds 6 (TS: 4) k-blocks.
 // ROWOP = true: the Epilogue::rowop instantiation (softmax / sampling-location epilogues of the encoder's query projections), kept
 // out of the other kernels so that their epilogues carry none of its registers (154 instead of 126 with it compiled in).
-template <bool EXTRA, bool TS, bool CTA2, bool ROWOP = false>
+// SPEC (TMA-store kernels): 0 = every epilogue option, 1 = the lean half-tile epilogues only (bias, ReLU / GELU, bf16 residual or
+// activation-derivative operand: most launches of a training step), 2 = the dual-GELU epilogue only -- the all-options kernel is
+// ~9 000 SASS instructions (146 KB, far beyond the instruction cache), its specialisations a fraction of that.
+template <bool EXTRA, bool TS, bool CTA2, bool ROWOP = false, int SPEC = 0>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                              const CUtensorMap& tmR, const TcParams& p) {
   // ring depth: pair 6 (TS: 4, or 5 with single-buffered output staging when there is no side input), single CTA 4 (TS: 3)
@@ -325,7 +328,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
     float* aux = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)));
     float* bias_s = aux + AUX_BIAS / 4; float* gam_s = aux + AUX_GAM / 4; float* bet_s = aux + AUX_BET / 4;
     float* stats_s = aux + AUX_STATS / 4;
-    const bool do_ln = p.ln_g != nullptr;
+    const bool do_ln = SPEC == 0 && p.ln_g != nullptr;
     if (do_ln) { gam_s[et] = p.ln_g[et]; bet_s[et] = p.ln_b[et]; }   // N == 256, one n-tile
     int acc = 0; uint32_t acc_phase = 0;
     int etile = 0;
@@ -479,18 +482,19 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
             if (p.stg_single && hf == 1) { if (lane == 0) bulk_wait_read<0>(); __syncwarp(); }
             if (p.side && !do_ln) mbar_wait(rbar + 8 * hf, hf ? rph1 : rph0);
             CQ_TRACE_E(1 + hf * 6);
-            if (p.dual) {
+            if (SPEC == 2 || (SPEC == 0 && p.dual)) {
               // both boxes of this warp are reused by the second half: its stores must have read them
               if (hf == 1) { if (lane == 0) bulk_wait_read<0>(); __syncwarp(); }
               ts_dual_gelu_half(t_addr + hf * 64, bcur + c0 + hf * 64, my_row, my_row + STG_BOX_BYTES, sw);
-            } else if (p.lean) {
+            } else if (SPEC == 1 || (SPEC == 0 && p.lean)) {
               const float lo = p.act == CQVAD_ACT_RELU ? 0.f : -INFINITY;
               const bool ge = p.act == CQVAD_ACT_GELU;
-              if (p.side == 0) ts_lean_half<0>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge);
-              else if (p.side == 1) ts_lean_half<1>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge);
-              else if (p.mul_mode == 1) ts_lean_half<2>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge, p.mul_scale);
-              else ts_lean_half<3>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge);
-            } else {
+              // specialised kernels: the side-input variants (0 / 1) live in the EXTRA = false instantiation, the multiply variants in EXTRA = true
+              if ((SPEC == 0 || !EXTRA) && p.side == 0) ts_lean_half<0>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge);
+              else if ((SPEC == 0 || !EXTRA) && p.side == 1) ts_lean_half<1>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge);
+              else if ((SPEC == 0 || EXTRA) && p.mul_mode == 1) ts_lean_half<2>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge, p.mul_scale);
+              else if (SPEC == 0 || EXTRA) ts_lean_half<3>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge);
+            } else if constexpr (SPEC == 0) {
 #pragma unroll 1
             for (int cc = 0; cc < 64; cc += 32) {
               const int c = hf * 64 + cc;
@@ -555,7 +559,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              if (p.dual) {
+              if (SPEC == 2 || (SPEC == 0 && p.dual)) {
                 tma_store_2d(&tmC, stg, colw + hf * 64, row0);
                 tma_store_2d(&tmR, stg + STG_BOX_BYTES, colw + hf * 64, row0);   // tmR carries the second output here
               } else {
@@ -767,6 +771,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
   gemm_tc_body<EXTRA, TS, true>(tmA, tmB, tmC, tmR, p);
 }
+template <bool EXTRA, int SPEC>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_spec_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
+  gemm_tc_body<EXTRA, true, false, false, SPEC>(tmA, tmB, tmC, tmR, p);
+}
+template <bool EXTRA, int SPEC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tc2_spec_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
+  gemm_tc_body<EXTRA, true, true, false, SPEC>(tmA, tmB, tmC, tmR, p);
+}
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_rowop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
@@ -805,6 +821,12 @@ void init_once() {
   if (cudaFuncSetAttribute(gemm_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
   if (cudaFuncSetAttribute(gemm_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
   if (cudaFuncSetAttribute(gemm_tc_rowop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc_spec_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc_spec_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc_spec_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc2_spec_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc2_spec_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc2_spec_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
   if (cudaFuncSetAttribute(gemm_tc2_rowop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
 }
 
@@ -940,9 +962,18 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
     else if (ts) KERN<false, true><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);            \
     else KERN<false, false><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);                   \
   } while (0)
+  static const bool no_spec = getenv("CQVAD_GEMM_NO_SPEC") != nullptr;
   if (epi.rowop) {
     if (pair) gemm_tc2_rowop_kernel<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);
     else gemm_tc_rowop_kernel<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);
+  } else if (ts && !no_spec && p.dual) {          // dual-GELU epilogue only
+    if (pair) gemm_tc2_spec_kernel<true, 2><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);
+    else gemm_tc_spec_kernel<true, 2><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);
+  } else if (ts && !no_spec && p.lean) {          // lean half-tile epilogues only
+    if (pair) { if (extra) gemm_tc2_spec_kernel<true, 1><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);
+                else gemm_tc2_spec_kernel<false, 1><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p); }
+    else { if (extra) gemm_tc_spec_kernel<true, 1><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);
+           else gemm_tc_spec_kernel<false, 1><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p); }
   } else if (pair) CQ_LAUNCH_TC(gemm_tc2_kernel);
   else CQ_LAUNCH_TC(gemm_tc_kernel);
 #undef CQ_LAUNCH_TC
