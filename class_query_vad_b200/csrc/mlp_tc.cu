@@ -66,10 +66,12 @@ __device__ __forceinline__ long long mlp_gtimer() {
 }
 #define MLP_TRACE(slot, idx, lim) do { if (p.trace && blockIdx.x == 0 && (idx) < (lim)) p.trace[(slot) + (idx)] = mlp_gtimer(); } while (0)
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-              const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY,
-              const __grid_constant__ CUtensorMap tmR, const MlpParams p) {
+// SPEC: 0 = every option at run time (fp32 residual / fp32 + transposed copies of the class FFN, direct stores), 1 = GELU, no LN,
+// TMA output (ConvBlock), 2 = ReLU + LN, TMA output (the FFNs).  The all-options kernel is 5 200 SASS instructions (84 KB); what a
+// launch does not use is compiled out of its specialisation (the same lesson as the GEMM's lean / dual-GELU instantiations).
+template <int SPEC>
+__device__ __forceinline__ void mlp_tc_body(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmY,
+                                            const CUtensorMap& tmR, const MlpParams& p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);   // 1024-byte aligned (128-B swizzle atoms)
   const uint32_t sX = base, sH = base + X_BYTES, sW = sH + NB * HS_BYTES;
@@ -254,7 +256,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             float bs[8];
             load8(b1 + g8 * 8, bs);
             uint32_t pk[4];
-            if (p.act == CQVAD_ACT_GELU) {
+            if (SPEC == 1 || (SPEC == 0 && p.act == CQVAD_ACT_GELU)) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const uint64_t x2 = f2add(f2pack(__uint_as_float(r[g8 * 8 + 2 * e]), __uint_as_float(r[g8 * 8 + 2 * e + 1])),
@@ -289,7 +291,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       // The bf16 residual is fetched one 32-column step ahead (4 x 16 bytes in flight per thread): one exposed L2 round
       // trip per step instead of one per 8 columns (ncu: 18% of all stall samples sat on these loads while Y blocked the
       // next tile).  Hoisting all 16 loads above the y_full wait was tried and lost to register spills.
-      const bool res_bf16 = p.res != nullptr && p.res32 == nullptr && row_ok && !p.ts_res;
+      const bool res_bf16 = SPEC == 0 && p.res != nullptr && p.res32 == nullptr && row_ok && !p.ts_res;
       const uint4* rp = reinterpret_cast<const uint4*>(p.res + (res_bf16 ? grow * C + g * 128 : 0));
       uint4 rnext[4];
 #pragma unroll
@@ -320,7 +322,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       const bool zero_row = p.zero_period > 0 && (int)(grow % p.zero_period) >= p.zero_valid;
       const uint32_t t_yrow = t_y + lane_off + g * 128;
       const int col0 = g * 128;
-      const bool do_ln = p.ln_g != nullptr;
+      const bool do_ln = SPEC == 2 || (SPEC == 0 && p.ln_g != nullptr);
       float mean = 0.f, rstd = 1.f;
       // address of the 16-byte chunk holding columns [c + 8 g8, +8) of this thread's row inside the warp's two staging boxes
       auto ychunk = [&](int c, int g8) { return ymy + (uint32_t)((c >> 6) * 4096) + (uint32_t)(((((c & 63) >> 3) + g8) ^ ysw) << 4); };
@@ -343,8 +345,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             float bs[8], rs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             load8(p.b2 + col0 + c + g8 * 8, bs);
             if (p.ts_res) unpack8(lds128(ychunk(c, g8)), rs);
-            else if (p.res32) { if (row_ok) load8(p.res32 + grow * C + col0 + c + g8 * 8, rs); }
-            else unpack8(rcur[g8], rs);
+            else if (SPEC == 0 && p.res32) { if (row_ok) load8(p.res32 + grow * C + col0 + c + g8 * 8, rs); }
+            else if (SPEC == 0) unpack8(rcur[g8], rs);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const float v = __uint_as_float(r[g8 * 8 + e]) + bs[e] + rs[e];
@@ -365,7 +367,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         rstd = rsqrtf(var + p.ln_eps);
         if (trw) { MLP_TRACE(tbase + 768, tix + 3, 256); }
       }
-      if (p.ts_out) {
+      if (SPEC != 0 || p.ts_out) {
         // lean store pass (plain bf16 output): no per-output branches or 64-bit address arithmetic in the inner loop
         const float zm = zero_row ? 0.f : 1.f;
 #pragma unroll 1
@@ -401,7 +403,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             if (lane == 0) { tma_store_2d(&tmY, ystg + (uint32_t)((c >> 6) * 4096), col0 + (c >> 6) * 64, tile * BM + q * 32); bulk_commit(); }
           }
         }
-      } else {
+      } else if constexpr (SPEC == 0) {
 #pragma unroll 1
       for (int c = 0; c < 128; c += 32) {
         uint4 rcur[4];
@@ -454,7 +456,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       __syncwarp();
       if (lane == 0) mbar_arrive(y_empty);
       if (trw) { MLP_TRACE(tbase + 768, tix + 4, 256); }
-      if (p.ts_out) {   // the stores have read the staging boxes before any warp's next chunk epilogue writes the H tiles
+      if (SPEC != 0 || p.ts_out) {   // the stores have read the staging boxes before any warp's next chunk epilogue writes the H tiles
         if (lane == 0) bulk_wait_read<0>();
         asm volatile("bar.sync 1, 256;" ::: "memory");
       } else if (do_ln) {
@@ -472,6 +474,14 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   }
 }
 
+template <int SPEC>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+              const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY,
+              const __grid_constant__ CUtensorMap tmR, const MlpParams p) {
+  mlp_tc_body<SPEC>(tmX, tmW1, tmW2, tmY, tmR, p);
+}
+
 bool g_attr_set = false;
 
 }  // namespace
@@ -487,7 +497,9 @@ int mlp_tc(const bf16* X, const bf16* W1, const float* b1, const bf16* W2, const
   const int sms = tc_num_sms();
   if (sms <= 0) return set_error(CQVAD_E_CUDA, "tcgen05 path: initialisation failed");
   if (!g_attr_set) {
-    CQ_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CQ_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CQ_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CQ_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     g_attr_set = true;
   }
   CUtensorMap tmX, tmW1, tmW2, tmY, tmR;
@@ -527,7 +539,10 @@ int mlp_tc(const bf16* X, const bf16* W1, const float* b1, const bf16* W2, const
   p.res32 = res32; p.Y32 = Y32; p.ts_out = ts_out ? 1 : 0; p.ts_res = (ts_out && res && !res32) ? 1 : 0;
   p.YT = YT; p.ldyt = ldyt; p.yt_rows = yt_rows > 0 ? yt_rows : 1; p.yt_pitch = yt_pitch;
   const int grid = p.m_tiles < sms ? p.m_tiles : sms;
-  mlp_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmX, tmW1, tmW2, tmY, tmR, p);
+  static const bool no_spec = getenv("CQVAD_MLP_NO_SPEC") != nullptr;
+  if (ts_out && !no_spec && act == CQVAD_ACT_GELU && !ln_g) mlp_tc_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmX, tmW1, tmW2, tmY, tmR, p);
+  else if (ts_out && !no_spec && act == CQVAD_ACT_RELU && ln_g) mlp_tc_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmX, tmW1, tmW2, tmY, tmR, p);
+  else mlp_tc_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmX, tmW1, tmW2, tmY, tmR, p);
   CQ_LAUNCH_CHECK();
   return 0;
 }
