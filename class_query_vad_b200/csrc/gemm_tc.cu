@@ -194,7 +194,8 @@ __device__ __forceinline__ void rowop_loc_step(float (&x)[32], const float (&ref
 // ROWOP = true: the Epilogue::rowop instantiation (softmax / sampling-location epilogues of the encoder's query projections), kept
 // out of the other kernels so that their epilogues carry none of its registers (154 instead of 126 with it compiled in).
 // SPEC (TMA-store kernels): 0 = every epilogue option, 1 = the lean half-tile epilogues only (bias, ReLU / GELU, bf16 residual or
-// activation-derivative operand: most launches of a training step), 2 = the dual-GELU epilogue only -- the all-options kernel is
+// activation-derivative operand: most launches of a training step), 2 = the dual-GELU epilogue only, 3 = the LayerNorm epilogue only
+// (out_proj + norm GEMMs of the encoder / decoder layers) -- the all-options kernel is
 // ~9 000 SASS instructions (146 KB, far beyond the instruction cache), its specialisations a fraction of that.
 template <bool EXTRA, bool TS, bool CTA2, bool ROWOP = false, int SPEC = 0>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
@@ -328,7 +329,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
     float* aux = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)));
     float* bias_s = aux + AUX_BIAS / 4; float* gam_s = aux + AUX_GAM / 4; float* bet_s = aux + AUX_BET / 4;
     float* stats_s = aux + AUX_STATS / 4;
-    const bool do_ln = SPEC == 0 && p.ln_g != nullptr;
+    const bool do_ln = SPEC == 3 || (SPEC == 0 && p.ln_g != nullptr);
     if (do_ln) { gam_s[et] = p.ln_g[et]; bet_s[et] = p.ln_b[et]; }   // N == 256, one n-tile
     int acc = 0; uint32_t acc_phase = 0;
     int etile = 0;
@@ -494,7 +495,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
               else if ((SPEC == 0 || !EXTRA) && p.side == 1) ts_lean_half<1>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge);
               else if ((SPEC == 0 || EXTRA) && p.mul_mode == 1) ts_lean_half<2>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge, p.mul_scale);
               else if (SPEC == 0 || EXTRA) ts_lean_half<3>(t_addr + hf * 64, bcur + c0 + hf * 64, buf, sw, lo, ge);
-            } else if constexpr (SPEC == 0) {
+            } else if constexpr (SPEC == 0 || SPEC == 3) {
 #pragma unroll 1
             for (int cc = 0; cc < 64; cc += 32) {
               const int c = hf * 64 + cc;
@@ -821,6 +822,8 @@ void init_once() {
   if (cudaFuncSetAttribute(gemm_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
   if (cudaFuncSetAttribute(gemm_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
   if (cudaFuncSetAttribute(gemm_tc_rowop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc_spec_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
+  if (cudaFuncSetAttribute(gemm_tc2_spec_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
   if (cudaFuncSetAttribute(gemm_tc_spec_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
   if (cudaFuncSetAttribute(gemm_tc_spec_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
   if (cudaFuncSetAttribute(gemm_tc_spec_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_TS) != cudaSuccess) g_init_err = 2;
@@ -969,6 +972,9 @@ int gemm_tc(const bf16* A, long lda, const bf16* W, bf16* C, long ldc, long M, i
   } else if (ts && !no_spec && p.dual) {          // dual-GELU epilogue only
     if (pair) gemm_tc2_spec_kernel<true, 2><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);
     else gemm_tc_spec_kernel<true, 2><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);
+  } else if (ts && !no_spec && !extra && epi.ln_g && getenv("CQVAD_GEMM_NO_SPEC_LN") == nullptr) {   // LayerNorm epilogue only
+    if (pair) gemm_tc2_spec_kernel<false, 3><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);
+    else gemm_tc_spec_kernel<false, 3><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);
   } else if (ts && !no_spec && p.lean) {          // lean half-tile epilogues only
     if (pair) { if (extra) gemm_tc2_spec_kernel<true, 1><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);
                 else gemm_tc2_spec_kernel<false, 1><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p); }
