@@ -16,20 +16,19 @@ from ..functions.ms_deform_attn_func import MSDeformAttnFunction
 from .ops import linear
 
 
-def _is_power_of_2(n):
-    if (not isinstance(n, int)) or (n < 0):
-        raise ValueError("invalid input for _is_power_of_2: {} (type: {})".format(n, type(n)))
-    return (n & (n - 1) == 0) and n != 0
+def _head_dim_is_power_of_two(d_model, n_heads):
+    d = d_model // n_heads
+    return d > 0 and (d & (d - 1)) == 0
 
 
 class MSDeformAttn3D(nn.Module):
     def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
         super().__init__()
-        if d_model % n_heads != 0:
-            raise ValueError('d_model must be divisible by n_heads, but got {} and {}'.format(d_model, n_heads))
-        if not _is_power_of_2(d_model // n_heads):
-            warnings.warn("You'd better set d_model in MSDeformAttn3D to make the dimension of each attention head a power of 2")
-        self.im2col_step = 64
+        if not isinstance(d_model, int) or not isinstance(n_heads, int) or n_heads <= 0 or d_model % n_heads != 0:
+            raise ValueError(f"MSDeformAttn3D: d_model ({d_model}) has to be a positive multiple of n_heads ({n_heads})")
+        if not _head_dim_is_power_of_two(d_model, n_heads):
+            warnings.warn("MSDeformAttn3D: a power-of-two head dimension (d_model / n_heads) is what the sampling kernels are laid out for")
+        self.im2col_step = 64       # kept for state / attribute compatibility; this library has no im2col batching
         self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
         self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 3)
         self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
@@ -38,19 +37,22 @@ class MSDeformAttn3D(nn.Module):
         self._reset_parameters()
 
     def _reset_parameters(self):
-        # ops/modules/ms_deform_attn.py:149-165
-        constant_(self.sampling_offsets.weight.data, 0.)
-        thetas = torch.arange(self.n_heads // 2, dtype=torch.float32) * (2.0 * math.pi / (self.n_heads // 2))
-        t_extent = torch.cat([torch.ones(self.n_heads // 2), torch.zeros(self.n_heads // 2)], 0)
-        grid_init = torch.stack([thetas.cos().repeat(2), thetas.sin().repeat(2), t_extent], -1)
-        grid_init = (grid_init / grid_init.abs().max(-1, keepdim=True)[0]).view(self.n_heads, 1, 1, 3) \
-            .repeat(1, self.n_levels, self.n_points, 1)
-        for i in range(self.n_points):
-            grid_init[:, :, i, :] *= i + 1
+        """Initial values of ops/modules/ms_deform_attn.py:149-165 (pinned bit for bit by tests/golden/msda_module_init.npz): zero
+        offset / attention weights; offset bias = for head h the unit direction (cos, sin) of angle 2 pi (h mod H/2) / (H/2) with
+        a time component 1 for the first half of the heads and 0 for the second, normalised by its largest component and scaled
+        by (point index + 1), identical for every level; Xavier-uniform value / output projections (in that RNG order)."""
+        H, half = self.n_heads, self.n_heads // 2
+        angle = torch.arange(half, dtype=torch.float32) * (2.0 * math.pi / half)
+        direction = torch.stack([angle.cos().repeat(2), angle.sin().repeat(2),
+                                 torch.cat([torch.ones(half), torch.zeros(half)], 0)], -1)
+        direction = direction / direction.abs().max(-1, keepdim=True)[0]
+        reach = torch.arange(1, self.n_points + 1, dtype=torch.float32).view(1, 1, self.n_points, 1)
+        bias = (direction.view(H, 1, 1, 3) * reach).expand(H, self.n_levels, self.n_points, 3)
         with torch.no_grad():
-            self.sampling_offsets.bias = nn.Parameter(grid_init.view(-1))
-        constant_(self.attention_weights.weight.data, 0.)
-        constant_(self.attention_weights.bias.data, 0.)
+            self.sampling_offsets.weight.zero_()
+            self.sampling_offsets.bias = nn.Parameter(bias.reshape(-1).clone())
+            self.attention_weights.weight.zero_()
+            self.attention_weights.bias.zero_()
         xavier_uniform_(self.value_proj.weight.data)
         constant_(self.value_proj.bias.data, 0.)
         xavier_uniform_(self.output_proj.weight.data)
