@@ -179,18 +179,23 @@ class DeformableTransformerEncoder(nn.Module):
 
     @staticmethod
     def get_reference_points(spatio_temporal_shapes, valid_ratios, device):
-        # dab_transformer.py:433-452
-        reference_points_list = []
+        """Reference points [B, Len, L, 3] of dab_transformer.py:433-449 (bit for bit: tests/test_reference_points_cpu.py): voxel
+        centres (i + 0.5) / (valid_ratio * extent) per axis in (x, y, t) order, every level's points then rescaled by the valid
+        ratios of ALL levels.  Built per axis and broadcast over the level's grid: the per-voxel divisions of the meshgrid
+        formulation are the same divisions on replicated operands."""
+        B = valid_ratios.shape[0]
+
+        def centres(extent, ratio):                      # [B, extent]
+            grid = torch.linspace(0.5, extent - 0.5, extent, dtype=torch.float32, device=device)
+            return grid[None] / (ratio[:, None] * extent)
+
+        per_level = []
         for lvl, (T_, H_, W_) in enumerate(_lib.host_shapes(spatio_temporal_shapes)):
-            ref_t, ref_y, ref_x = torch.meshgrid(torch.linspace(0.5, T_ - 0.5, T_, dtype=torch.float32, device=device),
-                                                 torch.linspace(0.5, H_ - 0.5, H_, dtype=torch.float32, device=device),
-                                                 torch.linspace(0.5, W_ - 0.5, W_, dtype=torch.float32, device=device), indexing="ij")
-            ref_t = ref_t.reshape(-1)[None] / (valid_ratios[:, None, lvl, 2] * T_)
-            ref_y = ref_y.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * H_)
-            ref_x = ref_x.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * W_)
-            reference_points_list.append(torch.stack((ref_x, ref_y, ref_t), -1))
-        reference_points = torch.cat(reference_points_list, 1)
-        return reference_points[:, :, None] * valid_ratios[:, None]
+            t = centres(T_, valid_ratios[:, lvl, 2])[:, :, None, None].expand(B, T_, H_, W_)
+            y = centres(H_, valid_ratios[:, lvl, 1])[:, None, :, None].expand(B, T_, H_, W_)
+            x = centres(W_, valid_ratios[:, lvl, 0])[:, None, None, :].expand(B, T_, H_, W_)
+            per_level.append(torch.stack((x, y, t), -1).reshape(B, T_ * H_ * W_, 3))
+        return torch.cat(per_level, 1)[:, :, None] * valid_ratios[:, None]
 
     def forward(self, src, spatio_temporal_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None):
         output = src
